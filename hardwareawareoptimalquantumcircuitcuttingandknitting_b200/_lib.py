@@ -1,0 +1,173 @@
+"""ctypes binding of ``libqck.so`` (the C ABI declared in ``include/qck.h``).
+
+This is the only way the Python host side reaches the GPU kernels.  There is no
+CPU fallback: if the shared library is missing, cannot be loaded, or no sm_100
+device is present, every entry point raises.  ``build()`` compiles the library
+in-tree with nvcc for ``sm_100a`` (works without a GPU).
+
+C status codes map to the exception types the reference raises on the same
+conditions: invalid argument -> ``ValueError``, CUDA failure ->
+``RuntimeError``, unsupported -> ``NotImplementedError``, out of memory ->
+``MemoryError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqck.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+MAX_TILE_QUBITS = 14
+MAX_DIGITS = 16
+MAX_OUT_BITS = 40
+MAX_FRAGMENTS = 8
+MAX_VARIANTS = 8
+OP_U1, OP_CX, OP_CZ, OP_U2 = 0, 1, 2, 3
+
+
+class QckSweep(C.Structure):
+    _fields_ = [("n_tile", C.c_int32), ("op_begin", C.c_int32), ("op_end", C.c_int32),
+                ("reserved", C.c_int32), ("pos", C.c_int32 * (MAX_TILE_QUBITS + 2))]
+
+
+class QckSimPlan(C.Structure):
+    _fields_ = [("n_state_qubits", C.c_int32), ("n_sweeps", C.c_int32),
+                ("sweeps", C.POINTER(QckSweep)), ("d_ops", C.c_void_p), ("d_mats", C.c_void_p),
+                ("n_digits", C.c_int32), ("radix", C.c_int32 * MAX_DIGITS),
+                ("n_out_bits", C.c_int32), ("out_pos", C.c_int32 * MAX_OUT_BITS),
+                ("sum_mask", C.c_uint64), ("sign_mask", C.c_uint64)]
+
+
+class QckStats(C.Structure):
+    _fields_ = [("sum", C.c_double), ("min", C.c_double), ("sum_sqrt", C.c_double), ("nnz", C.c_double)]
+
+
+_PROTOTYPES = {
+    "qck_abi_version": (C.c_int, []),
+    "qck_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "qck_destroy": (C.c_int, [C.c_void_p]),
+    "qck_last_error_string": (C.c_char_p, [C.c_void_p]),
+    "qck_status_string": (C.c_char_p, [C.c_int]),
+    "qck_launch_count": (C.c_int64, [C.c_void_p]),
+    "qck_sim_fragments": (C.c_int, [C.c_void_p, C.POINTER(QckSimPlan), C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qck_sim_statevector": (C.c_int, [C.c_void_p, C.POINTER(QckSimPlan), C.c_int32, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
+    "qck_knit_outer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int,
+                                 C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qck_knit_contract": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_int, C.c_void_p]),
+    "qck_stats_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_void_p]),
+    "qck_hellinger": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "qck_npd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.POINTER(C.c_double),
+                          C.POINTER(C.c_double), C.c_void_p]),
+    "qck_qd_prune": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p]),
+    "qck_qd_sqrt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "qck_qd_axpby": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                               C.c_uint64, C.c_double, C.c_void_p]),
+    "qck_qd_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_double, C.c_void_p]),
+    "qck_qd_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                               C.c_uint64, C.c_double, C.c_void_p]),
+    "qck_qd_knit_level": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_uint64, C.c_int,
+                                    C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile ``libqck.so`` in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "qck.h"))
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(s) for s in srcs)
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    cmd = ["make", "-C", CSRC, "-j8"] + (["-B"] if force else [])
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"building libqck.so failed:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the library (never builds implicitly on a GPU box: the .so travels in-tree)."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU fallback for the simulation / knit path)")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in _PROTOTYPES.items():
+                fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+_EXC = {1: ValueError, 2: RuntimeError, 3: NotImplementedError, 4: MemoryError}
+
+
+class Handle:
+    """One ``qck_handle`` (per thread, per device).  Owns nothing but the C handle."""
+
+    def __init__(self, device: int = 0) -> None:
+        self.lib = load()
+        self.device = int(device)
+        ptr = C.c_void_p()
+        rc = self.lib.qck_create(self.device, C.byref(ptr))
+        if rc != 0:
+            raise _EXC.get(rc, RuntimeError)(
+                f"qck_create(device={device}) failed: {self.lib.qck_status_string(rc).decode()} "
+                "(a B200 / sm_100 GPU is required; there is no CPU fallback)")
+        self.ptr = ptr
+
+    def check(self, rc: int) -> None:
+        if rc != 0:
+            msg = self.lib.qck_last_error_string(self.ptr).decode(errors="replace")
+            raise _EXC.get(rc, RuntimeError)(f"{self.lib.qck_status_string(rc).decode()}: {msg}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.qck_launch_count(self.ptr))
+
+    def close(self) -> None:
+        if getattr(self, "ptr", None):
+            self.lib.qck_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_tls = threading.local()
+
+
+def get_handle(device: int = 0) -> Handle:
+    """Thread-local handle cache: the reference calls the hot path from several
+    Python threads at once (``src/HwAwareCutter/Utilities.py:85-101``)."""
+    cache = getattr(_tls, "handles", None)
+    if cache is None:
+        cache = _tls.handles = {}
+    h = cache.get(device)
+    if h is None:
+        h = cache[device] = Handle(device)
+    return h

@@ -1,0 +1,463 @@
+"""Fragment circuit -> device programs (the host half of fragment execution).
+
+The reference materialises every instance as a Qiskit circuit
+(``third_party/qvm/qvm/virtual_circuit.py:183-213``: copy the fragment, add the
+``vgate_c`` register, splice in ``VirtualGateEndpoint.instantiate(label[k])``,
+``decompose()``) and hands the list to Aer (``run.py:42``).  Here a fragment is
+compiled ONCE into a template whose virtual-gate endpoints are *slots*; an
+instance is just a mixed-radix label decoded on the device, where each digit
+selects the slot's variant matrices from a table.  Instances that share the same
+set of measuring slots (a *pattern*) share one program (``qck_sim_plan``):
+
+* a slot variant is ``pre-matrix, measure?, post-matrix`` (the one-qubit share
+  of ``_instantiations()[id]``, ``virtual_gates.py:134-150``; at most one
+  measurement, ``:45-50``);
+* a measurement whose qubit is used afterwards (gate cuts: the wire continues to
+  its final measurement) becomes ``CX(qubit -> fresh ancilla bit)``: the two
+  halves of the enlarged state are the two un-normalised branches of SURVEY.md
+  A.2; a measurement on a wire that ends there (the old end of a wire cut,
+  ``Cutter.py:624-643``) is read off ``|amp|^2`` directly;
+* the output row of an instance is indexed by the fragment's finally-measured
+  clbits in ascending clbit order (so a fragment's row index is
+  ``pext(key, out_mask)``); config bits are folded with sign ``(-1)^bit`` (exact
+  mode) or kept as extra row bits (``fold=False``, for the
+  reference-faithful pruning mode);
+* consecutive one-qubit gates on a wire are multiplied together on the host
+  (complex128), also into the following slot's pre-matrices;
+* programs whose state (qubits + ancillas) exceeds the on-chip limit are cut into
+  *sweeps*: runs of ops that only touch <= ``STREAM_TILE`` qubits, always
+  including the ``LOW_RUN`` lowest ones so that every tile is a set of
+  contiguous >= 512-byte runs in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .circuit import Barrier, Gate, Measure, QuantumCircuit, QuantumRegister
+from .virtual_gates import VirtualBinaryGate, VirtualGateEndpoint
+
+ONCHIP_MAX_QUBITS = 13      # 2^13 complex128 = 128 KiB of the 227 KiB shared memory
+STREAM_TILE = 12            # 64 KiB tiles -> 3 CTAs per SM overlap load / compute / store
+LOW_RUN = 5                 # tiles always hold qubits 0..4: 32 amplitudes = 512 contiguous bytes
+
+_I2 = np.eye(2, dtype=np.complex128)
+
+
+def _is_identity(m: np.ndarray) -> bool:
+    return bool(np.array_equal(m, _I2))
+
+
+@dataclass
+class Slot:
+    digit: int                  # position of the owning virtual gate in the fragment label
+    vgate_idx: int
+    side: int
+    qubit: int                  # local qubit (state bit position)
+    terminal: bool              # nothing acts on the qubit afterwards
+    pre: list                   # per variant: 2x2 complex matrix
+    meas: list                  # per variant: bool
+    post: list                  # per variant: 2x2 complex matrix
+    pre_off: int = -1           # matrix-pool offsets (doubles); -1: all identity
+    post_off: int = -1
+
+
+@dataclass
+class PlanHost:
+    pattern: int
+    labels: np.ndarray                  # int32 fragment-label indices using this program
+    n_state: int
+    ops: np.ndarray                     # [n_ops, 8] int32
+    sweeps: list                        # [(positions, op_begin, op_end)]
+    out_pos: list
+    sum_mask: int
+    sign_mask: int
+    op_base: int = 0                    # offset of this plan's ops in the fragment's device op array
+
+
+class FragmentProgram:
+    """Template + per-pattern programs of one fragment."""
+
+    def __init__(self, frag_circuit: QuantumCircuit, fragment: QuantumRegister, num_clbits: int,
+                 onchip_max: int = ONCHIP_MAX_QUBITS, stream_tile: int = STREAM_TILE) -> None:
+        self.fragment = fragment
+        self.n_qubits = len(fragment)
+        self.num_clbits = num_clbits
+        self.onchip_max = onchip_max
+        self.stream_tile = stream_tile
+        self._pool: list[np.ndarray] = []
+        self._pool_len = 0
+        self._lower(frag_circuit)
+        self._plans: dict[bool, list[PlanHost]] = {}
+
+    # ------------------------------------------------------------------ template
+    def _add_matrix(self, m: np.ndarray) -> int:
+        flat = np.ascontiguousarray(m, dtype=np.complex128).reshape(-1).view(np.float64)
+        off = self._pool_len
+        self._pool.append(flat)
+        self._pool_len += flat.size
+        return off
+
+    def _lower(self, circ: QuantumCircuit) -> None:
+        frag_qubits = list(self.fragment)
+        qset = set(frag_qubits)
+        instrs = [ins for ins in circ.data if not (isinstance(ins.operation, Barrier)
+                                                   and not isinstance(ins.operation, VirtualGateEndpoint))]
+        for ins in instrs:
+            if not set(ins.qubits) <= qset:
+                raise ValueError("Circuit contains gates that act on multiple fragments.")
+        last_use = {}
+        for i, ins in enumerate(instrs):
+            for q in ins.qubits:
+                last_use[q] = i
+        # finally-measured clbits (terminal measurements) define the output row
+        terminal = []                    # (clbit index, qubit)
+        for i, ins in enumerate(instrs):
+            if isinstance(ins.operation, Measure) and last_use[ins.qubits[0]] == i:
+                terminal.append((circ.clbit_index(ins.clbits[0]), ins.qubits[0]))
+        terminal.sort(key=lambda t: t[0])
+        if len({c for c, _ in terminal}) != len(terminal):
+            raise ValueError("two terminal measurements write the same clbit")
+        order = [q for _, q in terminal] + [q for q in frag_qubits if q not in {t[1] for t in terminal}]
+        pos = {q: i for i, q in enumerate(order)}
+        self.qubit_order = order
+
+        # virtual gates touching this fragment, in circuit (= vgate index) order
+        touched = sorted({ins.operation.vgate_idx for ins in instrs
+                          if isinstance(ins.operation, VirtualGateEndpoint)})
+        self.vgate_indices = touched
+        digit_of = {k: d for d, k in enumerate(touched)}
+        self.radix = [0] * len(touched)
+
+        out_bits = [(c, pos[q]) for c, q in terminal]      # (clbit, state position or ("anc", i))
+        tops: list[tuple] = []
+        slots: list[Slot] = []
+        pending: dict[int, np.ndarray] = {}
+
+        def flush(q: int) -> None:
+            m = pending.pop(q, None)
+            if m is not None and not _is_identity(m):
+                tops.append(("u1", q, self._add_matrix(m)))
+
+        mid_measures = 0
+        for i, ins in enumerate(instrs):
+            op = ins.operation
+            qs = [pos[q] for q in ins.qubits]
+            if isinstance(op, VirtualGateEndpoint):
+                vg: VirtualBinaryGate = op.virtual_gate
+                table = vg._table()
+                d = digit_of[op.vgate_idx]
+                self.radix[d] = len(table)
+                pre, meas, post = [], [], []
+                for inst in table:
+                    a, b, seen = _I2, _I2, False
+                    for name, params, q in inst:
+                        if q != op.qubit_idx:
+                            continue
+                        if name == "measure":
+                            if seen:
+                                raise ValueError("instantiation measures a qubit twice")
+                            seen = True
+                            continue
+                        m = Gate(name, 1, params).to_matrix()
+                        if seen:
+                            b = m @ b
+                        else:
+                            a = m @ a
+                    pre.append(a)
+                    meas.append(seen)
+                    post.append(b)
+                pend = pending.pop(qs[0], None)
+                if pend is not None:
+                    pre = [a @ pend for a in pre]
+                slot = Slot(digit=d, vgate_idx=op.vgate_idx, side=op.qubit_idx, qubit=qs[0],
+                            terminal=(last_use[ins.qubits[0]] == i), pre=pre, meas=meas, post=post)
+                if not all(_is_identity(a) for a in pre):
+                    slot.pre_off = self._add_matrix(np.stack(pre))
+                if not slot.terminal and not all(_is_identity(b) for b in post):
+                    slot.post_off = self._add_matrix(np.stack(post))
+                tops.append(("slot", len(slots)))
+                slots.append(slot)
+            elif isinstance(op, Measure):
+                flush(qs[0])
+                if last_use[ins.qubits[0]] != i:          # mid-circuit measurement of the input circuit
+                    tops.append(("mmeas", qs[0], circ.clbit_index(ins.clbits[0])))
+                    mid_measures += 1
+            elif isinstance(op, Gate):
+                if op.num_qubits == 1:
+                    m = op.to_matrix()
+                    pending[qs[0]] = m @ pending[qs[0]] if qs[0] in pending else m
+                elif op.num_qubits == 2:
+                    flush(qs[0]); flush(qs[1])
+                    if op._matrix is None and op.name == "cx":
+                        tops.append(("cx", qs[0], qs[1]))
+                    elif op._matrix is None and op.name == "cz":
+                        tops.append(("cz", qs[0], qs[1]))
+                    else:
+                        tops.append(("u2", qs[0], qs[1], self._add_matrix(op.to_matrix())))
+                else:
+                    raise NotImplementedError(f"{op.name}: gates on more than two qubits are not supported")
+            else:
+                raise TypeError(f"cannot lower operation {op!r}")
+        # one-qubit gates still pending act on wires that are never measured afterwards: they
+        # cannot change any probability and are dropped
+        pending.clear()
+        self.tops = tops
+        self.slots = slots
+        self.out_bits = out_bits
+        self.out_clbits = [c for c, _ in out_bits]
+        self.has_mid_measure = mid_measures > 0
+        self.out_mask = 0
+        for c in self.out_clbits:
+            self.out_mask |= 1 << c
+        # does any instance of this fragment measure anything at all?  (run.py:49-58 drops
+        # fragments whose circuits have no measurement)
+        self.measures_anything = bool(out_bits) or mid_measures > 0 or any(any(s.meas) for s in slots)
+        self.num_labels = int(np.prod(self.radix, dtype=np.int64)) if self.radix else 1
+        self.mats = np.concatenate(self._pool) if self._pool else np.zeros(8)
+
+    # ------------------------------------------------------------------ patterns
+    def label_digits(self, labels: np.ndarray) -> np.ndarray:
+        if not self.radix:
+            return np.zeros((len(labels), 0), dtype=np.int64)
+        return np.stack(np.unravel_index(np.asarray(labels, dtype=np.int64), self.radix), axis=1)
+
+    def plans(self, fold: bool = True) -> list[PlanHost]:
+        if fold in self._plans:
+            return self._plans[fold]
+        labels = np.arange(self.num_labels, dtype=np.int64)
+        digits = self.label_digits(labels)
+        pat = np.zeros(self.num_labels, dtype=np.int64)
+        for s, slot in enumerate(self.slots):
+            flags = np.asarray(slot.meas, dtype=np.int64)[digits[:, slot.digit]]
+            pat |= flags << s
+        plans = []
+        op_base = 0
+        for p in np.unique(pat):
+            plan = self._build_plan(int(p), labels[pat == p].astype(np.int32), fold)
+            plan.op_base = op_base
+            op_base += len(plan.ops)
+            plans.append(plan)
+        self._plans[fold] = plans
+        return plans
+
+    def _build_plan(self, pattern: int, labels: np.ndarray, fold: bool) -> PlanHost:
+        n = self.n_qubits
+        n_anc = 0
+        ops: list[list[int]] = []
+        cfg_pos: dict[int, int] = {}          # digit -> state bit carrying the config bit
+        extra_out: list[tuple[int, int]] = [] # (clbit, ancilla position) of mid-circuit measurements
+
+        def emit(kind, q0, q1=0, mat=0, sel=-1, stride=0):
+            ops.append([kind, q0, q1, mat, sel, stride, n + n_anc, 0])
+
+        for top in self.tops:
+            if top[0] == "u1":
+                emit(_lib.OP_U1, top[1], 0, top[2])
+            elif top[0] == "cx":
+                emit(_lib.OP_CX, top[1], top[2])
+            elif top[0] == "cz":
+                emit(_lib.OP_CZ, top[1], top[2])
+            elif top[0] == "u2":
+                emit(_lib.OP_U2, top[1], top[2], top[3])
+            elif top[0] == "mmeas":
+                anc = n + n_anc
+                n_anc += 1
+                emit(_lib.OP_CX, top[1], anc)
+                extra_out.append((top[2], anc))
+            else:
+                s = top[1]
+                slot = self.slots[s]
+                measures = bool((pattern >> s) & 1)
+                if slot.pre_off >= 0:
+                    emit(_lib.OP_U1, slot.qubit, 0, slot.pre_off, slot.digit, 8)
+                if measures:
+                    if slot.digit in cfg_pos:
+                        raise NotImplementedError("both ends of a virtual gate measure inside one fragment")
+                    if slot.terminal:
+                        cfg_pos[slot.digit] = slot.qubit
+                    else:
+                        anc = n + n_anc
+                        n_anc += 1
+                        emit(_lib.OP_CX, slot.qubit, anc)
+                        cfg_pos[slot.digit] = anc
+                if slot.post_off >= 0:
+                    emit(_lib.OP_U1, slot.qubit, 0, slot.post_off, slot.digit, 8)
+        n_state = n + n_anc
+        if n_state > 40:
+            raise NotImplementedError(f"instance state of {n_state} qubits is out of range")
+        bits = sorted(self.out_bits + extra_out)
+        if len({c for c, _ in bits}) != len(bits):
+            raise ValueError("a clbit is written by more than one measurement")
+        out_pos = [p for _, p in bits]
+        if not fold:
+            out_pos += [cfg_pos.get(d, -1) for d in range(len(self.radix))]
+        used = {p for p in out_pos if p >= 0}
+        sum_mask = 0
+        for b in range(n_state):
+            if b not in used:
+                sum_mask |= 1 << b
+        sign_mask = 0
+        if fold:
+            for p in cfg_pos.values():
+                sign_mask |= 1 << p
+        ops_arr = np.asarray(ops, dtype=np.int32).reshape(-1, 8)
+        if n_state <= self.onchip_max:
+            sweeps = [(list(range(n_state)), 0, len(ops_arr))]
+        else:
+            ops_arr, sweeps = _schedule_sweeps(ops_arr, n_state, self.stream_tile)
+        return PlanHost(pattern, labels, n_state, ops_arr, sweeps, out_pos, sum_mask, sign_mask)
+
+    @property
+    def row_bits(self) -> int:
+        """log2 of the folded output row length."""
+        return len(self.out_bits) + sum(1 for t in self.tops if t[0] == "mmeas")
+
+    def row_len(self, fold: bool = True) -> int:
+        bits = self.row_bits + (0 if fold else len(self.radix))
+        return 1 << bits
+
+
+def _op_qubits(op) -> tuple[int, ...]:
+    return (int(op[1]),) if op[0] == _lib.OP_U1 else (int(op[1]), int(op[2]))
+
+
+def _schedule_sweeps(ops: np.ndarray, n_state: int, tile: int):
+    """Greedy list scheduling: each sweep takes, in program order, every op whose qubits are
+    not blocked by an earlier unscheduled op and still fit into the tile."""
+    tile = min(tile, n_state)
+    low = min(LOW_RUN, tile)
+    remaining = list(range(len(ops)))
+    new_ops, sweeps = [], []
+    while remaining:
+        tile_set = set(range(low))
+        blocked: set[int] = set()
+        taken, rest = [], []
+        for i in remaining:
+            qs = _op_qubits(ops[i])
+            if not (set(qs) & blocked) and len(tile_set | set(qs)) <= tile:
+                tile_set |= set(qs)
+                taken.append(i)
+            else:
+                blocked |= set(qs)
+                rest.append(i)
+        if not taken:
+            raise NotImplementedError("an op does not fit into a tile")
+        for b in range(n_state):                 # pad with the lowest free qubits: longer contiguous runs
+            if len(tile_set) >= tile:
+                break
+            tile_set.add(b)
+        positions = sorted(tile_set)
+        local = {p: j for j, p in enumerate(positions)}
+        begin = len(new_ops)
+        for i in taken:
+            op = ops[i].copy()
+            op[1] = local[int(op[1])]
+            if op[0] != _lib.OP_U1:
+                op[2] = local[int(op[2])]
+            op[6] = 0                            # n_live is meaningless inside a tile
+            new_ops.append(op)
+        sweeps.append((positions, begin, len(new_ops)))
+        remaining = rest
+    return np.asarray(new_ops, dtype=np.int32).reshape(-1, 8), sweeps
+
+
+# ---------------------------------------------------------------------- device side
+class FragmentExecutor:
+    """Uploads a FragmentProgram and runs all (or some) of its instances on the GPU."""
+
+    def __init__(self, program: FragmentProgram, device, fold: bool = True) -> None:
+        import torch
+        self.torch = torch
+        self.program = program
+        self.device = torch.device(device)
+        self.fold = fold
+        self.plans = program.plans(fold)
+        ops = np.concatenate([p.ops for p in self.plans]) if self.plans else np.zeros((0, 8), np.int32)
+        if len(ops) == 0:
+            ops = np.zeros((1, 8), np.int32)
+        labels = np.concatenate([p.labels for p in self.plans])
+        # one pinned staging buffer, one H2D copy per array
+        self._h_ops = torch.from_numpy(np.ascontiguousarray(ops)).pin_memory() if torch.cuda.is_available() \
+            else torch.from_numpy(np.ascontiguousarray(ops))
+        self._h_mats = torch.from_numpy(np.ascontiguousarray(program.mats))
+        self._h_labels = torch.from_numpy(np.ascontiguousarray(labels))
+        if torch.cuda.is_available():
+            self._h_mats = self._h_mats.pin_memory()
+            self._h_labels = self._h_labels.pin_memory()
+        self.h2d_bytes = self._h_ops.numel() * 4 + self._h_mats.numel() * 8 + self._h_labels.numel() * 4
+        self.d_ops = self.d_mats = self.d_labels = None
+        self._sweep_arrays = []
+        self._structs = []
+        off = 0
+        for p in self.plans:
+            arr = (_lib.QckSweep * len(p.sweeps))()
+            for i, (positions, b, e) in enumerate(p.sweeps):
+                arr[i].n_tile = len(positions)
+                arr[i].op_begin = p.op_base + b
+                arr[i].op_end = p.op_base + e
+                for j, x in enumerate(positions):
+                    arr[i].pos[j] = x
+            self._sweep_arrays.append(arr)
+            st = _lib.QckSimPlan()
+            st.n_state_qubits = p.n_state
+            st.n_sweeps = len(p.sweeps)
+            st.sweeps = arr
+            st.n_digits = len(program.radix)
+            for k, r in enumerate(program.radix):
+                st.radix[k] = r
+            st.n_out_bits = len(p.out_pos)
+            for j, x in enumerate(p.out_pos):
+                st.out_pos[j] = x
+            st.sum_mask = p.sum_mask
+            st.sign_mask = p.sign_mask
+            self._structs.append((st, off, len(p.labels)))
+            off += len(p.labels)
+        self.row_len = program.row_len(fold)
+        self.max_state = max(p.n_state for p in self.plans)
+        self.streaming = self.max_state > program.onchip_max
+        self._work = None
+
+    def upload(self) -> None:
+        """Host -> device copy of ops, matrices and label lists (part of the e2e timed region)."""
+        dev = self.device
+        self.d_ops = self._h_ops.to(dev, non_blocking=True)
+        self.d_mats = self._h_mats.to(dev, non_blocking=True)
+        self.d_labels = self._h_labels.to(dev, non_blocking=True)
+
+    def run(self, handle: "_lib.Handle", out=None, label_range: tuple[int, int] | None = None):
+        """-> device tensor [num_labels, row_len] float64 (rows outside label_range untouched / 0)."""
+        torch = self.torch
+        if self.d_ops is None:
+            self.upload()
+        prog = self.program
+        if out is None:
+            alloc = torch.zeros if label_range is not None else torch.empty
+            out = alloc((prog.num_labels, self.row_len), dtype=torch.float64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self.streaming and self._work is None:
+            free, _ = torch.cuda.mem_get_info(self.device)
+            per = 16 << self.max_state
+            n = max(1, min(prog.num_labels, int(free * 0.5) // per, 64))
+            self._work = torch.empty(n * per, dtype=torch.uint8, device=self.device)
+        for st, off, count in self._structs:
+            labels_ptr = self.d_labels.data_ptr() + 4 * off
+            if label_range is not None:
+                # label lists are ascending inside a plan: clip to the requested range
+                host = self._h_labels[off:off + count].numpy()
+                lo = int(np.searchsorted(host, label_range[0], side="left"))
+                hi = int(np.searchsorted(host, label_range[1], side="left"))
+                labels_ptr += 4 * lo
+                count = hi - lo
+                if count <= 0:
+                    continue
+            st.d_ops = self.d_ops.data_ptr()
+            st.d_mats = self.d_mats.data_ptr()
+            work_ptr = self._work.data_ptr() if self._work is not None else None
+            work_bytes = self._work.numel() if self._work is not None else 0
+            handle.check(handle.lib.qck_sim_fragments(handle.ptr, C.byref(st), labels_ptr, count, out.data_ptr(),
+                                                      self.row_len, work_ptr, work_bytes, stream))
+        return out

@@ -1,0 +1,93 @@
+// Handle lifetime, error strings and scratch management of libqck.so.
+#include "qck_common.cuh"
+
+#include <new>
+
+extern "C" int qck_abi_version(void) { return QCK_ABI_VERSION; }
+
+extern "C" const char* qck_status_string(int status) {
+    switch (status) {
+        case QCK_OK: return "ok";
+        case QCK_ERR_INVALID_ARG: return "invalid argument";
+        case QCK_ERR_CUDA: return "CUDA error";
+        case QCK_ERR_UNSUPPORTED: return "unsupported";
+        case QCK_ERR_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int qck_create(int device, qck_handle** out) {
+    if (!out) return QCK_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return QCK_ERR_CUDA;
+    if (device < 0 || device >= count) return QCK_ERR_INVALID_ARG;
+    qck_handle* full = new (std::nothrow) qck_handle;
+    if (!full) return QCK_ERR_NOMEM;
+    memset(full, 0, sizeof(*full));
+    qck_handle* h = full;
+    h->device = device;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete full;
+        return QCK_ERR_CUDA;
+    }
+    if (prop.major < 10) {  // sm_100a only: no fallback code path exists
+        delete full;
+        return QCK_ERR_UNSUPPORTED;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->partials_count = 1 << 16;
+    if (cudaMalloc(&h->d_partials, h->partials_count * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) != cudaSuccess) {
+        if (h->d_partials) cudaFree(h->d_partials);
+        delete full;
+        return QCK_ERR_NOMEM;
+    }
+    *out = h;
+    return QCK_OK;
+}
+
+extern "C" int qck_destroy(qck_handle* h) {
+    if (!h) return QCK_OK;
+    DeviceGuard guard(h->device);
+    if (h->d_partials) cudaFree(h->d_partials);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->scratch) cudaFree(h->scratch);
+    delete h;
+    return QCK_OK;
+}
+
+extern "C" const char* qck_last_error_string(const qck_handle* h) { return h ? h->err : "null handle"; }
+
+extern "C" int64_t qck_launch_count(const qck_handle* h) { return h ? h->launches : 0; }
+
+int qck_ensure_partials(qck_handle* h, size_t count) {
+    if (count <= h->partials_count) return QCK_OK;
+    // partials are consumed by the kernel enqueued right after they are written, on the same
+    // stream; growing here would race with in-flight work, so the size is fixed at create time
+    QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "reduction scratch too small (%zu > %zu)", count, h->partials_count);
+}
+
+int qck_ensure_scratch(qck_handle* h, size_t bytes, void** out) {
+    if (bytes > h->scratch_bytes) {
+        // synchronous by design: cudaFree waits for in-flight users of the old block
+        if (h->scratch) {
+            cudaError_t e = cudaFree(h->scratch);
+            h->scratch = nullptr;
+            h->scratch_bytes = 0;
+            if (e != cudaSuccess) QCK_FAIL(h, QCK_ERR_CUDA, "cudaFree(scratch): %s", cudaGetErrorString(e));
+        }
+        size_t want = bytes + (bytes >> 2);
+        cudaError_t e = cudaMalloc(&h->scratch, want);
+        if (e != cudaSuccess) {
+            h->scratch = nullptr;
+            QCK_FAIL(h, QCK_ERR_NOMEM, "cudaMalloc(%zu bytes of scratch): %s", want, cudaGetErrorString(e));
+        }
+        h->scratch_bytes = want;
+    }
+    *out = h->scratch;
+    return QCK_OK;
+}

@@ -1,0 +1,579 @@
+// Knitting kernels (sm_100a): exact closed form of VirtualCircuit.knit
+// (third_party/qvm/qvm/virtual_circuit.py:50-68,150-171,216-228 + virtual_gates.py knit rules).
+//
+//   knit_outer    K = 0:  out[y] = prod_f T_f[pext(y, mask_f)]             (HBM-write bound)
+//   knit_contract K >= 1: out[y] = sum_l w(l) prod_f Q_f[l_f][pext(y, mask_f)]  (FP64 FMA bound)
+//
+// knit_outer is a pure streaming-store kernel.  The output index is split into a chunk
+// (low c = 12 bits, 32 KiB of output) and a chunk number.  Within a chunk the table index
+// of every fragment is (row chosen by the high bits) + (offset given by the low bits): the
+// offsets are per-thread loop invariants kept in registers, the rows are staged in shared
+// memory and reloaded only when they change.  Chunks are enumerated so that the bits of
+// fragments with small rows vary fastest, which makes row reloads rare (for syc-32 the
+// 18-qubit fragment's row changes every 16384 chunks).  Warp 0 prepares the next chunk's
+// descriptor (address, row numbers, scalar factors) while the CTA streams the current one.
+#include "qck_common.cuh"
+
+#define KO_MAXF 8
+#define KO_CHUNK_BITS 12
+#define KO_THREADS 256
+#define KO_ITEMS ((1 << KO_CHUNK_BITS) / (2 * KO_THREADS))
+
+struct OuterParams {
+    int n_frag, n_vec;
+    const double* table[KO_MAXF];
+    unsigned long long hi_mask[KO_MAXF];  // mask >> c
+    unsigned int lo_mask[KO_MAXF];        // mask & (2^c - 1)
+    int nlo[KO_MAXF];
+    int row_off[KO_MAXF];
+    int n_free;
+    int order[32];
+    unsigned long long y_hi_base;
+    unsigned long long n_chunks;
+    unsigned long long y_begin;
+    double* out;
+    double* partials;
+};
+
+struct ChunkDesc {
+    unsigned long long y_hi;
+    unsigned int hi[KO_MAXF];
+    double scal;  // product of the scalar fragments
+};
+
+__device__ __forceinline__ void st_stream(double* p, double a, double b) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+
+__device__ __forceinline__ void make_desc(const OuterParams& P, unsigned long long g, ChunkDesc* d) {
+    // called by warp 0 only
+    const int lane = threadIdx.x;
+    unsigned int part = 0;
+    if (lane < P.n_free) part = (unsigned int)((g >> lane) & 1ull) << P.order[lane];
+    unsigned int spread = __reduce_or_sync(0xffffffffu, part);
+    unsigned long long y_hi = P.y_hi_base | spread;
+    double sc = 1.0;
+    unsigned int hi = 0;
+    if (lane < P.n_frag) {
+        hi = (unsigned int)soft_pext(y_hi, P.hi_mask[lane]);
+        if (lane >= P.n_vec) sc = __ldg(P.table[lane] + hi);
+    }
+    // product of scalar factors in fixed order (deterministic)
+    double prod = 1.0;
+    for (int f = P.n_vec; f < P.n_frag; ++f) prod *= __shfl_sync(0xffffffffu, sc, f);
+    if (lane < P.n_frag) d->hi[lane] = hi;
+    if (lane == 0) {
+        d->y_hi = y_hi;
+        d->scal = prod;
+    }
+}
+
+template <int FV, bool WRITE>
+__global__ void __launch_bounds__(KO_THREADS) knit_outer_kernel(const __grid_constant__ OuterParams P) {
+    extern __shared__ __align__(16) double rows[];
+    __shared__ ChunkDesc desc[2];
+    const int tid = threadIdx.x;
+    // contiguous chunk range of this CTA
+    const unsigned long long g0 = (P.n_chunks * blockIdx.x) / gridDim.x;
+    const unsigned long long g1 = (P.n_chunks * (blockIdx.x + 1ull)) / gridDim.x;
+
+    // loop-invariant row offsets of this thread's elements
+    unsigned short idx[KO_ITEMS][FV > 0 ? FV : 1];
+    unsigned int delta[FV > 0 ? FV : 1];
+#pragma unroll
+    for (int f = 0; f < FV; ++f) {
+        delta[f] = P.lo_mask[f] & 1u;
+#pragma unroll
+        for (int e = 0; e < KO_ITEMS; ++e)
+            idx[e][f] = (unsigned short)soft_pext(2u * (e * KO_THREADS + tid), P.lo_mask[f]);
+    }
+    unsigned int loaded[FV > 0 ? FV : 1];
+#pragma unroll
+    for (int f = 0; f < FV; ++f) loaded[f] = 0xffffffffu;
+
+    double sum = 0.0, mn = INFINITY, nnz = 0.0;
+    if (g0 < g1 && tid < 32) make_desc(P, g0, &desc[0]);
+    __syncthreads();
+    for (unsigned long long g = g0; g < g1; ++g) {
+        const int cur = (int)((g - g0) & 1ull);
+        if (tid < 32 && g + 1 < g1) make_desc(P, g + 1, &desc[cur ^ 1]);
+        const ChunkDesc& D = desc[cur];
+        bool reload = false;
+#pragma unroll
+        for (int f = 0; f < FV; ++f) reload |= (D.hi[f] != loaded[f]);
+        if (reload) {  // uniform across the CTA
+#pragma unroll
+            for (int f = 0; f < FV; ++f) {
+                if (D.hi[f] != loaded[f]) {
+                    const double* src = P.table[f] + ((unsigned long long)D.hi[f] << P.nlo[f]);
+                    double* dst = rows + P.row_off[f];
+                    for (int i = tid; i < (1 << P.nlo[f]); i += KO_THREADS) dst[i] = __ldg(src + i);
+                    loaded[f] = D.hi[f];
+                }
+            }
+            __syncthreads();
+        }
+        const double sc = D.scal;
+        double* dst = WRITE ? P.out + (((D.y_hi << KO_CHUNK_BITS)) - P.y_begin) : nullptr;
+#pragma unroll
+        for (int e = 0; e < KO_ITEMS; ++e) {
+            double v0 = sc, v1 = sc;
+#pragma unroll
+            for (int f = 0; f < FV; ++f) {
+                const double* r = rows + P.row_off[f];
+                v0 *= r[idx[e][f]];
+                v1 *= r[idx[e][f] + delta[f]];
+            }
+            if (WRITE) st_stream(dst + 2 * (e * KO_THREADS + tid), v0, v1);
+            sum += v0 + v1;
+            mn = fmin(mn, fmin(v0, v1));
+            nnz += (v0 != 0.0 ? 1.0 : 0.0) + (v1 != 0.0 ? 1.0 : 0.0);
+        }
+        __syncthreads();
+    }
+    // deterministic CTA reduction -> partials[blockIdx][3]
+    __shared__ double red[3][KO_THREADS / 32];
+    sum = warp_sum(sum);
+    mn = warp_min(mn);
+    nnz = warp_sum(nnz);
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = sum;
+        red[1][tid >> 5] = mn;
+        red[2][tid >> 5] = nnz;
+    }
+    __syncthreads();
+    if (tid == 0 && P.partials) {
+        double s = 0.0, m = INFINITY, z = 0.0;
+        for (int w = 0; w < KO_THREADS / 32; ++w) {
+            s += red[0][w];
+            m = fmin(m, red[1][w]);
+            z += red[2][w];
+        }
+        P.partials[3 * blockIdx.x + 0] = s;
+        P.partials[3 * blockIdx.x + 1] = m;
+        P.partials[3 * blockIdx.x + 2] = z;
+    }
+}
+
+// generic fallback: one thread per element (small or unaligned ranges, many vector fragments)
+struct OuterSimpleParams {
+    int n_frag;
+    const double* table[KO_MAXF];
+    unsigned long long mask[KO_MAXF];
+    unsigned long long y_begin, y_end;
+    double* out;
+    double* partials;
+};
+
+__global__ void __launch_bounds__(256) knit_outer_simple_kernel(const __grid_constant__ OuterSimpleParams P) {
+    double sum = 0.0, mn = INFINITY, nnz = 0.0;
+    const unsigned long long n = P.y_end - P.y_begin;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long y = P.y_begin + i;
+        double v = 1.0;
+        for (int f = 0; f < P.n_frag; ++f) v *= __ldg(P.table[f] + soft_pext(y, P.mask[f]));
+        if (P.out) P.out[i] = v;
+        sum += v;
+        mn = fmin(mn, v);
+        nnz += (v != 0.0 ? 1.0 : 0.0);
+    }
+    __shared__ double red[3][8];
+    sum = warp_sum(sum);
+    mn = warp_min(mn);
+    nnz = warp_sum(nnz);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = sum;
+        red[1][threadIdx.x >> 5] = mn;
+        red[2][threadIdx.x >> 5] = nnz;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && P.partials) {
+        double s = 0.0, m = INFINITY, z = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            s += red[0][w];
+            m = fmin(m, red[1][w]);
+            z += red[2][w];
+        }
+        P.partials[3 * blockIdx.x + 0] = s;
+        P.partials[3 * blockIdx.x + 1] = m;
+        P.partials[3 * blockIdx.x + 2] = z;
+    }
+}
+
+__global__ void finalize_stats_kernel(const double* __restrict__ partials, int n, qck_stats* stats) {
+    // one warp, fixed order -> bitwise reproducible
+    double s = 0.0, m = INFINITY, z = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) {
+        s += partials[3 * i + 0];
+        m = fmin(m, partials[3 * i + 1]);
+        z += partials[3 * i + 2];
+    }
+    s = warp_sum(s);
+    m = warp_min(m);
+    z = warp_sum(z);
+    if (threadIdx.x == 0) {
+        stats->sum = s;
+        stats->min = m;
+        stats->sum_sqrt = 0.0;
+        stats->nnz = z;
+    }
+}
+
+int qck_ensure_partials(qck_handle* h, size_t count);  // api.cu
+
+template <bool WRITE>
+static void launch_outer(int n_vec, int grid, size_t smem, cudaStream_t st, const OuterParams& P) {
+    switch (n_vec) {
+        case 0: knit_outer_kernel<0, WRITE><<<grid, KO_THREADS, smem, st>>>(P); break;
+        case 1: knit_outer_kernel<1, WRITE><<<grid, KO_THREADS, smem, st>>>(P); break;
+        case 2: knit_outer_kernel<2, WRITE><<<grid, KO_THREADS, smem, st>>>(P); break;
+        case 3: knit_outer_kernel<3, WRITE><<<grid, KO_THREADS, smem, st>>>(P); break;
+        default: knit_outer_kernel<4, WRITE><<<grid, KO_THREADS, smem, st>>>(P); break;
+    }
+}
+
+extern "C" int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
+                              int n_out_bits, uint64_t y_begin, uint64_t y_end, double* d_out, qck_stats* d_stats,
+                              qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    if (n_frag < 1 || n_frag > KO_MAXF) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_frag=%d out of range [1,%d]", n_frag, KO_MAXF);
+    if (!d_tables || !masks) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "tables / masks NULL");
+    if (n_out_bits < 0 || n_out_bits > QCK_MAX_OUT_BITS) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_out_bits=%d", n_out_bits);
+    const uint64_t full = n_out_bits >= 64 ? ~0ull : ((1ull << n_out_bits) - 1ull);
+    for (int f = 0; f < n_frag; ++f) {
+        if (!d_tables[f]) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "table %d is NULL", f);
+        if (masks[f] & ~full) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "mask %d has bits >= n_out_bits", f);
+    }
+    if (y_end < y_begin || y_end > (1ull << n_out_bits)) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad output range");
+    if (y_end == y_begin) return QCK_OK;
+    if (!d_out && !d_stats) return QCK_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+
+    const uint64_t span = y_end - y_begin;
+    const bool pow2_block = (span & (span - 1)) == 0 && (y_begin % span) == 0;
+    int n_vec = 0;
+    for (int f = 0; f < n_frag; ++f)
+        if (masks[f] & ((1ull << KO_CHUNK_BITS) - 1ull)) ++n_vec;
+    int r = 0;
+    while ((1ull << r) < span) ++r;
+    const bool fast = pow2_block && r >= KO_CHUNK_BITS && n_vec <= 4 && (n_out_bits - KO_CHUNK_BITS) <= 32 &&
+                      (d_out == nullptr || (reinterpret_cast<uintptr_t>(d_out) % 16) == 0);
+    int grid;
+    if (fast) {
+        OuterParams P;
+        memset(&P, 0, sizeof(P));
+        // vector fragments first (largest row first), then scalars
+        int order_f[KO_MAXF], nf = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int f = 0; f < n_frag; ++f) {
+                bool vec = (masks[f] & ((1ull << KO_CHUNK_BITS) - 1ull)) != 0;
+                if (vec == (pass == 0)) order_f[nf++] = f;
+            }
+        P.n_frag = n_frag;
+        P.n_vec = n_vec;
+        int off = 0;
+        for (int i = 0; i < n_frag; ++i) {
+            int f = order_f[i];
+            P.table[i] = d_tables[f];
+            P.hi_mask[i] = masks[f] >> KO_CHUNK_BITS;
+            P.lo_mask[i] = (unsigned int)(masks[f] & ((1ull << KO_CHUNK_BITS) - 1ull));
+            P.nlo[i] = __builtin_popcount(P.lo_mask[i]);
+            P.row_off[i] = off;
+            if (i < n_vec) off += (1 << P.nlo[i]);
+        }
+        // free high bits, fastest first: bits owned by fragments with the smallest rows
+        const int n_free = r - KO_CHUNK_BITS;
+        int weight[64];
+        for (int b = 0; b < n_free; ++b) {
+            int w = 0;  // largest row among the fragments that own this bit
+            for (int i = 0; i < n_frag; ++i)
+                if ((P.hi_mask[i] >> b) & 1ull) w = w > P.nlo[i] ? w : P.nlo[i];
+            weight[b] = w;
+        }
+        int cnt = 0;
+        for (int w = 0; w <= KO_CHUNK_BITS; ++w)
+            for (int b = 0; b < n_free; ++b)
+                if (weight[b] == w) P.order[cnt++] = b;
+        P.n_free = n_free;
+        P.y_hi_base = y_begin >> KO_CHUNK_BITS;
+        P.n_chunks = span >> KO_CHUNK_BITS;
+        P.y_begin = y_begin;
+        P.out = d_out;
+        size_t smem = (size_t)off * sizeof(double);
+        grid = h->sm_count * 4;
+        if ((unsigned long long)grid > P.n_chunks) grid = (int)P.n_chunks;
+        int rc = qck_ensure_partials(h, (size_t)grid * 3);
+        if (rc) return rc;
+        P.partials = d_stats ? h->d_partials : nullptr;
+        if (d_out)
+            launch_outer<true>(n_vec, grid, smem, st, P);
+        else
+            launch_outer<false>(n_vec, grid, smem, st, P);
+        QCK_CHECK_LAUNCH(h);
+    } else {
+        OuterSimpleParams P;
+        memset(&P, 0, sizeof(P));
+        P.n_frag = n_frag;
+        for (int f = 0; f < n_frag; ++f) {
+            P.table[f] = d_tables[f];
+            P.mask[f] = masks[f];
+        }
+        P.y_begin = y_begin;
+        P.y_end = y_end;
+        P.out = d_out;
+        unsigned long long want = (span + 255) / 256;
+        grid = (int)(want < (unsigned long long)h->sm_count * 8 ? want : (unsigned long long)h->sm_count * 8);
+        int rc = qck_ensure_partials(h, (size_t)grid * 3);
+        if (rc) return rc;
+        P.partials = d_stats ? h->d_partials : nullptr;
+        knit_outer_simple_kernel<<<grid, 256, 0, st>>>(P);
+        QCK_CHECK_LAUNCH(h);
+    }
+    if (d_stats) {
+        finalize_stats_kernel<<<1, 32, 0, st>>>(h->d_partials, grid, d_stats);
+        QCK_CHECK_LAUNCH(h);
+    }
+    return QCK_OK;
+}
+
+// ====================================================================== knit_contract
+// prep: w[l] = prod_k coef[k][digit_k(l)], rows[f][l] = sum_k digit_k(l) * frag_stride[f][k]
+struct PrepParams {
+    int n_digits, n_frag;
+    int radix[QCK_MAX_DIGITS];
+    double coef[QCK_MAX_DIGITS][QCK_MAX_VARIANTS];
+    int stride[KO_MAXF][QCK_MAX_DIGITS];
+    long long l_begin, count;
+    double* w;
+    int* rows;  // [n_frag][count]
+};
+
+__global__ void contract_prep_kernel(const __grid_constant__ PrepParams P) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.count;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long rem = P.l_begin + i;
+        double w = 1.0;
+        int rows[KO_MAXF];
+#pragma unroll
+        for (int f = 0; f < KO_MAXF; ++f) rows[f] = 0;
+        // digits from the last (fastest) to the first; the weight is multiplied in the order
+        // k = 0..K-1 on the host reference, the product of <= 16 doubles differs by O(1e-16)
+        int digit[QCK_MAX_DIGITS];
+        for (int k = P.n_digits - 1; k >= 0; --k) {
+            digit[k] = (int)(rem % P.radix[k]);
+            rem /= P.radix[k];
+        }
+        for (int k = 0; k < P.n_digits; ++k) {
+            w *= P.coef[k][digit[k]];
+#pragma unroll
+            for (int f = 0; f < KO_MAXF; ++f)
+                if (f < P.n_frag) rows[f] += digit[k] * P.stride[f][k];
+        }
+        P.w[i] = w;
+        for (int f = 0; f < P.n_frag; ++f) P.rows[(long long)f * P.count + i] = rows[f];
+    }
+}
+
+struct ContractParams {
+    int n_frag;
+    const double* table[KO_MAXF];
+    unsigned long long mask[KO_MAXF];
+    long long row_stride[KO_MAXF];
+    int n_out_bits;
+    long long count;  // labels
+    const double* w;
+    const int* rows;
+    double* out;
+    int accumulate;
+};
+
+// generic: one thread per output entry, loops over the labels
+__global__ void __launch_bounds__(256) contract_generic_kernel(const __grid_constant__ ContractParams P) {
+    const unsigned long long n = 1ull << P.n_out_bits;
+    for (unsigned long long y = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; y < n;
+         y += (unsigned long long)gridDim.x * blockDim.x) {
+        const double* base[KO_MAXF];
+        for (int f = 0; f < P.n_frag; ++f) base[f] = P.table[f] + soft_pext(y, P.mask[f]);
+        double acc = 0.0;
+        for (long long l = 0; l < P.count; ++l) {
+            double t = __ldg(P.w + l);
+            for (int f = 0; f < P.n_frag; ++f)
+                t *= __ldg(base[f] + (long long)__ldg(P.rows + (long long)f * P.count + l) * P.row_stride[f]);
+            acc += t;
+        }
+        P.out[y] = P.accumulate ? P.out[y] + acc : acc;
+    }
+}
+
+// two fragments: C[i][j] = sum_l w[l] A[rowA[l]][i] B[rowB[l]][j]  (64x64 tile, split over l)
+#define GT 64
+#define GK 16
+__global__ void __launch_bounds__(256) contract_gemm_kernel(const __grid_constant__ ContractParams P, int n_split,
+                                                            double* __restrict__ partial, int M, int N) {
+    __shared__ double As[GK][GT + 4];
+    __shared__ double Bs[GK][GT + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.x * GT, j0 = blockIdx.y * GT;
+    const long long per = (P.count + n_split - 1) / n_split;
+    const long long lb = per * blockIdx.z, le = (lb + per < P.count) ? lb + per : P.count;
+    const int* rowA = P.rows;
+    const int* rowB = P.rows + P.count;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (long long l0 = lb; l0 < le; l0 += GK) {
+#pragma unroll
+        for (int k = 0; k < (GK * GT) / 256; ++k) {
+            int e = tid + 256 * k, rr = e / GT, cc = e % GT;
+            long long l = l0 + rr;
+            double a = 0.0, b = 0.0;
+            if (l < le) {
+                a = __ldg(P.w + l) * __ldg(P.table[0] + (long long)__ldg(rowA + l) * P.row_stride[0] + i0 + cc);
+                b = __ldg(P.table[1] + (long long)__ldg(rowB + l) * P.row_stride[1] + j0 + cc);
+            }
+            As[rr][cc] = a;
+            Bs[rr][cc] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = As[kk][ty * 4 + u];
+                b[u] = Bs[kk][tx * 4 + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+    double* dst = partial + (long long)blockIdx.z * M * N;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dst[(long long)(i0 + ty * 4 + u) * N + (j0 + tx * 4 + v)] = acc[u][v];
+}
+
+__global__ void __launch_bounds__(256) contract_scatter_kernel(const double* __restrict__ partial, int n_split, int M,
+                                                               int N, unsigned long long maskA,
+                                                               unsigned long long maskB, int n_out_bits,
+                                                               double* __restrict__ out, int accumulate) {
+    const unsigned long long n = 1ull << n_out_bits;
+    for (unsigned long long y = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; y < n;
+         y += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long i = (long long)soft_pext(y, maskA), j = (long long)soft_pext(y, maskB);
+        double acc = 0.0;
+        for (int s = 0; s < n_split; ++s) acc += partial[((long long)s * M + i) * N + j];
+        out[y] = accumulate ? out[y] + acc : acc;
+    }
+}
+
+int qck_ensure_scratch(qck_handle* h, size_t bytes, void** out);  // api.cu
+
+extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
+                                 const int64_t* row_strides, int n_out_bits, int n_digits, const int32_t* radix,
+                                 const double* coef, const int32_t* frag_stride, int64_t l_begin, int64_t l_end,
+                                 double* d_out, int accumulate, qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    if (n_frag < 1 || n_frag > KO_MAXF) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_frag=%d out of range", n_frag);
+    if (n_digits < 0 || n_digits > QCK_MAX_DIGITS) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_digits=%d out of range", n_digits);
+    if (!d_tables || !masks || !row_strides || !d_out || (n_digits > 0 && (!radix || !coef || !frag_stride)))
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "NULL argument");
+    if (n_out_bits < 0 || n_out_bits > 34) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_out_bits=%d out of range", n_out_bits);
+    long long total = 1;
+    for (int k = 0; k < n_digits; ++k) {
+        if (radix[k] < 1 || radix[k] > QCK_MAX_VARIANTS) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "radix[%d]=%d", k, radix[k]);
+        total *= radix[k];
+    }
+    if (l_begin < 0 || l_end > total || l_end < l_begin) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad label range");
+    uint64_t seen = 0;
+    for (int f = 0; f < n_frag; ++f) {
+        if (masks[f] & seen) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "fragment masks overlap");
+        seen |= masks[f];
+    }
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long count = l_end - l_begin;
+    if (count == 0) {
+        if (!accumulate) QCK_CUDA(h, cudaMemsetAsync(d_out, 0, sizeof(double) << n_out_bits, st));
+        return QCK_OK;
+    }
+    // scratch: w[count] + rows[n_frag][count] (+ split partials for the GEMM path)
+    const int mA = __builtin_popcountll(masks[0]);
+    const int mB = n_frag >= 2 ? __builtin_popcountll(masks[1]) : 0;
+    const bool gemm = (n_frag == 2) && mA >= 6 && mB >= 6;
+    int n_split = 1;
+    size_t partial_bytes = 0;
+    if (gemm) {
+        long long tiles = (1ll << (mA - 6)) * (1ll << (mB - 6));
+        long long want = (4ll * h->sm_count + tiles - 1) / tiles;
+        long long maxs = (count + 4 * GK - 1) / (4 * GK);
+        n_split = (int)(want < maxs ? want : maxs);
+        if (n_split < 1) n_split = 1;
+        if (n_split > 64) n_split = 64;
+        partial_bytes = (size_t)n_split * sizeof(double) << (mA + mB);
+    }
+    size_t w_bytes = ((size_t)count * sizeof(double) + 255) & ~(size_t)255;
+    size_t r_bytes = ((size_t)count * n_frag * sizeof(int) + 255) & ~(size_t)255;
+    void* scratch = nullptr;
+    int rc = qck_ensure_scratch(h, w_bytes + r_bytes + partial_bytes, &scratch);
+    if (rc) return rc;
+    double* d_w = (double*)scratch;
+    int* d_rows = (int*)((char*)scratch + w_bytes);
+    double* d_partial = (double*)((char*)scratch + w_bytes + r_bytes);
+
+    PrepParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.n_digits = n_digits;
+    pp.n_frag = n_frag;
+    for (int k = 0; k < n_digits; ++k) {
+        pp.radix[k] = radix[k];
+        for (int v = 0; v < QCK_MAX_VARIANTS; ++v) pp.coef[k][v] = coef[k * QCK_MAX_VARIANTS + v];
+        for (int f = 0; f < n_frag; ++f) pp.stride[f][k] = frag_stride[f * QCK_MAX_DIGITS + k];
+    }
+    pp.l_begin = l_begin;
+    pp.count = count;
+    pp.w = d_w;
+    pp.rows = d_rows;
+    int pgrid = (int)((count + 255) / 256 < 1024 ? (count + 255) / 256 : 1024);
+    contract_prep_kernel<<<pgrid, 256, 0, st>>>(pp);
+    QCK_CHECK_LAUNCH(h);
+
+    ContractParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.n_frag = n_frag;
+    for (int f = 0; f < n_frag; ++f) {
+        cp.table[f] = d_tables[f];
+        cp.mask[f] = masks[f];
+        cp.row_stride[f] = row_strides[f];
+    }
+    cp.n_out_bits = n_out_bits;
+    cp.count = count;
+    cp.w = d_w;
+    cp.rows = d_rows;
+    cp.out = d_out;
+    cp.accumulate = accumulate;
+    const unsigned long long n = 1ull << n_out_bits;
+    int ggrid = (int)((n + 255) / 256 < (unsigned long long)h->sm_count * 8 ? (n + 255) / 256
+                                                                           : (unsigned long long)h->sm_count * 8);
+    if (gemm && (seen == (n_out_bits >= 64 ? ~0ull : (1ull << n_out_bits) - 1ull))) {
+        const int M = 1 << mA, N = 1 << mB;
+        dim3 grid(M / GT, N / GT, n_split);
+        contract_gemm_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N);
+        QCK_CHECK_LAUNCH(h);
+        contract_scatter_kernel<<<ggrid, 256, 0, st>>>(d_partial, n_split, M, N, masks[0], masks[1], n_out_bits,
+                                                        d_out, accumulate);
+        QCK_CHECK_LAUNCH(h);
+    } else {
+        contract_generic_kernel<<<ggrid, 256, 0, st>>>(cp);
+        QCK_CHECK_LAUNCH(h);
+    }
+    return QCK_OK;
+}

@@ -1,0 +1,108 @@
+// Shared plumbing for libqck.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/qck.h"
+
+struct qck_handle {
+    int device;
+    int sm_count;
+    int max_smem_optin;
+    int64_t launches;
+    char err[512];
+    // small device scratch for reductions (per-CTA partials)
+    double* d_partials;
+    size_t partials_count;
+    // pinned host scratch for scalar read-backs
+    double* h_pinned;
+    // growable device scratch (contraction weights, split-K partials)
+    void* scratch;
+    size_t scratch_bytes;
+};
+
+#define QCK_FAIL(h, code, ...)                                    \
+    do {                                                          \
+        if (h) snprintf((h)->err, sizeof((h)->err), __VA_ARGS__); \
+        return (code);                                            \
+    } while (0)
+
+#define QCK_CUDA(h, expr)                                                                 \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            QCK_FAIL(h, QCK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                 \
+    } while (0)
+
+#define QCK_CHECK_LAUNCH(h)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            QCK_FAIL(h, QCK_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                     \
+        (h)->launches++;                                                                      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev;
+    bool changed;
+    explicit DeviceGuard(int dev) : prev(-1), changed(false) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            cudaSetDevice(dev);
+            changed = true;
+        }
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+// ---- bit helpers -----------------------------------------------------------------------
+// insert a zero bit at position q:  ...hhh lll -> ...hhh 0 lll
+__host__ __device__ __forceinline__ uint32_t insert_zero(uint32_t p, int q) {
+    uint32_t lo = p & ((1u << q) - 1u);
+    return ((p >> q) << (q + 1)) | lo;
+}
+__host__ __device__ __forceinline__ uint64_t insert_zero64(uint64_t p, int q) {
+    uint64_t lo = p & ((1ull << q) - 1ull);
+    return ((p >> q) << (q + 1)) | lo;
+}
+
+// generic software pext / pdep (no hardware instruction on NVIDIA GPUs)
+__host__ __device__ __forceinline__ uint64_t soft_pext(uint64_t y, uint64_t mask) {
+    uint64_t out = 0;
+    int j = 0;
+    while (mask) {
+        uint64_t low = mask & (~mask + 1);  // lowest set bit
+        if (y & low) out |= (1ull << j);
+        ++j;
+        mask ^= low;
+    }
+    return out;
+}
+__host__ __device__ __forceinline__ uint64_t soft_pdep(uint64_t x, uint64_t mask) {
+    uint64_t out = 0;
+    int j = 0;
+    while (mask) {
+        uint64_t low = mask & (~mask + 1);
+        if ((x >> j) & 1ull) out |= low;
+        ++j;
+        mask ^= low;
+    }
+    return out;
+}
+
+// ---- block reductions ------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}

@@ -1,0 +1,390 @@
+// Batched statevector simulation of fragment instances (sm_100a).
+//
+// Replaces the reference's per-instance circuit construction and Aer run
+// (third_party/qvm/qvm/virtual_circuit.py:183-213, run.py:36-58).  One CTA owns one
+// tile of one instance: the tile (2^n_tile complex128 amplitudes) lives in shared
+// memory while a run of gates that only touch tile-local qubits is applied.
+//   * on-chip regime  (n_state <= 13): one sweep, the whole state is the tile, HBM is
+//     touched only by the output row;
+//   * streaming regime (n_state  > 13): the state lives in HBM/L2, every sweep is one
+//     coalesced read + one coalesced write of the state (tiles always contain the low
+//     qubits so that a tile is made of >= 256-byte contiguous runs).
+// Measurements whose qubit lives on are CX gates onto ancilla bits (deferred
+// measurement); the epilogue folds |amp|^2 into the instance's output row with the
+// (-1)^bit weights of the knit rules.
+#include "qck_common.cuh"
+
+struct PlanDev {
+    int n_state;
+    const qck_op* ops;
+    const double* mats;
+    int n_digits;
+    int radix[QCK_MAX_DIGITS];
+    int n_out_bits;
+    int out_pos[QCK_MAX_OUT_BITS];
+    unsigned long long sum_mask, sign_mask;
+};
+
+struct SweepDev {
+    int n_tile;
+    int op_begin, op_end;
+    int n_low;  // pos[i] == i for i < n_low (contiguous low run)
+    int init;   // 1: synthesise |0..0> instead of reading
+    int pos[QCK_MAX_TILE_QUBITS + 2];
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {  // a*b + c
+    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+
+__device__ __forceinline__ void decode_digits(const PlanDev& plan, int label, int* digits) {
+    int rem = label;
+    for (int k = plan.n_digits - 1; k >= 0; --k) {
+        int r = plan.radix[k];
+        digits[k] = rem % r;
+        rem /= r;
+    }
+}
+
+// Apply ops[begin, end) to the tile `s` (2^T amplitudes in shared memory).  All threads of
+// the CTA call this with identical arguments; ends with the state synchronised.
+__device__ void apply_ops(double2* s, int T, const qck_op* __restrict__ ops, int begin, int end,
+                          const double* __restrict__ mats, const int* digits) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int i = begin; i < end; ++i) {
+        const int4 w0 = __ldg(reinterpret_cast<const int4*>(ops + i));
+        const int4 w1 = __ldg(reinterpret_cast<const int4*>(ops + i) + 1);
+        const int kind = w0.x, q0 = w0.y, q1 = w0.z;
+        int moff = w0.w;
+        if (w1.x >= 0) moff += digits[w1.x] * w1.y;
+        int nl = w1.z;
+        if (nl <= 0 || nl > T) nl = T;
+        if (kind == QCK_OP_U1) {
+            const double2* m = reinterpret_cast<const double2*>(mats + moff);
+            const double2 m00 = __ldg(m), m01 = __ldg(m + 1), m10 = __ldg(m + 2), m11 = __ldg(m + 3);
+            const bool offdiag0 = (m01.x == 0.0 && m01.y == 0.0 && m10.x == 0.0 && m10.y == 0.0);
+            if (offdiag0) {
+                const bool id0 = (m00.x == 1.0 && m00.y == 0.0), id1 = (m11.x == 1.0 && m11.y == 0.0);
+                if (id0 && id1) continue;  // identity variant: nothing to do (uniform branch)
+                const uint32_t n = 1u << (nl - 1);
+                if (id0) {
+                    for (uint32_t p = tid; p < n; p += nth) {
+                        uint32_t i1 = insert_zero(p, q0) | (1u << q0);
+                        s[i1] = cmul(m11, s[i1]);
+                    }
+                } else {
+                    for (uint32_t p = tid; p < n; p += nth) {
+                        uint32_t i0 = insert_zero(p, q0), i1 = i0 | (1u << q0);
+                        s[i0] = cmul(m00, s[i0]);
+                        s[i1] = cmul(m11, s[i1]);
+                    }
+                }
+            } else {
+                const uint32_t n = 1u << (nl - 1);
+                for (uint32_t p = tid; p < n; p += nth) {
+                    uint32_t i0 = insert_zero(p, q0), i1 = i0 | (1u << q0);
+                    double2 a0 = s[i0], a1 = s[i1];
+                    s[i0] = cfma(m01, a1, cmul(m00, a0));
+                    s[i1] = cfma(m11, a1, cmul(m10, a0));
+                }
+            }
+        } else if (kind == QCK_OP_CX || kind == QCK_OP_CZ) {
+            const int lo = q0 < q1 ? q0 : q1, hi = q0 < q1 ? q1 : q0;
+            const uint32_t n = 1u << (nl - 2);
+            const uint32_t b0 = 1u << q0, b1 = 1u << q1;
+            if (kind == QCK_OP_CX) {
+                for (uint32_t p = tid; p < n; p += nth) {
+                    uint32_t base = insert_zero(insert_zero(p, lo), hi) | b0;  // control set
+                    double2 a = s[base], b = s[base | b1];
+                    s[base] = b;
+                    s[base | b1] = a;
+                }
+            } else {
+                for (uint32_t p = tid; p < n; p += nth) {
+                    uint32_t idx = insert_zero(insert_zero(p, lo), hi) | b0 | b1;
+                    double2 a = s[idx];
+                    s[idx] = make_double2(-a.x, -a.y);
+                }
+            }
+        } else {  // QCK_OP_U2: generic 4x4, row/col index = bit(q0) + 2 bit(q1)
+            const int lo = q0 < q1 ? q0 : q1, hi = q0 < q1 ? q1 : q0;
+            const uint32_t n = 1u << (nl - 2);
+            const uint32_t b0 = 1u << q0, b1 = 1u << q1;
+            const double2* m = reinterpret_cast<const double2*>(mats + moff);
+            for (uint32_t p = tid; p < n; p += nth) {
+                uint32_t base = insert_zero(insert_zero(p, lo), hi);
+                double2 a[4] = {s[base], s[base | b0], s[base | b1], s[base | b0 | b1]};
+                double2 r[4];
+#pragma unroll
+                for (int row = 0; row < 4; ++row) {
+                    double2 acc = cmul(__ldg(m + row * 4), a[0]);
+#pragma unroll
+                    for (int c = 1; c < 4; ++c) acc = cfma(__ldg(m + row * 4 + c), a[c], acc);
+                    r[row] = acc;
+                }
+                s[base] = r[0];
+                s[base | b0] = r[1];
+                s[base | b1] = r[2];
+                s[base | b0 | b1] = r[3];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// |amp|^2 folded into the output row (deterministic order, no atomics): one thread per
+// output entry walks the summed-out bits with the masked-increment trick.
+template <typename LoadAmp>
+__device__ __forceinline__ double fold_entry(const PlanDev& plan, uint64_t o, LoadAmp load) {
+    uint64_t base = 0;
+    for (int j = 0; j < plan.n_out_bits; ++j) {
+        if ((o >> j) & 1ull) {
+            if (plan.out_pos[j] < 0) return 0.0;  // that bit is never written in this pattern
+            base |= 1ull << plan.out_pos[j];
+        }
+    }
+    const uint64_t sm = plan.sum_mask, sg = plan.sign_mask;
+    double acc = 0.0;
+    uint64_t sub = 0;
+    do {
+        double2 a = load(base | sub);
+        double p = fma(a.x, a.x, a.y * a.y);
+        acc += (__popcll(sub & sg) & 1) ? -p : p;
+        sub = (sub - sm) & sm;
+    } while (sub != 0);
+    return acc;
+}
+
+// ------------------------------------------------------------------ on-chip regime
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+__global__ void __launch_bounds__(512) sim_onchip_kernel(PlanDev plan, int op_begin, int op_end,
+                                                         const int32_t* __restrict__ labels,
+                                                         double* __restrict__ out, long long row_stride) {
+    double2* s = reinterpret_cast<double2*>(smem_raw);
+    __shared__ int digits[QCK_MAX_DIGITS];
+    const int label = labels[blockIdx.x];
+    if (threadIdx.x == 0) decode_digits(plan, label, digits);
+    const uint32_t n_amp = 1u << plan.n_state;
+    for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
+    __syncthreads();
+    apply_ops(s, plan.n_state, plan.ops, op_begin, op_end, plan.mats, digits);
+    const uint64_t n_out = 1ull << plan.n_out_bits;
+    double* row = out + (long long)label * row_stride;
+    for (uint64_t o = threadIdx.x; o < n_out; o += blockDim.x)
+        row[o] = fold_entry(plan, o, [&](uint64_t idx) { return s[idx]; });
+}
+
+// ------------------------------------------------------------------ streaming regime
+__global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev sw,
+                                                        const int32_t* __restrict__ labels, int inst_base,
+                                                        double2* __restrict__ work,
+                                                        unsigned long long state_stride) {
+    double2* s = reinterpret_cast<double2*>(smem_raw);
+    __shared__ int digits[QCK_MAX_DIGITS];
+    __shared__ unsigned long long hi_off[1 << 10];
+    const int T = sw.n_tile, c = sw.n_low;
+    const int label = labels[inst_base + blockIdx.y];
+    if (threadIdx.x == 0) decode_digits(plan, label, digits);
+    // offsets of the non-contiguous tile bits
+    const int n_hi = T - c;
+    for (uint32_t j = threadIdx.x; j < (1u << n_hi); j += blockDim.x) {
+        unsigned long long off = 0;
+        for (int b = 0; b < n_hi; ++b)
+            if ((j >> b) & 1u) off |= 1ull << sw.pos[c + b];
+        hi_off[j] = off;
+    }
+    // base address of this tile: spread the tile index over the non-tile bit positions
+    unsigned long long base = blockIdx.x;
+    for (int j = 0; j < T; ++j) base = insert_zero64(base, sw.pos[j]);
+    double2* st = work + (unsigned long long)blockIdx.y * state_stride;
+    __syncthreads();
+    const uint32_t n_amp = 1u << T, low_mask = (1u << c) - 1u;
+    if (sw.init) {
+        for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
+            s[j] = make_double2((j == 0 && base == 0) ? 1.0 : 0.0, 0.0);
+    } else {
+        for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
+            s[j] = __ldcs(st + (base | hi_off[j >> c] | (j & low_mask)));
+    }
+    __syncthreads();
+    apply_ops(s, T, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits);
+    for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
+        __stcs(st + (base | hi_off[j >> c] | (j & low_mask)), s[j]);
+}
+
+__global__ void __launch_bounds__(256) fold_probs_kernel(PlanDev plan, const int32_t* __restrict__ labels,
+                                                         int inst_base, const double2* __restrict__ work,
+                                                         unsigned long long state_stride,
+                                                         double* __restrict__ out, long long row_stride) {
+    const int label = labels[inst_base + blockIdx.y];
+    const double2* st = work + (unsigned long long)blockIdx.y * state_stride;
+    double* row = out + (long long)label * row_stride;
+    const uint64_t n_out = 1ull << plan.n_out_bits;
+    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_out;
+         o += (uint64_t)gridDim.x * blockDim.x)
+        row[o] = fold_entry(plan, o, [&](uint64_t idx) { return __ldcs(st + idx); });
+}
+
+// ------------------------------------------------------------------ host side
+static int validate_plan(qck_handle* h, const qck_sim_plan* plan) {
+    if (!plan) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "plan is NULL");
+    if (plan->n_state_qubits < 1 || plan->n_state_qubits > 40)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_state_qubits=%d out of range [1,40]", plan->n_state_qubits);
+    if (plan->n_sweeps < 1 || !plan->sweeps) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "plan has no sweeps");
+    if (plan->n_digits < 0 || plan->n_digits > QCK_MAX_DIGITS)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_digits=%d out of range", plan->n_digits);
+    if (plan->n_out_bits < 0 || plan->n_out_bits > QCK_MAX_OUT_BITS)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_out_bits=%d out of range", plan->n_out_bits);
+    for (int k = 0; k < plan->n_digits; ++k)
+        if (plan->radix[k] < 1) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "radix[%d]=%d", k, plan->radix[k]);
+    for (int j = 0; j < plan->n_out_bits; ++j)
+        if (plan->out_pos[j] >= plan->n_state_qubits)
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "out_pos[%d]=%d >= n_state_qubits", j, plan->out_pos[j]);
+    for (int i = 0; i < plan->n_sweeps; ++i) {
+        const qck_sweep& sw = plan->sweeps[i];
+        if (sw.n_tile < 1 || sw.n_tile > QCK_MAX_TILE_QUBITS || sw.n_tile > plan->n_state_qubits)
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "sweep %d: n_tile=%d invalid", i, sw.n_tile);
+        for (int j = 0; j < sw.n_tile; ++j) {
+            if (sw.pos[j] < 0 || sw.pos[j] >= plan->n_state_qubits || (j > 0 && sw.pos[j] <= sw.pos[j - 1]))
+                QCK_FAIL(h, QCK_ERR_INVALID_ARG, "sweep %d: tile positions must be ascending and < n_state", i);
+        }
+        if (sw.op_begin < 0 || sw.op_end < sw.op_begin)
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "sweep %d: bad op range", i);
+    }
+    if ((plan->n_sweeps > 0 && plan->sweeps[0].op_end > plan->sweeps[0].op_begin) && (!plan->d_ops || !plan->d_mats))
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "plan has ops but d_ops/d_mats is NULL");
+    return QCK_OK;
+}
+
+static PlanDev to_dev(const qck_sim_plan* plan) {
+    PlanDev d;
+    memset(&d, 0, sizeof(d));
+    d.n_state = plan->n_state_qubits;
+    d.ops = plan->d_ops;
+    d.mats = plan->d_mats;
+    d.n_digits = plan->n_digits;
+    for (int k = 0; k < QCK_MAX_DIGITS; ++k) d.radix[k] = k < plan->n_digits ? plan->radix[k] : 1;
+    d.n_out_bits = plan->n_out_bits;
+    for (int j = 0; j < QCK_MAX_OUT_BITS; ++j) d.out_pos[j] = j < plan->n_out_bits ? plan->out_pos[j] : -1;
+    d.sum_mask = plan->sum_mask;
+    d.sign_mask = plan->sign_mask;
+    return d;
+}
+
+static SweepDev sweep_dev(const qck_sweep& sw, bool init) {
+    SweepDev s;
+    memset(&s, 0, sizeof(s));
+    s.n_tile = sw.n_tile;
+    s.op_begin = sw.op_begin;
+    s.op_end = sw.op_end;
+    s.init = init ? 1 : 0;
+    int c = 0;
+    while (c < sw.n_tile && sw.pos[c] == c) ++c;
+    s.n_low = c;
+    for (int j = 0; j < sw.n_tile; ++j) s.pos[j] = sw.pos[j];
+    return s;
+}
+
+static bool is_onchip(const qck_sim_plan* plan) {
+    return plan->n_sweeps == 1 && plan->sweeps[0].n_tile == plan->n_state_qubits;
+}
+
+static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd, const int32_t* d_labels,
+                      int inst_base, int batch, double2* work, unsigned long long state_stride,
+                      cudaStream_t st) {
+    for (int i = 0; i < plan->n_sweeps; ++i) {
+        SweepDev sd = sweep_dev(plan->sweeps[i], i == 0);
+        if (sd.n_tile - sd.n_low > 10)
+            QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "sweep %d: more than 10 non-contiguous tile bits", i);
+        size_t smem = (size_t)16 << sd.n_tile;
+        if ((int)smem + 12 * 1024 > h->max_smem_optin)
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "sweep %d: tile of 2^%d amplitudes does not fit shared memory", i,
+                     sd.n_tile);
+        QCK_CUDA(h, cudaFuncSetAttribute(sim_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unsigned long long tiles = 1ull << (plan->n_state_qubits - sd.n_tile);
+        if (tiles > 0x7fffffffull) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "too many tiles");
+        dim3 grid((unsigned)tiles, (unsigned)batch);
+        sim_sweep_kernel<<<grid, 256, smem, st>>>(pd, sd, d_labels, inst_base, work, state_stride);
+        QCK_CHECK_LAUNCH(h);
+    }
+    return QCK_OK;
+}
+
+extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const int32_t* d_labels,
+                                 int64_t n_instances, double* d_out, int64_t out_row_stride, void* d_work,
+                                 size_t work_bytes, qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    int rc = validate_plan(h, plan);
+    if (rc) return rc;
+    if (n_instances == 0) return QCK_OK;
+    if (n_instances < 0 || !d_labels || !d_out) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad instance list / output");
+    if (out_row_stride < (1ll << plan->n_out_bits))
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "out_row_stride smaller than the row (2^%d)", plan->n_out_bits);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    PlanDev pd = to_dev(plan);
+    if (is_onchip(plan)) {
+        const int N = plan->n_state_qubits;
+        size_t smem = (size_t)16 << N;
+        if ((int)smem + 1024 > h->max_smem_optin)
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "on-chip plan with %d qubits does not fit shared memory", N);
+        QCK_CUDA(h, cudaFuncSetAttribute(sim_onchip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int threads = 1 << (N > 1 ? N - 1 : 0);
+        if (threads < 32) threads = 32;
+        if (threads > 512) threads = 512;
+        const qck_sweep& sw = plan->sweeps[0];
+        for (int64_t done = 0; done < n_instances;) {
+            int64_t batch = n_instances - done;
+            if (batch > (1ll << 30)) batch = 1ll << 30;
+            sim_onchip_kernel<<<(unsigned)batch, threads, smem, st>>>(pd, sw.op_begin, sw.op_end, d_labels + done,
+                                                                       d_out, (long long)out_row_stride);
+            QCK_CHECK_LAUNCH(h);
+            done += batch;
+        }
+        return QCK_OK;
+    }
+    // streaming regime
+    const unsigned long long state_amps = 1ull << plan->n_state_qubits;
+    const size_t state_bytes = (size_t)state_amps * 16;
+    if (!d_work || work_bytes < state_bytes)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "streaming regime needs >= %zu bytes of work space, got %zu", state_bytes,
+                 work_bytes);
+    int64_t cap = (int64_t)(work_bytes / state_bytes);
+    if (cap > 65535) cap = 65535;
+    for (int64_t done = 0; done < n_instances;) {
+        int batch = (int)((n_instances - done) < cap ? (n_instances - done) : cap);
+        rc = run_sweeps(h, plan, pd, d_labels, (int)done, batch, (double2*)d_work, state_amps, st);
+        if (rc) return rc;
+        unsigned long long n_out = 1ull << plan->n_out_bits;
+        unsigned gx = (unsigned)((n_out + 255) / 256 < 148ull * 16 ? (n_out + 255) / 256 : 148ull * 16);
+        fold_probs_kernel<<<dim3(gx, batch), 256, 0, st>>>(pd, d_labels, (int)done, (const double2*)d_work,
+                                                             state_amps, d_out, (long long)out_row_stride);
+        QCK_CHECK_LAUNCH(h);
+        done += batch;
+    }
+    return QCK_OK;
+}
+
+extern "C" int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t label, void* d_state,
+                                   size_t state_bytes, qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    int rc = validate_plan(h, plan);
+    if (rc) return rc;
+    if (is_onchip(plan) && plan->n_state_qubits > 0) {
+        // an on-chip plan is also a valid one-sweep streaming plan
+    }
+    const unsigned long long state_amps = 1ull << plan->n_state_qubits;
+    if (!d_state || state_bytes < state_amps * 16)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "state buffer too small: need %llu bytes", state_amps * 16);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // the label travels through a one-element device list kept in the handle scratch
+    int32_t* d_label = reinterpret_cast<int32_t*>(h->d_partials);
+    QCK_CUDA(h, cudaMemcpyAsync(d_label, &label, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PlanDev pd = to_dev(plan);
+    return run_sweeps(h, plan, pd, d_label, 0, 1, (double2*)d_state, state_amps, st);
+}

@@ -1,0 +1,319 @@
+"""VirtualCircuit: fragments, instance labels, execution plug-in and knit.
+
+Mirror of ``third_party/qvm/qvm/virtual_circuit.py`` with the same public
+surface (``VirtualCircuit``, ``get_instance_labels``, ``knit``,
+``fragment_circuits``, ``replace_fragment_circuit``, ``get_backend`` /
+``set_backend`` / ``set_backend_for_all``, ``generate_instantiations``,
+``_instantiate_fragment``), re-designed around the device:
+
+* the default backend of every fragment is ``B200Backend`` instead of
+  ``AerSimulator()`` (``virtual_circuit.py:35-37``);
+* ``simulate_fragments()`` runs *all* instances of *all* fragments on the GPU
+  straight from the compiled template (no per-instance host objects) and
+  returns, per fragment, a device table ``Q_f[label, x_f]`` of signed-folded
+  rows;
+* ``knit_tables()`` contracts those tables into the dense full-circuit
+  quasi-distribution with ``qck_knit_outer`` (no virtual gates) or
+  ``qck_knit_contract`` (closed form of the level loop ``:59-68``);
+* ``knit(results, pool)`` keeps the reference signature and operation order
+  (merge per global label, then one level per virtual gate from the last to the
+  first, chunks of ``n_k``) on device-resident ``QuasiDistr`` objects; it is the
+  reference-faithful path (pruning after every operation) and the cross-check
+  of the closed form.  ``pool`` is accepted and ignored.
+
+Integer conventions (bit-exact with the reference): vgate index = circuit order
+(``:22-27``); labels = ``itertools.product`` over the touched gates, ``-1``
+elsewhere, last gate fastest (``:39-48``); config bit of gate ``k`` is key bit
+``num_clbits + k`` (``:60,202-211``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+
+import numpy as np
+
+from . import _lib
+from .circuit import Barrier, ClassicalRegister, QuantumCircuit, QuantumRegister as Fragment
+from .compiler import FragmentExecutor, FragmentProgram
+from .quasi_distr import QuasiDistr, default_device
+from .virtual_gates import VirtualBinaryGate, VirtualGateEndpoint, VirtualMove
+
+InstanceLabelType = tuple[int, ...]
+
+__all__ = ["VirtualCircuit", "generate_instantiations", "InstanceLabelType", "Fragment"]
+
+
+class VirtualCircuit:
+    def __init__(self, circuit: QuantumCircuit) -> None:
+        from .backend import B200Backend
+        self._vgate_instrs = [
+            instr for instr in circuit
+            if isinstance(instr.operation, VirtualBinaryGate) or isinstance(instr.operation, VirtualMove)
+        ]
+        self._circuit = self._replace_vgates_with_endpoints(circuit)
+        self._frag_circs = {qreg: self._circuit_on_fragment(self._circuit, qreg) for qreg in circuit.qregs}
+        self._frag_to_backend = {qreg: B200Backend() for qreg in self._frag_circs.keys()}
+        self._programs: dict[Fragment, FragmentProgram] = {}
+        self._executors: dict = {}
+
+    # ------------------------------------------------------------------ reference API
+    @property
+    def num_clbits(self) -> int:
+        return self._circuit.num_clbits
+
+    @property
+    def vgates(self) -> list[VirtualBinaryGate]:
+        return [instr.operation for instr in self._vgate_instrs]
+
+    def _touches(self, fragment: Fragment) -> list[bool]:
+        fq = set(fragment)
+        return [bool(set(vg.qubits) & fq) for vg in self._vgate_instrs]
+
+    def get_instance_labels(self, fragment: Fragment) -> list[InstanceLabelType]:
+        if len(self._vgate_instrs) == 0:
+            return [()]
+        inst_l = [
+            tuple(range(vg.operation.num_instantiations)) if touch else (-1,)
+            for vg, touch in zip(self._vgate_instrs, self._touches(fragment))
+        ]
+        return list(itertools.product(*inst_l))
+
+    @property
+    def fragment_circuits(self) -> dict[Fragment, QuantumCircuit]:
+        return self._frag_circs.copy()
+
+    def replace_fragment_circuit(self, fragment: Fragment, circuit: QuantumCircuit) -> None:
+        self._frag_circs[fragment] = circuit
+        self._programs.pop(fragment, None)
+        self._executors = {k: v for k, v in self._executors.items() if k[0] is not fragment}
+
+    def get_backend(self, fragment: Fragment):
+        if fragment not in self._frag_to_backend:
+            raise ValueError("Fragment not found.")
+        return self._frag_to_backend[fragment]
+
+    def set_backend(self, fragment: Fragment, backend) -> None:
+        if fragment not in self._frag_to_backend:
+            raise ValueError("Fragment not found.")
+        self._frag_to_backend[fragment] = backend
+
+    def set_backend_for_all(self, backend) -> None:
+        self._frag_to_backend = {qreg: backend for qreg in self._frag_circs.keys()}
+
+    @staticmethod
+    def _replace_vgates_with_endpoints(circuit: QuantumCircuit) -> QuantumCircuit:
+        new_circuit = QuantumCircuit(*circuit.qregs, *circuit.cregs, name=circuit.name)
+        vgate_index = 0
+        for instr in circuit:
+            op, qubits, clbits = instr.operation, instr.qubits, instr.clbits
+            if isinstance(op, VirtualBinaryGate):
+                for i in range(2):
+                    new_circuit.append(VirtualGateEndpoint(op, vgate_idx=vgate_index, qubit_idx=i), [qubits[i]], [])
+                vgate_index += 1
+                continue
+            new_circuit.append(op, qubits, clbits)
+        return new_circuit
+
+    @staticmethod
+    def _circuit_on_fragment(circuit: QuantumCircuit, fragment: Fragment) -> QuantumCircuit:
+        new_circuit = QuantumCircuit(fragment, *circuit.cregs)
+        fq = set(fragment)
+        for instr in circuit.data:
+            op, qubits, clbits = instr.operation, instr.qubits, instr.clbits
+            if set(qubits) <= fq:
+                new_circuit.append(op, qubits, clbits)
+                continue
+            elif isinstance(op, Barrier) and not isinstance(op, VirtualGateEndpoint):
+                continue
+            elif set(qubits) & fq:
+                raise ValueError(f"Circuit contains gates that act on multiple fragments. {op}")
+        return new_circuit
+
+    def _global_inst_labels(self) -> list[InstanceLabelType]:
+        return list(itertools.product(*[range(vg.operation.num_instantiations) for vg in self._vgate_instrs]))
+
+    def _global_to_fragment_inst_label(self, fragment: Fragment, global_inst_label) -> InstanceLabelType:
+        return tuple(g if touch else -1 for g, touch in zip(global_inst_label, self._touches(fragment)))
+
+    def _fragment_results(self, fragment: Fragment, results: list) -> list:
+        labeled = dict(zip(self.get_instance_labels(fragment), results))
+        return [labeled[self._global_to_fragment_inst_label(fragment, g)] for g in self._global_inst_labels()]
+
+    def knit(self, results: dict, pool=None) -> QuasiDistr:
+        """Reference-order knit on device-resident ``QuasiDistr`` lists (``:50-68``)."""
+        distr_lists = [self._fragment_results(frag, distrs) for frag, distrs in results.items()]
+        merged_results = [_merge_distrs(group) for group in zip(*distr_lists)]
+        if len(self._vgate_instrs) == 0:
+            return merged_results[0]
+        vgates = self.vgates
+        clbit_idx = self._circuit.num_clbits + len(vgates) - 1
+        while len(vgates) > 0:
+            vgate = vgates.pop(-1)
+            chunks = _chunk(merged_results, vgate.num_instantiations)
+            merged_results = [vgate.knit(chunk, clbit_idx) for chunk in chunks]
+            clbit_idx -= 1
+        return merged_results[0]
+
+    # ------------------------------------------------------------------ device fast path
+    def program(self, fragment: Fragment) -> FragmentProgram:
+        if fragment not in self._programs:
+            self._programs[fragment] = FragmentProgram(self._frag_circs[fragment], fragment, self.num_clbits)
+        return self._programs[fragment]
+
+    def executor(self, fragment: Fragment, device, fold: bool = True) -> FragmentExecutor:
+        key = (fragment, str(device), fold)
+        if key not in self._executors:
+            self._executors[key] = FragmentExecutor(self.program(fragment), device, fold)
+        return self._executors[key]
+
+    def active_fragments(self) -> list[Fragment]:
+        """Fragments whose instances measure something (``run.py:49-58`` drops the others)."""
+        return [f for f in self._frag_circs if self.program(f).measures_anything]
+
+    def global_radices(self) -> list[int]:
+        return [vg.operation.num_instantiations for vg in self._vgate_instrs]
+
+    def num_global_labels(self) -> int:
+        return int(np.prod(self.global_radices(), dtype=np.int64)) if self._vgate_instrs else 1
+
+    def fragment_label_range(self, fragment: Fragment, l_begin: int, l_end: int) -> tuple[int, int]:
+        """Smallest contiguous range of fragment labels covering global labels [l_begin, l_end)."""
+        prog = self.program(fragment)
+        if not prog.radix or l_end <= l_begin:
+            return (0, prog.num_labels if l_end > l_begin else 0)
+        radices = self.global_radices()
+        strides = self._fragment_strides(fragment)
+        idx = np.arange(l_begin, l_end, dtype=np.int64)
+        digits = np.stack(np.unravel_index(idx, radices), axis=1)
+        lf = digits @ np.asarray(strides, dtype=np.int64)
+        return int(lf.min()), int(lf.max()) + 1
+
+    def _fragment_strides(self, fragment: Fragment) -> list[int]:
+        """lf = sum_k digit_k * stride_k maps a global label to the fragment's label index."""
+        touch = self._touches(fragment)
+        radices = self.global_radices()
+        strides, acc = [0] * len(radices), 1
+        for k in reversed(range(len(radices))):
+            if touch[k]:
+                strides[k] = acc
+                acc *= radices[k]
+        return strides
+
+    def simulate_fragments(self, device=None, label_range: tuple[int, int] | None = None) -> dict:
+        """All instances of all active fragments -> {fragment: device tensor [L_f, 2^m_f]}.
+        ``label_range`` (global labels) restricts the work to what one rank needs."""
+        device = default_device() if device is None else device
+        handle = _lib.get_handle(getattr(device, "index", None) or 0)
+        tables = {}
+        for frag in self.active_fragments():
+            ex = self.executor(frag, device, True)
+            rng = None
+            if label_range is not None and self._vgate_instrs:
+                rng = self.fragment_label_range(frag, *label_range)
+            tables[frag] = ex.run(handle, label_range=rng)
+        return tables
+
+    def output_masks(self) -> tuple[dict, int]:
+        """-> ({fragment: clbit mask of its output row}, union).  The dense result lives on the
+        union's bits (compacted when some clbit is never written)."""
+        masks = {f: self.program(f).out_mask for f in self.active_fragments()}
+        union = 0
+        for f, m in masks.items():
+            if m & union:
+                raise ValueError("two fragments write the same clbit")
+            union |= m
+        return masks, union
+
+    def knit_tables(self, tables: dict, device=None, label_range: tuple[int, int] | None = None,
+                    out=None, y_range: tuple[int, int] | None = None, stats=None):
+        """Dense exact knit.  Returns a device tensor over the written clbits (index bit j = j-th
+        written clbit in ascending order; for ``measure_all`` circuits index == key)."""
+        import torch
+        device = default_device() if device is None else device
+        handle = _lib.get_handle(getattr(device, "index", None) or 0)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        masks, union = self.output_masks()
+        frags = list(tables.keys())
+        n_out = bin(union).count("1")
+        cmask = [_compress_mask(masks[f], union) for f in frags]
+        ptrs = (C.c_void_p * len(frags))(*[tables[f].data_ptr() for f in frags])
+        cm = (C.c_uint64 * len(frags))(*cmask)
+        K = len(self._vgate_instrs)
+        if K == 0:
+            y0, y1 = y_range if y_range is not None else (0, 1 << n_out)
+            if out is None:
+                out = torch.empty(y1 - y0, dtype=torch.float64, device=device)
+            handle.check(handle.lib.qck_knit_outer(handle.ptr, len(frags), ptrs, cm, n_out, y0, y1, out.data_ptr(),
+                                                   stats.data_ptr() if stats is not None else None, stream))
+            return out
+        if y_range is not None:
+            raise NotImplementedError("output sharding is only available without virtual gates")
+        radices = self.global_radices()
+        coef = (C.c_double * (K * _lib.MAX_VARIANTS))()
+        for k, vg in enumerate(self.vgates):
+            for i, (a, _b) in enumerate(vg.knit_coefficients()):
+                coef[k * _lib.MAX_VARIANTS + i] = a       # signed fold already carries the -b half
+        strides = (C.c_int32 * (len(frags) * _lib.MAX_DIGITS))()
+        for i, f in enumerate(frags):
+            for k, s in enumerate(self._fragment_strides(f)):
+                strides[i * _lib.MAX_DIGITS + k] = s
+        row_strides = (C.c_int64 * len(frags))(*[tables[f].shape[1] for f in frags])
+        rad = (C.c_int32 * K)(*radices)
+        l0, l1 = label_range if label_range is not None else (0, self.num_global_labels())
+        if out is None:
+            out = torch.empty(1 << n_out, dtype=torch.float64, device=device)
+        handle.check(handle.lib.qck_knit_contract(handle.ptr, len(frags), ptrs, cm, row_strides, n_out, K, rad,
+                                                  coef, strides, l0, l1, out.data_ptr(), 0, stream))
+        if stats is not None:
+            handle.check(handle.lib.qck_stats_dense(handle.ptr, out.data_ptr(), out.numel(), 0.0,
+                                                    stats.data_ptr(), stream))
+        return out
+
+
+def _compress_mask(mask: int, union: int) -> int:
+    """Positions of ``mask``'s bits among the set bits of ``union``."""
+    out, j = 0, 0
+    b = 0
+    while union >> b:
+        if (union >> b) & 1:
+            if (mask >> b) & 1:
+                out |= 1 << j
+            j += 1
+        b += 1
+    return out
+
+
+def generate_instantiations(fragment_circuit: QuantumCircuit, inst_labels: list) -> list[QuantumCircuit]:
+    return [_instantiate_fragment(fragment_circuit, inst_label) for inst_label in inst_labels]
+
+
+def _chunk(lst: list, n: int) -> list[list]:
+    return [lst[i:i + n] for i in range(0, len(lst), n)]
+
+
+def _instantiate_fragment(fragment_circuit: QuantumCircuit, inst_label: InstanceLabelType) -> QuantumCircuit:
+    """Host-side instance circuit (``:197-213``) - only needed for foreign duck-typed backends;
+    the B200 path never builds these."""
+    if len(inst_label) == 0:
+        return fragment_circuit.copy()
+    config_register = ClassicalRegister(len(inst_label), "vgate_c")
+    new_circuit = QuantumCircuit(*fragment_circuit.qregs, *(fragment_circuit.cregs + [config_register]))
+    for instr in fragment_circuit:
+        op, qubits, clbits = instr.operation, instr.qubits, instr.clbits
+        if isinstance(op, VirtualGateEndpoint):
+            vgate_idx = op.vgate_idx
+            sub = op.instantiate(inst_label[vgate_idx])
+            for s in sub.data:                      # inline = one level of decompose()
+                new_circuit.append(s.operation, qubits, [config_register[vgate_idx]] if s.clbits else [])
+            continue
+        new_circuit.append(op, qubits, clbits)
+    return new_circuit
+
+
+def _merge_distrs(distrs: tuple) -> QuasiDistr:
+    assert len(distrs) > 0
+    merged = distrs[0]
+    for res in distrs[1:]:
+        merged = merged.merge(res)
+    return merged

@@ -1,0 +1,211 @@
+/*
+ * qck.h - C ABI of libqck.so: B200 (sm_100a) fragment simulation + knitting.
+ *
+ * Drop-in boundary for the hot path of
+ * thangktran/HardwareAwareOptimalQuantumCircuitCuttingAndKnitting, i.e. what
+ * third_party/qvm/qvm/run.py:23-71 (run_virtual_circuit) delegates to a Qiskit
+ * backend and a multiprocessing.Pool today.  The reference is pure Python, so
+ * the binding a maintainer adds is a ctypes stub; every
+ * entry point below names the reference call site it replaces.
+ *
+ * Conventions
+ *   - plain C, no exceptions, every function returns a qck_status (0 = ok);
+ *     qck_last_error_string(h) gives the detail for the last failure on h.
+ *   - pointers named d_* are DEVICE pointers owned by the caller (torch on the
+ *     Python side); the library allocates only small scratch inside the handle.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); all work
+ *     is enqueued asynchronously on it; nothing synchronises unless documented.
+ *   - one handle per host thread (the reference calls run_virtual_circuit from
+ *     several Python threads at once, src/HwAwareCutter/Utilities.py:85-101);
+ *     handles share no mutable state.
+ *   - bitstring convention: bit i of an output index = classical bit i of the
+ *     cut circuit (quasi_distr.py:13-20).  Statevector index bit q = local
+ *     qubit q of the fragment (little endian, as Qiskit).
+ */
+#ifndef QCK_H
+#define QCK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define QCK_API __attribute__((visibility("default")))
+#else
+#define QCK_API
+#endif
+
+typedef enum {
+    QCK_OK = 0,
+    QCK_ERR_INVALID_ARG = 1,   /* -> ValueError on the Python side   */
+    QCK_ERR_CUDA = 2,          /* -> RuntimeError                    */
+    QCK_ERR_UNSUPPORTED = 3,   /* -> NotImplementedError             */
+    QCK_ERR_NOMEM = 4          /* -> MemoryError                     */
+} qck_status;
+
+typedef struct qck_handle qck_handle;
+typedef void* qck_stream;
+
+QCK_API int qck_abi_version(void);
+QCK_API int qck_create(int device, qck_handle** out);
+QCK_API int qck_destroy(qck_handle* h);
+QCK_API const char* qck_last_error_string(const qck_handle* h);
+QCK_API const char* qck_status_string(int status);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+QCK_API int64_t qck_launch_count(const qck_handle* h);
+
+/* ------------------------------------------------------------------ fragment simulation
+ * Replaces: virt.get_backend(frag).run(instantiations, shots) + get_counts()
+ *           (run.py:36-58) together with generate_instantiations /
+ *           _instantiate_fragment (virtual_circuit.py:183-213) and
+ *           VirtualGateEndpoint.instantiate (virtual_gates.py:134-150):
+ * instances are never materialised on the host; each CTA decodes its
+ * mixed-radix label and picks the variant matrices itself.
+ */
+#define QCK_MAX_TILE_QUBITS 14
+#define QCK_MAX_DIGITS 16
+#define QCK_MAX_OUT_BITS 40
+
+enum { QCK_OP_U1 = 0, QCK_OP_CX = 1, QCK_OP_CZ = 2, QCK_OP_U2 = 3 };
+
+/* One gate application.  Qubits are TILE-LOCAL bit positions of the sweep the op
+ * belongs to.  A measurement whose qubit lives on is a QCK_OP_CX onto a fresh
+ * ancilla bit (deferred measurement: the two halves of the state are the two
+ * un-normalised branches of SURVEY.md A.2). */
+typedef struct {
+    int32_t kind;        /* QCK_OP_*                                                     */
+    int32_t q0, q1;      /* U1: q0.  CX: control q0, target q1.  CZ/U2: q0 (bit0), q1     */
+    int32_t mat;         /* offset (in doubles) into the matrix pool; U1: 8, U2: 32       */
+    int32_t sel_digit;   /* -1, or the label digit that selects the variant matrix:       */
+    int32_t sel_stride;  /*   offset = mat + digit[sel_digit] * sel_stride                */
+    int32_t n_live;      /* ops touch only the first 2^n_live amplitudes of the tile      */
+    int32_t reserved;
+} qck_op;
+
+/* A sweep = one pass over the state: every CTA stages a 2^n_tile tile (the
+ * amplitudes that differ only in the listed bit positions) in shared memory,
+ * applies ops[op_begin, op_end) there and writes it back. */
+typedef struct {
+    int32_t n_tile;
+    int32_t op_begin, op_end;
+    int32_t reserved;
+    int32_t pos[QCK_MAX_TILE_QUBITS + 2];  /* ascending state-bit positions of the tile bits */
+} qck_sweep;
+
+/* Program of one (fragment, measurement pattern): all instances that share it
+ * differ only in the matrices the label digits select. */
+typedef struct {
+    int32_t n_state_qubits;          /* fragment qubits + branch ancillas                 */
+    int32_t n_sweeps;                /* 1 and n_tile == n_state_qubits: on-chip regime     */
+    const qck_sweep* sweeps;         /* HOST array                                        */
+    const qck_op* d_ops;             /* device                                            */
+    const double* d_mats;            /* device, interleaved re/im                         */
+    int32_t n_digits;                /* digits of a fragment label, last fastest          */
+    int32_t radix[QCK_MAX_DIGITS];
+    /* output row: bit j of the row index <- state bit out_pos[j] (-1: the bit is
+     * never set, entries with it set are 0).  Bits in sum_mask are summed out,
+     * those also in sign_mask with weight (-1)^bit (signed fold of the config
+     * bits). */
+    int32_t n_out_bits;
+    int32_t out_pos[QCK_MAX_OUT_BITS];
+    uint64_t sum_mask;
+    uint64_t sign_mask;
+} qck_sim_plan;
+
+/* d_labels[i] = fragment-label index of instance i (row-major over the touched
+ * virtual gates, last fastest: virtual_circuit.py:39-48); its row is written at
+ * d_out + d_labels[i] * out_row_stride.  d_work: scratch for the streaming
+ * regime (>= 16 << n_state_qubits bytes, more = more instances in flight);
+ * ignored in the on-chip regime. */
+QCK_API int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const int32_t* d_labels,
+                      int64_t n_instances, double* d_out, int64_t out_row_stride,
+                      void* d_work, size_t work_bytes, qck_stream stream);
+
+/* Final statevector of ONE instance in the streaming regime left in d_work
+ * (used for the uncut reference run, Utilities.py:39-69). */
+QCK_API int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t label,
+                        void* d_state, size_t state_bytes, qck_stream stream);
+
+/* ------------------------------------------------------------------ knitting
+ * Replaces: VirtualCircuit.knit (virtual_circuit.py:50-68), _merge /
+ *           _merge_distrs / QuasiDistr.merge (virtual_circuit.py:150-171,216-228;
+ *           quasi_distr.py:55-60) and Virtual*.knit (virtual_gates.py:105-124,
+ *           179-194,262-286) in their exact (unpruned) closed form.
+ */
+#define QCK_MAX_FRAGMENTS 8
+
+/* running statistics of a produced distribution (all doubles, device memory) */
+typedef struct {
+    double sum;      /* sum of entries                                   */
+    double min;      /* smallest entry                                   */
+    double sum_sqrt; /* sum of sqrt(max(entry, 0))                       */
+    double nnz;      /* number of entries != 0                           */
+} qck_stats;
+
+/* K = 0: out[y - y_begin] = prod_f tables[f][pext(y, masks[f])], y in [y_begin, y_end).
+ * d_tables / masks are HOST arrays of n_frag device pointers / bit masks (masks may overlap;
+ * every mask bit < n_out_bits).  d_out may be NULL: statistics only -
+ * called with the square-rooted tables of the cut fragments AND of a factorised
+ * reference distribution this yields the Bhattacharyya sum of the Hellinger
+ * fidelity without materialising anything.  d_stats may be NULL. */
+QCK_API int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
+                   int n_out_bits, uint64_t y_begin, uint64_t y_end, double* d_out,
+                   qck_stats* d_stats, qck_stream stream);
+
+/* K >= 1: out[y] (+)= sum_{l in [l_begin, l_end)} w(l) prod_f Q_f[lf(l)][pext(y, masks[f])]
+ * with l the global label (last virtual gate fastest), w(l) = prod_k coef[k][l_k],
+ * lf(l) = sum_k l_k * frag_stride[f][k] (0 when gate k does not touch f).
+ * coef: HOST array, n_digits rows of QCK_MAX_VARIANTS doubles.
+ * frag_stride: HOST array [n_frag][QCK_MAX_DIGITS]. */
+#define QCK_MAX_VARIANTS 8
+QCK_API int qck_knit_contract(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
+                      const int64_t* row_strides, int n_out_bits,
+                      int n_digits, const int32_t* radix, const double* coef,
+                      const int32_t* frag_stride, int64_t l_begin, int64_t l_end,
+                      double* d_out, int accumulate, qck_stream stream);
+
+/* ------------------------------------------------------------------ reductions
+ * qck_stats_dense: sum / min / nnz of a dense vector (entries |v| <= acc count as absent).
+ * qck_hellinger: result[0..2] = sum p, sum q, sum sqrt(p q) over max(.,0) entries; the
+ *   fidelity (Utilities.py:224, qiskit hellinger_fidelity) is (r2 / sqrt(r0 r1))^2.
+ * qck_npd: QuasiDistr.nearest_probability_distribution (quasi_distr.py:28-43) on a dense
+ *   vector, in place.  Synchronises the stream (the threshold search is host-driven). */
+QCK_API int qck_stats_dense(qck_handle* h, const double* d_p, uint64_t n, double acc, qck_stats* d_stats,
+                    qck_stream stream);
+QCK_API int qck_hellinger(qck_handle* h, const double* d_p, const double* d_q, uint64_t n, double* d_result3,
+                  qck_stream stream);
+QCK_API int qck_npd(qck_handle* h, double* d_p, uint64_t n, double acc, double* host_beta, double* host_num,
+            qck_stream stream);
+
+/* ------------------------------------------------------------------ dense QuasiDistr algebra
+ * Device forms of quasi_distr.py:45-86 on dense vectors of 2^n_bits doubles with
+ * the reference's pruning (v = |v| > acc ? v : 0 after every operation).  They
+ * back the per-gate operator API VirtualBinaryGate.knit(results, clbit_idx)
+ * (virtual_gates.py:39) and the reference-faithful (acc = 1e-5) mode.
+ */
+QCK_API int qck_qd_prune(qck_handle* h, double* d_v, uint64_t n, double acc, qck_stream stream);
+/* out = sqrt(max(v, 0)) (Hellinger building block) */
+QCK_API int qck_qd_sqrt(qck_handle* h, const double* d_v, double* d_out, uint64_t n, qck_stream stream);
+/* out = prune(a * x + b * y); y may be NULL */
+QCK_API int qck_qd_axpby(qck_handle* h, double a, const double* d_x, double b, const double* d_y,
+                 double* d_out, uint64_t n, double acc, qck_stream stream);
+/* split on bit: lo[i] = v[insert0(i)], hi[i] = v[insert1(i)], each pruned; n = size of v */
+QCK_API int qck_qd_split(qck_handle* h, const double* d_v, uint64_t n, int bit, double* d_lo, double* d_hi,
+                 double acc, qck_stream stream);
+/* merge: out[k] = a[k & mask_a] * b[k & mask_b] pruned (disjoint supports, XOR = OR) */
+QCK_API int qck_qd_merge(qck_handle* h, const double* d_a, uint64_t mask_a, const double* d_b, uint64_t mask_b,
+                 double* d_out, uint64_t n, double acc, qck_stream stream);
+/* one exact knit level: out[i] = sum_r coef0[r] * v_r[insert0(i)] + coef1[r] * v_r[insert1(i)] */
+QCK_API int qck_qd_knit_level(qck_handle* h, int n_results, const double* const* d_results, uint64_t n,
+                      int bit, const double* coef0, const double* coef1, double* d_out,
+                      qck_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCK_H */

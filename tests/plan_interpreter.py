@@ -1,0 +1,91 @@
+"""Numpy interpreter of compiled device programs (test tool, CPU only).
+
+Executes exactly the data ``qck_sim_fragments`` consumes - the op records, the
+sweeps with their tile positions, the matrix pool, the label digits and the
+fold masks - the way ``csrc/sim.cu`` does, so that the host compiler
+(``compiler.py``) can be checked against the oracle without a GPU.  It is not a
+fallback: the product never imports it.
+"""
+import numpy as np
+
+from hardwareawareoptimalquantumcircuitcuttingandknitting_b200 import _lib
+
+
+def _bits(idx, q):
+    return (idx >> q) & 1
+
+
+def run_plan(program, plan, label):
+    """-> output row (1-D float64) of one instance."""
+    mats = program.mats
+    digits = list(np.unravel_index(int(label), program.radix)) if program.radix else []
+    N = plan.n_state
+    psi = np.zeros(1 << N, dtype=np.complex128)
+    psi[0] = 1.0
+    idx = np.arange(1 << N)
+    for positions, b, e in plan.sweeps:
+        for op in plan.ops[b:e]:
+            kind, q0, q1, mat, sel, stride, n_live, _ = (int(x) for x in op)
+            moff = mat + (digits[sel] * stride if sel >= 0 else 0)
+            g0 = positions[q0]
+            if kind == _lib.OP_U1:
+                m = mats[moff:moff + 8].view(np.complex128).reshape(2, 2)
+                lo = psi[(_bits(idx, g0) == 0)]
+                hi = psi[(_bits(idx, g0) == 1)]
+                new = psi.copy()
+                new[_bits(idx, g0) == 0] = m[0, 0] * lo + m[0, 1] * hi
+                new[_bits(idx, g0) == 1] = m[1, 0] * lo + m[1, 1] * hi
+                psi = new
+            elif kind == _lib.OP_CX:
+                g1 = positions[q1]
+                src = np.where(_bits(idx, g0) == 1, idx ^ (1 << g1), idx)
+                psi = psi[src]
+            elif kind == _lib.OP_CZ:
+                g1 = positions[q1]
+                psi = np.where((_bits(idx, g0) & _bits(idx, g1)) == 1, -psi, psi)
+            else:
+                g1 = positions[q1]
+                m = mats[moff:moff + 32].view(np.complex128).reshape(4, 4)
+                sub = _bits(idx, g0) + 2 * _bits(idx, g1)
+                base = idx & ~((1 << g0) | (1 << g1))
+                new = np.zeros_like(psi)
+                for r in range(4):
+                    for c in range(4):
+                        srcidx = base | ((c & 1) << g0) | ((c >> 1) << g1)
+                        new += np.where(sub == r, m[r, c] * psi[srcidx], 0)
+                psi = new
+            if n_live > 0 and len(plan.sweeps) == 1:
+                assert np.all(psi[(1 << n_live):] == 0), "amplitudes beyond n_live must stay zero"
+    prob = psi.real ** 2 + psi.imag ** 2
+    n_out = len(plan.out_pos)
+    row = np.zeros(1 << n_out)
+    for o in range(1 << n_out):
+        base, dead = 0, False
+        for j in range(n_out):
+            if (o >> j) & 1:
+                if plan.out_pos[j] < 0:
+                    dead = True
+                    break
+                base |= 1 << plan.out_pos[j]
+        if dead:
+            continue
+        sub, acc = 0, 0.0
+        while True:
+            sign = -1.0 if bin(sub & plan.sign_mask).count("1") & 1 else 1.0
+            acc += sign * prob[base | sub]
+            sub = (sub - plan.sum_mask) & plan.sum_mask
+            if sub == 0:
+                break
+        row[o] = acc
+    return row
+
+
+def run_program(program, fold=True, labels=None):
+    """-> [num_labels, row_len] table like FragmentExecutor.run."""
+    out = np.zeros((program.num_labels, program.row_len(fold)))
+    for plan in program.plans(fold):
+        for label in plan.labels:
+            if labels is not None and label not in labels:
+                continue
+            out[label] = run_plan(program, plan, label)
+    return out
