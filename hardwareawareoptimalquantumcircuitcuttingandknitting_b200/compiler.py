@@ -329,7 +329,7 @@ def _schedule_sweeps(ops: np.ndarray, n_state: int, tile: int):
     """Greedy list scheduling: each sweep takes, in program order, every op whose qubits are
     not blocked by an earlier unscheduled op and still fit into the tile."""
     tile = min(tile, n_state)
-    low = min(LOW_RUN, tile)
+    low = max(0, min(LOW_RUN, tile - 2))     # always leave room for a two-qubit gate
     remaining = list(range(len(ops)))
     new_ops, sweeps = [], []
     while remaining:

@@ -166,3 +166,12 @@ def baseline_cut_spec(config: str, circuit: QuantumCircuit) -> CutSpec:
     if config in ("qft16", "aqft16", "add6"):
         return CutSpec()
     raise KeyError(config)
+
+
+def make_baseline(config: str, seed: int = 0) -> tuple[QuantumCircuit, QuantumCircuit]:
+    """-> (decomposed input circuit, cut circuit) of a BASELINE.json config, i.e. the two
+    arguments of ``compareOriginalCircWithCutCirc`` (``benchmarks/benchmark.py:99``)."""
+    from .generators import gen_circ
+    name, n, depth, _p, _q = BASELINE_CONFIGS[config]
+    circ = gen_circ(name, n, depth, seed=seed).decompose_two_qubit()
+    return circ, apply_cuts(circ, baseline_cut_spec(config, circ))

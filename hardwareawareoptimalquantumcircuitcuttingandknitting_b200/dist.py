@@ -1,0 +1,88 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, torch.distributed).
+
+The reference has exactly one form of parallelism on this path: a fixed
+``multiprocessing.Pool(8)`` that maps global instance labels, then chunks, to
+worker processes and pickles every distribution through pipes
+(``third_party/qvm/qvm/run.py:64``, ``virtual_circuit.py:63-66,224-228``).  The
+B200 equivalent shards the same two axes across the GPUs of one box:
+
+* no virtual gates (syc-32): the output index ``y`` is sharded by its top
+  ``log2(world)`` bits; every rank re-simulates the (tiny) fragments and streams
+  its own slice of the 2^n_out result, which is never gathered.  The only
+  exchange is a scalar all-reduce of (sum, min, Bhattacharyya sum).
+* virtual gates: the global label range is sharded; every rank simulates the
+  fragment instances its labels need and contracts them into a dense partial
+  result, summed with one all-reduce (512 KiB at 16 output bits - latency bound,
+  NCCL over NVLink is the right tool; there is no compute to overlap with).
+
+The host logic here is backend-agnostic and is covered on CPU with ``gloo``
+(``tests/test_dist_gloo.py``).
+"""
+from __future__ import annotations
+
+import os
+
+__all__ = ["shard_range", "shard_pow2", "init_from_env", "allreduce_stats", "allreduce_sum_", "world"]
+
+
+def shard_range(total: int, rank: int, world_size: int, align: int = 1) -> tuple[int, int]:
+    """Contiguous, disjoint, exhaustive split of ``range(total)``; boundaries are multiples of
+    ``align`` (keeps a whole innermost knit chunk on one rank)."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    units = (total + align - 1) // align
+    lo = (units * rank) // world_size * align
+    hi = (units * (rank + 1)) // world_size * align
+    return min(lo, total), min(hi, total)
+
+
+def shard_pow2(n_bits: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Slice of ``[0, 2^n_bits)`` owned by ``rank`` when the index is sharded by its top bits."""
+    if world_size & (world_size - 1):
+        raise ValueError("output sharding needs a power-of-two world size")
+    if world_size > (1 << n_bits):
+        raise ValueError("more ranks than output entries")
+    span = (1 << n_bits) // world_size
+    return rank * span, (rank + 1) * span
+
+
+def world() -> tuple[int, int, int]:
+    """(rank, local_rank, world_size) from the torchrun environment (1 process = 1 GPU)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def init_from_env(backend: str | None = None):
+    """Initialise torch.distributed when launched under torchrun; returns (rank, local_rank, world)."""
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world_size = world()
+    if world_size > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world_size)
+    return rank, local_rank, world_size
+
+
+def allreduce_stats(stats, group=None):
+    """``stats`` = tensor [sum, min, sum_sqrt, nnz] (a qck_stats); reduced in place across ranks:
+    sums are added, the minimum is min-reduced."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats
+    mn = stats[1:2].clone()
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    stats[1:2] = mn
+    return stats
+
+
+def allreduce_sum_(tensor, group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+    return tensor

@@ -82,9 +82,16 @@ def _all_b200(virt: VirtualCircuit) -> bool:
     return all(isinstance(virt.get_backend(f), B200Backend) for f in virt.fragment_circuits)
 
 
-def run_virtual_circuit_dense(virt: VirtualCircuit, shots: int = 20000, device=None,
-                              nearest: bool = True) -> tuple[DenseResult, RunTimeInfo]:
+def run_virtual_circuit_dense(virt: VirtualCircuit, shots: int = 20000, device=None, nearest: bool = True,
+                              rank: int = 0, world_size: int = 1, group=None,
+                              out=None) -> tuple[DenseResult, RunTimeInfo]:
+    """Whole path on the GPU.  With ``world_size > 1`` (one process per GPU) the work is
+    partitioned as described in ``dist.py``: without virtual gates this rank produces the
+    output slice whose top bits equal ``rank`` (``DenseResult.y_begin`` tells where it
+    starts); with virtual gates the labels are sharded and the dense result is all-reduced,
+    so every rank returns the full vector."""
     import torch
+    from . import dist as qdist
     if not _all_b200(virt):
         raise ValueError("run_virtual_circuit_dense needs every fragment on a B200Backend")
     device = default_device() if device is None else torch.device(device)
@@ -93,26 +100,46 @@ def run_virtual_circuit_dense(virt: VirtualCircuit, shots: int = 20000, device=N
     logger.info(f"Running virtualizer with {len(frags)} "
                 + f"{tuple(circ.num_qubits for circ in frags.values())} "
                 + f"fragments and {len(virt._vgate_instrs)} vgates...")
+    K = len(virt._vgate_instrs)
+    label_range = None
+    if K > 0 and world_size > 1:
+        label_range = qdist.shard_range(virt.num_global_labels(), rank, world_size,
+                                        align=virt.global_radices()[-1])
     now = perf_counter()
     logger.info(f"Running {sum(virt.program(f).num_labels for f in virt.active_fragments())} instances...")
-    tables = virt.simulate_fragments(device)
-    torch.cuda.synchronize(device)
-    run_time = perf_counter() - now
+    tables = virt.simulate_fragments(device, label_range=label_range)
+    run_time = perf_counter() - now          # enqueue time; the device work is timed with the knit
 
     logger.info("Knitting...")
     now = perf_counter()
     stats = torch.zeros(4, dtype=torch.float64, device=device)
-    values = virt.knit_tables(tables, device, stats=stats)
-    host_stats = stats.cpu().numpy()
+    _, union = virt.output_masks()
+    y_begin = 0
+    if K == 0:
+        n_out = bin(union).count("1")
+        y_range = qdist.shard_pow2(n_out, rank, world_size) if world_size > 1 else None
+        y_begin = y_range[0] if y_range else 0
+        values = virt.knit_tables(tables, device, stats=stats, y_range=y_range, out=out)
+        qdist.allreduce_stats(stats, group)
+    else:
+        values = virt.knit_tables(tables, device, label_range=label_range, out=out,
+                                  stats=None if world_size > 1 else stats)
+        if world_size > 1:
+            qdist.allreduce_sum_(values, group)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            handle.check(handle.lib.qck_stats_dense(handle.ptr, values.data_ptr(), values.numel(), 0.0,
+                                                    stats.data_ptr(), stream))
+    host_stats = stats.cpu().numpy()          # the step's device -> host read (synchronises)
     total, minimum = float(host_stats[0]), float(host_stats[1])
     if nearest and minimum < 0.0:
+        if K == 0 and world_size > 1:
+            raise NotImplementedError("nearest_probability_distribution on an output-sharded result")
         stream = torch.cuda.current_stream(device).cuda_stream
         handle.check(handle.lib.qck_npd(handle.ptr, values.data_ptr(), values.numel(), 0.0, None, None, stream))
     torch.cuda.synchronize(device)
     knit_time = perf_counter() - now
     logger.info(f"Knitted in {knit_time:.2f}s.")
-    _, union = virt.output_masks()
-    return DenseResult(values, union, total, minimum), RunTimeInfo(run_time, knit_time)
+    return DenseResult(values, union, total, minimum, y_begin), RunTimeInfo(run_time, knit_time)
 
 
 def run_virtual_circuit(virt: VirtualCircuit, shots: int = 20000) -> tuple[dict[int, float], RunTimeInfo]:

@@ -1,0 +1,134 @@
+"""Host compiler (templates, slots, patterns, ancillas, sweeps, fold masks) against the oracle,
+executed by the numpy plan interpreter (tests/plan_interpreter.py).  CPU only."""
+import numpy as np
+import pytest
+
+import plan_interpreter as pi
+from conftest import make_semcheck_circuit
+from oracle import dense as od
+from oracle import instantiate as oi
+from oracle import statevector as sv
+
+PKG = "hardwareawareoptimalquantumcircuitcuttingandknitting_b200"
+from importlib import import_module
+
+cutting = import_module(f"{PKG}.cutting")
+vcm = import_module(f"{PKG}.virtual_circuit")
+compiler = import_module(f"{PKG}.compiler")
+circuit = import_module(f"{PKG}.circuit")
+
+
+def _tables(virt):
+    return {f: pi.run_program(virt.program(f)) for f in virt.active_fragments()}
+
+
+def _contract(virt, tables):
+    masks, union = virt.output_masks()
+    frags = list(tables)
+    coeffs = [[c[0] for c in vg.knit_coefficients()] for vg in virt.vgates]
+    return od.contract([tables[f] for f in frags], [virt._touches(f) for f in frags], coeffs,
+                       [vcm._compress_mask(masks[f], union) for f in frags], bin(union).count("1"))
+
+
+@pytest.mark.parametrize("gname,theta", [("cx", None), ("cz", None), ("cy", None), ("rzz", 0.83), ("cp", 0.83)])
+def test_semcheck_every_instance_and_knit(gname, theta):
+    qc, cut = make_semcheck_circuit(gname, theta)
+    virt = vcm.VirtualCircuit(cut)
+    ov = oi.OracleVirtualCircuit(cut)
+    tables = _tables(virt)
+    K = len(virt.vgates)
+    for f in virt.active_fragments():
+        prog = virt.program(f)
+        labels = ov.instance_labels(f)
+        assert labels == virt.get_instance_labels(f)            # bit-exact enumeration
+        for li, lab in enumerate(labels):
+            want = od.signed_fold(sv.exact_distribution(ov.instance(f, lab)), ov.n_clbits, K, prog.out_mask)
+            assert np.abs(want - tables[f][li]).max() < 1e-14
+    res = _contract(virt, tables)
+    uncut = sv.dense(sv.exact_distribution(qc), qc.num_clbits)
+    if gname != "cp":
+        assert np.abs(res - uncut).max() < 1e-13
+
+
+def test_unfolded_rows_carry_config_bits():
+    qc, cut = make_semcheck_circuit("cx")
+    virt = vcm.VirtualCircuit(cut)
+    ov = oi.OracleVirtualCircuit(cut)
+    K = len(virt.vgates)
+    for f in virt.active_fragments():
+        prog = virt.program(f)
+        table = pi.run_program(prog, fold=False)
+        m = bin(prog.out_mask).count("1")
+        for li, lab in enumerate(ov.instance_labels(f)):
+            dist = sv.exact_distribution(ov.instance(f, lab))
+            want = np.zeros(1 << (m + len(prog.radix)))
+            for key, v in dist.items():
+                x = int(od.pext(np.uint64(key & ((1 << ov.n_clbits) - 1)), prog.out_mask))
+                cfg = key >> ov.n_clbits
+                idx = x
+                for d, k in enumerate(prog.vgate_indices):
+                    idx |= ((cfg >> k) & 1) << (m + d)
+                want[idx] += v
+            assert np.abs(want - table[li]).max() < 1e-14
+
+
+def test_bv16_wire_cut():
+    circ, cut = cutting.make_baseline("bv16")
+    virt = vcm.VirtualCircuit(cut)
+    assert sorted(len(f) for f in virt.fragment_circuits) == [8, 9]
+    assert virt.num_global_labels() == 8
+    res = _contract(virt, _tables(virt))
+    want = np.zeros(1 << 16)
+    want[(1 << 16) - 1] = 1.0                      # secret = fifteen ones, ancilla measured as 1
+    assert np.abs(res - want).max() < 1e-13
+
+
+def test_streaming_schedule_equals_onchip():
+    """The same program forced into sweeps (tile 6) gives the same rows."""
+    circ, cut = cutting.make_baseline("bv16")
+    virt = vcm.VirtualCircuit(cut)
+    for f in virt.active_fragments():
+        a = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits)
+        b = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits, onchip_max=4, stream_tile=7)
+        assert any(len(p.sweeps) > 1 for p in b.plans())
+        for p in b.plans():
+            for positions, _, _ in p.sweeps:
+                assert positions[:5] == [0, 1, 2, 3, 4] and positions == sorted(positions)
+        assert np.abs(pi.run_program(a) - pi.run_program(b)).max() < 1e-14
+
+
+def test_mid_circuit_measurement_of_input_circuit():
+    qc = circuit.QuantumCircuit(circuit.QuantumRegister(2, "q"), circuit.ClassicalRegister(3, "c"))
+    qc.h(0); qc.cx(0, 1); qc.measure(0, 0); qc.h(0); qc.ry(0.4, 1); qc.measure(0, 1); qc.measure(1, 2)
+    virt = vcm.VirtualCircuit(qc)
+    (f,) = virt.active_fragments()
+    row = pi.run_program(virt.program(f))[0]
+    want = sv.dense(sv.exact_distribution(qc), 3)
+    assert np.abs(row - want).max() < 1e-14
+
+
+def test_errors_mirror_reference():
+    qc = circuit.QuantumCircuit(circuit.QuantumRegister(1, "a"), circuit.QuantumRegister(1, "b"))
+    qc.cx(qc.qregs[0][0], qc.qregs[1][0])
+    with pytest.raises(ValueError, match="multiple fragments"):
+        vcm.VirtualCircuit(qc)
+    ok = circuit.QuantumCircuit(circuit.QuantumRegister(1, "a"))
+    v = vcm.VirtualCircuit(ok)
+    with pytest.raises(ValueError, match="Fragment not found"):
+        v.get_backend(circuit.QuantumRegister(1, "zz"))
+    with pytest.raises(ValueError, match="Fragment not found"):
+        v.set_backend(circuit.QuantumRegister(1, "zz"), object())
+
+
+def test_baseline_config_shapes():
+    shapes = {"bv16": ([8, 9], 1, 8), "hwe16d5": ([8, 8], 5, 7776), "syc16d5": ([8, 8], 4, 1296),
+              "syc32d1": ([14, 18], 0, 1)}
+    for cfg, (frag_sizes, K, L) in shapes.items():
+        _, cut = cutting.make_baseline(cfg)
+        v = vcm.VirtualCircuit(cut)
+        assert sorted(len(f) for f in v.fragment_circuits) == frag_sizes
+        assert len(v.vgates) == K and v.num_global_labels() == L
+    _, cut = cutting.make_baseline("syc32d1")
+    v = vcm.VirtualCircuit(cut)
+    masks, union = v.output_masks()
+    assert sorted(masks.values()) == [0x7EFF0000, 0x8100FFFF] and union == 0xFFFFFFFF

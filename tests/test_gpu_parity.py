@@ -1,0 +1,474 @@
+"""GPU parity: the CUDA path (through the C ABI / ctypes) against the oracle and the golden
+fixtures.  Run on the GPU box with `pytest -m gpu`; /root/reference is NOT needed."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, make_semcheck_circuit, oracle_knit
+
+pytestmark = pytest.mark.gpu
+
+PKG = "hardwareawareoptimalquantumcircuitcuttingandknitting_b200"
+from importlib import import_module
+
+torch = pytest.importorskip("torch")
+cutting = import_module(f"{PKG}.cutting")
+vcm = import_module(f"{PKG}.virtual_circuit")
+runm = import_module(f"{PKG}.run")
+qdm = import_module(f"{PKG}.quasi_distr")
+fidm = import_module(f"{PKG}.fidelity")
+backend = import_module(f"{PKG}.backend")
+circuit = import_module(f"{PKG}.circuit")
+compiler = import_module(f"{PKG}.compiler")
+_lib = import_module(f"{PKG}._lib")
+gen = import_module(f"{PKG}.generators")
+
+from oracle import cport  # noqa: E402
+from oracle import dense as od  # noqa: E402
+from oracle import instantiate as oi  # noqa: E402
+from oracle import qpd_tables as qt  # noqa: E402
+from oracle import sparse_knit as sk  # noqa: E402
+from oracle import statevector as sv  # noqa: E402
+
+TOL_P = 1e-10       # north_star: probabilities within 1e-10 absolute in FP64
+TOL_F = 1e-8        # north_star: Hellinger fidelity within 1e-8
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _dense(d, nbits):
+    v = np.zeros(1 << nbits)
+    for k, x in d.items():
+        v[k] = x
+    return v
+
+
+def test_native_library_is_loaded(dev):
+    h = _lib.get_handle(0)
+    assert h.lib.qck_abi_version() == 1
+    assert any("libqck.so" in line for line in open("/proc/self/maps"))
+
+
+# ------------------------------------------------------------------ fragment simulation
+@pytest.mark.parametrize("gname,theta", [("cx", None), ("cz", None), ("cy", None), ("rzz", 0.83), ("cp", 0.83)])
+def test_every_instance_matches_oracle(dev, gname, theta):
+    qc, cut = make_semcheck_circuit(gname, theta)
+    virt = vcm.VirtualCircuit(cut)
+    ov = oi.OracleVirtualCircuit(cut)
+    tables = virt.simulate_fragments(dev)
+    K = len(virt.vgates)
+    for f in virt.active_fragments():
+        prog = virt.program(f)
+        got = tables[f].cpu().numpy()
+        for li, lab in enumerate(ov.instance_labels(f)):
+            want = od.signed_fold(sv.exact_distribution(ov.instance(f, lab)), ov.n_clbits, K, prog.out_mask)
+            assert np.abs(want - got[li]).max() < TOL_P
+
+
+def test_semcheck_against_golden_reference_knit(dev):
+    """End to end through run_virtual_circuit vs the REFERENCE's knit of the same instances."""
+    for case in load_golden("semcheck.json"):
+        if case["acc"] != 0.0:
+            continue
+        qc, cut = make_semcheck_circuit(case["gate"], case["theta"])
+        virt = vcm.VirtualCircuit(cut)
+        dense_res, info = runm.run_virtual_circuit_dense(virt, device=dev, nearest=False)
+        want = _dense({int(k): v for k, v in case["knit"]}, case["n_clbits"])
+        assert np.abs(dense_res.values.cpu().numpy() - want).max() < TOL_P
+        res, info = runm.run_virtual_circuit(virt)
+        want_npd = {int(k): v for k, v in case["npd"]}
+        keys = set(res) | set(want_npd)
+        assert max(abs(res.get(k, 0.0) - want_npd.get(k, 0.0)) for k in keys) < TOL_P
+        assert isinstance(info, runm.RunTimeInfo) and info.run_time >= 0 and info.knit_time >= 0
+
+
+def test_unfolded_rows(dev):
+    qc, cut = make_semcheck_circuit("cx")
+    virt = vcm.VirtualCircuit(cut)
+    h = _lib.get_handle(0)
+    import plan_interpreter as pi
+    for f in virt.active_fragments():
+        ex = virt.executor(f, dev, fold=False)
+        got = ex.run(h).cpu().numpy()
+        want = pi.run_program(virt.program(f), fold=False)
+        assert np.abs(got - want).max() < TOL_P
+
+
+@pytest.mark.parametrize("cfg", ["bv16", "syc16d5", "hwe16d5"])
+def test_baseline_16q_configs(dev, cfg):
+    circ, cut = cutting.make_baseline(cfg, seed=1)
+    virt = vcm.VirtualCircuit(cut)
+    dense_res, _ = runm.run_virtual_circuit_dense(virt, device=dev, nearest=False)
+    got = dense_res.values.cpu().numpy()
+    uncut = sv.dense(sv.exact_distribution(circ), circ.num_clbits)
+    assert np.abs(got - uncut).max() < TOL_P
+    assert abs(dense_res.total - 1.0) < 1e-9
+    # a sample of instances against the oracle simulator, labels bit-exact
+    ov = oi.OracleVirtualCircuit(cut)
+    tables = virt.simulate_fragments(dev)
+    rng = np.random.default_rng(0)
+    K = len(virt.vgates)
+    for f in virt.active_fragments():
+        labels = ov.instance_labels(f)
+        assert labels == virt.get_instance_labels(f)
+        prog = virt.program(f)
+        host = tables[f].cpu().numpy()
+        for li in rng.choice(len(labels), size=min(12, len(labels)), replace=False):
+            want = od.signed_fold(sv.exact_distribution(ov.instance(f, labels[li])), ov.n_clbits, K, prog.out_mask)
+            assert np.abs(want - host[li]).max() < TOL_P
+    # fidelity to the uncut circuit: GPU vs oracle
+    res, _ = runm.run_virtual_circuit(virt)
+    f_gpu = fidm.hellinger_fidelity(res, {i: float(v) for i, v in enumerate(uncut) if v != 0.0}, num_bits=16)
+    f_or = od.hellinger_fidelity(res, {i: float(v) for i, v in enumerate(uncut) if v != 0.0})
+    assert abs(f_gpu - f_or) < TOL_F and f_gpu > 1 - 1e-9
+
+
+@pytest.mark.parametrize("cfg", ["qft16", "aqft16", "add6"])
+def test_uncut_configs_streaming_regime(dev, cfg):
+    circ, cut = cutting.make_baseline(cfg)
+    virt = vcm.VirtualCircuit(cut)
+    res, _ = runm.run_virtual_circuit_dense(virt, device=dev, nearest=False)
+    ov = oi.OracleVirtualCircuit(cut)
+    frag = ov.fragments[0]
+    want = cport.simulate_probabilities(ov.instance(frag, ()))
+    assert np.abs(res.values.cpu().numpy() - want).max() < TOL_P
+
+
+def test_streaming_equals_onchip_on_device(dev):
+    circ, cut = cutting.make_baseline("bv16")
+    virt = vcm.VirtualCircuit(cut)
+    h = _lib.get_handle(0)
+    for f in virt.active_fragments():
+        a = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits)
+        b = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits, onchip_max=4, stream_tile=7)
+        ra = compiler.FragmentExecutor(a, dev).run(h).cpu().numpy()
+        rb = compiler.FragmentExecutor(b, dev).run(h).cpu().numpy()
+        assert np.abs(ra - rb).max() < 1e-13
+
+
+def test_b200_backend_duck_type(dev):
+    """backend.run(circuits, shots).result().get_counts() -> QuasiDistr.from_counts (run.py:42-56)."""
+    qc, cut = make_semcheck_circuit("cx")
+    virt = vcm.VirtualCircuit(cut)
+    be = backend.B200Backend()
+    frag = virt.active_fragments()[0]
+    labels = virt.get_instance_labels(frag)
+    insts = vcm.generate_instantiations(virt.fragment_circuits[frag], labels[:5])
+    counts = be.run(insts, shots=1000).result().get_counts()
+    assert isinstance(counts, list) and len(counts) == 5
+    ov = oi.OracleVirtualCircuit(cut)
+    width = virt.num_clbits + len(virt.vgates)
+    for lab, c in zip(labels[:5], counts):
+        assert all(" " in k for k in c)                      # registers separated, vgate_c leftmost
+        got = qdm.QuasiDistr.from_counts(c, num_bits=width, accuracy=0.0).to_dict()
+        want = sv.exact_distribution(ov.instance(frag, lab))
+        keys = set(got) | set(want)
+        assert max(abs(got.get(k, 0) - want.get(k, 0)) for k in keys) < TOL_P
+    # single circuit -> single dict; uncut circuit
+    single = be.run(qc, shots=1).result().get_counts()
+    assert isinstance(single, dict)
+    uncut = sv.exact_distribution(qc)
+    assert max(abs(single.get(format(k, "04b"), 0) - v) for k, v in uncut.items()) < TOL_P
+
+
+class _OracleBackend:
+    """Foreign duck-typed backend (stands for Aer): exact counts from the numpy oracle."""
+
+    def run(self, circuits, shots=1024):
+        counts = []
+        for c in circuits:
+            dist = sv.exact_distribution(c)
+            n = len(c.clbits)
+            counts.append({format(k, f"0{n}b"): v * shots for k, v in dist.items()})
+        outer = self
+
+        class _R:
+            def get_counts(self_inner):
+                return counts[0] if len(counts) == 1 else counts
+
+        class _J:
+            def result(self_inner):
+                return _R()
+        return _J()
+
+
+@pytest.mark.parametrize("acc", [0.0, 1e-5])
+def test_foreign_backend_and_reference_order_knit(dev, acc):
+    """The reference's literal flow (instantiate -> backend -> from_counts -> knit level by level)
+    on device-resident QuasiDistr, in exact and in reference-faithful (1e-5 pruning) mode,
+    against the REFERENCE's results for the same inputs (golden)."""
+    old = qdm.ACCURACY
+    qdm.ACCURACY = acc
+    try:
+        for case in load_golden("semcheck.json"):
+            if case["acc"] != acc or case["gate"] not in ("cx", "rzz", "cp"):
+                continue
+            qc, cut = make_semcheck_circuit(case["gate"], case["theta"])
+            virt = vcm.VirtualCircuit(cut)
+            virt.set_backend_for_all(_OracleBackend())
+            res, info = runm.run_virtual_circuit(virt, shots=1000)
+            want = {int(k): v for k, v in case["npd"]}
+            assert set(res) == set(want)
+            assert max(abs(res[k] - want[k]) for k in want) < 1e-12
+    finally:
+        qdm.ACCURACY = old
+
+
+# ------------------------------------------------------------------ QuasiDistr algebra on device
+def test_quasi_distr_ops_match_reference_golden(dev):
+    for c in load_golden("knit_cases.json")["ops"]:
+        acc, nb = c["acc"], c["nbits"]
+        a = qdm.QuasiDistr({int(k): v for k, v in c["a_raw"]}, num_bits=2 * nb, accuracy=acc)
+        b = qdm.QuasiDistr({int(k): v for k, v in c["b_raw"]}, num_bits=2 * nb, accuracy=acc)
+        for got, key in [(a + b, "add"), (a - b, "sub"), (a * c["scale"], "mul"), (c["scale"] * a, "rmul")]:
+            want = {int(k): v for k, v in c[key]}
+            assert got.to_dict() == want, key                 # bit-exact: same IEEE operations
+        bsh = qdm.QuasiDistr({int(k) << nb: v for k, v in c["b_raw"]}, num_bits=2 * nb, accuracy=acc)
+        assert a.merge(bsh).to_dict() == {int(k): v for k, v in c["merge"]}
+        with pytest.raises(TypeError):
+            a * "x"
+    # split on the top bit (the only way the knit uses it)
+    for c in load_golden("knit_cases.json")["knit"][:20]:
+        r = qdm.QuasiDistr({int(k): v for k, v in c["results_raw"][0]}, num_bits=c["nbits"], accuracy=c["acc"])
+        lo, hi = r.split(c["clbit"])
+        wlo, whi = sk.split(sk.prune({int(k): v for k, v in c["results_raw"][0]}, c["acc"]), c["clbit"], c["acc"])
+        assert lo.to_dict() == wlo and hi.to_dict() == whi
+
+
+def test_gate_knit_operator_api_matches_reference_golden(dev):
+    vgm = import_module(f"{PKG}.virtual_gates")
+    n = 0
+    for c in load_golden("knit_cases.json")["knit"]:
+        kind, th, acc = c["kind"], c["theta"], c["acc"]
+        if kind == "move":
+            g = vgm.VirtualMove(circuit.Gate("swap", 2, (), label="wc"))
+        elif th is None:
+            g = vgm.VIRTUAL_GATE_TYPES[kind](circuit.Gate(kind, 2, ()), "cut")
+        else:
+            g = vgm.VIRTUAL_GATE_TYPES[kind](circuit.Gate(kind, 2, (th,)), "cut")
+        results = [qdm.QuasiDistr({int(k): v for k, v in r}, num_bits=c["nbits"], accuracy=acc)
+                   for r in c["results_raw"]]
+        got = g.knit(results, c["clbit"]).to_dict()
+        want = {int(k): v for k, v in c["out"]}
+        if acc > 0:
+            assert got == want, (kind, th)                   # reference order replayed: bit-exact
+        else:
+            keys = set(got) | set(want)
+            assert max(abs(got.get(k, 0) - want.get(k, 0)) for k in keys) < 1e-13
+        n += 1
+    assert n > 100
+
+
+# ------------------------------------------------------------------ nearest_probability_distribution / hellinger
+def test_npd_matches_reference_golden(dev):
+    for c in load_golden("knit_cases.json")["npd"]:
+        q = qdm.QuasiDistr({int(k): v for k, v in c["raw"]}, num_bits=c["nbits"], accuracy=c["acc"])
+        got = q.nearest_probability_distribution()
+        want = {int(k): v for k, v in c["out"]}
+        assert set(got) == set(want)
+        assert max(abs(got[k] - want[k]) for k in want) < 1e-13 if want else True
+
+
+def test_npd_properties_large(dev):
+    rng = np.random.default_rng(3)
+    v = rng.random(1 << 20)
+    v /= v.sum()
+    v[rng.choice(1 << 20, 5000, replace=False)] -= 2e-6          # push some entries negative
+    q = qdm.QuasiDistr(torch.from_numpy(v).to(dev), accuracy=0.0, _pruned=True)
+    out = q.nearest_probability_distribution_dense().cpu().numpy()
+    want = od.nearest_probability_distribution(v)
+    assert np.abs(out - want).max() < 1e-13
+    assert out.min() >= 0.0 and abs(out.sum() - v.sum()) < 1e-12
+    # idempotent
+    q2 = qdm.QuasiDistr(torch.from_numpy(out).to(dev), accuracy=0.0, _pruned=True)
+    assert np.abs(q2.nearest_probability_distribution_dense().cpu().numpy() - out).max() == 0.0
+
+
+def test_hellinger_identities_and_random(dev):
+    p = {0: 0.25, 3: 0.75}
+    assert abs(fidm.hellinger_fidelity(p, p) - 1.0) < 1e-15
+    assert fidm.hellinger_fidelity(p, {1: 1.0}) == 0.0
+    assert fidm.hellinger_fidelity({}, {}) == 1.0
+    rng = np.random.default_rng(5)
+    a, b = rng.random(1 << 16), rng.random(1 << 16)
+    got = fidm.hellinger_fidelity(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))
+    assert abs(got - od.hellinger_fidelity_dense(a, b)) < TOL_F
+
+
+# ------------------------------------------------------------------ knit_outer
+def _outer(dev, tables, masks, n_out, y0, y1, want_out=True):
+    h = _lib.get_handle(0)
+    d_t = [torch.from_numpy(np.ascontiguousarray(t)).to(dev) for t in tables]
+    ptrs = (C.c_void_p * len(d_t))(*[t.data_ptr() for t in d_t])
+    cm = (C.c_uint64 * len(d_t))(*masks)
+    out = torch.empty(y1 - y0, dtype=torch.float64, device=dev) if want_out else None
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    h.check(h.lib.qck_knit_outer(h.ptr, len(d_t), ptrs, cm, n_out, y0, y1, out.data_ptr() if want_out else None,
+                                 stats.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return (out.cpu().numpy() if want_out else None), stats.cpu().numpy()
+
+
+@pytest.mark.parametrize("n_out,masks", [
+    (5, [0b10110, 0b01001]),                                   # tiny: generic kernel
+    (16, [0x3333, 0xCCCC]),                                    # interleaved bits, 2 vector fragments
+    (20, [0x8100F, 0x7EFF0]),                                  # syc-32-like shape scaled down
+    (18, [0x00FFF, 0x3F000]),                                  # low chunk entirely in one fragment
+    (18, [0x24924, 0x12492, 0x09249]),                         # three interleaved fragments
+    (22, [0x3FF, 0x1FFC00, 0x200000]),                         # scalar fragments only in the high bits
+])
+def test_knit_outer_bit_exact(dev, n_out, masks):
+    rng = np.random.default_rng(n_out)
+    tables = [rng.random(1 << bin(m).count("1")) for m in masks]
+    got, stats = _outer(dev, tables, masks, n_out, 0, 1 << n_out)
+    want = od.knit_outer(tables, masks, 0, 1 << n_out)
+    assert np.array_equal(got, want)                          # products of the same doubles: bit-exact
+    assert abs(stats[0] - want.sum()) < 1e-9 * want.sum() and stats[1] == want.min()
+    assert stats[3] == np.count_nonzero(want)
+    # a shard by the top bits equals the slice
+    half = 1 << (n_out - 1)
+    got2, _ = _outer(dev, tables, masks, n_out, half, 2 * half)
+    assert np.array_equal(got2, want[half:])
+    # unaligned range -> generic kernel, same values
+    got3, _ = _outer(dev, tables, masks, n_out, 3, min(1 << n_out, 1003))
+    assert np.array_equal(got3, want[3:min(1 << n_out, 1003)])
+
+
+def test_knit_outer_overlapping_masks_stats_only(dev):
+    rng = np.random.default_rng(11)
+    masks = [0x0FFFF, 0xF0000, 0x3FF, 0xFFC00]                 # two factorisations of the same 20 bits
+    tables = [rng.random(1 << bin(m).count("1")) for m in masks]
+    _, stats = _outer(dev, tables, masks, 20, 0, 1 << 20, want_out=False)
+    want = od.knit_outer(tables, masks, 0, 1 << 20)
+    assert abs(stats[0] - want.sum()) < 1e-9 * want.sum()
+
+
+def test_knit_outer_full_size_properties(dev):
+    """2^30 entries (8 GiB): size-independent properties - sum = product of table sums, a window
+    equals the oracle, linearity in one table."""
+    free, _ = torch.cuda.mem_get_info(dev)
+    n_out = 30 if free > 20 * 2**30 else 26
+    maskA = (0x8100FFFF >> 2) & ((1 << n_out) - 1)
+    maskB = ((1 << n_out) - 1) & ~maskA
+    rng = np.random.default_rng(1)
+    tA, tB = rng.random(1 << bin(maskA).count("1")), rng.random(1 << bin(maskB).count("1"))
+    tA /= tA.sum(); tB /= tB.sum()
+    h = _lib.get_handle(0)
+    d = [torch.from_numpy(tA).to(dev), torch.from_numpy(tB).to(dev)]
+    ptrs = (C.c_void_p * 2)(d[0].data_ptr(), d[1].data_ptr())
+    cm = (C.c_uint64 * 2)(maskA, maskB)
+    out = torch.empty(1 << n_out, dtype=torch.float64, device=dev)
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    h.check(h.lib.qck_knit_outer(h.ptr, 2, ptrs, cm, n_out, 0, 1 << n_out, out.data_ptr(), stats.data_ptr(),
+                                 torch.cuda.current_stream(dev).cuda_stream))
+    s = stats.cpu().numpy()
+    assert abs(s[0] - 1.0) < 1e-9 and s[1] >= 0.0
+    for start in (0, (1 << n_out) - (1 << 16), 123 << 12):
+        want = od.knit_outer([tA, tB], [maskA, maskB], start, start + (1 << 16))
+        assert np.array_equal(out[start:start + (1 << 16)].cpu().numpy(), want)
+    assert abs(out.sum().item() - 1.0) < 1e-9
+    del out
+
+
+# ------------------------------------------------------------------ knit_contract
+def test_knit_contract_generic_vs_oracle(dev):
+    """Three fragments, one of them untouched by one gate: the generic kernel."""
+    rng = np.random.default_rng(2)
+    radices = [6, 8]
+    masks = [0b000111, 0b011000, 0b100000]
+    touches = [[True, False], [True, True], [False, True]]
+    n_out = 6
+    tables, strides = [], []
+    for m, t in zip(masks, touches):
+        lf = int(np.prod([r for r, tt in zip(radices, t) if tt]))
+        tables.append(rng.normal(size=(lf, 1 << bin(m).count("1"))))
+        s, acc = [0, 0], 1
+        for k in (1, 0):
+            if t[k]:
+                s[k] = acc
+                acc *= radices[k]
+        strides.append(s)
+    coeffs = [list(rng.normal(size=6)), list(rng.normal(size=8))]
+    want = od.contract(tables, touches, coeffs, masks, n_out)
+    h = _lib.get_handle(0)
+    d_t = [torch.from_numpy(t).to(dev) for t in tables]
+    ptrs = (C.c_void_p * 3)(*[t.data_ptr() for t in d_t])
+    cm = (C.c_uint64 * 3)(*masks)
+    rs = (C.c_int64 * 3)(*[t.shape[1] for t in tables])
+    rad = (C.c_int32 * 2)(*radices)
+    coef = (C.c_double * (2 * _lib.MAX_VARIANTS))()
+    for k in range(2):
+        for i, v in enumerate(coeffs[k]):
+            coef[k * _lib.MAX_VARIANTS + i] = v
+    st = (C.c_int32 * (3 * _lib.MAX_DIGITS))()
+    for f in range(3):
+        for k in range(2):
+            st[f * _lib.MAX_DIGITS + k] = strides[f][k]
+    out = torch.empty(1 << n_out, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    h.check(h.lib.qck_knit_contract(h.ptr, 3, ptrs, cm, rs, n_out, 2, rad, coef, st, 0, 48, out.data_ptr(), 0, stream))
+    assert np.abs(out.cpu().numpy() - want).max() < 1e-12
+    # label sharding + accumulate = full
+    h.check(h.lib.qck_knit_contract(h.ptr, 3, ptrs, cm, rs, n_out, 2, rad, coef, st, 0, 16, out.data_ptr(), 0, stream))
+    h.check(h.lib.qck_knit_contract(h.ptr, 3, ptrs, cm, rs, n_out, 2, rad, coef, st, 16, 48, out.data_ptr(), 1, stream))
+    assert np.abs(out.cpu().numpy() - want).max() < 1e-12
+
+
+def test_label_sharded_run_equals_full(dev):
+    """What two ranks would compute, emulated on one GPU: partial contractions add up."""
+    circ, cut = cutting.make_baseline("syc16d5", seed=2)
+    virt = vcm.VirtualCircuit(cut)
+    qdist = import_module(f"{PKG}.dist")
+    full, _ = runm.run_virtual_circuit_dense(virt, device=dev, nearest=False)
+    acc = torch.zeros_like(full.values)
+    for r in range(2):
+        rng = qdist.shard_range(virt.num_global_labels(), r, 2, align=virt.global_radices()[-1])
+        tables = virt.simulate_fragments(dev, label_range=rng)
+        acc += virt.knit_tables(tables, dev, label_range=rng)
+    assert (acc - full.values).abs().max().item() < 1e-13
+
+
+# ------------------------------------------------------------------ error behaviour of the C ABI
+def test_c_abi_errors(dev):
+    h = _lib.get_handle(0)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with pytest.raises(ValueError, match="n_frag"):
+        h.check(h.lib.qck_knit_outer(h.ptr, 0, None, None, 4, 0, 16, None, None, stream))
+    t = torch.zeros(16, dtype=torch.float64, device=dev)
+    ptrs = (C.c_void_p * 1)(t.data_ptr())
+    cm = (C.c_uint64 * 1)(0xFF)
+    with pytest.raises(ValueError, match="mask"):
+        h.check(h.lib.qck_knit_outer(h.ptr, 1, ptrs, cm, 4, 0, 16, t.data_ptr(), None, stream))
+    with pytest.raises(ValueError, match="power-of-two"):
+        h.check(h.lib.qck_qd_split(h.ptr, t.data_ptr(), 12, 1, t.data_ptr(), None, 0.0, stream))
+    with pytest.raises(ValueError, match="overlap"):
+        h.check(h.lib.qck_qd_merge(h.ptr, t.data_ptr(), 3, t.data_ptr(), 1, t.data_ptr(), 16, 0.0, stream))
+    with pytest.raises(ValueError):
+        _lib.Handle(99)
+    with pytest.raises(ValueError, match="total mass"):
+        neg = torch.full((8,), -1.0, dtype=torch.float64, device=dev)
+        h.check(h.lib.qck_npd(h.ptr, neg.data_ptr(), 8, 0.0, None, None, stream))
+
+
+def test_reentrant_from_threads(dev):
+    """The reference calls the path from several Python threads (Utilities.py:85-101)."""
+    import threading
+    circ, cut = cutting.make_baseline("bv16")
+    out = {}
+
+    def work(i):
+        torch.cuda.set_device(0)
+        out[i] = runm.run_virtual_circuit(vcm.VirtualCircuit(cut))[0]
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert len(out) == 4
+    for i in range(4):
+        assert list(out[i]) == [0xFFFF] and abs(out[i][0xFFFF] - 1) < TOL_P
