@@ -54,7 +54,9 @@ __global__ void __launch_bounds__(256) qd_split_kernel(const double* __restrict_
 __global__ void __launch_bounds__(256) qd_merge_kernel(const double* __restrict__ a, unsigned long long mask_a,
                                                        const double* __restrict__ b, unsigned long long mask_b,
                                                        double* __restrict__ out, unsigned long long n, double acc) {
-    EW_LOOP(k, n) out[k] = prune1(a[k & mask_a] * b[k & mask_b], acc);
+    // a key with a bit outside both supports does not exist in the sparse reference
+    const unsigned long long outside = ~(mask_a | mask_b);
+    EW_LOOP(k, n) out[k] = (k & outside) ? 0.0 : prune1(a[k & mask_a] * b[k & mask_b], acc);
 }
 
 struct LevelParams {

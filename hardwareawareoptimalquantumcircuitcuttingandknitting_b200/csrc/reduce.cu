@@ -267,8 +267,9 @@ extern "C" int qck_npd(qck_handle* h, double* d_p, uint64_t n, double acc, doubl
             QCK_FAIL(h, QCK_ERR_INVALID_ARG, "nearest_probability_distribution: total mass %.3e is negative", r[0]);
         long long lo = ordered_of(vmin);       // G(lo) < 0
         long long hi = ordered_of(INFINITY);   // G(hi) >= 0
-        while (hi - lo > 1) {
-            long long mid = lo + (hi - lo) / 2;
+        // hi - lo can exceed 2^63 (lo < 0 < hi): overflow-free floor average
+        while ((unsigned long long)hi - (unsigned long long)lo > 1ull) {
+            long long mid = (lo >> 1) + (hi >> 1) + (lo & hi & 1);
             rc = probe(double_of(mid), r);
             if (rc) return rc;
             if (r[0] < 0.0)

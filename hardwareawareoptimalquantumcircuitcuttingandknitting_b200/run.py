@@ -169,10 +169,10 @@ def run_virtual_circuit(virt: VirtualCircuit, shots: int = 20000) -> tuple[dict[
         result = job.result()
         try:
             counts = result.get_counts()
-            counts = [counts] if isinstance(counts, dict) else counts
-            results[frag] = [QuasiDistr.from_counts(c, num_bits=width) for c in counts]
         except Exception:                       # run.py:57-58: a fragment without measurements vanishes
-            pass
+            continue
+        counts = [counts] if isinstance(counts, dict) else counts
+        results[frag] = [QuasiDistr.from_counts(c, num_bits=width) for c in counts]
     run_time = perf_counter() - now
     logger.info("Knitting...")
     now = perf_counter()
