@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-bits", type=int, default=None,
                     help="log2 of the output entries the CPU baseline knits per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="timed region only (for runs under ncu): no e2e leg, no oracle report, no CPU baseline")
     return ap.parse_args()
 
 
@@ -368,27 +370,29 @@ def main() -> None:
         host_stats = stats.cpu().numpy().copy()
 
     # ---- e2e: public API, fresh VirtualCircuit per step (host compile + H2D + kernels + D2H)
-    e2e_virts = [vc.VirtualCircuit(cut) for _ in range(args.steps + 1)]
-    runm.run_virtual_circuit_dense(e2e_virts[0], device=device, rank=rank, world_size=world, out=out, nearest=False)
-    barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    h2d = 0
-    for v in e2e_virts[1:]:
-        runm.run_virtual_circuit_dense(v, device=device, rank=rank, world_size=world, out=out, nearest=False)
-    g1.record()
-    barrier()
-    for f in e2e_virts[1].active_fragments():
-        h2d += e2e_virts[1].executor(f, device, True).h2d_bytes
-    e2e_ms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_ms.item()) / args.steps / 1e3
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    e2e_s, h2d = None, 0
+    if not args.profile:
+        e2e_virts = [vc.VirtualCircuit(cut) for _ in range(args.steps + 1)]
+        runm.run_virtual_circuit_dense(e2e_virts[0], device=device, rank=rank, world_size=world, out=out,
+                                       nearest=False)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for v in e2e_virts[1:]:
+            runm.run_virtual_circuit_dense(v, device=device, rank=rank, world_size=world, out=out, nearest=False)
+        g1.record()
+        barrier()
+        for f in e2e_virts[1].active_fragments():
+            h2d += e2e_virts[1].executor(f, device, True).h2d_bytes
+        e2e_ms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e_s = float(e2e_ms.item()) / args.steps / 1e3
 
     # ---- fidelity against the uncut circuit and parity against the oracle (outside the timed region)
     extra = {}
-    if rank == 0:
+    if rank == 0 and not args.profile:
         extra = correctness_report(args, virt, circ, cut, tables_holder["t"], out, y0, y1, device, fid, K, n_out)
 
     if rank != 0:
@@ -417,7 +421,7 @@ def main() -> None:
                 "kernel_share_of_step": knit_ms / ms_per_step}
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.profile:
         try:
             val, sample, cores = cpu_reference_step(args.workload, args.seed, args.cpu_sample_bits)
             cpu = {"value": val, "unit": "s", "cores": cores, "kind": "port", "sample": sample}
@@ -506,17 +510,45 @@ def correctness_report(args, virt, circ, cut, tables, out, y0, y1, device, fid, 
     return rep
 
 
-def uncut_component_tables(circ, device):
-    """Uncut circuit simulated on the GPU one connected component at a time
-    (until the sharded 32-qubit statevector exists)."""
+def uncut_component_tables(circ, device, max_bits: int = 16, max_groups: int = 6):
+    """Uncut circuit simulated on the GPU one connected component at a time (SURVEY.md 8f-1:
+    until the sharded 32-qubit statevector exists), then multiplied into <= max_groups
+    product tables of <= max_bits bits each (qck_knit_outer takes at most 8 tables)."""
+    import ctypes as C
+    import torch
     from importlib import import_module
     cutting = import_module(f"{PKG}.cutting")
     vc = import_module(f"{PKG}.virtual_circuit")
+    lib = import_module(f"{PKG}._lib")
     comp = cutting.apply_cuts(circ, cutting.CutSpec())          # no cuts: one register per component
     v = vc.VirtualCircuit(comp)
     tabs = v.simulate_fragments(device)
     masks, _ = v.output_masks()
-    return [tabs[f][0] for f in tabs], [masks[f] for f in tabs]
+    items = sorted(((masks[f], tabs[f][0]) for f in tabs), key=lambda t: t[0] & -t[0])
+    groups = []                                                  # [mask, [(mask, table)]]
+    for m, t in items:
+        for g in groups:
+            if bin(g[0] | m).count("1") <= max_bits and len(g[1]) < 8:
+                g[0] |= m
+                g[1].append((m, t))
+                break
+        else:
+            groups.append([m, [(m, t)]])
+    if len(groups) > max_groups:
+        raise NotImplementedError("uncut circuit has too many / too wide components for the factorised check")
+    handle = lib.get_handle(device.index or 0)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    out_tabs, out_masks = [], []
+    for gmask, members in groups:
+        nb = bin(gmask).count("1")
+        ptrs = (C.c_void_p * len(members))(*[t.data_ptr() for _, t in members])
+        cm = (C.c_uint64 * len(members))(*[vc._compress_mask(m, gmask) for m, _ in members])
+        table = torch.empty(1 << nb, dtype=torch.float64, device=device)
+        handle.check(handle.lib.qck_knit_outer(handle.ptr, len(members), ptrs, cm, nb, 0, 1 << nb,
+                                               table.data_ptr(), None, stream))
+        out_tabs.append(table)
+        out_masks.append(gmask)
+    return out_tabs, out_masks
 
 
 if __name__ == "__main__":

