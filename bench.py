@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-bits", type=int, default=None,
                     help="log2 of the output entries the CPU baseline knits per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--uncut-statevector", action="store_true",
+                    help="also simulate the UNCUT circuit as one statevector on this GPU (64 GiB at 32 qubits), "
+                         "report the streaming simulator against the HBM roofline and the dense fidelity")
     ap.add_argument("--profile", action="store_true",
                     help="timed region only (for runs under ncu): no e2e leg, no oracle report, no CPU baseline")
     return ap.parse_args()
@@ -415,6 +418,9 @@ def main() -> None:
     if rank == 0 and not args.profile:
         extra = correctness_report(args, virt, circ, cut, tables_holder["t"], out, y0, y1, device, fid, K, n_out)
 
+    if rank == 0 and world == 1 and args.uncut_statevector:
+        extra.update(uncut_statevector_report(circ, out, device, fid, vc, handle, peaks_hbm()))
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -477,6 +483,53 @@ def main() -> None:
     emit(line)
     if world > 1:
         dist.barrier()
+
+
+def peaks_hbm() -> float:
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def uncut_statevector_report(circ, cut_result, device, fid, vc, handle, peak) -> dict:
+    """the uncut circuit as ONE statevector on this GPU (Utilities.py:39-69 runs it on
+    Aer).  Streaming regime: every sweep reads and writes the whole state once."""
+    import torch
+    rep = {}
+    try:
+        virt_u = vc.VirtualCircuit(circ)                       # one register = one fragment, no cuts
+        (frag,) = virt_u.active_fragments()
+        ex = virt_u.executor(frag, device, True)
+        n = ex.max_state
+        sweeps = len(ex.plans[0].sweeps)
+        ex.upload()
+        table = ex.run(handle)                                 # warm-up (allocates state + row)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            ex.run(handle, out=table)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / reps
+        state_bytes = 16 << n
+        # first sweep synthesises |0..0> (write only), the others read + write; the fold reads the
+        # state and writes the probabilities
+        alg = state_bytes * (2 * sweeps - 1) + state_bytes + (8 << len(ex.plans[0].out_pos))
+        rep["uncut_statevector"] = {"qubits": n, "sweeps": sweeps, "ops": int(len(ex.plans[0].ops)), "ms": ms,
+                                    "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6,
+                                    "frac_of_measured_hbm_peak": alg / ms / 1e6 / peak}
+        if cut_result.numel() == table.numel():
+            rep["fidelity_cut_vs_uncut_dense_statevector"] = fid.hellinger_fidelity(cut_result, table[0])
+            worst, step = 0.0, 1 << 28                         # chunked: no 32 GiB temporary
+            for a in range(0, table.numel(), step):
+                worst = max(worst, float((cut_result[a:a + step] - table[0][a:a + step]).abs().max().item()))
+            rep["max_abs_err_cut_vs_uncut_dense"] = worst
+    except Exception as exc:
+        rep["uncut_statevector_error"] = repr(exc)
+    return rep
 
 
 def correctness_report(args, virt, circ, cut, tables, out, y0, y1, device, fid, K, n_out) -> dict:

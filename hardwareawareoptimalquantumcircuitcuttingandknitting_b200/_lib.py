@@ -26,7 +26,8 @@ MAX_DIGITS = 16
 MAX_OUT_BITS = 40
 MAX_FRAGMENTS = 8
 MAX_VARIANTS = 8
-OP_U1, OP_CX, OP_CZ, OP_U2 = 0, 1, 2, 3
+OP_U1, OP_CX, OP_CZ, OP_U2, OP_CLUSTER = 0, 1, 2, 3, 4
+CLUSTER_QUBITS = 3
 
 
 class QckSweep(C.Structure):

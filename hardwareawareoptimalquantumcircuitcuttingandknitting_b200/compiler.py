@@ -82,12 +82,14 @@ class FragmentProgram:
     """Template + per-pattern programs of one fragment."""
 
     def __init__(self, frag_circuit: QuantumCircuit, fragment: QuantumRegister, num_clbits: int,
-                 onchip_max: int = ONCHIP_MAX_QUBITS, stream_tile: int = STREAM_TILE) -> None:
+                 onchip_max: int = ONCHIP_MAX_QUBITS, stream_tile: int = STREAM_TILE,
+                 cluster: bool = True) -> None:
         self.fragment = fragment
         self.n_qubits = len(fragment)
         self.num_clbits = num_clbits
         self.onchip_max = onchip_max
         self.stream_tile = stream_tile
+        self.cluster = cluster
         self._pool: list[np.ndarray] = []
         self._pool_len = 0
         self._lower(frag_circuit)
@@ -309,6 +311,8 @@ class FragmentProgram:
             sweeps = [(list(range(n_state)), 0, len(ops_arr))]
         else:
             ops_arr, sweeps = _schedule_sweeps(ops_arr, n_state, self.stream_tile)
+        if self.cluster:
+            ops_arr, sweeps = _cluster_sweeps(ops_arr, sweeps)
         return PlanHost(pattern, labels, n_state, ops_arr, sweeps, out_pos, sum_mask, sign_mask)
 
     @property
@@ -327,42 +331,108 @@ def _op_qubits(op) -> tuple[int, ...]:
 
 def _schedule_sweeps(ops: np.ndarray, n_state: int, tile: int):
     """Greedy list scheduling: each sweep takes, in program order, every op whose qubits are
-    not blocked by an earlier unscheduled op and still fit into the tile."""
+    not blocked by an earlier unscheduled op and still fit into the tile (bit-mask sets)."""
     tile = min(tile, n_state)
     low = max(0, min(LOW_RUN, tile - 2))     # always leave room for a two-qubit gate
-    remaining = list(range(len(ops)))
+    rows = ops.tolist()
+    masks = [(1 << r[1]) if r[0] == _lib.OP_U1 else ((1 << r[1]) | (1 << r[2])) for r in rows]
+    remaining = list(range(len(rows)))
     new_ops, sweeps = [], []
     while remaining:
-        tile_set = set(range(low))
-        blocked: set[int] = set()
+        tile_set = (1 << low) - 1
+        blocked = 0
         taken, rest = [], []
         for i in remaining:
-            qs = _op_qubits(ops[i])
-            if not (set(qs) & blocked) and len(tile_set | set(qs)) <= tile:
-                tile_set |= set(qs)
+            m = masks[i]
+            if not (m & blocked) and bin(tile_set | m).count("1") <= tile:
+                tile_set |= m
                 taken.append(i)
             else:
-                blocked |= set(qs)
+                blocked |= m
                 rest.append(i)
         if not taken:
             raise NotImplementedError("an op does not fit into a tile")
-        for b in range(n_state):                 # pad with the lowest free qubits: longer contiguous runs
-            if len(tile_set) >= tile:
-                break
-            tile_set.add(b)
-        positions = sorted(tile_set)
+        b = 0
+        while bin(tile_set).count("1") < tile:   # pad with the lowest free qubits: longer contiguous runs
+            tile_set |= 1 << b
+            b += 1
+        positions = [q for q in range(n_state) if (tile_set >> q) & 1]
         local = {p: j for j, p in enumerate(positions)}
         begin = len(new_ops)
         for i in taken:
-            op = ops[i].copy()
-            op[1] = local[int(op[1])]
-            if op[0] != _lib.OP_U1:
-                op[2] = local[int(op[2])]
-            op[6] = 0                            # n_live is meaningless inside a tile
-            new_ops.append(op)
+            r = list(rows[i])
+            r[1] = local[r[1]]
+            if r[0] != _lib.OP_U1:
+                r[2] = local[r[2]]
+            r[6] = 0                             # n_live is meaningless inside a tile
+            new_ops.append(r)
         sweeps.append((positions, begin, len(new_ops)))
         remaining = rest
     return np.asarray(new_ops, dtype=np.int32).reshape(-1, 8), sweeps
+
+
+MAX_CLUSTER_OPS = 32        # QCK_MAX_CLUSTER_OPS: a cluster must fit the staged chunk
+
+
+def _cluster_sweeps(ops: np.ndarray, sweeps: list):
+    """Group the ops of every sweep into clusters acting on <= 3 tile qubits (list scheduling as
+    in _schedule_sweeps, qubit sets as bit masks).  A cluster is emitted as a QCK_OP_CLUSTER
+    header followed by its member ops, whose qubits are re-expressed as ranks among the cluster's
+    three ascending positions."""
+    R = _lib.CLUSTER_QUBITS
+    rows = ops.tolist()
+    out, new_sweeps = [], []
+    for positions, b, e in sweeps:
+        T = len(positions)
+        begin = len(out)
+        seg = rows[b:e]
+        if T < R:
+            out.extend(seg)
+            new_sweeps.append((positions, begin, len(out)))
+            continue
+        masks = [(1 << r[1]) if r[0] == _lib.OP_U1 else ((1 << r[1]) | (1 << r[2])) for r in seg]
+        remaining = list(range(len(seg)))
+        nl_run = 0      # n_live must never shrink in EXECUTION order: a reordered ancilla CX may
+        #                 already have populated a higher bit when an "earlier" op finally runs
+        while remaining:
+            cset = blocked = 0
+            taken, rest = [], []
+            for i in remaining:
+                m = masks[i]
+                if not (m & blocked) and bin(cset | m).count("1") <= R and len(taken) < MAX_CLUSTER_OPS:
+                    cset |= m
+                    taken.append(i)
+                else:
+                    blocked |= m
+                    rest.append(i)
+            nl = max(seg[i][6] for i in taken)
+            nl = 0 if (nl <= 0 or nl_run < 0) else max(nl, nl_run)
+            nl_run = nl if nl > 0 else -1      # 0 / -1: whole tile from here on
+            live = nl if 0 < nl <= T else T
+            if live < R:                       # fewer live bits than register qubits: plain ops
+                for i in taken:
+                    r = list(seg[i])
+                    r[6] = nl
+                    out.append(r)
+                remaining = rest
+                continue
+            p = 0
+            while bin(cset).count("1") < R:    # pad with the lowest free live positions
+                if not (cset >> p) & 1:
+                    cset |= 1 << p
+                p += 1
+            pos = [q for q in range(T) if (cset >> q) & 1]
+            rank = {q: j for j, q in enumerate(pos)}
+            out.append([_lib.OP_CLUSTER, len(taken), R, pos[0], pos[1], pos[2], nl, 0])
+            for i in taken:
+                r = list(seg[i])
+                r[1] = rank[r[1]]
+                if r[0] != _lib.OP_U1:
+                    r[2] = rank[r[2]]
+                out.append(r)
+            remaining = rest
+        new_sweeps.append((positions, begin, len(out)))
+    return np.asarray(out, dtype=np.int32).reshape(-1, 8), new_sweeps
 
 
 # ---------------------------------------------------------------------- device side

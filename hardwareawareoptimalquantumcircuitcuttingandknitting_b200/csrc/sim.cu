@@ -22,6 +22,7 @@ struct PlanDev {
     int radix[QCK_MAX_DIGITS];
     int n_out_bits;
     int out_pos[QCK_MAX_OUT_BITS];
+    int out_ident;  // out_pos[j] == j for j < out_ident: those row bits map straight to state bits
     unsigned long long sum_mask, sign_mask;
 };
 
@@ -49,74 +50,198 @@ __device__ __forceinline__ void decode_digits(const PlanDev& plan, int label, in
     }
 }
 
-// Apply ops[begin, end) to the tile `s` (2^T amplitudes in shared memory).  All threads of
-// the CTA call this with identical arguments; ends with the state synchronised.
-__device__ void apply_ops(double2* s, int T, const qck_op* __restrict__ ops, int begin, int end,
-                          const double* __restrict__ mats, const int* digits) {
-    const int tid = threadIdx.x, nth = blockDim.x;
-    for (int i = begin; i < end; ++i) {
-        const int4 w0 = __ldg(reinterpret_cast<const int4*>(ops + i));
-        const int4 w1 = __ldg(reinterpret_cast<const int4*>(ops + i) + 1);
-        const int kind = w0.x, q0 = w0.y, q1 = w0.z;
-        int moff = w0.w;
-        if (w1.x >= 0) moff += digits[w1.x] * w1.y;
-        int nl = w1.z;
-        if (nl <= 0 || nl > T) nl = T;
-        if (kind == QCK_OP_U1) {
-            const double2* m = reinterpret_cast<const double2*>(mats + moff);
-            const double2 m00 = __ldg(m), m01 = __ldg(m + 1), m10 = __ldg(m + 2), m11 = __ldg(m + 3);
-            const bool offdiag0 = (m01.x == 0.0 && m01.y == 0.0 && m10.x == 0.0 && m10.y == 0.0);
-            if (offdiag0) {
-                const bool id0 = (m00.x == 1.0 && m00.y == 0.0), id1 = (m11.x == 1.0 && m11.y == 0.0);
-                if (id0 && id1) continue;  // identity variant: nothing to do (uniform branch)
-                const uint32_t n = 1u << (nl - 1);
-                if (id0) {
-                    for (uint32_t p = tid; p < n; p += nth) {
-                        uint32_t i1 = insert_zero(p, q0) | (1u << q0);
-                        s[i1] = cmul(m11, s[i1]);
-                    }
-                } else {
-                    for (uint32_t p = tid; p < n; p += nth) {
-                        uint32_t i0 = insert_zero(p, q0), i1 = i0 | (1u << q0);
-                        s[i0] = cmul(m00, s[i0]);
-                        s[i1] = cmul(m11, s[i1]);
-                    }
-                }
-            } else {
-                const uint32_t n = 1u << (nl - 1);
-                for (uint32_t p = tid; p < n; p += nth) {
-                    uint32_t i0 = insert_zero(p, q0), i1 = i0 | (1u << q0);
-                    double2 a0 = s[i0], a1 = s[i1];
-                    s[i0] = cfma(m01, a1, cmul(m00, a0));
-                    s[i1] = cfma(m11, a1, cmul(m10, a0));
-                }
+// Shared-memory layout: amplitude i lives at slot swz(i).  The XOR folds index bits 3-5 into
+// bits 0-2 so that eight lanes that differ in *any* three of those six bits hit eight different
+// 16-byte bank groups: cluster passes whose register qubits are the low qubits (lane stride
+// 128 B) stay conflict-free.  The permutation stays inside 128-byte lines.
+__device__ __forceinline__ uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 7u); }
+
+// ---- register-tiled gate application: a[k], k in [0, 8), bit j of k = cluster qubit j
+template <int J>
+__device__ __forceinline__ void reg_u1(double2 (&a)[8], double2 m00, double2 m01, double2 m10, double2 m11) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (!(k & (1 << J))) {
+            const double2 x = a[k], y = a[k | (1 << J)];
+            a[k] = cfma(m01, y, cmul(m00, x));
+            a[k | (1 << J)] = cfma(m11, y, cmul(m10, x));
+        }
+}
+template <int J>
+__device__ __forceinline__ void reg_diag(double2 (&a)[8], double2 d0, double2 d1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = cmul((k & (1 << J)) ? d1 : d0, a[k]);
+}
+template <int J0, int J1>
+__device__ __forceinline__ void reg_cx(double2 (&a)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if ((k & (1 << J0)) && !(k & (1 << J1))) {
+            const double2 t = a[k];
+            a[k] = a[k | (1 << J1)];
+            a[k | (1 << J1)] = t;
+        }
+}
+template <int J0, int J1>
+__device__ __forceinline__ void reg_cz(double2 (&a)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if ((k & (1 << J0)) && (k & (1 << J1))) a[k] = make_double2(-a[k].x, -a[k].y);
+}
+template <int J0, int J1>
+__device__ __forceinline__ void reg_u2(double2 (&a)[8], const double2* __restrict__ m) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (!(k & ((1 << J0) | (1 << J1)))) {
+            const double2 x[4] = {a[k], a[k | (1 << J0)], a[k | (1 << J1)], a[k | (1 << J0) | (1 << J1)]};
+            double2 r[4];
+#pragma unroll
+            for (int row = 0; row < 4; ++row) {
+                double2 acc = cmul(__ldg(m + row * 4), x[0]);
+#pragma unroll
+                for (int c = 1; c < 4; ++c) acc = cfma(__ldg(m + row * 4 + c), x[c], acc);
+                r[row] = acc;
             }
-        } else if (kind == QCK_OP_CX || kind == QCK_OP_CZ) {
-            const int lo = q0 < q1 ? q0 : q1, hi = q0 < q1 ? q1 : q0;
-            const uint32_t n = 1u << (nl - 2);
-            const uint32_t b0 = 1u << q0, b1 = 1u << q1;
-            if (kind == QCK_OP_CX) {
-                for (uint32_t p = tid; p < n; p += nth) {
-                    uint32_t base = insert_zero(insert_zero(p, lo), hi) | b0;  // control set
-                    double2 a = s[base], b = s[base | b1];
-                    s[base] = b;
-                    s[base | b1] = a;
+            a[k] = r[0];
+            a[k | (1 << J0)] = r[1];
+            a[k | (1 << J1)] = r[2];
+            a[k | (1 << J0) | (1 << J1)] = r[3];
+        }
+}
+
+#define QCK_PAIR_DISPATCH(FN, ...)                                     \
+    switch (q0 * 3 + q1) {                                             \
+        case 1: FN<0, 1>(__VA_ARGS__); break;                          \
+        case 2: FN<0, 2>(__VA_ARGS__); break;                          \
+        case 3: FN<1, 0>(__VA_ARGS__); break;                          \
+        case 5: FN<1, 2>(__VA_ARGS__); break;                          \
+        case 6: FN<2, 0>(__VA_ARGS__); break;                          \
+        default: FN<2, 1>(__VA_ARGS__); break;                         \
+    }
+
+// ---- program staging --------------------------------------------------------------------------
+// Op records and the (label-digit-resolved) 2x2 matrices of a chunk of the program are staged in
+// shared memory once per CTA, so that per-op fetches are broadcast LDS instead of two dependent
+// global loads (op record -> matrix), which dominated the run time of small instances.
+struct StagedOp {
+    int4 w0, w1;    // the qck_op words; w0.w = resolved matrix offset
+    double2 m[4];   // U1: the matrix
+};
+#define QCK_STAGE_OPS 128
+#define QCK_MAX_CLUSTER_OPS 32
+
+__device__ __forceinline__ void stage_ops(StagedOp* so, const qck_op* __restrict__ ops, int c0, int n,
+                                          const double* __restrict__ mats, const int* digits) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int4 w0 = __ldg(reinterpret_cast<const int4*>(ops + c0 + i));
+        const int4 w1 = __ldg(reinterpret_cast<const int4*>(ops + c0 + i) + 1);
+        if (w0.x == QCK_OP_U1 || w0.x == QCK_OP_U2) {
+            if (w1.x >= 0) w0.w += digits[w1.x] * w1.y;
+            if (w0.x == QCK_OP_U1) {
+                const double2* m = reinterpret_cast<const double2*>(mats + w0.w);
+                so[i].m[0] = __ldg(m);
+                so[i].m[1] = __ldg(m + 1);
+                so[i].m[2] = __ldg(m + 2);
+                so[i].m[3] = __ldg(m + 3);
+            }
+        }
+        so[i].w0 = w0;
+        so[i].w1 = w1;
+    }
+}
+
+// One cluster: header so[h], members so[h+1 .. h+n].  Every thread owns groups of 8 amplitudes
+// (the 3 cluster bits enumerated) and applies all member ops in registers.
+__device__ void run_cluster(double2* s, int T, const StagedOp* so, int h, const double* __restrict__ mats) {
+    const int4 h0 = so[h].w0, h1 = so[h].w1;
+    const int n_ops = h0.y, p0 = h0.w, p1 = h1.x, p2 = h1.y;
+    int nl = h1.z;
+    if (nl <= 0 || nl > T) nl = T;
+    const uint32_t n_groups = 1u << (nl - 3);
+    const uint32_t b0 = 1u << p0, b1 = 1u << p1, b2 = 1u << p2;
+    for (uint32_t g = threadIdx.x; g < n_groups; g += blockDim.x) {
+        const uint32_t base = insert_zero(insert_zero(insert_zero(g, p0), p1), p2);
+        double2 a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            a[k] = s[swz(base | ((k & 1) ? b0 : 0u) | ((k & 2) ? b1 : 0u) | ((k & 4) ? b2 : 0u))];
+        for (int i = h + 1; i <= h + n_ops; ++i) {
+            const int4 w0 = so[i].w0;
+            const int kind = w0.x, q0 = w0.y, q1 = w0.z;
+            if (kind == QCK_OP_U1) {
+                const double2 m00 = so[i].m[0], m01 = so[i].m[1], m10 = so[i].m[2], m11 = so[i].m[3];
+                if (m01.x == 0.0 && m01.y == 0.0 && m10.x == 0.0 && m10.y == 0.0) {
+                    if (m00.x == 1.0 && m00.y == 0.0 && m11.x == 1.0 && m11.y == 0.0) continue;
+                    if (q0 == 0) reg_diag<0>(a, m00, m11);
+                    else if (q0 == 1) reg_diag<1>(a, m00, m11);
+                    else reg_diag<2>(a, m00, m11);
+                } else {
+                    if (q0 == 0) reg_u1<0>(a, m00, m01, m10, m11);
+                    else if (q0 == 1) reg_u1<1>(a, m00, m01, m10, m11);
+                    else reg_u1<2>(a, m00, m01, m10, m11);
                 }
+            } else if (kind == QCK_OP_CX) {
+                QCK_PAIR_DISPATCH(reg_cx, a)
+            } else if (kind == QCK_OP_CZ) {
+                QCK_PAIR_DISPATCH(reg_cz, a)
             } else {
-                for (uint32_t p = tid; p < n; p += nth) {
-                    uint32_t idx = insert_zero(insert_zero(p, lo), hi) | b0 | b1;
-                    double2 a = s[idx];
-                    s[idx] = make_double2(-a.x, -a.y);
-                }
+                const double2* m = reinterpret_cast<const double2*>(mats + w0.w);
+                QCK_PAIR_DISPATCH(reg_u2, a, m)
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            s[swz(base | ((k & 1) ? b0 : 0u) | ((k & 2) ? b1 : 0u) | ((k & 4) ? b2 : 0u))] = a[k];
+    }
+    __syncthreads();
+}
+
+// One un-clustered op (states with fewer than 3 live bits, or clustering disabled).
+__device__ void run_single(double2* s, int T, const StagedOp& op, const double* __restrict__ mats) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int kind = op.w0.x, q0 = op.w0.y, q1 = op.w0.z;
+    int nl = op.w1.z;
+    if (nl <= 0 || nl > T) nl = T;
+    if (kind == QCK_OP_U1) {
+        const double2 m00 = op.m[0], m01 = op.m[1], m10 = op.m[2], m11 = op.m[3];
+        const uint32_t n = 1u << (nl - 1);
+        if (m01.x == 0.0 && m01.y == 0.0 && m10.x == 0.0 && m10.y == 0.0) {
+            if (m00.x == 1.0 && m00.y == 0.0 && m11.x == 1.0 && m11.y == 0.0) return;  // uniform
+            for (uint32_t p = tid; p < n; p += nth) {
+                const uint32_t i0 = insert_zero(p, q0), i1 = i0 | (1u << q0);
+                s[swz(i0)] = cmul(m00, s[swz(i0)]);
+                s[swz(i1)] = cmul(m11, s[swz(i1)]);
+            }
+        } else {
+            for (uint32_t p = tid; p < n; p += nth) {
+                const uint32_t i0 = insert_zero(p, q0), i1 = i0 | (1u << q0);
+                const double2 a0 = s[swz(i0)], a1 = s[swz(i1)];
+                s[swz(i0)] = cfma(m01, a1, cmul(m00, a0));
+                s[swz(i1)] = cfma(m11, a1, cmul(m10, a0));
+            }
+        }
+    } else {
+        const int lo = q0 < q1 ? q0 : q1, hi = q0 < q1 ? q1 : q0;
+        const uint32_t n = 1u << (nl - 2);
+        const uint32_t b0 = 1u << q0, b1 = 1u << q1;
+        if (kind == QCK_OP_CX) {
+            for (uint32_t p = tid; p < n; p += nth) {
+                const uint32_t base = insert_zero(insert_zero(p, lo), hi) | b0;  // control set
+                const double2 a = s[swz(base)], b = s[swz(base | b1)];
+                s[swz(base)] = b;
+                s[swz(base | b1)] = a;
+            }
+        } else if (kind == QCK_OP_CZ) {
+            for (uint32_t p = tid; p < n; p += nth) {
+                const uint32_t idx = insert_zero(insert_zero(p, lo), hi) | b0 | b1;
+                const double2 a = s[swz(idx)];
+                s[swz(idx)] = make_double2(-a.x, -a.y);
             }
         } else {  // QCK_OP_U2: generic 4x4, row/col index = bit(q0) + 2 bit(q1)
-            const int lo = q0 < q1 ? q0 : q1, hi = q0 < q1 ? q1 : q0;
-            const uint32_t n = 1u << (nl - 2);
-            const uint32_t b0 = 1u << q0, b1 = 1u << q1;
-            const double2* m = reinterpret_cast<const double2*>(mats + moff);
+            const double2* m = reinterpret_cast<const double2*>(mats + op.w0.w);
             for (uint32_t p = tid; p < n; p += nth) {
-                uint32_t base = insert_zero(insert_zero(p, lo), hi);
-                double2 a[4] = {s[base], s[base | b0], s[base | b1], s[base | b0 | b1]};
+                const uint32_t base = insert_zero(insert_zero(p, lo), hi);
+                const double2 a[4] = {s[swz(base)], s[swz(base | b0)], s[swz(base | b1)], s[swz(base | b0 | b1)]};
                 double2 r[4];
 #pragma unroll
                 for (int row = 0; row < 4; ++row) {
@@ -125,13 +250,39 @@ __device__ void apply_ops(double2* s, int T, const qck_op* __restrict__ ops, int
                     for (int c = 1; c < 4; ++c) acc = cfma(__ldg(m + row * 4 + c), a[c], acc);
                     r[row] = acc;
                 }
-                s[base] = r[0];
-                s[base | b0] = r[1];
-                s[base | b1] = r[2];
-                s[base | b0 | b1] = r[3];
+                s[swz(base)] = r[0];
+                s[swz(base | b0)] = r[1];
+                s[swz(base | b1)] = r[2];
+                s[swz(base | b0 | b1)] = r[3];
             }
         }
+    }
+    __syncthreads();
+}
+
+// Apply ops[begin, end) to the tile `s` (2^T amplitudes in shared memory).  All threads of the
+// CTA call this with identical arguments; the state is synchronised on return.
+__device__ void apply_ops(double2* s, int T, StagedOp* so, const qck_op* __restrict__ ops, int begin, int end,
+                          const double* __restrict__ mats, const int* digits) {
+    int c0 = begin;
+    while (c0 < end) {
+        const int n = (end - c0) < QCK_STAGE_OPS ? (end - c0) : QCK_STAGE_OPS;
+        stage_ops(so, ops, c0, n, mats, digits);
         __syncthreads();
+        int i = 0;
+        while (i < n) {
+            if (so[i].w0.x == QCK_OP_CLUSTER) {
+                const int members = so[i].w0.y;
+                if (i + members >= n && c0 + n < end) break;  // cluster continues past the staged chunk
+                run_cluster(s, T, so, i, mats);
+                i += 1 + members;
+            } else {
+                run_single(s, T, so[i], mats);
+                ++i;
+            }
+        }
+        c0 += i;
+        __syncthreads();  // everyone is done with so[] before it is restaged
     }
 }
 
@@ -139,8 +290,8 @@ __device__ void apply_ops(double2* s, int T, const qck_op* __restrict__ ops, int
 // output entry walks the summed-out bits with the masked-increment trick.
 template <typename LoadAmp>
 __device__ __forceinline__ double fold_entry(const PlanDev& plan, uint64_t o, LoadAmp load) {
-    uint64_t base = 0;
-    for (int j = 0; j < plan.n_out_bits; ++j) {
+    uint64_t base = o & ((1ull << plan.out_ident) - 1ull);
+    for (int j = plan.out_ident; j < plan.n_out_bits; ++j) {
         if ((o >> j) & 1ull) {
             if (plan.out_pos[j] < 0) return 0.0;  // that bit is never written in this pattern
             base |= 1ull << plan.out_pos[j];
@@ -161,21 +312,22 @@ __device__ __forceinline__ double fold_entry(const PlanDev& plan, uint64_t o, Lo
 // ------------------------------------------------------------------ on-chip regime
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-__global__ void __launch_bounds__(512) sim_onchip_kernel(PlanDev plan, int op_begin, int op_end,
+__global__ void __launch_bounds__(256) sim_onchip_kernel(PlanDev plan, int op_begin, int op_end,
                                                          const int32_t* __restrict__ labels,
                                                          double* __restrict__ out, long long row_stride) {
     double2* s = reinterpret_cast<double2*>(smem_raw);
+    StagedOp* so = reinterpret_cast<StagedOp*>(smem_raw + ((size_t)16 << plan.n_state));
     __shared__ int digits[QCK_MAX_DIGITS];
     const int label = labels[blockIdx.x];
     if (threadIdx.x == 0) decode_digits(plan, label, digits);
     const uint32_t n_amp = 1u << plan.n_state;
-    for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
+    for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
     __syncthreads();
-    apply_ops(s, plan.n_state, plan.ops, op_begin, op_end, plan.mats, digits);
+    apply_ops(s, plan.n_state, so, plan.ops, op_begin, op_end, plan.mats, digits);
     const uint64_t n_out = 1ull << plan.n_out_bits;
     double* row = out + (long long)label * row_stride;
     for (uint64_t o = threadIdx.x; o < n_out; o += blockDim.x)
-        row[o] = fold_entry(plan, o, [&](uint64_t idx) { return s[idx]; });
+        row[o] = fold_entry(plan, o, [&](uint64_t idx) { return s[swz((uint32_t)idx)]; });
 }
 
 // ------------------------------------------------------------------ streaming regime
@@ -183,14 +335,14 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
                                                         const int32_t* __restrict__ labels, int inst_base,
                                                         double2* __restrict__ work,
                                                         unsigned long long state_stride) {
+    const int T = sw.n_tile, c = sw.n_low, n_hi = T - c;
     double2* s = reinterpret_cast<double2*>(smem_raw);
+    unsigned long long* hi_off = reinterpret_cast<unsigned long long*>(smem_raw + ((size_t)16 << T));
+    StagedOp* so = reinterpret_cast<StagedOp*>(smem_raw + ((size_t)16 << T) + ((((size_t)8 << n_hi) + 15) & ~(size_t)15));
     __shared__ int digits[QCK_MAX_DIGITS];
-    __shared__ unsigned long long hi_off[1 << 10];
-    const int T = sw.n_tile, c = sw.n_low;
     const int label = labels[inst_base + blockIdx.y];
     if (threadIdx.x == 0) decode_digits(plan, label, digits);
     // offsets of the non-contiguous tile bits
-    const int n_hi = T - c;
     for (uint32_t j = threadIdx.x; j < (1u << n_hi); j += blockDim.x) {
         unsigned long long off = 0;
         for (int b = 0; b < n_hi; ++b)
@@ -205,15 +357,22 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
     const uint32_t n_amp = 1u << T, low_mask = (1u << c) - 1u;
     if (sw.init) {
         for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
-            s[j] = make_double2((j == 0 && base == 0) ? 1.0 : 0.0, 0.0);
+            s[j] = make_double2((j == 0 && base == 0) ? 1.0 : 0.0, 0.0);  // swz(0) == 0
     } else {
-        for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
-            s[j] = __ldcs(st + (base | hi_off[j >> c] | (j & low_mask)));
+        // cp.async (LDGSTS): every thread has all of its 16-byte loads in flight at once, the
+        // data goes straight to shared memory (L1 bypassed)
+        const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s);
+        for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x) {
+            const double2* src = st + (base | hi_off[j >> c] | (j & low_mask));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + swz(j) * 16u), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    apply_ops(s, T, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits);
+    apply_ops(s, T, so, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits);
     for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
-        __stcs(st + (base | hi_off[j >> c] | (j & low_mask)), s[j]);
+        __stcs(st + (base | hi_off[j >> c] | (j & low_mask)), s[swz(j)]);
 }
 
 __global__ void __launch_bounds__(256) fold_probs_kernel(PlanDev plan, const int32_t* __restrict__ labels,
@@ -270,6 +429,8 @@ static PlanDev to_dev(const qck_sim_plan* plan) {
     for (int k = 0; k < QCK_MAX_DIGITS; ++k) d.radix[k] = k < plan->n_digits ? plan->radix[k] : 1;
     d.n_out_bits = plan->n_out_bits;
     for (int j = 0; j < QCK_MAX_OUT_BITS; ++j) d.out_pos[j] = j < plan->n_out_bits ? plan->out_pos[j] : -1;
+    d.out_ident = 0;
+    while (d.out_ident < plan->n_out_bits && plan->out_pos[d.out_ident] == d.out_ident) ++d.out_ident;
     d.sum_mask = plan->sum_mask;
     d.sign_mask = plan->sign_mask;
     return d;
@@ -300,8 +461,9 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
         SweepDev sd = sweep_dev(plan->sweeps[i], i == 0);
         if (sd.n_tile - sd.n_low > 10)
             QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "sweep %d: more than 10 non-contiguous tile bits", i);
-        size_t smem = (size_t)16 << sd.n_tile;
-        if ((int)smem + 12 * 1024 > h->max_smem_optin)
+        size_t smem = ((size_t)16 << sd.n_tile) + ((((size_t)8 << (sd.n_tile - sd.n_low)) + 15) & ~(size_t)15) +
+                      sizeof(StagedOp) * QCK_STAGE_OPS;
+        if ((int)smem + 1024 > h->max_smem_optin)
             QCK_FAIL(h, QCK_ERR_INVALID_ARG, "sweep %d: tile of 2^%d amplitudes does not fit shared memory", i,
                      sd.n_tile);
         QCK_CUDA(h, cudaFuncSetAttribute(sim_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -329,13 +491,13 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
     PlanDev pd = to_dev(plan);
     if (is_onchip(plan)) {
         const int N = plan->n_state_qubits;
-        size_t smem = (size_t)16 << N;
+        size_t smem = ((size_t)16 << N) + sizeof(StagedOp) * QCK_STAGE_OPS;
         if ((int)smem + 1024 > h->max_smem_optin)
             QCK_FAIL(h, QCK_ERR_INVALID_ARG, "on-chip plan with %d qubits does not fit shared memory", N);
         QCK_CUDA(h, cudaFuncSetAttribute(sim_onchip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int threads = 1 << (N > 1 ? N - 1 : 0);
+        int threads = 1 << (N > 3 ? N - 3 : 0);  // one thread per group of 8 amplitudes
         if (threads < 32) threads = 32;
-        if (threads > 512) threads = 512;
+        if (threads > 256) threads = 256;
         const qck_sweep& sw = plan->sweeps[0];
         for (int64_t done = 0; done < n_instances;) {
             int64_t batch = n_instances - done;

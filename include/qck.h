@@ -71,12 +71,17 @@ QCK_API int64_t qck_launch_count(const qck_handle* h);
 #define QCK_MAX_DIGITS 16
 #define QCK_MAX_OUT_BITS 40
 
-enum { QCK_OP_U1 = 0, QCK_OP_CX = 1, QCK_OP_CZ = 2, QCK_OP_U2 = 3 };
+enum { QCK_OP_U1 = 0, QCK_OP_CX = 1, QCK_OP_CZ = 2, QCK_OP_U2 = 3, QCK_OP_CLUSTER = 4 };
+#define QCK_CLUSTER_QUBITS 3
 
 /* One gate application.  Qubits are TILE-LOCAL bit positions of the sweep the op
  * belongs to.  A measurement whose qubit lives on is a QCK_OP_CX onto a fresh
  * ancilla bit (deferred measurement: the two halves of the state are the two
- * un-normalised branches of SURVEY.md A.2). */
+ * un-normalised branches of SURVEY.md A.2).
+ * QCK_OP_CLUSTER is a header: the next q0 ops act only on the QCK_CLUSTER_QUBITS
+ * tile positions (mat, sel_digit, sel_stride) = ascending positions p0 < p1 < p2 and
+ * address them by their rank 0..2; each thread applies the whole cluster to its 8
+ * amplitudes in registers (one shared-memory round trip for several gates). */
 typedef struct {
     int32_t kind;        /* QCK_OP_*                                                     */
     int32_t q0, q1;      /* U1: q0.  CX: control q0, target q1.  CZ/U2: q0 (bit0), q1     */

@@ -24,8 +24,24 @@ def run_plan(program, plan, label):
     psi[0] = 1.0
     idx = np.arange(1 << N)
     for positions, b, e in plan.sweeps:
+        cluster_pos, members_left = None, 0
         for op in plan.ops[b:e]:
             kind, q0, q1, mat, sel, stride, n_live, _ = (int(x) for x in op)
+            if kind == _lib.OP_CLUSTER:           # header: members address the 3 positions by rank
+                cluster_pos, members_left = [mat, sel, stride], q0
+                assert cluster_pos == sorted(cluster_pos) and len(set(cluster_pos)) == 3
+                live = n_live if 0 < n_live <= len(positions) else len(positions)
+                assert all(0 <= p < live for p in cluster_pos)
+                cluster_live = n_live
+                if n_live > 0 and len(plan.sweeps) == 1:
+                    assert np.all(psi[(1 << n_live):] == 0), "cluster n_live hides populated amplitudes"
+                continue
+            if members_left > 0:
+                members_left -= 1
+                n_live = cluster_live          # the device uses the header's n_live for every member
+                q0 = cluster_pos[q0]
+                if kind != _lib.OP_U1:
+                    q1 = cluster_pos[q1]
             moff = mat + (digits[sel] * stride if sel >= 0 else 0)
             g0 = positions[q0]
             if kind == _lib.OP_U1:
