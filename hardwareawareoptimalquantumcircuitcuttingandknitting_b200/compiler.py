@@ -83,15 +83,17 @@ class FragmentProgram:
 
     def __init__(self, frag_circuit: QuantumCircuit, fragment: QuantumRegister, num_clbits: int,
                  onchip_max: int = ONCHIP_MAX_QUBITS, stream_tile: int = STREAM_TILE,
-                 cluster: bool = True) -> None:
+                 cluster: bool = True, fuse: bool = True) -> None:
         self.fragment = fragment
         self.n_qubits = len(fragment)
         self.num_clbits = num_clbits
         self.onchip_max = onchip_max
         self.stream_tile = stream_tile
         self.cluster = cluster
+        self.fuse = fuse
         self._pool: list[np.ndarray] = []
         self._pool_len = 0
+        self._mat_by_off: dict[int, np.ndarray] = {}
         self._lower(frag_circuit)
         self._plans: dict[bool, list[PlanHost]] = {}
 
@@ -101,6 +103,7 @@ class FragmentProgram:
         off = self._pool_len
         self._pool.append(flat)
         self._pool_len += flat.size
+        self._mat_by_off[off] = np.asarray(m, dtype=np.complex128)
         return off
 
     def _lower(self, circ: QuantumCircuit) -> None:
@@ -207,8 +210,8 @@ class FragmentProgram:
         # one-qubit gates still pending act on wires that are never measured afterwards: they
         # cannot change any probability and are dropped
         pending.clear()
-        self.tops = tops
         self.slots = slots
+        self.tops = self._fuse_pairs(tops) if self.fuse else tops
         self.out_bits = out_bits
         self.out_clbits = [c for c, _ in out_bits]
         self.has_mid_measure = mid_measures > 0
@@ -220,6 +223,83 @@ class FragmentProgram:
         self.measures_anything = bool(out_bits) or mid_measures > 0 or any(any(s.meas) for s in slots)
         self.num_labels = int(np.prod(self.radix, dtype=np.int64)) if self.radix else 1
         self.mats = np.concatenate(self._pool) if self._pool else np.zeros(8)
+
+    # ------------------------------------------------------------------ gate fusion
+    _SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+    _CX01 = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=np.complex128)
+    _CZ = np.diag([1, 1, 1, -1]).astype(np.complex128)
+    _OVERHEAD = 6.0      # per-op dispatch cost in units of FP64 instructions per amplitude
+
+    def _fuse_pairs(self, tops: list[tuple]) -> list[tuple]:
+        """Merge runs of gates that act inside one qubit pair into a single 4x4 unitary when a
+        cost model (FP64 work per amplitude + per-op overhead) says the dense product is cheaper
+        than the separate gates.  Slots and mid-circuit measurements are barriers on their qubit.
+        Only reorders gates on disjoint qubits; per-qubit order is preserved."""
+        out: list[tuple] = []
+        group_of: dict[int, dict] = {}          # qubit -> open pair group
+        pending: dict[int, list] = {}           # qubit -> 1q ops waiting for a partner
+
+        def op_cost(t) -> float:
+            if t[0] == "u1":
+                m = self._mat_by_off[t[2]]
+                return 2.0 if (m[0, 1] == 0 and m[1, 0] == 0) else 8.0
+            if t[0] in ("cx", "cz"):
+                return 1.0
+            return 16.0
+
+        def embed(t, a, b) -> np.ndarray:
+            if t[0] == "u1":
+                u = self._mat_by_off[t[2]]
+                return np.kron(np.eye(2), u) if t[1] == a else np.kron(u, np.eye(2))
+            m = self._CX01 if t[0] == "cx" else self._CZ if t[0] == "cz" else self._mat_by_off[t[3]].reshape(4, 4)
+            return m if (t[1], t[2]) == (a, b) else self._SWAP @ m @ self._SWAP
+
+        def close(g) -> None:
+            for q in (g["a"], g["b"]):
+                if group_of.get(q) is g:
+                    del group_of[q]
+            ops = g["ops"]
+            separate = sum(op_cost(t) + self._OVERHEAD for t in ops)
+            if len(ops) > 1 and separate > 16.0 + self._OVERHEAD:
+                m = np.eye(4, dtype=np.complex128)
+                for t in ops:
+                    m = embed(t, g["a"], g["b"]) @ m
+                out.append(("u2", g["a"], g["b"], self._add_matrix(m)))
+            else:
+                out.extend(ops)
+
+        def flush_pending(q) -> None:
+            out.extend(pending.pop(q, []))
+
+        for t in tops:
+            if t[0] == "u1":
+                q = t[1]
+                if q in group_of:
+                    group_of[q]["ops"].append(t)
+                else:
+                    pending.setdefault(q, []).append(t)
+            elif t[0] in ("cx", "cz", "u2"):
+                a, b = t[1], t[2]
+                g = group_of.get(a)
+                if g is not None and g is group_of.get(b):
+                    g["ops"].append(t)
+                    continue
+                for q in (a, b):
+                    if q in group_of:
+                        close(group_of[q])
+                g = {"a": a, "b": b, "ops": pending.pop(a, []) + pending.pop(b, []) + [t]}
+                group_of[a] = group_of[b] = g
+            else:                                   # slot / mmeas: barrier on its qubit
+                q = self.slots[t[1]].qubit if t[0] == "slot" else t[1]
+                if q in group_of:
+                    close(group_of[q])
+                flush_pending(q)
+                out.append(t)
+        for g in list({id(g): g for g in group_of.values()}.values()):
+            close(g)
+        for q in list(pending):
+            flush_pending(q)
+        return out
 
     # ------------------------------------------------------------------ patterns
     def label_digits(self, labels: np.ndarray) -> np.ndarray:

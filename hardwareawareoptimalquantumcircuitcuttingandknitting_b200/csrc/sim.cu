@@ -14,6 +14,8 @@
 // (-1)^bit weights of the knit rules.
 #include "qck_common.cuh"
 
+#include <stdlib.h>
+
 struct PlanDev {
     int n_state;
     const qck_op* ops;
@@ -23,6 +25,7 @@ struct PlanDev {
     int n_out_bits;
     int out_pos[QCK_MAX_OUT_BITS];
     int out_ident;  // out_pos[j] == j for j < out_ident: those row bits map straight to state bits
+    int n_stage;    // capacity (records) of the shared-memory program stage of this launch
     unsigned long long sum_mask, sign_mask;
 };
 
@@ -89,7 +92,7 @@ __device__ __forceinline__ void reg_cz(double2 (&a)[8]) {
         if ((k & (1 << J0)) && (k & (1 << J1))) a[k] = make_double2(-a[k].x, -a[k].y);
 }
 template <int J0, int J1>
-__device__ __forceinline__ void reg_u2(double2 (&a)[8], const double2* __restrict__ m) {
+__device__ __forceinline__ void reg_u2(double2 (&a)[8], const double2* m) {
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         if (!(k & ((1 << J0) | (1 << J1)))) {
@@ -97,9 +100,9 @@ __device__ __forceinline__ void reg_u2(double2 (&a)[8], const double2* __restric
             double2 r[4];
 #pragma unroll
             for (int row = 0; row < 4; ++row) {
-                double2 acc = cmul(__ldg(m + row * 4), x[0]);
+                double2 acc = cmul(m[row * 4], x[0]);
 #pragma unroll
-                for (int c = 1; c < 4; ++c) acc = cfma(__ldg(m + row * 4 + c), x[c], acc);
+                for (int c = 1; c < 4; ++c) acc = cfma(m[row * 4 + c], x[c], acc);
                 r[row] = acc;
             }
             a[k] = r[0];
@@ -124,10 +127,10 @@ __device__ __forceinline__ void reg_u2(double2 (&a)[8], const double2* __restric
 // shared memory once per CTA, so that per-op fetches are broadcast LDS instead of two dependent
 // global loads (op record -> matrix), which dominated the run time of small instances.
 struct StagedOp {
-    int4 w0, w1;    // the qck_op words; w0.w = resolved matrix offset
-    double2 m[4];   // U1: the matrix
+    int4 w0, w1;     // the qck_op words; w0.w = resolved matrix offset
+    double2 m[16];   // U1: m[0..3]; U2: the 4x4 matrix, row major
 };
-#define QCK_STAGE_OPS 128
+#define QCK_STAGE_OPS 96
 #define QCK_MAX_CLUSTER_OPS 32
 
 __device__ __forceinline__ void stage_ops(StagedOp* so, const qck_op* __restrict__ ops, int c0, int n,
@@ -137,13 +140,9 @@ __device__ __forceinline__ void stage_ops(StagedOp* so, const qck_op* __restrict
         const int4 w1 = __ldg(reinterpret_cast<const int4*>(ops + c0 + i) + 1);
         if (w0.x == QCK_OP_U1 || w0.x == QCK_OP_U2) {
             if (w1.x >= 0) w0.w += digits[w1.x] * w1.y;
-            if (w0.x == QCK_OP_U1) {
-                const double2* m = reinterpret_cast<const double2*>(mats + w0.w);
-                so[i].m[0] = __ldg(m);
-                so[i].m[1] = __ldg(m + 1);
-                so[i].m[2] = __ldg(m + 2);
-                so[i].m[3] = __ldg(m + 3);
-            }
+            const double2* m = reinterpret_cast<const double2*>(mats + w0.w);
+            const int n_m = w0.x == QCK_OP_U1 ? 4 : 16;
+            for (int e = 0; e < n_m; ++e) so[i].m[e] = __ldg(m + e);
         }
         so[i].w0 = w0;
         so[i].w1 = w1;
@@ -185,7 +184,7 @@ __device__ void run_cluster(double2* s, int T, const StagedOp* so, int h, const 
             } else if (kind == QCK_OP_CZ) {
                 QCK_PAIR_DISPATCH(reg_cz, a)
             } else {
-                const double2* m = reinterpret_cast<const double2*>(mats + w0.w);
+                const double2* m = so[i].m;
                 QCK_PAIR_DISPATCH(reg_u2, a, m)
             }
         }
@@ -238,16 +237,16 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
                 s[swz(idx)] = make_double2(-a.x, -a.y);
             }
         } else {  // QCK_OP_U2: generic 4x4, row/col index = bit(q0) + 2 bit(q1)
-            const double2* m = reinterpret_cast<const double2*>(mats + op.w0.w);
+            const double2* m = op.m;
             for (uint32_t p = tid; p < n; p += nth) {
                 const uint32_t base = insert_zero(insert_zero(p, lo), hi);
                 const double2 a[4] = {s[swz(base)], s[swz(base | b0)], s[swz(base | b1)], s[swz(base | b0 | b1)]};
                 double2 r[4];
 #pragma unroll
                 for (int row = 0; row < 4; ++row) {
-                    double2 acc = cmul(__ldg(m + row * 4), a[0]);
+                    double2 acc = cmul(m[row * 4], a[0]);
 #pragma unroll
-                    for (int c = 1; c < 4; ++c) acc = cfma(__ldg(m + row * 4 + c), a[c], acc);
+                    for (int c = 1; c < 4; ++c) acc = cfma(m[row * 4 + c], a[c], acc);
                     r[row] = acc;
                 }
                 s[swz(base)] = r[0];
@@ -262,13 +261,15 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
 
 // Apply ops[begin, end) to the tile `s` (2^T amplitudes in shared memory).  All threads of the
 // CTA call this with identical arguments; the state is synchronised on return.
-__device__ void apply_ops(double2* s, int T, StagedOp* so, const qck_op* __restrict__ ops, int begin, int end,
-                          const double* __restrict__ mats, const int* digits) {
+__device__ void apply_ops(double2* s, int T, StagedOp* so, int n_stage, const qck_op* __restrict__ ops, int begin,
+                          int end, const double* __restrict__ mats, const int* digits, bool prestaged) {
     int c0 = begin;
     while (c0 < end) {
-        const int n = (end - c0) < QCK_STAGE_OPS ? (end - c0) : QCK_STAGE_OPS;
-        stage_ops(so, ops, c0, n, mats, digits);
-        __syncthreads();
+        const int n = (end - c0) < n_stage ? (end - c0) : n_stage;
+        if (!(prestaged && c0 == begin)) {  // the caller may have staged the first chunk already
+            stage_ops(so, ops, c0, n, mats, digits);
+            __syncthreads();
+        }
         int i = 0;
         while (i < n) {
             if (so[i].w0.x == QCK_OP_CLUSTER) {
@@ -321,9 +322,14 @@ __global__ void __launch_bounds__(256) sim_onchip_kernel(PlanDev plan, int op_be
     const int label = labels[blockIdx.x];
     if (threadIdx.x == 0) decode_digits(plan, label, digits);
     const uint32_t n_amp = 1u << plan.n_state;
+    __syncthreads();  // digits visible
+    {
+        const int n0 = (op_end - op_begin) < plan.n_stage ? (op_end - op_begin) : plan.n_stage;
+        stage_ops(so, plan.ops, op_begin, n0, plan.mats, digits);  // global loads overlap the state init
+    }
     for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
     __syncthreads();
-    apply_ops(s, plan.n_state, so, plan.ops, op_begin, op_end, plan.mats, digits);
+    apply_ops(s, plan.n_state, so, plan.n_stage, plan.ops, op_begin, op_end, plan.mats, digits, true);
     const uint64_t n_out = 1ull << plan.n_out_bits;
     double* row = out + (long long)label * row_stride;
     for (uint64_t o = threadIdx.x; o < n_out; o += blockDim.x)
@@ -367,12 +373,121 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + swz(j) * 16u), "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+    {   // stage the program while the tile is in flight
+        const int n0 = (sw.op_end - sw.op_begin) < plan.n_stage ? (sw.op_end - sw.op_begin) : plan.n_stage;
+        stage_ops(so, plan.ops, sw.op_begin, n0, plan.mats, digits);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    apply_ops(s, T, so, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits);
+    apply_ops(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, true);
     for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
         __stcs(st + (base | hi_off[j >> c] | (j & low_mask)), s[swz(j)]);
+}
+
+// Pipelined, persistent form of the sweep for states that do not fit L2: one CTA per SM keeps a
+// ring of PIPE_STAGES tiles in shared memory.  While tile i is transformed in place, the loads of
+// tiles i+1 .. i+PIPE_STAGES-1 are in flight (cp.async groups) and the stores of tile i-1 drain,
+// so HBM stays busy during the gate passes.  Tiles are claimed from an atomic counter (a static
+// split of a streaming kernel leaves ~15 % on the table on B200, see knit.cu).
+#define PIPE_STAGES 3
+#define PIPE_THREADS 512
+__global__ void __launch_bounds__(PIPE_THREADS, 1) sim_sweep_pipe_kernel(PlanDev plan, SweepDev sw,
+                                                                const int32_t* __restrict__ labels,
+                                                                int inst_base, double2* __restrict__ work,
+                                                                unsigned long long state_stride,
+                                                                unsigned long long tiles_per_inst,
+                                                                unsigned long long n_work,
+                                                                unsigned long long* __restrict__ counter) {
+    const int T = sw.n_tile, c = sw.n_low, n_hi = T - c;
+    const size_t stage_bytes = (size_t)16 << T;
+    unsigned long long* hi_off = reinterpret_cast<unsigned long long*>(smem_raw + PIPE_STAGES * stage_bytes);
+    StagedOp* so =
+        reinterpret_cast<StagedOp*>(smem_raw + PIPE_STAGES * stage_bytes + ((((size_t)8 << n_hi) + 15) & ~(size_t)15));
+    __shared__ int digits[QCK_MAX_DIGITS];
+    __shared__ unsigned long long claimed[PIPE_STAGES];
+    const uint32_t n_amp = 1u << T, low_mask = (1u << c) - 1u;
+    const unsigned long long NONE = ~0ull;
+
+    for (uint32_t j = threadIdx.x; j < (1u << n_hi); j += blockDim.x) {
+        unsigned long long off = 0;
+        for (int b = 0; b < n_hi; ++b)
+            if ((j >> b) & 1u) off |= 1ull << sw.pos[c + b];
+        hi_off[j] = off;
+    }
+    auto tile_base = [&](unsigned long long w, double2*& st) {
+        const unsigned long long inst = w / tiles_per_inst;
+        unsigned long long base = w - inst * tiles_per_inst;
+        for (int j = 0; j < T; ++j) base = insert_zero64(base, sw.pos[j]);
+        st = work + inst * state_stride;
+        return base;
+    };
+    auto issue_load = [&](int stage) {  // all threads; claimed[stage] already visible
+        const unsigned long long w = claimed[stage];
+        if (w != NONE && !sw.init) {
+            double2* st;
+            const unsigned long long base = tile_base(w, st);
+            const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw + stage * stage_bytes);
+            for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x) {
+                const double2* src = st + (base | hi_off[j >> c] | (j & low_mask));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + swz(j) * 16u), "l"(src)
+                             : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // always: keeps the group count uniform
+    };
+    // prologue: claim and start loading the first PIPE_STAGES - 1 tiles
+    if (threadIdx.x == 0) {  // one thread: claims must be ordered (NONE only ever follows valid tiles)
+        for (int st = 0; st < PIPE_STAGES - 1; ++st) {
+            const unsigned long long w = atomicAdd(counter, 1ull);
+            claimed[st] = w < n_work ? w : NONE;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int st = 0; st < PIPE_STAGES - 1; ++st) issue_load(st);
+    long long staged_inst = -1;
+    for (int k = 0;; ++k) {
+        const int cur = k % PIPE_STAGES, nxt = (k + PIPE_STAGES - 1) % PIPE_STAGES;
+        if (threadIdx.x == 0) {
+            const unsigned long long w = atomicAdd(counter, 1ull);
+            claimed[nxt] = w < n_work ? w : NONE;
+        }
+        __syncthreads();  // claimed[nxt] visible; everyone finished storing the tile that lived in nxt
+        issue_load(nxt);
+        asm volatile("cp.async.wait_group %0;" ::"n"(PIPE_STAGES - 1) : "memory");
+        __syncthreads();  // tile `cur` resident for all threads
+        const unsigned long long w = claimed[cur];
+        if (w == NONE) break;  // tiles are claimed in order: nothing later is pending either
+        double2* s = reinterpret_cast<double2*>(smem_raw + cur * stage_bytes);
+        double2* st;
+        const unsigned long long base = tile_base(w, st);
+        const long long inst = (long long)(w / tiles_per_inst);
+        if (sw.init) {
+            for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
+                s[j] = make_double2((j == 0 && base == 0) ? 1.0 : 0.0, 0.0);  // swz(0) == 0
+            __syncthreads();
+        }
+        if (inst != staged_inst) {  // uniform; the matrices depend on the instance's label digits
+            if (threadIdx.x == 0) decode_digits(plan, labels[inst_base + inst], digits);
+            __syncthreads();
+            stage_ops(so, plan.ops, sw.op_begin, sw.op_end - sw.op_begin, plan.mats, digits);
+            __syncthreads();
+            staged_inst = inst;
+        }
+        for (int i = 0; i < sw.op_end - sw.op_begin;) {
+            if (so[i].w0.x == QCK_OP_CLUSTER) {
+                run_cluster(s, T, so, i, plan.mats);
+                i += 1 + so[i].w0.y;
+            } else {
+                run_single(s, T, so[i], plan.mats);
+                ++i;
+            }
+        }
+        for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
+            __stcs(st + (base | hi_off[j >> c] | (j & low_mask)), s[swz(j)]);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256) fold_probs_kernel(PlanDev plan, const int32_t* __restrict__ labels,
@@ -450,9 +565,18 @@ static SweepDev sweep_dev(const qck_sweep& sw, bool init) {
     return s;
 }
 
+// records to stage for an op range: everything when it fits, else the largest chunk (a cluster of
+// up to QCK_MAX_CLUSTER_OPS members + header must fit)
+static int stage_records(int n_ops) {
+    int n = n_ops < QCK_STAGE_OPS ? n_ops : QCK_STAGE_OPS;
+    return n < 1 ? 1 : n;
+}
+
 static bool is_onchip(const qck_sim_plan* plan) {
     return plan->n_sweeps == 1 && plan->sweeps[0].n_tile == plan->n_state_qubits;
 }
+
+int qck_ensure_partials(qck_handle* h, size_t count);  // api.cu
 
 static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd, const int32_t* d_labels,
                       int inst_base, int batch, double2* work, unsigned long long state_stride,
@@ -461,16 +585,37 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
         SweepDev sd = sweep_dev(plan->sweeps[i], i == 0);
         if (sd.n_tile - sd.n_low > 10)
             QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "sweep %d: more than 10 non-contiguous tile bits", i);
-        size_t smem = ((size_t)16 << sd.n_tile) + ((((size_t)8 << (sd.n_tile - sd.n_low)) + 15) & ~(size_t)15) +
-                      sizeof(StagedOp) * QCK_STAGE_OPS;
+        PlanDev pdl = pd;
+        pdl.n_stage = stage_records(sd.op_end - sd.op_begin);
+        const size_t aux = ((((size_t)8 << (sd.n_tile - sd.n_low)) + 15) & ~(size_t)15) + sizeof(StagedOp) * pdl.n_stage;
+        size_t smem = ((size_t)16 << sd.n_tile) + aux;
         if ((int)smem + 1024 > h->max_smem_optin)
             QCK_FAIL(h, QCK_ERR_INVALID_ARG, "sweep %d: tile of 2^%d amplitudes does not fit shared memory", i,
                      sd.n_tile);
-        QCK_CUDA(h, cudaFuncSetAttribute(sim_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         unsigned long long tiles = 1ull << (plan->n_state_qubits - sd.n_tile);
         if (tiles > 0x7fffffffull) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "too many tiles");
+        // pipelined persistent kernel when there is enough work to fill the machine several times
+        const size_t pipe_smem = PIPE_STAGES * ((size_t)16 << sd.n_tile) + aux;
+        int want_pipe = 0;  // measured slower than the plain kernel on B200 (305 vs 229 ms at 32 qubits);
+        //                     kept behind QCK_SIM_PIPE=1 for tuning
+        if (const char* env = getenv("QCK_SIM_PIPE")) want_pipe = atoi(env);
+        const bool pipe = want_pipe && tiles * (unsigned long long)batch >= 8ull * h->sm_count &&
+                          (sd.op_end - sd.op_begin) <= pdl.n_stage && (int)pipe_smem + 1024 <= h->max_smem_optin;
+        if (pipe) {
+            int rc = qck_ensure_partials(h, 8);
+            if (rc) return rc;
+            unsigned long long* counter = reinterpret_cast<unsigned long long*>(h->d_partials);
+            QCK_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+            QCK_CUDA(h, cudaFuncSetAttribute(sim_sweep_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)pipe_smem));
+            sim_sweep_pipe_kernel<<<h->sm_count, PIPE_THREADS, pipe_smem, st>>>(pdl, sd, d_labels, inst_base, work, state_stride,
+                                                                        tiles, tiles * (unsigned long long)batch, counter);
+            QCK_CHECK_LAUNCH(h);
+            continue;
+        }
+        QCK_CUDA(h, cudaFuncSetAttribute(sim_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)tiles, (unsigned)batch);
-        sim_sweep_kernel<<<grid, 256, smem, st>>>(pd, sd, d_labels, inst_base, work, state_stride);
+        sim_sweep_kernel<<<grid, 256, smem, st>>>(pdl, sd, d_labels, inst_base, work, state_stride);
         QCK_CHECK_LAUNCH(h);
     }
     return QCK_OK;
@@ -491,7 +636,9 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
     PlanDev pd = to_dev(plan);
     if (is_onchip(plan)) {
         const int N = plan->n_state_qubits;
-        size_t smem = ((size_t)16 << N) + sizeof(StagedOp) * QCK_STAGE_OPS;
+        const qck_sweep& sw0 = plan->sweeps[0];
+        pd.n_stage = stage_records(sw0.op_end - sw0.op_begin);
+        size_t smem = ((size_t)16 << N) + sizeof(StagedOp) * pd.n_stage;
         if ((int)smem + 1024 > h->max_smem_optin)
             QCK_FAIL(h, QCK_ERR_INVALID_ARG, "on-chip plan with %d qubits does not fit shared memory", N);
         QCK_CUDA(h, cudaFuncSetAttribute(sim_onchip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
