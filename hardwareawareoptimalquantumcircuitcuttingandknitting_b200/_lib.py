@@ -56,6 +56,9 @@ _PROTOTYPES = {
     "qck_launch_count": (C.c_int64, [C.c_void_p]),
     "qck_sim_fragments": (C.c_int, [C.c_void_p, C.POINTER(QckSimPlan), C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qck_sim_fragments_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(QckSimPlan), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t,
+                                          C.c_void_p]),
     "qck_sim_statevector": (C.c_int, [C.c_void_p, C.POINTER(QckSimPlan), C.c_int32, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
     "qck_knit_outer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int,

@@ -631,7 +631,13 @@ class FragmentExecutor:
                 free, _ = torch.cuda.mem_get_info(self.device)
                 n = max(1, min(prog.num_labels, int(free * 0.5) // per, 64))
             self._work = torch.empty(n * per, dtype=torch.uint8, device=self.device)
-        for st, off, count in self._structs:
+        n = len(self._structs)
+        plans = (_lib.QckSimPlan * n)()
+        label_ptrs = (C.c_void_p * n)()
+        counts = (C.c_int64 * n)()
+        ops_ptr = self.d_blob.data_ptr() + self._off_ops
+        mats_ptr = self.d_blob.data_ptr()
+        for i, (st, off, count) in enumerate(self._structs):
             labels_ptr = self.d_blob.data_ptr() + self._off_labels + 4 * off
             if label_range is not None:
                 # label lists are ascending inside a plan: clip to the requested range
@@ -639,13 +645,14 @@ class FragmentExecutor:
                 lo = int(np.searchsorted(host, label_range[0], side="left"))
                 hi = int(np.searchsorted(host, label_range[1], side="left"))
                 labels_ptr += 4 * lo
-                count = hi - lo
-                if count <= 0:
-                    continue
-            st.d_ops = self.d_blob.data_ptr() + self._off_ops
-            st.d_mats = self.d_blob.data_ptr()
-            work_ptr = self._work.data_ptr() if self._work is not None else None
-            work_bytes = self._work.numel() if self._work is not None else 0
-            handle.check(handle.lib.qck_sim_fragments(handle.ptr, C.byref(st), labels_ptr, count, out.data_ptr(),
-                                                      self.row_len, work_ptr, work_bytes, stream))
+                count = max(0, hi - lo)
+            st.d_ops = ops_ptr
+            st.d_mats = mats_ptr
+            plans[i] = st
+            label_ptrs[i] = labels_ptr
+            counts[i] = count
+        work_ptr = self._work.data_ptr() if self._work is not None else None
+        work_bytes = self._work.numel() if self._work is not None else 0
+        handle.check(handle.lib.qck_sim_fragments_batch(handle.ptr, n, plans, label_ptrs, counts, out.data_ptr(),
+                                                        self.row_len, work_ptr, work_bytes, stream))
         return out

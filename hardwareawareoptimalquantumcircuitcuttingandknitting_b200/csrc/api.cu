@@ -56,6 +56,13 @@ extern "C" int qck_destroy(qck_handle* h) {
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->scratch) cudaFree(h->scratch);
+    if (h->side_ready) {
+        for (int i = 0; i < QCK_SIDE_STREAMS; ++i) {
+            cudaStreamDestroy(h->side[i]);
+            cudaEventDestroy(h->side_done[i]);
+        }
+        cudaEventDestroy(h->fork);
+    }
     delete h;
     return QCK_OK;
 }

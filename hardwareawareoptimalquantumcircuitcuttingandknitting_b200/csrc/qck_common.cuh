@@ -7,6 +7,8 @@
 
 #include "../../include/qck.h"
 
+#define QCK_SIDE_STREAMS 8
+
 struct qck_handle {
     int device;
     int sm_count;
@@ -21,6 +23,11 @@ struct qck_handle {
     // growable device scratch (contraction weights, split-K partials)
     void* scratch;
     size_t scratch_bytes;
+    // side streams for fanning out independent small launches (created lazily)
+    cudaStream_t side[QCK_SIDE_STREAMS];
+    cudaEvent_t side_done[QCK_SIDE_STREAMS];
+    cudaEvent_t fork;
+    int side_ready;
 };
 
 #define QCK_FAIL(h, code, ...)                                    \

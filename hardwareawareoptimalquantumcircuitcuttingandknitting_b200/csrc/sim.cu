@@ -678,6 +678,61 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
     return QCK_OK;
 }
 
+static int ensure_side_streams(qck_handle* h) {
+    if (h->side_ready) return QCK_OK;
+    for (int i = 0; i < QCK_SIDE_STREAMS; ++i) {
+        QCK_CUDA(h, cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+        QCK_CUDA(h, cudaEventCreateWithFlags(&h->side_done[i], cudaEventDisableTiming));
+    }
+    QCK_CUDA(h, cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
+    h->side_ready = 1;
+    return QCK_OK;
+}
+
+extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim_plan* plans,
+                                       const int32_t* const* d_labels, const int64_t* n_instances, double* d_out,
+                                       int64_t out_row_stride, void* d_work, size_t work_bytes, qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    if (n_plans < 0 || (n_plans > 0 && (!plans || !d_labels || !n_instances)))
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad plan list");
+    int n_onchip = 0;
+    for (int i = 0; i < n_plans; ++i) {
+        int rc = validate_plan(h, &plans[i]);
+        if (rc) return rc;
+        if (is_onchip(&plans[i]) && n_instances[i] > 0) ++n_onchip;
+    }
+    DeviceGuard guard(h->device);
+    cudaStream_t main_st = (cudaStream_t)stream;
+    const bool fan = n_onchip >= 2;
+    int used = 0;
+    if (fan) {
+        int rc = ensure_side_streams(h);
+        if (rc) return rc;
+        QCK_CUDA(h, cudaEventRecord(h->fork, main_st));
+    }
+    int k = 0;
+    for (int i = 0; i < n_plans; ++i) {
+        if (n_instances[i] <= 0) continue;
+        cudaStream_t st = main_st;
+        if (fan && is_onchip(&plans[i])) {
+            const int slot = k++ % QCK_SIDE_STREAMS;
+            st = h->side[slot];
+            if (slot >= used) {  // first use of this side stream in this call: order after the fork point
+                QCK_CUDA(h, cudaStreamWaitEvent(st, h->fork, 0));
+                used = slot + 1;
+            }
+        }
+        int rc = qck_sim_fragments(h, &plans[i], d_labels[i], n_instances[i], d_out, out_row_stride, d_work,
+                                   work_bytes, (qck_stream)st);
+        if (rc) return rc;
+    }
+    for (int s = 0; s < used; ++s) {  // join
+        QCK_CUDA(h, cudaEventRecord(h->side_done[s], h->side[s]));
+        QCK_CUDA(h, cudaStreamWaitEvent(main_st, h->side_done[s], 0));
+    }
+    return QCK_OK;
+}
+
 extern "C" int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t label, void* d_state,
                                    size_t state_bytes, qck_stream stream) {
     if (!h) return QCK_ERR_INVALID_ARG;

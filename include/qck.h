@@ -131,6 +131,15 @@ QCK_API int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const int
                       int64_t n_instances, double* d_out, int64_t out_row_stride,
                       void* d_work, size_t work_bytes, qck_stream stream);
 
+/* Several programs of one fragment in one call (one per measurement pattern).  On-chip
+ * programs are independent small launches: they are fanned out over internal side streams
+ * (forked from and joined back into `stream` with events) so that they overlap on the GPU;
+ * streaming programs run one after the other on `stream`, sharing d_work. */
+QCK_API int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim_plan* plans,
+                                    const int32_t* const* d_labels, const int64_t* n_instances,
+                                    double* d_out, int64_t out_row_stride, void* d_work, size_t work_bytes,
+                                    qck_stream stream);
+
 /* Final statevector of ONE instance in the streaming regime left in d_work
  * (used for the uncut reference run, Utilities.py:39-69). */
 QCK_API int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t label,
