@@ -3,6 +3,9 @@
 
 #include <new>
 
+int qck_sim_init(qck_handle* h);   // sim.cu
+int qck_knit_init(qck_handle* h);  // knit.cu
+
 extern "C" int qck_abi_version(void) { return QCK_ABI_VERSION; }
 
 extern "C" const char* qck_status_string(int status) {
@@ -45,6 +48,12 @@ extern "C" int qck_create(int device, qck_handle** out) {
         if (h->d_partials) cudaFree(h->d_partials);
         delete full;
         return QCK_ERR_NOMEM;
+    }
+    if (qck_sim_init(h) != QCK_OK || qck_knit_init(h) != QCK_OK) {
+        cudaFree(h->d_partials);
+        cudaFreeHost(h->h_pinned);
+        delete full;
+        return QCK_ERR_CUDA;
     }
     *out = h;
     return QCK_OK;

@@ -277,13 +277,25 @@ int qck_ensure_partials(qck_handle* h, size_t count);  // api.cu
 
 template <int FV, bool WRITE>
 static cudaError_t launch_outer_one(int grid, size_t smem, cudaStream_t st, const OuterParams& P) {
-    if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(knit_outer_kernel<FV, WRITE>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
     knit_outer_kernel<FV, WRITE><<<grid, KO_THREADS, smem, st>>>(P);
     return cudaSuccess;
+}
+
+template <int FV>
+static cudaError_t outer_attr(int limit) {
+    cudaError_t e = qck_allow_max_smem(knit_outer_kernel<FV, true>, limit);
+    if (e != cudaSuccess) return e;
+    return qck_allow_max_smem(knit_outer_kernel<FV, false>, limit);
+}
+
+// see qck_sim_init: opt-in shared-memory limits are set once per process, not per launch
+int qck_knit_init(qck_handle* h) {
+    QCK_CUDA(h, outer_attr<0>(h->max_smem_optin));
+    QCK_CUDA(h, outer_attr<1>(h->max_smem_optin));
+    QCK_CUDA(h, outer_attr<2>(h->max_smem_optin));
+    QCK_CUDA(h, outer_attr<3>(h->max_smem_optin));
+    QCK_CUDA(h, outer_attr<4>(h->max_smem_optin));
+    return QCK_OK;
 }
 
 template <bool WRITE>
@@ -366,6 +378,8 @@ extern "C" int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_
         P.y_begin = y_begin;
         P.out = d_out;
         size_t smem = (size_t)off * sizeof(double);
+        if ((int)smem + 4096 > h->max_smem_optin)
+            QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "knit_outer: fragment rows (%zu bytes) do not fit shared memory", smem);
         int per_sm = 2;  // resident CTAs per SM; QCK_KO_CTAS_PER_SM overrides (tuning knob)
         if (const char* env = getenv("QCK_KO_CTAS_PER_SM")) {
             int v = atoi(env);

@@ -53,6 +53,15 @@ struct qck_handle {
         (h)->launches++;                                                                      \
     } while (0)
 
+// Allow a kernel to use all opt-in shared memory that its static allocation leaves free.
+template <typename K>
+static inline cudaError_t qck_allow_max_smem(K kernel, int optin) {
+    cudaFuncAttributes attr;
+    cudaError_t e = cudaFuncGetAttributes(&attr, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)attr.sharedSizeBytes);
+}
+
 struct DeviceGuard {
     int prev;
     bool changed;

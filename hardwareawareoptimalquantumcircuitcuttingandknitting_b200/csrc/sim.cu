@@ -606,14 +606,11 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
             if (rc) return rc;
             unsigned long long* counter = reinterpret_cast<unsigned long long*>(h->d_partials);
             QCK_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-            QCK_CUDA(h, cudaFuncSetAttribute(sim_sweep_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)pipe_smem));
             sim_sweep_pipe_kernel<<<h->sm_count, PIPE_THREADS, pipe_smem, st>>>(pdl, sd, d_labels, inst_base, work, state_stride,
                                                                         tiles, tiles * (unsigned long long)batch, counter);
             QCK_CHECK_LAUNCH(h);
             continue;
         }
-        QCK_CUDA(h, cudaFuncSetAttribute(sim_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)tiles, (unsigned)batch);
         sim_sweep_kernel<<<grid, 256, smem, st>>>(pdl, sd, d_labels, inst_base, work, state_stride);
         QCK_CHECK_LAUNCH(h);
@@ -641,7 +638,6 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
         size_t smem = ((size_t)16 << N) + sizeof(StagedOp) * pd.n_stage;
         if ((int)smem + 1024 > h->max_smem_optin)
             QCK_FAIL(h, QCK_ERR_INVALID_ARG, "on-chip plan with %d qubits does not fit shared memory", N);
-        QCK_CUDA(h, cudaFuncSetAttribute(sim_onchip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int threads = 1 << (N > 3 ? N - 3 : 0);  // one thread per group of 8 amplitudes
         if (threads < 32) threads = 32;
         if (threads > 256) threads = 256;
@@ -675,6 +671,15 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
         QCK_CHECK_LAUNCH(h);
         done += batch;
     }
+    return QCK_OK;
+}
+
+// Opt-in shared-memory limits are per-function process state: set them ONCE to the device maximum
+// (at handle creation) - setting them per launch races between host threads.
+int qck_sim_init(qck_handle* h) {
+    QCK_CUDA(h, qck_allow_max_smem(sim_onchip_kernel, h->max_smem_optin));
+    QCK_CUDA(h, qck_allow_max_smem(sim_sweep_kernel, h->max_smem_optin));
+    QCK_CUDA(h, qck_allow_max_smem(sim_sweep_pipe_kernel, h->max_smem_optin));
     return QCK_OK;
 }
 
