@@ -43,6 +43,12 @@ class QckSimPlan(C.Structure):
                 ("sum_mask", C.c_uint64), ("sign_mask", C.c_uint64)]
 
 
+class QckFaithfulGate(C.Structure):
+    _fields_ = [("n_variants", C.c_int32), ("form", C.c_int32), ("degenerate", C.c_int32), ("reserved", C.c_int32),
+                ("sign", C.c_double * MAX_VARIANTS), ("cos_half", C.c_double), ("sin_half", C.c_double),
+                ("cos_half_sq", C.c_double), ("sin_half_sq", C.c_double)]
+
+
 class QckStats(C.Structure):
     _fields_ = [("sum", C.c_double), ("min", C.c_double), ("sum_sqrt", C.c_double), ("nnz", C.c_double)]
 
@@ -67,6 +73,10 @@ _PROTOTYPES = {
                                     C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int32),
                                     C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_int, C.c_void_p]),
+    "qck_knit_faithful": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(QckFaithfulGate),
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.c_double,
+                                    C.c_void_p, C.c_void_p]),
     "qck_stats_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_void_p]),
     "qck_hellinger": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "qck_npd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.POINTER(C.c_double),

@@ -84,7 +84,7 @@ def _all_b200(virt: VirtualCircuit) -> bool:
 
 def run_virtual_circuit_dense(virt: VirtualCircuit, shots: int = 20000, device=None, nearest: bool = True,
                               rank: int = 0, world_size: int = 1, group=None,
-                              out=None) -> tuple[DenseResult, RunTimeInfo]:
+                              out=None, accuracy: float | None = None) -> tuple[DenseResult, RunTimeInfo]:
     """Whole path on the GPU.  With ``world_size > 1`` (one process per GPU) the work is
     partitioned as described in ``dist.py``: without virtual gates this rank produces the
     output slice whose top bits equal ``rank`` (``DenseResult.y_begin`` tells where it
@@ -101,6 +101,10 @@ def run_virtual_circuit_dense(virt: VirtualCircuit, shots: int = 20000, device=N
                 + f"{tuple(circ.num_qubits for circ in frags.values())} "
                 + f"fragments and {len(virt._vgate_instrs)} vgates...")
     K = len(virt._vgate_instrs)
+    from . import quasi_distr as _qd
+    accuracy = _qd.ACCURACY if accuracy is None else float(accuracy)
+    if accuracy > 0.0:
+        return _run_faithful(virt, device, handle, nearest, accuracy, world_size, out)
     label_range = None
     if K > 0 and world_size > 1:
         label_range = qdist.shard_range(virt.num_global_labels(), rank, world_size,
@@ -140,6 +144,31 @@ def run_virtual_circuit_dense(virt: VirtualCircuit, shots: int = 20000, device=N
     knit_time = perf_counter() - now
     logger.info(f"Knitted in {knit_time:.2f}s.")
     return DenseResult(values, union, total, minimum, y_begin), RunTimeInfo(run_time, knit_time)
+
+
+def _run_faithful(virt, device, handle, nearest, accuracy, world_size, out):
+    """ACCURACY > 0: exact instance distributions, then the reference's pruned algebra in the
+    reference's order, fused per output entry (``qck_knit_faithful``).  Single GPU."""
+    import torch
+    if world_size > 1:
+        raise NotImplementedError("the reference-faithful knit is not sharded")
+    now = perf_counter()
+    tables = virt.simulate_fragments(device, fold=False)
+    run_time = perf_counter() - now
+    logger.info("Knitting...")
+    now = perf_counter()
+    stats = torch.zeros(4, dtype=torch.float64, device=device)
+    values = virt.knit_tables_faithful(tables, accuracy, device, out=out, stats=stats)
+    host_stats = stats.cpu().numpy()
+    total, minimum = float(host_stats[0]), float(host_stats[1])
+    if nearest and host_stats[3] > 0 and minimum < 0.0:
+        stream = torch.cuda.current_stream(device).cuda_stream
+        handle.check(handle.lib.qck_npd(handle.ptr, values.data_ptr(), values.numel(), accuracy, None, None, stream))
+    torch.cuda.synchronize(device)
+    knit_time = perf_counter() - now
+    logger.info(f"Knitted in {knit_time:.2f}s.")
+    _, union = virt.output_masks()
+    return DenseResult(values, union, total, minimum, 0), RunTimeInfo(run_time, knit_time)
 
 
 def run_virtual_circuit(virt: VirtualCircuit, shots: int = 20000) -> tuple[dict[int, float], RunTimeInfo]:

@@ -200,14 +200,16 @@ class VirtualCircuit:
                 acc *= radices[k]
         return strides
 
-    def simulate_fragments(self, device=None, label_range: tuple[int, int] | None = None) -> dict:
+    def simulate_fragments(self, device=None, label_range: tuple[int, int] | None = None,
+                           fold: bool = True) -> dict:
         """All instances of all active fragments -> {fragment: device tensor [L_f, 2^m_f]}.
-        ``label_range`` (global labels) restricts the work to what one rank needs."""
+        ``label_range`` (global labels) restricts the work to what one rank needs.  ``fold=False``
+        keeps the config bits as extra column bits (input of the reference-faithful knit)."""
         device = default_device() if device is None else device
         handle = _lib.get_handle(getattr(device, "index", None) or 0)
         tables = {}
         for frag in self.active_fragments():
-            ex = self.executor(frag, device, True)
+            ex = self.executor(frag, device, fold)
             rng = None
             if label_range is not None and self._vgate_instrs:
                 rng = self.fragment_label_range(frag, *label_range)
@@ -269,6 +271,65 @@ class VirtualCircuit:
             handle.check(handle.lib.qck_stats_dense(handle.ptr, out.data_ptr(), out.numel(), 0.0,
                                                     stats.data_ptr(), stream))
         return out
+
+    def knit_tables_faithful(self, tables: dict, accuracy: float, device=None, out=None, stats=None):
+        """Reference-faithful knit (``ACCURACY = accuracy`` pruning after every operation, reference
+        order) of UNFOLDED fragment tables (``simulate_fragments(fold=False)``), fused per output
+        entry on the device (``qck_knit_faithful``)."""
+        import torch
+        device = default_device() if device is None else device
+        handle = _lib.get_handle(getattr(device, "index", None) or 0)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        masks, union = self.output_masks()
+        frags = list(tables.keys())
+        n_out = bin(union).count("1")
+        K = len(self._vgate_instrs)
+        ptrs = (C.c_void_p * len(frags))(*[tables[f].data_ptr() for f in frags])
+        cm = (C.c_uint64 * len(frags))(*[_compress_mask(masks[f], union) for f in frags])
+        row_strides = (C.c_int64 * len(frags))(*[tables[f].shape[1] for f in frags])
+        gates = (_lib.QckFaithfulGate * max(K, 1))(*[_faithful_gate(vg) for vg in self.vgates])
+        strides = (C.c_int32 * (len(frags) * _lib.MAX_DIGITS))()
+        cfg_bit = (C.c_int32 * (len(frags) * _lib.MAX_DIGITS))(*([-1] * (len(frags) * _lib.MAX_DIGITS)))
+        measures = (C.c_uint8 * (len(frags) * _lib.MAX_DIGITS * _lib.MAX_VARIANTS))()
+        for i, f in enumerate(frags):
+            prog = self.program(f)
+            if tables[f].shape[1] != prog.row_len(False):
+                raise ValueError("knit_tables_faithful needs unfolded tables (simulate_fragments(fold=False))")
+            for k, s_ in enumerate(self._fragment_strides(f)):
+                strides[i * _lib.MAX_DIGITS + k] = s_
+            for d, k in enumerate(prog.vgate_indices):
+                cfg_bit[i * _lib.MAX_DIGITS + k] = d
+            for slot in prog.slots:
+                for v, m in enumerate(slot.meas):
+                    if m:
+                        measures[(i * _lib.MAX_DIGITS + slot.vgate_idx) * _lib.MAX_VARIANTS + v] = 1
+        if out is None:
+            out = torch.empty(1 << n_out, dtype=torch.float64, device=device)
+        handle.check(handle.lib.qck_knit_faithful(handle.ptr, len(frags), ptrs, cm, row_strides, n_out, K, gates,
+                                                  strides, cfg_bit, measures, float(accuracy), out.data_ptr(),
+                                                  stream))
+        if stats is not None:
+            handle.check(handle.lib.qck_stats_dense(handle.ptr, out.data_ptr(), out.numel(), float(accuracy),
+                                                    stats.data_ptr(), stream))
+        return out
+
+
+def _faithful_gate(vg) -> "_lib.QckFaithfulGate":
+    from math import cos, sin
+    from .virtual_gates import RZZ_ACCURACY
+    g = _lib.QckFaithfulGate()
+    g.n_variants = vg.num_instantiations
+    if vg.knit_form == "chain":
+        g.form = 0
+        for i, (a, _b) in enumerate(vg.knit_coefficients()):
+            g.sign[i] = 1.0 if a > 0 else -1.0
+    else:
+        m_theta = -vg.params[0]                     # virtual_gates.py:263
+        c, s_ = cos(m_theta / 2), sin(m_theta / 2)
+        g.form = 1
+        g.degenerate = 1 if abs(c) < RZZ_ACCURACY else 2 if abs(s_) < RZZ_ACCURACY else 0
+        g.cos_half, g.sin_half, g.cos_half_sq, g.sin_half_sq = c, s_, c ** 2, s_ ** 2
+    return g
 
 
 def _compress_mask(mask: int, union: int) -> int:

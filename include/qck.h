@@ -152,6 +152,7 @@ QCK_API int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t
  *           179-194,262-286) in their exact (unpruned) closed form.
  */
 #define QCK_MAX_FRAGMENTS 8
+#define QCK_MAX_VARIANTS 8
 
 /* running statistics of a produced distribution (all doubles, device memory) */
 typedef struct {
@@ -176,12 +177,33 @@ QCK_API int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_tab
  * lf(l) = sum_k l_k * frag_stride[f][k] (0 when gate k does not touch f).
  * coef: HOST array, n_digits rows of QCK_MAX_VARIANTS doubles.
  * frag_stride: HOST array [n_frag][QCK_MAX_DIGITS]. */
-#define QCK_MAX_VARIANTS 8
 QCK_API int qck_knit_contract(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
                       const int64_t* row_strides, int n_out_bits,
                       int n_digits, const int32_t* radix, const double* coef,
                       const int32_t* frag_stride, int64_t l_begin, int64_t l_end,
                       double* d_out, int accumulate, qck_stream stream);
+
+/* Reference-faithful knit: the same result as VirtualCircuit.knit with
+ * QuasiDistr.ACCURACY = accuracy (quasi_distr.py:3,7-10), i.e. |v| <= accuracy is dropped after
+ * from_counts, after every merge fold, every split half and every + / - / scalar * of the per-gate
+ * formulas, evaluated in the reference's order (virtual_circuit.py:59-68,216-228;
+ * virtual_gates.py:105-124,179-194,262-286).  Tables are UNFOLDED fragment tables: row = fragment
+ * label, column = pext(key, mask_f) | (config bits of f's gates, in digit order) << popcount(mask_f).
+ * gates: HOST array; frag_stride / cfg_bit: HOST [n_frag][QCK_MAX_DIGITS]; measures: HOST
+ * [n_frag][QCK_MAX_DIGITS][QCK_MAX_VARIANTS] (does f's instance measure gate k under variant v). */
+typedef struct {
+    int32_t n_variants;
+    int32_t form;         /* 0: 0.5 * signed chain of (r_i0 - r_i1) (move, cz, cx, cy); 1: rzz / cp form */
+    int32_t degenerate;   /* form 1: 0 = six variants, 1 = |cos| < 1e-5 (r * sin^2), 2 = |sin| < 1e-5 */
+    int32_t reserved;
+    double sign[QCK_MAX_VARIANTS];                          /* form 0: +1 / -1 per variant */
+    double cos_half, sin_half, cos_half_sq, sin_half_sq;    /* form 1: of m_theta / 2 */
+} qck_faithful_gate;
+
+QCK_API int qck_knit_faithful(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
+                              const int64_t* row_strides, int n_out_bits, int n_gates,
+                              const qck_faithful_gate* gates, const int32_t* frag_stride, const int32_t* cfg_bit,
+                              const uint8_t* measures, double accuracy, double* d_out, qck_stream stream);
 
 /* ------------------------------------------------------------------ reductions
  * qck_stats_dense: sum / min / nnz of a dense vector (entries |v| <= acc count as absent).

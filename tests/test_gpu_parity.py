@@ -479,3 +479,83 @@ def test_reentrant_from_threads(dev):
     assert len(out) == 4
     for i in range(4):
         assert abs(out[i][0xFFFF] - 1) < TOL_P and all(abs(v) < 1e-15 for k, v in out[i].items() if k != 0xFFFF)
+
+
+# ------------------------------------------------------------------ reference-faithful (pruned) knit, fused
+def _near_threshold(a, b, acc):
+    """Entries may legitimately differ when a value sits within rounding distance of the pruning
+    threshold (the simulators agree to ~1e-16, the threshold is a step function)."""
+    return abs(abs(a) - acc) < 1e-9 or abs(abs(b) - acc) < 1e-9 or abs(a - b) < 1e-10
+
+
+def test_faithful_fused_against_golden_reference(dev):
+    """qck_knit_faithful vs the REFERENCE's own level-by-level knit at ACCURACY = 1e-5 (golden)."""
+    n = 0
+    for case in load_golden("semcheck.json"):
+        if case["acc"] != 1e-5:
+            continue
+        qc, cut = make_semcheck_circuit(case["gate"], case["theta"])
+        virt = vcm.VirtualCircuit(cut)
+        res, _ = runm.run_virtual_circuit_dense(virt, device=dev, nearest=False, accuracy=1e-5)
+        got = res.values.cpu().numpy()
+        want = _dense({int(k): v for k, v in case["knit"]}, case["n_clbits"])
+        assert np.abs(got - want).max() < 1e-12, case["gate"]
+        res2, _ = runm.run_virtual_circuit_dense(virt, device=dev, nearest=True, accuracy=1e-5)
+        want_npd = _dense({int(k): v for k, v in case["npd"]}, case["n_clbits"])
+        assert np.abs(res2.values.cpu().numpy() - want_npd).max() < 1e-12
+        n += 1
+    assert n == 5
+
+
+def _syc8_two_cuts(seed):
+    circ = gen.gen_circ("syc", 8, 5, seed=seed).decompose_two_qubit()
+    cuts = []
+    for a, b in ((5, 6), (1, 2)):
+        cuts += cutting._two_qubit_indices(circ, a, b)
+    return circ, cutting.apply_cuts(circ, cutting.CutSpec(gate_cuts=sorted(cuts)))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_faithful_fused_vs_oracle_and_levelwise(dev, seed):
+    """Mid-size: fused kernel == oracle's sparse reference-order knit == device level-by-level
+    path, all at ACCURACY = 1e-5; and it differs from the exact result (pruning is visible)."""
+    circ, cut = _syc8_two_cuts(seed)
+    virt = vcm.VirtualCircuit(cut)
+    assert len(virt.vgates) == 2
+    fused, _ = runm.run_virtual_circuit_dense(virt, device=dev, nearest=False, accuracy=1e-5)
+    got = fused.values.cpu().numpy()
+    want_d, _ = oracle_knit(cut, 1e-5)
+    want = _dense(want_d, 8)
+    bad = [i for i in range(256) if not _near_threshold(got[i], want[i], 1e-5)]
+    assert not bad, (bad[:5], got[bad[:5]], want[bad[:5]])
+    # device level-by-level path (QuasiDistr ops) on the same exact instance distributions
+    old = qdm.ACCURACY
+    qdm.ACCURACY = 1e-5
+    try:
+        v2 = vcm.VirtualCircuit(cut)
+        v2.set_backend_for_all(_OracleBackend())
+        res, _ = runm.run_virtual_circuit(v2, shots=1)
+    finally:
+        qdm.ACCURACY = old
+    npd_fused, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=True, accuracy=1e-5)
+    lv = _dense(res, 8)
+    fu = npd_fused.values.cpu().numpy()
+    assert all(_near_threshold(fu[i], lv[i], 1e-5) for i in range(256))
+    exact, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=False, accuracy=0.0)
+    assert np.abs(exact.values.cpu().numpy() - sv.dense(sv.exact_distribution(circ), 8)).max() < TOL_P
+
+
+def test_faithful_fused_baseline_configs(dev):
+    """The reference's own pruning at the BASELINE 16-qubit configs: runs at full size; the result
+    stays within the accumulated pruning error of the exact one; bv16's delta survives."""
+    circ, cut = cutting.make_baseline("bv16")
+    res, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, accuracy=1e-5)
+    v = res.values.cpu().numpy()
+    assert abs(v[0xFFFF] - 1.0) < 1e-9 and np.count_nonzero(v) == 1
+    circ, cut = cutting.make_baseline("syc16d5", seed=1)
+    virt = vcm.VirtualCircuit(cut)
+    faithful, _ = runm.run_virtual_circuit_dense(virt, device=dev, nearest=False, accuracy=1e-5)
+    exact, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=False, accuracy=0.0)
+    f, e = faithful.values.cpu().numpy(), exact.values.cpu().numpy()
+    assert np.abs(f - e).max() < 1296 * 1e-5          # at most one dropped term per label
+    assert np.abs(f - e).max() > 0.0                  # and the pruning is really applied
