@@ -394,7 +394,7 @@ def main() -> None:
 
     # ---- e2e: public API, fresh VirtualCircuit per step (host compile + H2D + kernels + D2H)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    e2e_s, h2d = None, 0
+    e2e_s, e2e_warm_s, h2d = None, None, 0
     if not args.profile:
         e2e_virts = [vc.VirtualCircuit(cut) for _ in range(args.steps + 1)]
         runm.run_virtual_circuit_dense(e2e_virts[0], device=device, rank=rank, world_size=world, out=out,
@@ -403,9 +403,23 @@ def main() -> None:
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for v in e2e_virts[1:]:
+            vc.clear_program_cache()            # e2e is the COLD path: every step compiles its programs
             runm.run_virtual_circuit_dense(v, device=device, rank=rank, world_size=world, out=out, nearest=False)
         g1.record()
         barrier()
+        # same call with the process-wide program cache warm (what a second run of the same cut
+        # circuit costs, e.g. the reference's ideal + noisy pair)
+        warm_virts = [vc.VirtualCircuit(cut) for _ in range(args.steps)]
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for v in warm_virts:
+            runm.run_virtual_circuit_dense(v, device=device, rank=rank, world_size=world, out=out, nearest=False)
+        w1.record()
+        barrier()
+        warm_ms = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(warm_ms, op=dist.ReduceOp.MAX)
+        e2e_warm_s = float(warm_ms.item()) / args.steps / 1e3
         for f in e2e_virts[1].active_fragments():
             h2d += e2e_virts[1].executor(f, device, True).h2d_bytes
         e2e_ms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
@@ -472,7 +486,8 @@ def main() -> None:
                           "no flush needed" if 8 * (y1 - y0) > (1 << 28) else
                           "working set fits L2; small config, launch/latency bound")},
         "clocks": clocks,
-        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32},
+        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
+                "program_cache": "cold (cleared every step)", "value_program_cache_warm": e2e_warm_s},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -329,6 +329,8 @@ class QuantumCircuit:
     def sdg(self, q): self._g("sdg", [q])
     def t(self, q): self._g("t", [q])
     def tdg(self, q): self._g("tdg", [q])
+    def sx(self, q): self._g("sx", [q])
+    def id(self, q): self._g("id", [q])
     def rx(self, theta, q): self._g("rx", [q], [theta])
     def ry(self, theta, q): self._g("ry", [q], [theta])
     def rz(self, theta, q): self._g("rz", [q], [theta])

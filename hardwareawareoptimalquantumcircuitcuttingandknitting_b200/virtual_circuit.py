@@ -157,8 +157,21 @@ class VirtualCircuit:
 
     # ------------------------------------------------------------------ device fast path
     def program(self, fragment: Fragment) -> FragmentProgram:
+        """Compiled program of a fragment.  Programs are immutable and depend only on the
+        fragment circuit's structure, so they are shared process-wide through a small LRU cache
+        (the reference runs every cut circuit at least twice, ``Utilities.py:85-86``)."""
         if fragment not in self._programs:
-            self._programs[fragment] = FragmentProgram(self._frag_circs[fragment], fragment, self.num_clbits)
+            circ = self._frag_circs[fragment]
+            key = _structure_key(circ, fragment) if PROGRAM_CACHE_SIZE > 0 else None
+            prog = _program_cache.get(key) if key is not None else None
+            if prog is None:
+                prog = FragmentProgram(circ, fragment, self.num_clbits)
+                if key is not None:
+                    with _program_cache_lock:
+                        _program_cache[key] = prog
+                        while len(_program_cache) > PROGRAM_CACHE_SIZE:
+                            _program_cache.pop(next(iter(_program_cache)))
+            self._programs[fragment] = prog
         return self._programs[fragment]
 
     def executor(self, fragment: Fragment, device, fold: bool = True) -> FragmentExecutor:
@@ -312,6 +325,35 @@ class VirtualCircuit:
             handle.check(handle.lib.qck_stats_dense(handle.ptr, out.data_ptr(), out.numel(), float(accuracy),
                                                     stats.data_ptr(), stream))
         return out
+
+
+PROGRAM_CACHE_SIZE = 64          # set to 0 to disable the process-wide program cache
+_program_cache: dict = {}
+_program_cache_lock = __import__("threading").Lock()
+
+
+def clear_program_cache() -> None:
+    with _program_cache_lock:
+        _program_cache.clear()
+
+
+def _structure_key(circ: QuantumCircuit, fragment: Fragment):
+    """Hashable description of everything FragmentProgram reads from a fragment circuit."""
+    qpos = {q: i for i, q in enumerate(fragment)}
+    cpos = {c: i for i, c in enumerate(circ.clbits)}
+    items = [len(fragment), len(cpos)]
+    for ins in circ.data:
+        op = ins.operation
+        if isinstance(op, VirtualGateEndpoint):
+            vg = op.virtual_gate
+            items.append(("ep", type(vg).__name__, tuple(vg.params), op.vgate_idx, op.qubit_idx, qpos[ins.qubits[0]]))
+        elif isinstance(op, Barrier):
+            continue
+        else:
+            m = getattr(op, "_matrix", None)
+            items.append((op.name, tuple(getattr(op, "params", ())), None if m is None else m.tobytes(),
+                          tuple(qpos[q] for q in ins.qubits), tuple(cpos[c] for c in ins.clbits)))
+    return tuple(items)
 
 
 def _faithful_gate(vg) -> "_lib.QckFaithfulGate":

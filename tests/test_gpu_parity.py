@@ -559,3 +559,26 @@ def test_faithful_fused_baseline_configs(dev):
     f, e = faithful.values.cpu().numpy(), exact.values.cpu().numpy()
     assert np.abs(f - e).max() < 1296 * 1e-5          # at most one dropped term per label
     assert np.abs(f - e).max() > 0.0                  # and the pruning is really applied
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_cut_circuits_on_device(dev, seed):
+    """Randomised cut circuits (every virtual-gate kind, wire cuts, 2-4 fragments) end to end on the
+    GPU against the oracle's instance-by-instance simulation + sparse reference-order knit."""
+    import random
+    import test_random_circuits_cpu as rc
+    rng = random.Random(2000 + seed)
+    n = rng.randint(4, 7)
+    qc = rc.random_circuit(rng, n, rng.randint(12, 30))
+    cut = cutting.apply_cuts(qc, rc.random_cut(rng, qc, max_gate_cuts=2, wire_cut=(seed % 2 == 0)))
+    virt = vcm.VirtualCircuit(cut)
+    res, _ = runm.run_virtual_circuit_dense(virt, device=dev, nearest=False)
+    want_d, _ = oracle_knit(cut, 0.0)
+    want = _dense(want_d, n)
+    assert np.abs(res.values.cpu().numpy() - want).max() < TOL_P, (seed, [len(r) for r in cut.qregs])
+    # and the reference-faithful mode on the same circuit
+    res5, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=False, accuracy=1e-5)
+    want5_d, _ = oracle_knit(cut, 1e-5)
+    want5 = _dense(want5_d, n)
+    got5 = res5.values.cpu().numpy()
+    assert all(_near_threshold(got5[i], want5[i], 1e-5) for i in range(1 << n)), seed
