@@ -81,10 +81,13 @@ class B200Backend:
         return out
 
     def run(self, circuits, shots: int = 1024, **_ignored) -> B200Job:
-        if isinstance(circuits, QuantumCircuit):
+        if isinstance(circuits, QuantumCircuit) or not isinstance(circuits, (list, tuple)):
             circuits = [circuits]
         counts = []
         for circ in circuits:
+            if not isinstance(circ, QuantumCircuit):     # a qiskit circuit (duck typed): convert
+                from .adapters import circuit_from_qiskit
+                circ = circuit_from_qiskit(circ)
             dist = self.exact_distribution(circ)
             counts.append({self._format_key(k, circ.cregs): v * shots for k, v in dist.items()})
         return B200Job(B200Result(counts))

@@ -47,6 +47,9 @@ __all__ = ["VirtualCircuit", "generate_instantiations", "InstanceLabelType", "Fr
 class VirtualCircuit:
     def __init__(self, circuit: QuantumCircuit) -> None:
         from .backend import B200Backend
+        if not isinstance(circuit, QuantumCircuit):      # a qiskit circuit (duck typed): convert
+            from .adapters import circuit_from_qiskit
+            circuit = circuit_from_qiskit(circuit)
         self._vgate_instrs = [
             instr for instr in circuit
             if isinstance(instr.operation, VirtualBinaryGate) or isinstance(instr.operation, VirtualMove)
