@@ -336,6 +336,66 @@ __global__ void __launch_bounds__(256) sim_onchip_kernel(PlanDev plan, int op_be
         row[o] = fold_entry(plan, o, [&](uint64_t idx) { return s[swz((uint32_t)idx)]; });
 }
 
+// Grouped form: one launch covers several programs (measurement patterns) of the same state size.
+// The per-program parts travel in the kernel parameters (CUDA >= 12.1 allows 32 KB of them), the CTA
+// looks up its program from its block index.  Replaces one launch per pattern (64 per step at
+// hwe-16-d5) by one per state size.
+#define QCK_GROUP_MAX 24
+struct PlanVarDev {
+    int op_begin, op_end;
+    int n_out_bits, out_ident;
+    signed char out_pos[QCK_MAX_OUT_BITS];
+    unsigned long long sum_mask, sign_mask;
+    const int32_t* labels;
+    int cta_begin, n_stage_unused;
+};
+struct GroupDev {
+    int n_state, n_vars, n_stage, n_digits;
+    const qck_op* ops;
+    const double* mats;
+    int radix[QCK_MAX_DIGITS];
+    PlanVarDev var[QCK_GROUP_MAX];
+};
+
+__global__ void __launch_bounds__(256) sim_onchip_group_kernel(const __grid_constant__ GroupDev G,
+                                                               double* __restrict__ out, long long row_stride) {
+    double2* s = reinterpret_cast<double2*>(smem_raw);
+    StagedOp* so = reinterpret_cast<StagedOp*>(smem_raw + ((size_t)16 << G.n_state));
+    __shared__ int digits[QCK_MAX_DIGITS];
+    __shared__ PlanDev plan;
+    int v = 0;
+    while (v + 1 < G.n_vars && (int)blockIdx.x >= G.var[v + 1].cta_begin) ++v;  // uniform
+    const PlanVarDev& pv = G.var[v];
+    const int label = __ldg(pv.labels + ((int)blockIdx.x - pv.cta_begin));
+    if (threadIdx.x == 0) {
+        plan.n_state = G.n_state;
+        plan.ops = G.ops;
+        plan.mats = G.mats;
+        plan.n_digits = G.n_digits;
+        for (int k = 0; k < QCK_MAX_DIGITS; ++k) plan.radix[k] = G.radix[k];
+        plan.n_out_bits = pv.n_out_bits;
+        plan.out_ident = pv.out_ident;
+        for (int j = 0; j < QCK_MAX_OUT_BITS; ++j) plan.out_pos[j] = pv.out_pos[j];
+        plan.sum_mask = pv.sum_mask;
+        plan.sign_mask = pv.sign_mask;
+        plan.n_stage = G.n_stage;
+        decode_digits(plan, label, digits);
+    }
+    __syncthreads();
+    {
+        const int n0 = (pv.op_end - pv.op_begin) < G.n_stage ? (pv.op_end - pv.op_begin) : G.n_stage;
+        stage_ops(so, G.ops, pv.op_begin, n0, G.mats, digits);
+    }
+    const uint32_t n_amp = 1u << G.n_state;
+    for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
+    __syncthreads();
+    apply_ops(s, G.n_state, so, G.n_stage, G.ops, pv.op_begin, pv.op_end, G.mats, digits, true);
+    const uint64_t n_out = 1ull << plan.n_out_bits;
+    double* row = out + (long long)label * row_stride;
+    for (uint64_t o = threadIdx.x; o < n_out; o += blockDim.x)
+        row[o] = fold_entry(plan, o, [&](uint64_t idx) { return s[swz((uint32_t)idx)]; });
+}
+
 // ------------------------------------------------------------------ streaming regime
 __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev sw,
                                                         const int32_t* __restrict__ labels, int inst_base,
@@ -678,6 +738,7 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
 // (at handle creation) - setting them per launch races between host threads.
 int qck_sim_init(qck_handle* h) {
     QCK_CUDA(h, qck_allow_max_smem(sim_onchip_kernel, h->max_smem_optin));
+    QCK_CUDA(h, qck_allow_max_smem(sim_onchip_group_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_pipe_kernel, h->max_smem_optin));
     return QCK_OK;
@@ -694,46 +755,112 @@ static int ensure_side_streams(qck_handle* h) {
     return QCK_OK;
 }
 
+static int launch_group(qck_handle* h, const qck_sim_plan* plans, const int* idx, int n, const int32_t* const* d_labels,
+                        const int64_t* n_instances, double* d_out, int64_t out_row_stride, cudaStream_t st) {
+    GroupDev G;
+    memset(&G, 0, sizeof(G));
+    const qck_sim_plan& p0 = plans[idx[0]];
+    G.n_state = p0.n_state_qubits;
+    G.n_vars = n;
+    G.n_digits = p0.n_digits;
+    G.ops = p0.d_ops;
+    G.mats = p0.d_mats;
+    for (int k = 0; k < QCK_MAX_DIGITS; ++k) G.radix[k] = k < p0.n_digits ? p0.radix[k] : 1;
+    long long ctas = 0;
+    int max_ops = 1;
+    for (int i = 0; i < n; ++i) {
+        const qck_sim_plan& p = plans[idx[i]];
+        if (p.d_ops != p0.d_ops || p.d_mats != p0.d_mats || p.n_digits != p0.n_digits)
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "plans of one batch must share the program blob and the label radices");
+        if (out_row_stride < (1ll << p.n_out_bits))
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "out_row_stride smaller than the row (2^%d)", p.n_out_bits);
+        PlanDev pd = to_dev(&p);
+        PlanVarDev& v = G.var[i];
+        v.op_begin = p.sweeps[0].op_begin;
+        v.op_end = p.sweeps[0].op_end;
+        v.n_out_bits = pd.n_out_bits;
+        v.out_ident = pd.out_ident;
+        for (int j = 0; j < QCK_MAX_OUT_BITS; ++j) v.out_pos[j] = (signed char)pd.out_pos[j];
+        v.sum_mask = pd.sum_mask;
+        v.sign_mask = pd.sign_mask;
+        v.labels = d_labels[idx[i]];
+        v.cta_begin = (int)ctas;
+        ctas += n_instances[idx[i]];
+        if (v.op_end - v.op_begin > max_ops) max_ops = v.op_end - v.op_begin;
+    }
+    if (ctas > 0x7fffffffll) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "too many instances in one group");
+    G.n_stage = stage_records(max_ops);
+    const int N = G.n_state;
+    size_t smem = ((size_t)16 << N) + sizeof(StagedOp) * G.n_stage;
+    if ((int)smem + 2048 > h->max_smem_optin)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "on-chip plan with %d qubits does not fit shared memory", N);
+    int threads = 1 << (N > 3 ? N - 3 : 0);
+    if (threads < 32) threads = 32;
+    if (threads > 256) threads = 256;
+    sim_onchip_group_kernel<<<(unsigned)ctas, threads, smem, st>>>(G, d_out, (long long)out_row_stride);
+    QCK_CHECK_LAUNCH(h);
+    return QCK_OK;
+}
+
 extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim_plan* plans,
                                        const int32_t* const* d_labels, const int64_t* n_instances, double* d_out,
                                        int64_t out_row_stride, void* d_work, size_t work_bytes, qck_stream stream) {
     if (!h) return QCK_ERR_INVALID_ARG;
-    if (n_plans < 0 || (n_plans > 0 && (!plans || !d_labels || !n_instances)))
+    if (n_plans < 0 || (n_plans > 0 && (!plans || !d_labels || !n_instances || !d_out)))
         QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad plan list");
-    int n_onchip = 0;
     for (int i = 0; i < n_plans; ++i) {
         int rc = validate_plan(h, &plans[i]);
         if (rc) return rc;
-        if (is_onchip(&plans[i]) && n_instances[i] > 0) ++n_onchip;
+        if (n_instances[i] < 0 || (n_instances[i] > 0 && !d_labels[i])) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad instance list");
     }
     DeviceGuard guard(h->device);
     cudaStream_t main_st = (cudaStream_t)stream;
-    const bool fan = n_onchip >= 2;
-    int used = 0;
+    // on-chip plans grouped by state size -> one launch per group (chunks of QCK_GROUP_MAX)
+    int n_groups = 0;
+    for (int N = 1; N <= QCK_MAX_TILE_QUBITS; ++N) {
+        int cnt = 0;
+        for (int i = 0; i < n_plans; ++i)
+            if (n_instances[i] > 0 && is_onchip(&plans[i]) && plans[i].n_state_qubits == N) ++cnt;
+        n_groups += (cnt + QCK_GROUP_MAX - 1) / QCK_GROUP_MAX;
+    }
+    const bool fan = n_groups >= 2;
+    int used = 0, k = 0;
     if (fan) {
         int rc = ensure_side_streams(h);
         if (rc) return rc;
         QCK_CUDA(h, cudaEventRecord(h->fork, main_st));
     }
-    int k = 0;
-    for (int i = 0; i < n_plans; ++i) {
-        if (n_instances[i] <= 0) continue;
-        cudaStream_t st = main_st;
-        if (fan && is_onchip(&plans[i])) {
-            const int slot = k++ % QCK_SIDE_STREAMS;
-            st = h->side[slot];
-            if (slot >= used) {  // first use of this side stream in this call: order after the fork point
-                QCK_CUDA(h, cudaStreamWaitEvent(st, h->fork, 0));
-                used = slot + 1;
+    for (int N = QCK_MAX_TILE_QUBITS; N >= 1; --N) {  // largest states first: they run longest
+        int idx[QCK_GROUP_MAX], cnt = 0;
+        for (int i = 0; i <= n_plans; ++i) {
+            const bool take = i < n_plans && n_instances[i] > 0 && is_onchip(&plans[i]) && plans[i].n_state_qubits == N;
+            if (take) idx[cnt++] = i;
+            if (cnt == QCK_GROUP_MAX || (i == n_plans && cnt > 0)) {
+                cudaStream_t st = main_st;
+                if (fan) {
+                    const int slot = k++ % QCK_SIDE_STREAMS;
+                    st = h->side[slot];
+                    if (slot >= used) {  // first use in this call: order after the fork point
+                        QCK_CUDA(h, cudaStreamWaitEvent(st, h->fork, 0));
+                        used = slot + 1;
+                    }
+                }
+                int rc = launch_group(h, plans, idx, cnt, d_labels, n_instances, d_out, out_row_stride, st);
+                if (rc) return rc;
+                cnt = 0;
             }
         }
-        int rc = qck_sim_fragments(h, &plans[i], d_labels[i], n_instances[i], d_out, out_row_stride, d_work,
-                                   work_bytes, (qck_stream)st);
-        if (rc) return rc;
     }
     for (int s = 0; s < used; ++s) {  // join
         QCK_CUDA(h, cudaEventRecord(h->side_done[s], h->side[s]));
         QCK_CUDA(h, cudaStreamWaitEvent(main_st, h->side_done[s], 0));
+    }
+    // streaming plans: one after the other on the caller's stream, sharing d_work
+    for (int i = 0; i < n_plans; ++i) {
+        if (n_instances[i] <= 0 || is_onchip(&plans[i])) continue;
+        int rc = qck_sim_fragments(h, &plans[i], d_labels[i], n_instances[i], d_out, out_row_stride, d_work, work_bytes,
+                                   (qck_stream)main_st);
+        if (rc) return rc;
     }
     return QCK_OK;
 }
