@@ -496,6 +496,14 @@ def _cluster_sweeps(ops: np.ndarray, sweeps: list):
                     out.append(r)
                 remaining = rest
                 continue
+            if len(taken) == 1 and seg[taken[0]][0] in (_lib.OP_U2, _lib.OP_CX, _lib.OP_CZ):
+                # a lone two-qubit op: the plain pass (matrix in registers, every thread a few quads)
+                # beats a one-member cluster
+                r = list(seg[taken[0]])
+                r[6] = nl
+                out.append(r)
+                remaining = rest
+                continue
             p = 0
             while bin(cset).count("1") < R:    # pad with the lowest free live positions
                 if not (cset >> p) & 1:

@@ -237,22 +237,19 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
                 s[swz(idx)] = make_double2(-a.x, -a.y);
             }
         } else {  // QCK_OP_U2: generic 4x4, row/col index = bit(q0) + 2 bit(q1)
-            const double2* m = op.m;
+            // the matrix lives in registers for all of this thread's quads: the pass is then 64 FP64
+            // instructions per 4 amplitudes plus 4 LDS + 4 STS - FP64-pipe bound, not issue bound
+            double2 m[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) m[e] = op.m[e];
             for (uint32_t p = tid; p < n; p += nth) {
                 const uint32_t base = insert_zero(insert_zero(p, lo), hi);
-                const double2 a[4] = {s[swz(base)], s[swz(base | b0)], s[swz(base | b1)], s[swz(base | b0 | b1)]};
-                double2 r[4];
-#pragma unroll
-                for (int row = 0; row < 4; ++row) {
-                    double2 acc = cmul(m[row * 4], a[0]);
-#pragma unroll
-                    for (int c = 1; c < 4; ++c) acc = cfma(m[row * 4 + c], a[c], acc);
-                    r[row] = acc;
-                }
-                s[swz(base)] = r[0];
-                s[swz(base | b0)] = r[1];
-                s[swz(base | b1)] = r[2];
-                s[swz(base | b0 | b1)] = r[3];
+                const uint32_t i0 = swz(base), i1 = swz(base | b0), i2 = swz(base | b1), i3 = swz(base | b0 | b1);
+                const double2 a0 = s[i0], a1 = s[i1], a2 = s[i2], a3 = s[i3];
+                s[i0] = cfma(m[3], a3, cfma(m[2], a2, cfma(m[1], a1, cmul(m[0], a0))));
+                s[i1] = cfma(m[7], a3, cfma(m[6], a2, cfma(m[5], a1, cmul(m[4], a0))));
+                s[i2] = cfma(m[11], a3, cfma(m[10], a2, cfma(m[9], a1, cmul(m[8], a0))));
+                s[i3] = cfma(m[15], a3, cfma(m[14], a2, cfma(m[13], a1, cmul(m[12], a0))));
             }
         }
     }
