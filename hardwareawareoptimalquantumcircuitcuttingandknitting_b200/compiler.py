@@ -41,7 +41,9 @@ from .circuit import Barrier, Gate, Measure, QuantumCircuit, QuantumRegister
 from .virtual_gates import VirtualBinaryGate, VirtualGateEndpoint
 
 ONCHIP_MAX_QUBITS = 13      # 2^13 complex128 = 128 KiB of the 227 KiB shared memory
-STREAM_TILE = 12            # 64 KiB tiles -> 3 CTAs per SM overlap load / compute / store
+import os as _os
+
+STREAM_TILE = int(_os.environ.get("QCK_STREAM_TILE", "12"))   # 64 KiB tiles; env override = tuning knob
 LOW_RUN = 5                 # tiles always hold qubits 0..4: 32 amplitudes = 512 contiguous bytes
 
 _I2 = np.eye(2, dtype=np.complex128)

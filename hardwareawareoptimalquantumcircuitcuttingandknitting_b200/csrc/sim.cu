@@ -237,19 +237,38 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
                 s[swz(idx)] = make_double2(-a.x, -a.y);
             }
         } else {  // QCK_OP_U2: generic 4x4, row/col index = bit(q0) + 2 bit(q1)
-            // the matrix lives in registers for all of this thread's quads: the pass is then 64 FP64
-            // instructions per 4 amplitudes plus 4 LDS + 4 STS - FP64-pipe bound, not issue bound
+            // The matrix lives in registers for all of this thread's quads: 64 FP64 instructions per
+            // 4 amplitudes plus 4 LDS + 4 STS.  Index math: insert_zero and swz are bitwise-linear, so
+            // for p = tid + k * nth (nth a power of two) slot(p) = slot(tid) ^ slot(k * nth): the
+            // per-thread part is computed once per op, the per-k part is warp-uniform.
             double2 m[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) m[e] = op.m[e];
-            for (uint32_t p = tid; p < n; p += nth) {
-                const uint32_t base = insert_zero(insert_zero(p, lo), hi);
-                const uint32_t i0 = swz(base), i1 = swz(base | b0), i2 = swz(base | b1), i3 = swz(base | b0 | b1);
-                const double2 a0 = s[i0], a1 = s[i1], a2 = s[i2], a3 = s[i3];
-                s[i0] = cfma(m[3], a3, cfma(m[2], a2, cfma(m[1], a1, cmul(m[0], a0))));
-                s[i1] = cfma(m[7], a3, cfma(m[6], a2, cfma(m[5], a1, cmul(m[4], a0))));
-                s[i2] = cfma(m[11], a3, cfma(m[10], a2, cfma(m[9], a1, cmul(m[8], a0))));
-                s[i3] = cfma(m[15], a3, cfma(m[14], a2, cfma(m[13], a1, cmul(m[12], a0))));
+            const uint32_t x1 = swz(b0), x2 = swz(b1), x3 = x1 ^ x2;
+            if ((nth & (nth - 1)) == 0) {
+                const uint32_t st = swz(insert_zero(insert_zero((uint32_t)tid, lo), hi));
+                if ((uint32_t)tid < n) {
+#pragma unroll 2
+                    for (uint32_t pk = 0; pk < n; pk += nth) {
+                        const uint32_t i0 = st ^ swz(insert_zero(insert_zero(pk, lo), hi));
+                        const uint32_t i1 = i0 ^ x1, i2 = i0 ^ x2, i3 = i0 ^ x3;
+                        const double2 a0 = s[i0], a1 = s[i1], a2 = s[i2], a3 = s[i3];
+                        s[i0] = cfma(m[3], a3, cfma(m[2], a2, cfma(m[1], a1, cmul(m[0], a0))));
+                        s[i1] = cfma(m[7], a3, cfma(m[6], a2, cfma(m[5], a1, cmul(m[4], a0))));
+                        s[i2] = cfma(m[11], a3, cfma(m[10], a2, cfma(m[9], a1, cmul(m[8], a0))));
+                        s[i3] = cfma(m[15], a3, cfma(m[14], a2, cfma(m[13], a1, cmul(m[12], a0))));
+                    }
+                }
+            } else {
+                for (uint32_t p = tid; p < n; p += nth) {
+                    const uint32_t i0 = swz(insert_zero(insert_zero(p, lo), hi));
+                    const uint32_t i1 = i0 ^ x1, i2 = i0 ^ x2, i3 = i0 ^ x3;
+                    const double2 a0 = s[i0], a1 = s[i1], a2 = s[i2], a3 = s[i3];
+                    s[i0] = cfma(m[3], a3, cfma(m[2], a2, cfma(m[1], a1, cmul(m[0], a0))));
+                    s[i1] = cfma(m[7], a3, cfma(m[6], a2, cfma(m[5], a1, cmul(m[4], a0))));
+                    s[i2] = cfma(m[11], a3, cfma(m[10], a2, cfma(m[9], a1, cmul(m[8], a0))));
+                    s[i3] = cfma(m[15], a3, cfma(m[14], a2, cfma(m[13], a1, cmul(m[12], a0))));
+                }
             }
         }
     }
@@ -424,10 +443,13 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
     } else {
         // cp.async (LDGSTS): every thread has all of its 16-byte loads in flight at once, the
         // data goes straight to shared memory (L1 bypassed)
+        // j = tid + k * 256: the low 8 bits (hence the swizzle term and, for c <= 8, the low-run
+        // offset) are per-thread constants; only the hi_off index advances with k
         const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s);
+        const uint32_t xr = (threadIdx.x >> 3) & 7u;
         for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x) {
             const double2* src = st + (base | hi_off[j >> c] | (j & low_mask));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + swz(j) * 16u), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + ((j ^ xr) << 4)), "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -438,8 +460,12 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     apply_ops(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, true);
-    for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
-        __stcs(st + (base | hi_off[j >> c] | (j & low_mask)), s[swz(j)]);
+    {
+        const uint32_t xr = (threadIdx.x >> 3) & 7u;  // blockDim.x == 256: bits 3-5 of j never change
+#pragma unroll 4
+        for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
+            __stcs(st + (base | hi_off[j >> c] | (j & low_mask)), s[j ^ xr]);
+    }
 }
 
 // Pipelined, persistent form of the sweep for states that do not fit L2: one CTA per SM keeps a
@@ -669,7 +695,14 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
             continue;
         }
         dim3 grid((unsigned)tiles, (unsigned)batch);
-        sim_sweep_kernel<<<grid, 256, smem, st>>>(pdl, sd, d_labels, inst_base, work, state_stride);
+        // few tiles (L2-resident states): latency bound, use all 256 threads per tile
+        int sweep_threads = tiles * (unsigned long long)batch >= 4ull * h->sm_count ? 128 : 256;  // 3 CTAs per SM de-phase load / compute / store (256 threads: 2 phase-locked CTAs);
+        //                           QCK_SWEEP_THREADS overrides (tuning knob; multiple of 64)
+        if (const char* env = getenv("QCK_SWEEP_THREADS")) {
+            int v = atoi(env);
+            if (v >= 64 && v <= 256 && v % 64 == 0) sweep_threads = v;
+        }
+        sim_sweep_kernel<<<grid, sweep_threads, smem, st>>>(pdl, sd, d_labels, inst_base, work, state_stride);
         QCK_CHECK_LAUNCH(h);
     }
     return QCK_OK;
