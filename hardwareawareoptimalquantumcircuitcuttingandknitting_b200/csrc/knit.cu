@@ -553,6 +553,76 @@ __global__ void __launch_bounds__(256) contract_gemm_kernel(const __grid_constan
         for (int v = 0; v < 4; ++v) dst[(long long)(i0 + ty * 4 + u) * N + (j0 + tx * 4 + v)] = acc[u][v];
 }
 
+// FP64 tensor-core form of the same tile (sm_100a: mma.sync.aligned.m8n8k4.f64 = DMMA; tcgen05 has
+// no FP64 kind).  64x64 output tile per CTA, 8 warps, each warp owns a 32x16 sub-tile = 4x2 DMMA
+// tiles (16 accumulator registers).  Per k-step of 4 labels a warp issues 8 DMMAs (2048 FMA) against
+// 6 LDS.64 per thread: 0.75 B of shared-memory traffic per FMA instead of 4 B on the FMA-pipe kernel,
+// which was shared-memory bound.  As/Bs rows are padded to 72 doubles so that a fragment load (lanes
+// vary the row by lane>>2 and k by lane&3) needs exactly two 128-byte wavefronts.
+#define GP 72
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) contract_dmma_kernel(const __grid_constant__ ContractParams P, int n_split,
+                                                            double* __restrict__ partial, int M, int N) {
+    __shared__ double As[GK][GP];
+    __shared__ double Bs[GK][GP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wi = (warp >> 2) * 32, wj = (warp & 3) * 16;  // warp sub-tile origin inside the CTA tile
+    const int gid = lane >> 2, tig = lane & 3;
+    const int i0 = blockIdx.x * GT, j0 = blockIdx.y * GT;
+    const long long per = (P.count + n_split - 1) / n_split;
+    const long long lb = per * blockIdx.z, le = (lb + per < P.count) ? lb + per : P.count;
+    const int* rowA = P.rows;
+    const int* rowB = P.rows + P.count;
+    double acc[4][2][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (long long l0 = lb; l0 < le; l0 += GK) {
+#pragma unroll
+        for (int k = 0; k < (GK * GT) / 256; ++k) {
+            const int e = tid + 256 * k, rr = e / GT, cc = e % GT;
+            const long long l = l0 + rr;
+            double a = 0.0, b = 0.0;
+            if (l < le) {
+                a = __ldg(P.w + l) * __ldg(P.table[0] + (long long)__ldg(rowA + l) * P.row_stride[0] + i0 + cc);
+                b = __ldg(P.table[1] + (long long)__ldg(rowB + l) * P.row_stride[1] + j0 + cc);
+            }
+            As[rr][cc] = a;
+            Bs[rr][cc] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k4 = 0; k4 < GK; k4 += 4) {
+            double af[4], bf[2];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = As[k4 + tig][wi + 8 * a + gid];  // A[m = gid][k = tig]
+#pragma unroll
+            for (int b = 0; b < 2; ++b) bf[b] = Bs[k4 + tig][wj + 8 * b + gid];  // B[k = tig][n = gid]
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        __syncthreads();
+    }
+    // C fragment: thread holds C[gid][2 * tig + {0, 1}] of every 8x8 tile
+    double* dst = partial + (long long)blockIdx.z * M * N;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const long long r = i0 + wi + 8 * a + gid, c = j0 + wj + 8 * b + 2 * tig;
+            dst[r * N + c] = acc[a][b][0];
+            dst[r * N + c + 1] = acc[a][b][1];
+        }
+}
+
 __global__ void __launch_bounds__(256) contract_scatter_kernel(const double* __restrict__ partial, int n_split, int M,
                                                                int N, unsigned long long maskA,
                                                                unsigned long long maskB, int n_out_bits,
@@ -658,7 +728,12 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
     if (gemm && (seen == (n_out_bits >= 64 ? ~0ull : (1ull << n_out_bits) - 1ull))) {
         const int M = 1 << mA, N = 1 << mB;
         dim3 grid(M / GT, N / GT, n_split);
-        contract_gemm_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N);
+        // FP64 tensor cores (DMMA) by default; QCK_CONTRACT_FMA=1 selects the FMA-pipe tile kernel
+        const char* fma_env = getenv("QCK_CONTRACT_FMA");
+        if (fma_env && atoi(fma_env) == 1)
+            contract_gemm_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N);
+        else
+            contract_dmma_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N);
         QCK_CHECK_LAUNCH(h);
         contract_scatter_kernel<<<ggrid, 256, 0, st>>>(d_partial, n_split, M, N, masks[0], masks[1], n_out_bits,
                                                         d_out, accumulate);
