@@ -67,6 +67,10 @@ _PROTOTYPES = {
                                           C.c_void_p]),
     "qck_sim_statevector": (C.c_int, [C.c_void_p, C.POINTER(QckSimPlan), C.c_int32, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
+    "qck_debug_tma_describe": (C.c_int, [C.POINTER(QckSimPlan), C.c_int, C.c_uint64, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "qck_knit_outer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int,
                                  C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qck_knit_contract": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),

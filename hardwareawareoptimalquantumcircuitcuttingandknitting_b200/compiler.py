@@ -519,6 +519,7 @@ def _cluster_sweeps(ops: np.ndarray, sweeps: list):
                 r[1] = rank[r[1]]
                 if r[0] != _lib.OP_U1:
                     r[2] = rank[r[2]]
+                r[7] = 1                       # cluster member: qubits are ranks, not tile positions
                 out.append(r)
             remaining = rest
         new_sweeps.append((positions, begin, len(out)))

@@ -14,7 +14,10 @@
 // (-1)^bit weights of the knit rules.
 #include "qck_common.cuh"
 
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
+
+#include <memory>
 
 struct PlanDev {
     int n_state;
@@ -133,16 +136,52 @@ struct StagedOp {
 #define QCK_STAGE_OPS 96
 #define QCK_MAX_CLUSTER_OPS 32
 
+// Which threads cooperate on a tile.  WholeCta: every thread of the block, __syncthreads().
+// ConsumerWarps<N>: threads [32, 32 + N) of a warp-specialised block (warp 0 drives TMA), named
+// barrier 1 - the producer warp never takes part in it.
+struct WholeCta {
+    __device__ static __forceinline__ int tid() { return threadIdx.x; }
+    __device__ static __forceinline__ int nth() { return blockDim.x; }
+    __device__ static __forceinline__ void sync() { __syncthreads(); }
+};
+template <int N>
+struct ConsumerWarps {
+    __device__ static __forceinline__ int tid() { return (int)threadIdx.x - 32; }
+    __device__ static __forceinline__ int nth() { return N; }
+    // small tiles leave lanes of a warp diverged in front of the barrier (fewer groups than lanes): bar.sync
+    // (= barrier.sync.aligned) would be undefined there, so reconverge first and use the unaligned form
+    __device__ static __forceinline__ void sync() {
+        __syncwarp();
+        asm volatile("barrier.sync 1, %0;" ::"n"(N) : "memory");
+    }
+};
+
+// `perm` (may be NULL) renames tile-local qubits: the TMA sweep kernel lays a tile out as
+// [low run | main run | scattered bits], not in ascending state-bit order.  Cluster members
+// address their cluster's qubits by rank (reserved == 1) and are left alone; the header's
+// positions are renamed (they may then be out of order, run_cluster sorts them).
+template <class P>
 __device__ __forceinline__ void stage_ops(StagedOp* so, const qck_op* __restrict__ ops, int c0, int n,
-                                          const double* __restrict__ mats, const int* digits) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                                          const double* __restrict__ mats, const int* digits,
+                                          const int* perm = nullptr) {
+    for (int i = P::tid(); i < n; i += P::nth()) {
         int4 w0 = __ldg(reinterpret_cast<const int4*>(ops + c0 + i));
-        const int4 w1 = __ldg(reinterpret_cast<const int4*>(ops + c0 + i) + 1);
+        int4 w1 = __ldg(reinterpret_cast<const int4*>(ops + c0 + i) + 1);
         if (w0.x == QCK_OP_U1 || w0.x == QCK_OP_U2) {
             if (w1.x >= 0) w0.w += digits[w1.x] * w1.y;
             const double2* m = reinterpret_cast<const double2*>(mats + w0.w);
             const int n_m = w0.x == QCK_OP_U1 ? 4 : 16;
             for (int e = 0; e < n_m; ++e) so[i].m[e] = __ldg(m + e);
+        }
+        if (perm) {
+            if (w0.x == QCK_OP_CLUSTER) {
+                w0.w = perm[w0.w];
+                w1.x = perm[w1.x];
+                w1.y = perm[w1.y];
+            } else if (w1.w == 0) {
+                w0.y = perm[w0.y];
+                if (w0.x != QCK_OP_U1) w0.z = perm[w0.z];
+            }
         }
         so[i].w0 = w0;
         so[i].w1 = w1;
@@ -151,6 +190,7 @@ __device__ __forceinline__ void stage_ops(StagedOp* so, const qck_op* __restrict
 
 // One cluster: header so[h], members so[h+1 .. h+n].  Every thread owns groups of 8 amplitudes
 // (the 3 cluster bits enumerated) and applies all member ops in registers.
+template <class P>
 __device__ void run_cluster(double2* s, int T, const StagedOp* so, int h, const double* __restrict__ mats) {
     const int4 h0 = so[h].w0, h1 = so[h].w1;
     const int n_ops = h0.y, p0 = h0.w, p1 = h1.x, p2 = h1.y;
@@ -158,8 +198,10 @@ __device__ void run_cluster(double2* s, int T, const StagedOp* so, int h, const 
     if (nl <= 0 || nl > T) nl = T;
     const uint32_t n_groups = 1u << (nl - 3);
     const uint32_t b0 = 1u << p0, b1 = 1u << p1, b2 = 1u << p2;
-    for (uint32_t g = threadIdx.x; g < n_groups; g += blockDim.x) {
-        const uint32_t base = insert_zero(insert_zero(insert_zero(g, p0), p1), p2);
+    // ascending order for the zero insertion (renamed positions may be out of order)
+    const int s0 = min(p0, min(p1, p2)), s2 = max(p0, max(p1, p2)), s1 = p0 + p1 + p2 - s0 - s2;
+    for (uint32_t g = P::tid(); g < n_groups; g += P::nth()) {
+        const uint32_t base = insert_zero(insert_zero(insert_zero(g, s0), s1), s2);
         double2 a[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -192,12 +234,13 @@ __device__ void run_cluster(double2* s, int T, const StagedOp* so, int h, const 
         for (int k = 0; k < 8; ++k)
             s[swz(base | ((k & 1) ? b0 : 0u) | ((k & 2) ? b1 : 0u) | ((k & 4) ? b2 : 0u))] = a[k];
     }
-    __syncthreads();
+    P::sync();
 }
 
 // One un-clustered op (states with fewer than 3 live bits, or clustering disabled).
+template <class P>
 __device__ void run_single(double2* s, int T, const StagedOp& op, const double* __restrict__ mats) {
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int tid = P::tid(), nth = P::nth();
     const int kind = op.w0.x, q0 = op.w0.y, q1 = op.w0.z;
     int nl = op.w1.z;
     if (nl <= 0 || nl > T) nl = T;
@@ -272,34 +315,35 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
             }
         }
     }
-    __syncthreads();
+    P::sync();
 }
 
 // Apply ops[begin, end) to the tile `s` (2^T amplitudes in shared memory).  All threads of the
 // CTA call this with identical arguments; the state is synchronised on return.
+template <class P>
 __device__ void apply_ops(double2* s, int T, StagedOp* so, int n_stage, const qck_op* __restrict__ ops, int begin,
                           int end, const double* __restrict__ mats, const int* digits, bool prestaged) {
     int c0 = begin;
     while (c0 < end) {
         const int n = (end - c0) < n_stage ? (end - c0) : n_stage;
         if (!(prestaged && c0 == begin)) {  // the caller may have staged the first chunk already
-            stage_ops(so, ops, c0, n, mats, digits);
-            __syncthreads();
+            stage_ops<P>(so, ops, c0, n, mats, digits);
+            P::sync();
         }
         int i = 0;
         while (i < n) {
             if (so[i].w0.x == QCK_OP_CLUSTER) {
                 const int members = so[i].w0.y;
                 if (i + members >= n && c0 + n < end) break;  // cluster continues past the staged chunk
-                run_cluster(s, T, so, i, mats);
+                run_cluster<P>(s, T, so, i, mats);
                 i += 1 + members;
             } else {
-                run_single(s, T, so[i], mats);
+                run_single<P>(s, T, so[i], mats);
                 ++i;
             }
         }
         c0 += i;
-        __syncthreads();  // everyone is done with so[] before it is restaged
+        P::sync();  // everyone is done with so[] before it is restaged
     }
 }
 
@@ -341,11 +385,11 @@ __global__ void __launch_bounds__(256) sim_onchip_kernel(PlanDev plan, int op_be
     __syncthreads();  // digits visible
     {
         const int n0 = (op_end - op_begin) < plan.n_stage ? (op_end - op_begin) : plan.n_stage;
-        stage_ops(so, plan.ops, op_begin, n0, plan.mats, digits);  // global loads overlap the state init
+        stage_ops<WholeCta>(so, plan.ops, op_begin, n0, plan.mats, digits);  // global loads overlap the state init
     }
     for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
     __syncthreads();
-    apply_ops(s, plan.n_state, so, plan.n_stage, plan.ops, op_begin, op_end, plan.mats, digits, true);
+    apply_ops<WholeCta>(s, plan.n_state, so, plan.n_stage, plan.ops, op_begin, op_end, plan.mats, digits, true);
     const uint64_t n_out = 1ull << plan.n_out_bits;
     double* row = out + (long long)label * row_stride;
     for (uint64_t o = threadIdx.x; o < n_out; o += blockDim.x)
@@ -400,12 +444,12 @@ __global__ void __launch_bounds__(256) sim_onchip_group_kernel(const __grid_cons
     __syncthreads();
     {
         const int n0 = (pv.op_end - pv.op_begin) < G.n_stage ? (pv.op_end - pv.op_begin) : G.n_stage;
-        stage_ops(so, G.ops, pv.op_begin, n0, G.mats, digits);
+        stage_ops<WholeCta>(so, G.ops, pv.op_begin, n0, G.mats, digits);
     }
     const uint32_t n_amp = 1u << G.n_state;
     for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
     __syncthreads();
-    apply_ops(s, G.n_state, so, G.n_stage, G.ops, pv.op_begin, pv.op_end, G.mats, digits, true);
+    apply_ops<WholeCta>(s, G.n_state, so, G.n_stage, G.ops, pv.op_begin, pv.op_end, G.mats, digits, true);
     const uint64_t n_out = 1ull << plan.n_out_bits;
     double* row = out + (long long)label * row_stride;
     for (uint64_t o = threadIdx.x; o < n_out; o += blockDim.x)
@@ -455,11 +499,11 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
     }
     {   // stage the program while the tile is in flight
         const int n0 = (sw.op_end - sw.op_begin) < plan.n_stage ? (sw.op_end - sw.op_begin) : plan.n_stage;
-        stage_ops(so, plan.ops, sw.op_begin, n0, plan.mats, digits);
+        stage_ops<WholeCta>(so, plan.ops, sw.op_begin, n0, plan.mats, digits);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    apply_ops(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, true);
+    apply_ops<WholeCta>(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, true);
     {
         const uint32_t xr = (threadIdx.x >> 3) & 7u;  // blockDim.x == 256: bits 3-5 of j never change
 #pragma unroll 4
@@ -468,109 +512,240 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
     }
 }
 
-// Pipelined, persistent form of the sweep for states that do not fit L2: one CTA per SM keeps a
-// ring of PIPE_STAGES tiles in shared memory.  While tile i is transformed in place, the loads of
-// tiles i+1 .. i+PIPE_STAGES-1 are in flight (cp.async groups) and the stores of tile i-1 drain,
-// so HBM stays busy during the gate passes.  Tiles are claimed from an atomic counter (a static
-// split of a streaming kernel leaves ~15 % on the table on B200, see knit.cu).
-#define PIPE_STAGES 3
-#define PIPE_THREADS 512
-__global__ void __launch_bounds__(PIPE_THREADS, 1) sim_sweep_pipe_kernel(PlanDev plan, SweepDev sw,
-                                                                const int32_t* __restrict__ labels,
-                                                                int inst_base, double2* __restrict__ work,
-                                                                unsigned long long state_stride,
-                                                                unsigned long long tiles_per_inst,
-                                                                unsigned long long n_work,
-                                                                unsigned long long* __restrict__ counter) {
-    const int T = sw.n_tile, c = sw.n_low, n_hi = T - c;
-    const size_t stage_bytes = (size_t)16 << T;
-    unsigned long long* hi_off = reinterpret_cast<unsigned long long*>(smem_raw + PIPE_STAGES * stage_bytes);
-    StagedOp* so =
-        reinterpret_cast<StagedOp*>(smem_raw + PIPE_STAGES * stage_bytes + ((((size_t)8 << n_hi) + 15) & ~(size_t)15));
-    __shared__ int digits[QCK_MAX_DIGITS];
-    __shared__ unsigned long long claimed[PIPE_STAGES];
-    const uint32_t n_amp = 1u << T, low_mask = (1u << c) - 1u;
-    const unsigned long long NONE = ~0ull;
+// ------------------------------------------------------------------ streaming regime, TMA pipeline
+// Persistent, warp-specialised form of the sweep (one CTA per SM):
+//   warp 0 (one elected lane)  TMA producer: cp.async.bulk.tensor loads of the next tiles into a ring of
+//                              TMA_STAGES shared-memory stages (mbarrier complete_tx), and the bulk-tensor
+//                              STORES of finished tiles (bulk groups); a stage is reloaded once the store
+//                              that read it has drained (cp.async.bulk.wait_group.read);
+//   warps 1..                  apply the sweep's gates to the resident tile in place.
+// HBM therefore stays busy in both directions while the FP64 pipe works.  The state is described to the
+// TMA unit as a 5-d tensor of doubles [16 | low run | gap | main run | rest]; SWIZZLE_128B yields exactly
+// the swz() shared-memory layout the gate passes expect.  Tile bits outside the low and main run
+// ("scattered") are enumerated as separate boxes.
+//
+// Live-qubit tracking: a qubit no earlier sweep has had in its tile is still |0>, so amplitudes with such
+// a bit set are known zeros.  Sweeps visit only tiles whose fixed bits are live, load only the live part
+// of a tile (the rest is zero-filled in shared memory) and store the whole tile; memory outside the live
+// region is never read before it is written.  The last sweep of a plan also writes the dead tiles (zeros)
+// so that the buffer is complete for the epilogue.  A depth-1 circuit thereby costs about one write of
+// the state instead of a read and a write per sweep.
+#define TMA_STAGES 3
+#define TMA_CONSUMERS 256
+#define TMA_MAX_BOXES 128
+#define TMA_TILE_DONE 0
+#define TMA_TILE_LIVE 1
+#define TMA_TILE_DEAD 2
 
-    for (uint32_t j = threadIdx.x; j < (1u << n_hi); j += blockDim.x) {
-        unsigned long long off = 0;
-        for (int b = 0; b < n_hi; ++b)
-            if ((j >> b) & 1u) off |= 1ull << sw.pos[c + b];
-        hi_off[j] = off;
-    }
-    auto tile_base = [&](unsigned long long w, double2*& st) {
-        const unsigned long long inst = w / tiles_per_inst;
-        unsigned long long base = w - inst * tiles_per_inst;
-        for (int j = 0; j < T; ++j) base = insert_zero64(base, sw.pos[j]);
-        st = work + inst * state_stride;
-        return base;
-    };
-    auto issue_load = [&](int stage) {  // all threads; claimed[stage] already visible
-        const unsigned long long w = claimed[stage];
-        if (w != NONE && !sw.init) {
-            double2* st;
-            const unsigned long long base = tile_base(w, st);
-            const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw + stage * stage_bytes);
-            for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x) {
-                const double2* src = st + (base | hi_off[j >> c] | (j & low_mask));
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + swz(j) * 16u), "l"(src)
-                             : "memory");
-            }
+struct TmaSweepDev {
+    int n_tile, op_begin, op_end, n_state;
+    int init;                 // nothing is live yet: no loads, tile 0 starts as |0..0>
+    int lowc, h, k;           // low run [0, lowc), main run [h, h + k) (state bit positions)
+    int n_load, n_store;      // boxes per tile
+    unsigned load_bytes;      // bytes per load box
+    int zf_shift;             // log2(amplitudes per load box)
+    unsigned zf_mask;         // load-box index bits that belong to non-live tile bits: those boxes are zero-filled
+    int n_enum_bits;          // work index = (instance << n_enum_bits) | tile number
+    unsigned long long enum_mask;    // state-bit positions the tile number is spread over
+    unsigned long long live_before;  // state bits that are live when this sweep starts
+    int perm[16];             // ascending tile-local bit -> position in the shared-memory layout
+    unsigned long long ld_off[TMA_MAX_BOXES], st_off[TMA_MAX_BOXES];  // amplitude offset of each box in the state
+    unsigned ld_slot[TMA_MAX_BOXES], st_slot[TMA_MAX_BOXES];          // first amplitude slot of each box in the stage
+};
+
+struct TmaTileDesc {
+    unsigned long long base;
+    int inst, flags;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// A wait that cannot be satisfied (a faulted TMA operation never completes its transaction bytes) must
+// not hang the GPU: after ~2 s the kernel reports which barrier it was and traps.
+__device__ __noinline__ void mbar_timeout(int who, unsigned long long tile, int stage, int step) {
+    printf("qck: sim_sweep_tma_kernel: %s stuck on tile %llu (stage %d, block %d, consumer step %d)\n",
+           who ? "consumer" : "producer", tile, stage, (int)blockIdx.x, step);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int who, unsigned long long tile, int stage,
+                                          const volatile int* step) {
+    uint32_t ok;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(smem_u32(b)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((spins & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > (who ? 4000000000ll : 6000000000ll) && (threadIdx.x & 31) == 0) mbar_timeout(who, tile, stage, *step);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");  // always: keeps the group count uniform
-    };
-    // prologue: claim and start loading the first PIPE_STAGES - 1 tiles
-    if (threadIdx.x == 0) {  // one thread: claims must be ordered (NONE only ever follows valid tiles)
-        for (int st = 0; st < PIPE_STAGES - 1; ++st) {
-            const unsigned long long w = atomicAdd(counter, 1ull);
-            claimed[st] = w < n_work ? w : NONE;
-        }
     }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(0), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(0), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
+    sim_sweep_tma_kernel(const __grid_constant__ CUtensorMap map_st, const __grid_constant__ CUtensorMap map_ld,
+                         const __grid_constant__ TmaSweepDev sw, PlanDev plan, const int32_t* __restrict__ labels,
+                         int inst_base, unsigned long long n_work) {
+    typedef ConsumerWarps<TMA_CONSUMERS> P;
+    const int T = sw.n_tile;
+    const uint32_t stage_bytes = 16u << T;
+    // SWIZZLE_128B repeats every 1024 bytes: the stages must be 1024-byte aligned
+    unsigned char* stage0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    StagedOp* so = reinterpret_cast<StagedOp*>(stage0 + TMA_STAGES * stage_bytes);
+    __shared__ __align__(8) uint64_t full_bar[TMA_STAGES], done_bar[TMA_STAGES];
+    __shared__ TmaTileDesc desc[TMA_STAGES];
+    __shared__ int digits[QCK_MAX_DIGITS];
+    __shared__ int perm_s[16];
+    __shared__ volatile int dbg_step;  // progress of the consumers, reported by the wait watchdog
+
+    if (threadIdx.x == 0) {
+        dbg_step = 0;
+        for (int i = 0; i < TMA_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&done_bar[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x < 16) perm_s[threadIdx.x] = sw.perm[threadIdx.x];
     __syncthreads();
-#pragma unroll
-    for (int st = 0; st < PIPE_STAGES - 1; ++st) issue_load(st);
-    long long staged_inst = -1;
-    for (int k = 0;; ++k) {
-        const int cur = k % PIPE_STAGES, nxt = (k + PIPE_STAGES - 1) % PIPE_STAGES;
-        if (threadIdx.x == 0) {
-            const unsigned long long w = atomicAdd(counter, 1ull);
-            claimed[nxt] = w < n_work ? w : NONE;
-        }
-        __syncthreads();  // claimed[nxt] visible; everyone finished storing the tile that lived in nxt
-        issue_load(nxt);
-        asm volatile("cp.async.wait_group %0;" ::"n"(PIPE_STAGES - 1) : "memory");
-        __syncthreads();  // tile `cur` resident for all threads
-        const unsigned long long w = claimed[cur];
-        if (w == NONE) break;  // tiles are claimed in order: nothing later is pending either
-        double2* s = reinterpret_cast<double2*>(smem_raw + cur * stage_bytes);
-        double2* st;
-        const unsigned long long base = tile_base(w, st);
-        const long long inst = (long long)(w / tiles_per_inst);
-        if (sw.init) {
-            for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
-                s[j] = make_double2((j == 0 && base == 0) ? 1.0 : 0.0, 0.0);  // swz(0) == 0
-            __syncthreads();
-        }
-        if (inst != staged_inst) {  // uniform; the matrices depend on the instance's label digits
-            if (threadIdx.x == 0) decode_digits(plan, labels[inst_base + inst], digits);
-            __syncthreads();
-            stage_ops(so, plan.ops, sw.op_begin, sw.op_end - sw.op_begin, plan.mats, digits);
-            __syncthreads();
-            staged_inst = inst;
-        }
-        for (int i = 0; i < sw.op_end - sw.op_begin;) {
-            if (so[i].w0.x == QCK_OP_CLUSTER) {
-                run_cluster(s, T, so, i, plan.mats);
-                i += 1 + so[i].w0.y;
+
+    if (threadIdx.x < 32) {
+        if (threadIdx.x != 0) return;
+        // ===== producer: TMA loads, TMA stores, stage recycling =====
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_st)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ld)) : "memory");
+        const int sh2 = sw.lowc, sh3 = sw.h, sh4 = sw.h + sw.k;
+        const unsigned long long m2 = (1ull << (sw.h - sw.lowc)) - 1ull, m3 = (1ull << sw.k) - 1ull;
+        const int inst_shift = sw.n_state - sh4;
+        const unsigned long long tile_mask = (1ull << sw.n_enum_bits) - 1ull;
+        auto issue_load = [&](unsigned long long kk) {
+            const int stg = (int)(kk % TMA_STAGES);
+            const unsigned long long w = blockIdx.x + kk * gridDim.x;
+            TmaTileDesc& d = desc[stg];
+            if (w >= n_work) {
+                d.flags = TMA_TILE_DONE;
+                mbar_arrive(&full_bar[stg]);
+                return;
+            }
+            const int inst = (int)(w >> sw.n_enum_bits);
+            const unsigned long long base = soft_pdep(w & tile_mask, sw.enum_mask);
+            const bool live = (base & ~sw.live_before) == 0ull;
+            d.base = base;
+            d.inst = inst;
+            d.flags = live ? TMA_TILE_LIVE : TMA_TILE_DEAD;
+            if (live && sw.n_load > 0) {
+                mbar_arrive_expect_tx(&full_bar[stg], (uint32_t)sw.n_load * sw.load_bytes);
+                const uint32_t dst0 = smem_u32(stage0 + (size_t)stg * stage_bytes);
+                for (int i = 0; i < sw.n_load; ++i) {
+                    const unsigned long long idx = base | sw.ld_off[i];
+                    tma_load_5d(dst0 + sw.ld_slot[i] * 16u, &map_ld, &full_bar[stg], (int)((idx >> sh2) & m2),
+                                (int)((idx >> sh3) & m3), (int)(idx >> sh4) + (inst << inst_shift));
+                }
             } else {
-                run_single(s, T, so[i], plan.mats);
-                ++i;
+                mbar_arrive(&full_bar[stg]);
+            }
+        };
+        for (int kk = 0; kk < TMA_STAGES; ++kk) issue_load(kk);
+        for (unsigned long long kk = 0;; ++kk) {
+            const unsigned long long w = blockIdx.x + kk * gridDim.x;
+            if (w >= n_work) break;
+            if (kk >= 1) {  // the store of tile kk-1 has finished reading its stage: reload it
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                issue_load(kk - 1 + TMA_STAGES);
+            }
+            const int stg = (int)(kk % TMA_STAGES);
+            mbar_wait(&done_bar[stg], (uint32_t)((kk / TMA_STAGES) & 1ull), 0, kk, stg, &dbg_step);
+            const TmaTileDesc d = desc[stg];
+            const uint32_t src0 = smem_u32(stage0 + (size_t)stg * stage_bytes);
+            for (int i = 0; i < sw.n_store; ++i) {
+                const unsigned long long idx = d.base | sw.st_off[i];
+                tma_store_5d(&map_st, src0 + sw.st_slot[i] * 16u, (int)((idx >> sh2) & m2), (int)((idx >> sh3) & m3),
+                             (int)(idx >> sh4) + (d.inst << inst_shift));
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        return;
+    }
+
+    // ===== consumers: gates on the resident tile =====
+    const int ctid = P::tid();
+    const uint32_t n_amp = 1u << T;
+    const int n_ops = sw.op_end - sw.op_begin;
+    int staged_inst = -1;
+    for (unsigned long long kk = 0;; ++kk) {
+        const int stg = (int)(kk % TMA_STAGES);
+        mbar_wait(&full_bar[stg], (uint32_t)((kk / TMA_STAGES) & 1ull), 1, kk, stg, &dbg_step);
+        if (ctid == 0) dbg_step = 1;
+        const TmaTileDesc d = desc[stg];
+        if (d.flags == TMA_TILE_DONE) {
+            if (ctid == 0) dbg_step = 9;
+            break;
+        }
+        double2* s = reinterpret_cast<double2*>(stage0 + (size_t)stg * stage_bytes);
+        if (d.flags == TMA_TILE_DEAD) {
+            for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS) s[j] = make_double2(0.0, 0.0);
+        } else {
+            if (d.inst != staged_inst) {  // uniform; the matrices depend on the instance's label digits
+                if (ctid == 0) decode_digits(plan, labels[inst_base + d.inst], digits);
+                P::sync();
+                stage_ops<P>(so, plan.ops, sw.op_begin, n_ops, plan.mats, digits, perm_s);
+                staged_inst = d.inst;
+            }
+            if (ctid == 0) dbg_step = 2;
+            if (sw.init) {
+                for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS) s[j] = make_double2(j == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
+            } else if (sw.zf_mask) {  // boxes of non-live tile bits were not loaded: they are zeros
+                const uint32_t box_amps = 1u << sw.zf_shift;
+                for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS)
+                    if ((j >> sw.zf_shift) & sw.zf_mask) s[j] = make_double2(0.0, 0.0);
+                (void)box_amps;
+            }
+            P::sync();
+            if (ctid == 0) dbg_step = 3;
+            for (int i = 0; i < n_ops;) {
+                if (so[i].w0.x == QCK_OP_CLUSTER) {
+                    run_cluster<P>(s, T, so, i, plan.mats);
+                    i += 1 + so[i].w0.y;
+                } else {
+                    run_single<P>(s, T, so[i], plan.mats);
+                    ++i;
+                }
             }
         }
-        for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
-            __stcs(st + (base | hi_off[j >> c] | (j & low_mask)), s[swz(j)]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
+        if (ctid == 0) dbg_step = 4;
+        P::sync();
+        if (ctid == 0) {
+            mbar_arrive(&done_bar[stg]);
+            dbg_step = 5;
+        }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256) fold_probs_kernel(PlanDev plan, const int32_t* __restrict__ labels,
@@ -659,11 +834,232 @@ static bool is_onchip(const qck_sim_plan* plan) {
     return plan->n_sweeps == 1 && plan->sweeps[0].n_tile == plan->n_state_qubits;
 }
 
-int qck_ensure_partials(qck_handle* h, size_t count);  // api.cu
+// ---- TMA sweep: host-side description of one sweep ------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+struct TmaLaunch {
+    TmaSweepDev sd;
+    CUtensorMap map_st, map_ld;
+    unsigned long long n_work;
+    size_t smem;
+    int n_stage;
+};
+
+static size_t tma_smem_bytes(int n_tile, int n_ops) {
+    return 1024 + (size_t)TMA_STAGES * ((size_t)16 << n_tile) + sizeof(StagedOp) * (size_t)(n_ops < 1 ? 1 : n_ops);
+}
+
+// Can this sweep run on the TMA kernel?  (pure host logic, no CUDA calls: unit-testable)
+// Fills everything but the tensor maps.  live_before: state bits some earlier sweep had in its tile.
+static bool tma_describe(const qck_sim_plan* plan, int i, unsigned long long live_before, bool last, int batch,
+                         int max_smem_optin, TmaLaunch& L) {
+    const qck_sweep& sw = plan->sweeps[i];
+    const int T = sw.n_tile, N = plan->n_state_qubits;
+    const int n_ops = sw.op_end - sw.op_begin;
+    if (T < 3 || T > 13 || N > 35) return false;
+    if ((int)tma_smem_bytes(T, n_ops) + 512 > max_smem_optin) return false;
+    int c = 0;
+    while (c < T && sw.pos[c] == c) ++c;
+    int lowc = c < 11 ? c : 11;
+    if (live_before) {  // the low run is loaded as one box: all of it must be live
+        int lp = 0;
+        while (lp < lowc && ((live_before >> lp) & 1ull)) ++lp;
+        lowc = lp;
+    }
+    if (lowc < 3) return false;
+    TmaSweepDev& d = L.sd;
+    memset(&d, 0, sizeof(d));
+    d.n_tile = T;
+    d.op_begin = sw.op_begin;
+    d.op_end = sw.op_end;
+    d.n_state = N;
+    d.init = live_before == 0ull;
+    d.lowc = lowc;
+    d.live_before = live_before;
+    // main run: the longest run of consecutive positions among the remaining tile bits (<= 8 bits: box
+    // extents are capped at 256), preferring a live one on ties
+    int best_b = -1, best_len = 0;
+    bool best_live = false;
+    for (int j = lowc; j < T;) {
+        int e = j;
+        while (e + 1 < T && sw.pos[e + 1] == sw.pos[e] + 1 && e + 1 - j < 8) ++e;
+        bool live = true;
+        for (int q = j; q <= e; ++q) live = live && ((live_before >> sw.pos[q]) & 1ull);
+        const int len = e - j + 1;
+        if (len > best_len || (len == best_len && live && !best_live)) {
+            best_b = j;
+            best_len = len;
+            best_live = live;
+        }
+        j = e + 1;
+    }
+    d.k = best_len;
+    d.h = best_len ? sw.pos[best_b] : lowc;
+    // shared-memory bit order: low run, main run, scattered bits (ascending)
+    int local_pos[16];  // state position of each layout bit
+    int n_local = 0;
+    for (int j = 0; j < lowc; ++j) {
+        d.perm[j] = n_local;
+        local_pos[n_local++] = sw.pos[j];
+    }
+    for (int j = best_b; j >= 0 && j < best_b + best_len; ++j) {
+        d.perm[j] = n_local;
+        local_pos[n_local++] = sw.pos[j];
+    }
+    for (int j = lowc; j < T; ++j) {
+        if (best_len && j >= best_b && j < best_b + best_len) continue;
+        d.perm[j] = n_local;
+        local_pos[n_local++] = sw.pos[j];
+    }
+    const int n_scat = T - lowc - best_len;
+    // stores: one box [low | main] per combination of the scattered bits
+    if (n_scat > 7) return false;
+    d.n_store = 1 << n_scat;
+    for (int i2 = 0; i2 < d.n_store; ++i2) {
+        unsigned long long off = 0;
+        for (int b2 = 0; b2 < n_scat; ++b2)
+            if ((i2 >> b2) & 1) off |= 1ull << local_pos[lowc + best_len + b2];
+        d.st_off[i2] = off;
+        d.st_slot[i2] = (unsigned)i2 << (lowc + best_len);
+    }
+    // loads: the box covers [low | main] when the whole main run is live, else the low run only; one
+    // box per combination of the LIVE layout bits above the box, the others stay zero
+    const bool box_main = best_live || best_len == 0;
+    const int box_bits = box_main ? lowc + best_len : lowc;
+    d.zf_shift = box_bits;
+    d.load_bytes = 16u << box_bits;
+    unsigned live_hi = 0, dead_hi = 0;  // over layout bits >= box_bits, shifted down
+    for (int b2 = box_bits; b2 < T; ++b2) {
+        if ((live_before >> local_pos[b2]) & 1ull) live_hi |= 1u << (b2 - box_bits);
+        else dead_hi |= 1u << (b2 - box_bits);
+    }
+    d.zf_mask = dead_hi;
+    if (d.init) {
+        d.n_load = 0;
+    } else {
+        const int n_live_hi = __builtin_popcount(live_hi);
+        if (n_live_hi > 7) return false;
+        d.n_load = 1 << n_live_hi;
+        for (int i2 = 0; i2 < d.n_load; ++i2) {
+            const unsigned hi = (unsigned)soft_pdep((uint64_t)i2, (uint64_t)live_hi);
+            unsigned long long off = 0;
+            for (int b2 = box_bits; b2 < T; ++b2)
+                if ((hi >> (b2 - box_bits)) & 1u) off |= 1ull << local_pos[b2];
+            d.ld_off[i2] = off;
+            d.ld_slot[i2] = hi << box_bits;
+        }
+    }
+    // work list: tiles whose fixed bits are live (the last sweep also visits - and zero-fills - the others)
+    unsigned long long tile_mask = 0;
+    for (int j = 0; j < T; ++j) tile_mask |= 1ull << sw.pos[j];
+    const unsigned long long all = N >= 64 ? ~0ull : ((1ull << N) - 1ull);
+    d.enum_mask = (last ? all : live_before) & ~tile_mask;
+    d.n_enum_bits = __builtin_popcountll(d.enum_mask);
+    L.n_work = (unsigned long long)batch << d.n_enum_bits;
+    L.smem = tma_smem_bytes(T, n_ops);
+    L.n_stage = n_ops < 1 ? 1 : n_ops;
+    // extents the tensor map can describe
+    if (((unsigned long long)batch << (N - d.h - d.k)) > 0xffffffffull) return false;
+    return true;
+}
+
+static int tma_encode(qck_handle* h, const TmaSweepDev& d, int batch, double2* work, bool box_main, CUtensorMap* out) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) QCK_FAIL(h, QCK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const int N = d.n_state, top = d.h + d.k;
+    cuuint64_t dims[5] = {16ull, 1ull << (d.lowc - 3), 1ull << (d.h - d.lowc), 1ull << d.k,
+                          (cuuint64_t)batch << (N - top)};
+    cuuint64_t strides[4] = {128ull, 16ull << d.lowc, 16ull << d.h, 16ull << top};
+    cuuint32_t box[5] = {16u, 1u << (d.lowc - 3), 1u, box_main ? (1u << d.k) : 1u, 1u};
+    cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)work, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        QCK_FAIL(h, QCK_ERR_CUDA,
+                 "cuTensorMapEncodeTiled failed (%d): dims {16,%llu,%llu,%llu,%llu} box {16,%u,1,%u,1} lowc=%d h=%d k=%d", (int)r,
+                 (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3],
+                 (unsigned long long)dims[4], box[1], box[3], d.lowc, d.h, d.k);
+    return QCK_OK;
+}
+
+// Exposed for the host-logic tests (no GPU needed): describe sweep `i` of `plan` the way the TMA kernel
+// would run it.  Returns 1 and fills the arrays when the sweep is eligible, else 0.
+extern "C" int qck_debug_tma_describe(const qck_sim_plan* plan, int sweep, uint64_t live_before, int last,
+                                              int batch, int32_t* geom /*[8]: lowc,h,k,n_load,n_store,zf_shift,zf_mask,n_enum_bits*/,
+                                              int32_t* perm /*[16]*/, uint64_t* ld_off, uint32_t* ld_slot, uint64_t* st_off,
+                                              uint32_t* st_slot, uint64_t* enum_mask, uint64_t* n_work) {
+    static TmaLaunch L;  // large: keep it off the stack; debug entry point, not re-entrant
+    if (!plan || sweep < 0 || sweep >= plan->n_sweeps) return 0;
+    if (!tma_describe(plan, sweep, live_before, last != 0, batch, 232448, L)) return 0;
+    const TmaSweepDev& d = L.sd;
+    const int32_t g[8] = {d.lowc, d.h, d.k, d.n_load, d.n_store, d.zf_shift, (int32_t)d.zf_mask, d.n_enum_bits};
+    for (int j = 0; j < 8; ++j) geom[j] = g[j];
+    for (int j = 0; j < 16; ++j) perm[j] = d.perm[j];
+    for (int j = 0; j < d.n_load; ++j) {
+        ld_off[j] = d.ld_off[j];
+        ld_slot[j] = d.ld_slot[j];
+    }
+    for (int j = 0; j < d.n_store; ++j) {
+        st_off[j] = d.st_off[j];
+        st_slot[j] = d.st_slot[j];
+    }
+    *enum_mask = d.enum_mask;
+    *n_work = L.n_work;
+    return 1;
+}
+
+static int tma_mode() {  // QCK_SIM_TMA: 0 = never, 1 = when eligible (default)
+    const char* env = getenv("QCK_SIM_TMA");
+    return env ? atoi(env) : 1;
+}
 
 static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd, const int32_t* d_labels,
                       int inst_base, int batch, double2* work, unsigned long long state_stride,
                       cudaStream_t st) {
+    // The TMA kernels track live qubits, i.e. they leave memory outside the live region unwritten between
+    // sweeps: a plan runs either entirely on them or entirely on the plain kernel.
+    bool use_tma = tma_mode() != 0 && state_stride == (1ull << plan->n_state_qubits) && tensor_map_encoder() != nullptr;
+    std::unique_ptr<TmaLaunch> L(use_tma ? new TmaLaunch : nullptr);  // ~5 KB of kernel parameters: off the stack
+    if (use_tma) {
+        unsigned long long live = 0;
+        for (int i = 0; i < plan->n_sweeps && use_tma; ++i) {
+            use_tma = tma_describe(plan, i, live, i == plan->n_sweeps - 1, batch, h->max_smem_optin, *L);
+            for (int j = 0; j < plan->sweeps[i].n_tile; ++j) live |= 1ull << plan->sweeps[i].pos[j];
+        }
+    }
+    if (use_tma) {
+        unsigned long long live = 0;
+        for (int i = 0; i < plan->n_sweeps; ++i) {
+            tma_describe(plan, i, live, i == plan->n_sweeps - 1, batch, h->max_smem_optin, *L);
+            for (int j = 0; j < plan->sweeps[i].n_tile; ++j) live |= 1ull << plan->sweeps[i].pos[j];
+            int rc = tma_encode(h, L->sd, batch, work, true, &L->map_st);
+            if (rc) return rc;
+            const bool box_main = L->sd.zf_shift == L->sd.lowc + L->sd.k;
+            rc = tma_encode(h, L->sd, batch, work, box_main, &L->map_ld);
+            if (rc) return rc;
+            PlanDev pdl = pd;
+            pdl.n_stage = L->n_stage;
+            unsigned long long grid = L->n_work < (unsigned long long)h->sm_count ? L->n_work : (unsigned long long)h->sm_count;
+            sim_sweep_tma_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(L->map_st, L->map_ld, L->sd, pdl, d_labels,
+                                                                                       inst_base, L->n_work);
+            QCK_CHECK_LAUNCH(h);
+        }
+        return QCK_OK;
+    }
     for (int i = 0; i < plan->n_sweeps; ++i) {
         SweepDev sd = sweep_dev(plan->sweeps[i], i == 0);
         if (sd.n_tile - sd.n_low > 10)
@@ -677,23 +1073,6 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
                      sd.n_tile);
         unsigned long long tiles = 1ull << (plan->n_state_qubits - sd.n_tile);
         if (tiles > 0x7fffffffull) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "too many tiles");
-        // pipelined persistent kernel when there is enough work to fill the machine several times
-        const size_t pipe_smem = PIPE_STAGES * ((size_t)16 << sd.n_tile) + aux;
-        int want_pipe = 0;  // measured slower than the plain kernel on B200 (305 vs 229 ms at 32 qubits);
-        //                     kept behind QCK_SIM_PIPE=1 for tuning
-        if (const char* env = getenv("QCK_SIM_PIPE")) want_pipe = atoi(env);
-        const bool pipe = want_pipe && tiles * (unsigned long long)batch >= 8ull * h->sm_count &&
-                          (sd.op_end - sd.op_begin) <= pdl.n_stage && (int)pipe_smem + 1024 <= h->max_smem_optin;
-        if (pipe) {
-            int rc = qck_ensure_partials(h, 8);
-            if (rc) return rc;
-            unsigned long long* counter = reinterpret_cast<unsigned long long*>(h->d_partials);
-            QCK_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-            sim_sweep_pipe_kernel<<<h->sm_count, PIPE_THREADS, pipe_smem, st>>>(pdl, sd, d_labels, inst_base, work, state_stride,
-                                                                        tiles, tiles * (unsigned long long)batch, counter);
-            QCK_CHECK_LAUNCH(h);
-            continue;
-        }
         dim3 grid((unsigned)tiles, (unsigned)batch);
         // few tiles (L2-resident states): latency bound, use all 256 threads per tile
         int sweep_threads = tiles * (unsigned long long)batch >= 4ull * h->sm_count ? 128 : 256;  // 3 CTAs per SM de-phase load / compute / store (256 threads: 2 phase-locked CTAs);
@@ -770,7 +1149,7 @@ int qck_sim_init(qck_handle* h) {
     QCK_CUDA(h, qck_allow_max_smem(sim_onchip_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_onchip_group_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_kernel, h->max_smem_optin));
-    QCK_CUDA(h, qck_allow_max_smem(sim_sweep_pipe_kernel, h->max_smem_optin));
+    QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_kernel, h->max_smem_optin));
     return QCK_OK;
 }
 

@@ -89,7 +89,7 @@ typedef struct {
     int32_t sel_digit;   /* -1, or the label digit that selects the variant matrix:       */
     int32_t sel_stride;  /*   offset = mat + digit[sel_digit] * sel_stride                */
     int32_t n_live;      /* ops touch only the first 2^n_live amplitudes of the tile      */
-    int32_t reserved;
+    int32_t reserved;    /* 1 on the member ops of a cluster (q0/q1 are ranks), else 0    */
 } qck_op;
 
 /* A sweep = one pass over the state: every CTA stages a 2^n_tile tile (the
@@ -144,6 +144,22 @@ QCK_API int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim_pl
  * (used for the uncut reference run, Utilities.py:39-69). */
 QCK_API int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t label,
                         void* d_state, size_t state_bytes, qck_stream stream);
+
+/* Host-logic probe (no CUDA call, usable without a GPU; not re-entrant): how the TMA sweep kernel
+ * would run sweep `sweep` of `plan` when the state bits in `live_before` are live (some earlier
+ * sweep had them in its tile; all other qubits are still |0>).  Returns 1 and fills the arrays when
+ * the sweep is eligible for the TMA path, else 0.
+ *   geom[8]  = { low-run length, main-run start, main-run length, load boxes per tile, store boxes
+ *                per tile, log2(amplitudes per load box), mask of load-box index bits that are
+ *                zero-filled instead of loaded, number of state bits the tile number is spread over }
+ *   perm[16] : ascending tile-local bit -> bit of the shared-memory layout [low | main | scattered]
+ *   ld_off / st_off [<= 128]: amplitude offset of each load / store box inside the state,
+ *   ld_slot / st_slot: first shared-memory amplitude slot of the box; enum_mask: the state bits a
+ *   tile number is spread over; n_work = batch << popcount(enum_mask) tiles are visited. */
+QCK_API int qck_debug_tma_describe(const qck_sim_plan* plan, int sweep, uint64_t live_before, int last,
+                                   int batch, int32_t* geom, int32_t* perm, uint64_t* ld_off,
+                                   uint32_t* ld_slot, uint64_t* st_off, uint32_t* st_slot,
+                                   uint64_t* enum_mask, uint64_t* n_work);
 
 /* ------------------------------------------------------------------ knitting
  * Replaces: VirtualCircuit.knit (virtual_circuit.py:50-68), _merge /

@@ -15,8 +15,34 @@ def _bits(idx, q):
     return (idx >> q) & 1
 
 
-def run_plan(program, plan, label):
-    """-> output row (1-D float64) of one instance."""
+def apply_op(psi, idx, kind, g0, g1, mats, moff):
+    """One op on bit positions g0 / g1 of the index space ``idx`` (whole state or one tile)."""
+    if kind == _lib.OP_U1:
+        m = mats[moff:moff + 8].view(np.complex128).reshape(2, 2)
+        lo = psi[(_bits(idx, g0) == 0)]
+        hi = psi[(_bits(idx, g0) == 1)]
+        new = psi.copy()
+        new[_bits(idx, g0) == 0] = m[0, 0] * lo + m[0, 1] * hi
+        new[_bits(idx, g0) == 1] = m[1, 0] * lo + m[1, 1] * hi
+        return new
+    if kind == _lib.OP_CX:
+        src = np.where(_bits(idx, g0) == 1, idx ^ (1 << g1), idx)
+        return psi[src]
+    if kind == _lib.OP_CZ:
+        return np.where((_bits(idx, g0) & _bits(idx, g1)) == 1, -psi, psi)
+    m = mats[moff:moff + 32].view(np.complex128).reshape(4, 4)
+    sub = _bits(idx, g0) + 2 * _bits(idx, g1)
+    base = idx & ~((1 << g0) | (1 << g1))
+    new = np.zeros_like(psi)
+    for r in range(4):
+        for c in range(4):
+            srcidx = base | ((c & 1) << g0) | ((c >> 1) << g1)
+            new += np.where(sub == r, m[r, c] * psi[srcidx], 0)
+    return new
+
+
+def run_plan(program, plan, label, return_state=False):
+    """-> output row (1-D float64) of one instance (or the final statevector)."""
     mats = program.mats
     digits = list(np.unravel_index(int(label), program.radix)) if program.radix else []
     N = plan.n_state
@@ -44,34 +70,12 @@ def run_plan(program, plan, label):
                     q1 = cluster_pos[q1]
             moff = mat + (digits[sel] * stride if sel >= 0 else 0)
             g0 = positions[q0]
-            if kind == _lib.OP_U1:
-                m = mats[moff:moff + 8].view(np.complex128).reshape(2, 2)
-                lo = psi[(_bits(idx, g0) == 0)]
-                hi = psi[(_bits(idx, g0) == 1)]
-                new = psi.copy()
-                new[_bits(idx, g0) == 0] = m[0, 0] * lo + m[0, 1] * hi
-                new[_bits(idx, g0) == 1] = m[1, 0] * lo + m[1, 1] * hi
-                psi = new
-            elif kind == _lib.OP_CX:
-                g1 = positions[q1]
-                src = np.where(_bits(idx, g0) == 1, idx ^ (1 << g1), idx)
-                psi = psi[src]
-            elif kind == _lib.OP_CZ:
-                g1 = positions[q1]
-                psi = np.where((_bits(idx, g0) & _bits(idx, g1)) == 1, -psi, psi)
-            else:
-                g1 = positions[q1]
-                m = mats[moff:moff + 32].view(np.complex128).reshape(4, 4)
-                sub = _bits(idx, g0) + 2 * _bits(idx, g1)
-                base = idx & ~((1 << g0) | (1 << g1))
-                new = np.zeros_like(psi)
-                for r in range(4):
-                    for c in range(4):
-                        srcidx = base | ((c & 1) << g0) | ((c >> 1) << g1)
-                        new += np.where(sub == r, m[r, c] * psi[srcidx], 0)
-                psi = new
+            g1 = positions[q1] if kind != _lib.OP_U1 else 0
+            psi = apply_op(psi, idx, kind, g0, g1, mats, moff)
             if n_live > 0 and len(plan.sweeps) == 1:
                 assert np.all(psi[(1 << n_live):] == 0), "amplitudes beyond n_live must stay zero"
+    if return_state:
+        return psi
     prob = psi.real ** 2 + psi.imag ** 2
     n_out = len(plan.out_pos)
     row = np.zeros(1 << n_out)

@@ -153,6 +153,65 @@ def test_streaming_equals_onchip_on_device(dev):
         assert np.abs(ra - rb).max() < 1e-13
 
 
+def _with_tma(flag, fn):
+    import os
+    old = os.environ.get("QCK_SIM_TMA")
+    os.environ["QCK_SIM_TMA"] = flag
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("QCK_SIM_TMA", None)
+        else:
+            os.environ["QCK_SIM_TMA"] = old
+
+
+@pytest.mark.parametrize("cfg,onchip,tile", [("syc16d5", 6, 7), ("hwe16d5", 6, 8), ("bv16", 5, 6)])
+def test_tma_sweep_kernel_equals_plain_kernel_on_cut_fragments(dev, cfg, onchip, tile):
+    """Warp-specialised TMA sweeps with live-qubit tracking (many instances per launch, label-selected
+    matrices, ancilla bits) against the plain sweep kernel and the on-chip kernel."""
+    circ, cut = cutting.make_baseline(cfg)
+    virt = vcm.VirtualCircuit(cut)
+    h = _lib.get_handle(0)
+    for f in virt.active_fragments():
+        a = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits)
+        b = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits, onchip_max=onchip, stream_tile=tile)
+        ra = compiler.FragmentExecutor(a, dev).run(h).cpu().numpy()
+        eb = compiler.FragmentExecutor(b, dev)
+        r_tma = _with_tma("1", lambda: eb.run(h).cpu().numpy())
+        r_plain = _with_tma("0", lambda: eb.run(h).cpu().numpy())
+        assert np.abs(r_tma - r_plain).max() < 1e-15
+        assert np.abs(r_tma - ra).max() < 1e-13
+
+
+@pytest.mark.parametrize("name,n,depth", [("syc", 20, 1), ("syc", 20, 4), ("hwe", 18, 3), ("qft", 17, 1), ("syc", 24, 2)])
+def test_tma_sweep_statevector_equals_plain(dev, name, n, depth):
+    """Full-size tiles (2^12 amplitudes): final statevector of the TMA path == plain path, amplitude by
+    amplitude, and its norm is 1."""
+    circ = gen.gen_circ(name, n, depth, seed=3).decompose_two_qubit()
+    virt = vcm.VirtualCircuit(circ)
+    (frag,) = virt.active_fragments()
+    ex = virt.executor(frag, dev, True)
+    ex.upload()
+    h = _lib.get_handle(0)
+    (st, _off, _cnt) = ex._structs[0]
+    st.d_ops = ex.d_blob.data_ptr() + ex._off_ops
+    st.d_mats = ex.d_blob.data_ptr()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def run():
+        buf = torch.full((2 << n,), float("nan"), dtype=torch.float64, device=dev)
+        h.check(h.lib.qck_sim_statevector(h.ptr, C.byref(st), 0, buf.data_ptr(), buf.numel() * 8, stream))
+        torch.cuda.synchronize()
+        return buf
+
+    a = _with_tma("1", run)
+    b = _with_tma("0", run)
+    assert not torch.isnan(a).any()
+    assert float((a - b).abs().max()) < 1e-15
+    assert abs(float((a * a).sum()) - 1.0) < 1e-12
+
+
 def test_b200_backend_duck_type(dev):
     """backend.run(circuits, shots).result().get_counts() -> QuasiDistr.from_counts (run.py:42-56)."""
     qc, cut = make_semcheck_circuit("cx")

@@ -1,0 +1,210 @@
+"""Host logic of the TMA sweep path (csrc/sim.cu: tma_describe) without a GPU.
+
+``qck_debug_tma_describe`` returns, for every sweep of a streaming plan, exactly what the
+warp-specialised kernel consumes: the shared-memory bit order, the load / store boxes, which boxes are
+zero-filled and which tiles are visited.  A numpy emulation of the kernel's data movement (state buffer
+pre-filled with NaN = "never written") then has to reproduce the plain plan interpreter bit for bit and
+must never load a NaN: live-qubit tracking may only skip memory that is provably zero.
+"""
+import ctypes as C
+from importlib import import_module
+
+import numpy as np
+import pytest
+
+import plan_interpreter as pi
+
+PKG = "hardwareawareoptimalquantumcircuitcuttingandknitting_b200"
+_lib = import_module(f"{PKG}._lib")
+compiler = import_module(f"{PKG}.compiler")
+gen = import_module(f"{PKG}.generators")
+vcm = import_module(f"{PKG}.virtual_circuit")
+circuit = import_module(f"{PKG}.circuit")
+
+
+def _pdep(x, mask):
+    out, j = 0, 0
+    while mask:
+        low = mask & -mask
+        if (x >> j) & 1:
+            out |= low
+        j += 1
+        mask ^= low
+    return out
+
+
+def _plan_struct(program, plan):
+    arr = (_lib.QckSweep * len(plan.sweeps))()
+    for i, (positions, b, e) in enumerate(plan.sweeps):
+        arr[i].n_tile = len(positions)
+        arr[i].op_begin = b
+        arr[i].op_end = e
+        for j, x in enumerate(positions):
+            arr[i].pos[j] = x
+    st = _lib.QckSimPlan()
+    st.n_state_qubits = plan.n_state
+    st.n_sweeps = len(plan.sweeps)
+    st.sweeps = arr
+    return st, arr
+
+
+def describe(st, i, live, last, batch=1):
+    lib = _lib.load()
+    geom = (C.c_int32 * 8)()
+    perm = (C.c_int32 * 16)()
+    ld_off, st_off = (C.c_uint64 * 128)(), (C.c_uint64 * 128)()
+    ld_slot, st_slot = (C.c_uint32 * 128)(), (C.c_uint32 * 128)()
+    enum_mask, n_work = C.c_uint64(), C.c_uint64()
+    ok = lib.qck_debug_tma_describe(C.byref(st), i, live, int(last), batch, geom, perm, ld_off, ld_slot, st_off,
+                                    st_slot, C.byref(enum_mask), C.byref(n_work))
+    if not ok:
+        return None
+    lowc, h, k, n_load, n_store, zf_shift, zf_mask, n_enum = list(geom)
+    return dict(lowc=lowc, h=h, k=k, zf_shift=zf_shift, zf_mask=zf_mask, n_enum=n_enum, perm=list(perm),
+                ld=[(ld_off[j], ld_slot[j]) for j in range(n_load)],
+                st=[(st_off[j], st_slot[j]) for j in range(n_store)],
+                enum_mask=enum_mask.value, n_work=n_work.value)
+
+
+def emulate(program, plan, label):
+    """-> (final state, bytes loaded, bytes stored) of the TMA path for one instance."""
+    st, _keep = _plan_struct(program, plan)
+    mats = program.mats
+    digits = list(np.unravel_index(int(label), program.radix)) if program.radix else []
+    N = plan.n_state
+    state = np.full(1 << N, np.nan + 1j * np.nan, dtype=np.complex128)
+    live = 0
+    loaded = stored = 0
+    for i, (positions, b, e) in enumerate(plan.sweeps):
+        T = len(positions)
+        last = i == len(plan.sweeps) - 1
+        d = describe(st, i, live, last)
+        assert d is not None, f"sweep {i} not eligible"
+        lowc, h, k = d["lowc"], d["h"], d["k"]
+        perm = d["perm"]
+        assert sorted(perm[:T]) == list(range(T))
+
+        def box_offsets(bits):       # box-local index -> amplitude offset in the state
+            j = np.arange(1 << bits)
+            off = j & ((1 << lowc) - 1)
+            for t in range(lowc, bits):
+                off = off | (((j >> t) & 1) << (h + t - lowc))
+            return off
+
+        ld_box, st_box = box_offsets(d["zf_shift"]), box_offsets(lowc + k)
+        assert d["n_work"] == 1 << d["n_enum"]
+        tidx = np.arange(1 << T)
+        for w in range(d["n_work"]):
+            base = _pdep(w, d["enum_mask"])
+            tile_live = (base & ~live) == 0
+            stage = np.full(1 << T, np.nan + 1j * np.nan, dtype=np.complex128)
+            if not tile_live:
+                assert last, "dead tiles are only visited by the last sweep"
+                stage[:] = 0
+            else:
+                if live == 0:
+                    assert not d["ld"]
+                    stage[:] = 0
+                    stage[0] = 1
+                else:
+                    for off, slot in d["ld"]:
+                        src = state[(base | off) | ld_box]
+                        assert not np.isnan(src).any(), "TMA load would read memory that was never written"
+                        stage[slot:slot + len(ld_box)] = src
+                        loaded += 16 * len(ld_box)
+                    zf = ((tidx >> d["zf_shift"]) & d["zf_mask"]) != 0
+                    assert np.isnan(stage[zf]).all(), "zero fill overlaps a loaded box"
+                    stage[zf] = 0
+                assert not np.isnan(stage).any(), "tile slots neither loaded nor zero-filled"
+                cluster_pos, members_left = None, 0
+                for op in plan.ops[b:e]:
+                    kind, q0, q1, mat, sel, stride, n_live, member = (int(x) for x in op)
+                    if kind == _lib.OP_CLUSTER:
+                        cluster_pos, members_left = [perm[mat], perm[sel], perm[stride]], q0
+                        continue
+                    if members_left > 0:
+                        assert member == 1
+                        members_left -= 1
+                        q0 = cluster_pos[q0]
+                        if kind != _lib.OP_U1:
+                            q1 = cluster_pos[q1]
+                    else:
+                        assert member == 0
+                        q0 = perm[q0]
+                        if kind != _lib.OP_U1:
+                            q1 = perm[q1]
+                    moff = mat + (digits[sel] * stride if sel >= 0 else 0)
+                    stage = pi.apply_op(stage, tidx, kind, q0, q1, mats, moff)
+            for off, slot in d["st"]:
+                state[(base | off) | st_box] = stage[slot:slot + len(st_box)]
+                stored += 16 * len(st_box)
+        for p in positions:
+            live |= 1 << p
+    return state, loaded, stored
+
+
+def _uncut_program(name, n, depth, **kw):
+    circ = gen.gen_circ(name, n, depth, seed=1).decompose_two_qubit()
+    virt = vcm.VirtualCircuit(circ)
+    (frag,) = virt.active_fragments()
+    return compiler.FragmentProgram(virt.fragment_circuits[frag], frag, circ.num_clbits, **kw)
+
+
+@pytest.mark.parametrize("name,n,depth,onchip,tile", [
+    ("syc", 12, 1, 6, 6), ("syc", 12, 3, 6, 6), ("syc", 12, 3, 7, 8), ("hwe", 11, 2, 6, 7), ("qft", 10, 1, 5, 6),
+    ("bv", 12, 1, 6, 6), ("aqft", 11, 1, 6, 7), ("syc", 14, 2, 8, 9),
+])
+def test_tma_path_equals_plain_interpreter(name, n, depth, onchip, tile):
+    prog = _uncut_program(name, n, depth, onchip_max=onchip, stream_tile=tile)
+    (plan,) = prog.plans()
+    assert len(plan.sweeps) > 1
+    want = pi.run_plan(prog, plan, 0, return_state=True)
+    got, loaded, stored = emulate(prog, plan, 0)
+    assert not np.isnan(got).any(), "the last sweep must leave the whole buffer written"
+    assert np.abs(got - want).max() < 1e-14
+    full = 16 << plan.n_state
+    assert stored <= full * len(plan.sweeps) and loaded <= full * (len(plan.sweeps) - 1)
+
+
+def test_live_tracking_saves_traffic_on_depth_one():
+    """A depth-1 circuit expands the state once: about one write of the state in total."""
+    prog = _uncut_program("syc", 14, 1, onchip_max=6, stream_tile=7)
+    (plan,) = prog.plans()
+    want = pi.run_plan(prog, plan, 0, return_state=True)
+    got, loaded, stored = emulate(prog, plan, 0)
+    assert np.abs(got - want).max() < 1e-14
+    full = 16 << plan.n_state
+    n_sw = len(plan.sweeps)
+    assert n_sw >= 4
+    # without tracking: n_sw stores and n_sw - 1 loads of the full state
+    assert stored < 2 * full, (stored, full)
+    assert loaded < full, (loaded, full)
+
+
+def test_cut_fragment_with_slots_and_ancillas():
+    """Gate-cut fragments (label-selected slot matrices, ancilla bits of mid-circuit measurements) forced
+    into the streaming regime."""
+    cutting = import_module(f"{PKG}.cutting")
+    circ, cut = cutting.make_baseline("syc16d5")
+    virt = vcm.VirtualCircuit(cut)
+    checked = 0
+    for f in virt.active_fragments():
+        prog = compiler.FragmentProgram(virt.fragment_circuits[f], f, cut.num_clbits, onchip_max=6, stream_tile=7)
+        for plan in prog.plans()[::5]:
+            assert len(plan.sweeps) >= 2
+            for label in plan.labels[:2]:
+                want = pi.run_plan(prog, plan, label, return_state=True)
+                got, _, _ = emulate(prog, plan, label)
+                assert not np.isnan(got).any()
+                assert np.abs(got - want).max() < 1e-14
+                checked += 1
+    assert checked >= 8
+
+
+def test_ineligible_sweeps_are_reported():
+    prog = _uncut_program("syc", 12, 1, onchip_max=6, stream_tile=6)
+    (plan,) = prog.plans()
+    st, _keep = _plan_struct(prog, plan)
+    assert describe(st, 0, 0, False) is not None
+    # live set that does not cover the low run -> the low-run box cannot be loaded
+    assert describe(st, 1, 0b1, False) is None

@@ -1,26 +1,69 @@
-"""Scratch: uncut syc-N d1 statevector run for profiling the streaming kernels."""
-import sys, os
+"""Uncut statevector run for profiling the streaming kernels.
+
+usage: prof_sweep.py [name=syc] [n=28] [depth=1] [reps=3]      (QCK_SIM_TMA=0 selects the plain kernel)
+Prints the time of the sweeps alone (qck_sim_statevector) and of the whole fragment run (sweeps + fold),
+and the bandwidth the sweeps would need if every sweep read and wrote the whole state (the plain
+kernel's traffic; the TMA path with live-qubit tracking moves less on shallow circuits).
+"""
+import ctypes as C
+import os
+import sys
+
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import torch
 from importlib import import_module
+
 PKG = "hardwareawareoptimalquantumcircuitcuttingandknitting_b200"
-gen = import_module(PKG + ".generators"); vcm = import_module(PKG + ".virtual_circuit"); _lib = import_module(PKG + "._lib")
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 28
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-circ = gen.gen_circ("syc", n, 1, seed=0).decompose_two_qubit()
+gen = import_module(PKG + ".generators")
+vcm = import_module(PKG + ".virtual_circuit")
+_lib = import_module(PKG + "._lib")
+
+name = sys.argv[1] if len(sys.argv) > 1 else "syc"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 28
+depth = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+circ = gen.gen_circ(name, n, depth, seed=0).decompose_two_qubit()
 virt = vcm.VirtualCircuit(circ)
 (frag,) = virt.active_fragments()
 dev = torch.device("cuda", 0)
 ex = virt.executor(frag, dev, True)
+ex.upload()
 h = _lib.get_handle(0)
-t = ex.run(h)
+pl = ex.plans[0]
+st, _, _ = ex._structs[0]
+st.d_ops = ex.d_blob.data_ptr() + ex._off_ops
+st.d_mats = ex.d_blob.data_ptr()
+stream = torch.cuda.current_stream(dev).cuda_stream
+state = torch.empty(2 << n, dtype=torch.float64, device=dev)
+
+
+def sweeps_only():
+    h.check(h.lib.qck_sim_statevector(h.ptr, C.byref(st), 0, state.data_ptr(), state.numel() * 8, stream))
+
+
+sweeps_only()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):
+    sweeps_only()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+n_sw = len(pl.sweeps)
+full_bytes = (2 * n_sw - 1) * (16 << n)
+norm = float((state * state).sum())
+print(f"{name}-{n} d{depth} uncut, QCK_SIM_TMA={os.environ.get('QCK_SIM_TMA', '1')}: sweeps {n_sw}, records {len(pl.ops)}, "
+      f"sweeps-only {ms:.3f} ms = {full_bytes / ms / 1e6:.0f} GB/s of full-sweep traffic ({full_bytes / 1e9:.1f} GB), "
+      f"norm {norm:.12f}")
+del state
+t = ex.run(h)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(reps):
     ex.run(h, out=t)
-e1.record(); torch.cuda.synchronize()
-pl = ex.plans[0]
-print(f"syc-{n} uncut: {e0.elapsed_time(e1)/reps:.2f} ms, sweeps {len(pl.sweeps)}, records {len(pl.ops)}, sum {t.sum().item():.12f}")
+e1.record()
+torch.cuda.synchronize()
+print(f"  sweeps + fold: {e0.elapsed_time(e1) / reps:.3f} ms, sum {t.sum().item():.12f}")
 for pos, b, e in pl.sweeps:
     print("  sweep tile", pos, "records", e - b)
