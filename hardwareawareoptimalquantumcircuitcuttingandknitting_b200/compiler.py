@@ -393,7 +393,9 @@ class FragmentProgram:
             sweeps = [(list(range(n_state)), 0, len(ops_arr))]
         else:
             ops_arr, sweeps = _schedule_sweeps(ops_arr, n_state, self.stream_tile)
-        if self.cluster:
+        # register clusters pay in the latency-bound on-chip kernel; in the streaming kernel the plain
+        # passes (matrix in registers, no per-op dispatch) measured faster (hwe-30 d3: 62 -> 45 ms)
+        if self.cluster and n_state <= self.onchip_max:
             ops_arr, sweeps = _cluster_sweeps(ops_arr, sweeps)
         return PlanHost(pattern, labels, n_state, ops_arr, sweeps, out_pos, sum_mask, sign_mask)
 

@@ -1022,6 +1022,38 @@ extern "C" int qck_debug_tma_describe(const qck_sim_plan* plan, int sweep, uint6
     return 1;
 }
 
+static int tma_mode();
+
+// Exact HBM traffic of the sweeps of `plan` for `batch` instances (host arithmetic only): what the TMA
+// path loads and stores with live-qubit tracking, or - when a sweep is not eligible for it - the plain
+// kernel's read + write of the whole state per sweep.
+extern "C" int qck_sim_plan_traffic(const qck_sim_plan* plan, int batch, uint64_t* bytes_loaded, uint64_t* bytes_stored,
+                                    int* uses_tma) {
+    if (!plan || !plan->sweeps || batch < 1 || !bytes_loaded || !bytes_stored) return QCK_ERR_INVALID_ARG;
+    std::unique_ptr<TmaLaunch> L(new TmaLaunch);
+    bool tma = tma_mode() != 0;
+    unsigned long long live = 0, ld = 0, st = 0;
+    for (int i = 0; i < plan->n_sweeps && tma; ++i) {
+        tma = tma_describe(plan, i, live, i == plan->n_sweeps - 1, batch, 232448, *L);
+        if (!tma) break;
+        const TmaSweepDev& d = L->sd;
+        // live tiles: the tile number is spread over enum_mask; a tile is live iff its bits outside the live set are 0
+        const unsigned long long live_tiles = (unsigned long long)batch << __builtin_popcountll(d.enum_mask & live);
+        ld += live_tiles * (unsigned long long)d.n_load * d.load_bytes;
+        st += L->n_work * ((unsigned long long)16 << d.n_tile);
+        for (int j = 0; j < plan->sweeps[i].n_tile; ++j) live |= 1ull << plan->sweeps[i].pos[j];
+    }
+    if (!tma) {
+        const unsigned long long full = ((unsigned long long)16 << plan->n_state_qubits) * (unsigned long long)batch;
+        ld = full * (unsigned long long)(plan->n_sweeps - 1);
+        st = full * (unsigned long long)plan->n_sweeps;
+    }
+    *bytes_loaded = ld;
+    *bytes_stored = st;
+    if (uses_tma) *uses_tma = tma ? 1 : 0;
+    return QCK_OK;
+}
+
 static int tma_mode() {  // QCK_SIM_TMA: 0 = never, 1 = when eligible (default)
     const char* env = getenv("QCK_SIM_TMA");
     return env ? atoi(env) : 1;

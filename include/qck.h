@@ -161,6 +161,12 @@ QCK_API int qck_debug_tma_describe(const qck_sim_plan* plan, int sweep, uint64_t
                                    uint32_t* ld_slot, uint64_t* st_off, uint32_t* st_slot,
                                    uint64_t* enum_mask, uint64_t* n_work);
 
+/* Exact HBM bytes the sweeps of a streaming plan move for `batch` instances (host arithmetic, no
+ * CUDA call): the TMA path with live-qubit tracking when every sweep is eligible (*uses_tma = 1),
+ * else one read + one write of the whole state per sweep.  bench.py's roofline figures use it. */
+QCK_API int qck_sim_plan_traffic(const qck_sim_plan* plan, int batch, uint64_t* bytes_loaded,
+                                 uint64_t* bytes_stored, int* uses_tma);
+
 /* ------------------------------------------------------------------ knitting
  * Replaces: VirtualCircuit.knit (virtual_circuit.py:50-68), _merge /
  *           _merge_distrs / QuasiDistr.merge (virtual_circuit.py:150-171,216-228;

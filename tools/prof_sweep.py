@@ -26,7 +26,12 @@ circ = gen.gen_circ(name, n, depth, seed=0).decompose_two_qubit()
 virt = vcm.VirtualCircuit(circ)
 (frag,) = virt.active_fragments()
 dev = torch.device("cuda", 0)
-ex = virt.executor(frag, dev, True)
+compiler = import_module(PKG + ".compiler")
+if os.environ.get("QCK_PROF_CLUSTER", "1") == "0":     # experiment: every op as its own shared-memory pass
+    prog = compiler.FragmentProgram(virt.fragment_circuits[frag], frag, circ.num_clbits, cluster=False)
+    ex = compiler.FragmentExecutor(prog, dev, True)
+else:
+    ex = virt.executor(frag, dev, True)
 ex.upload()
 h = _lib.get_handle(0)
 pl = ex.plans[0]
