@@ -26,13 +26,13 @@ MAX_DIGITS = 16
 MAX_OUT_BITS = 40
 MAX_FRAGMENTS = 8
 MAX_VARIANTS = 8
-OP_U1, OP_CX, OP_CZ, OP_U2, OP_CLUSTER = 0, 1, 2, 3, 4
+OP_U1, OP_CX, OP_CZ, OP_U2, OP_CLUSTER, OP_U1X, OP_TERM, OP_PHASE = 0, 1, 2, 3, 4, 5, 6, 7
 CLUSTER_QUBITS = 3
 
 
 class QckSweep(C.Structure):
     _fields_ = [("n_tile", C.c_int32), ("op_begin", C.c_int32), ("op_end", C.c_int32),
-                ("reserved", C.c_int32), ("pos", C.c_int32 * (MAX_TILE_QUBITS + 2))]
+                ("flags", C.c_int32), ("pos", C.c_int32 * (MAX_TILE_QUBITS + 2))]
 
 
 class QckSimPlan(C.Structure):

@@ -224,7 +224,16 @@ class FragmentProgram:
         # fragments whose circuits have no measurement)
         self.measures_anything = bool(out_bits) or mid_measures > 0 or any(any(s.meas) for s in slots)
         self.num_labels = int(np.prod(self.radix, dtype=np.int64)) if self.radix else 1
-        self.mats = np.concatenate(self._pool) if self._pool else np.zeros(8)
+
+    @property
+    def mats(self) -> np.ndarray:
+        """The matrix pool (float64, interleaved re/im).  Planning appends the tile-resolved variants
+        of ops whose diag qubits stay outside a tile, so read it AFTER ``plans()``."""
+        cached = getattr(self, "_mats_cache", None)
+        if cached is None or cached[0] != len(self._pool):
+            arr = np.concatenate(self._pool) if self._pool else np.zeros(8)
+            self._mats_cache = cached = (len(self._pool), arr)
+        return cached[1]
 
     # ------------------------------------------------------------------ gate fusion
     _SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
@@ -392,7 +401,7 @@ class FragmentProgram:
         if n_state <= self.onchip_max:
             sweeps = [(list(range(n_state)), 0, len(ops_arr))]
         else:
-            ops_arr, sweeps = _schedule_sweeps(ops_arr, n_state, self.stream_tile)
+            ops_arr, sweeps = _schedule_sweeps(ops_arr, n_state, self.stream_tile, self)
         # register clusters pay in the latency-bound on-chip kernel; in the streaming kernel the plain
         # passes (matrix in registers, no per-op dispatch) measured faster (hwe-30 d3: 62 -> 45 ms)
         if self.cluster and n_state <= self.onchip_max:
@@ -413,26 +422,94 @@ def _op_qubits(op) -> tuple[int, ...]:
     return (int(op[1]),) if op[0] == _lib.OP_U1 else (int(op[1]), int(op[2]))
 
 
-def _schedule_sweeps(ops: np.ndarray, n_state: int, tile: int):
-    """Greedy list scheduling: each sweep takes, in program order, every op whose qubits are
-    not blocked by an earlier unscheduled op and still fit into the tile (bit-mask sets)."""
+_DIAG_TOL = 1e-13           # |entry| below this counts as a structural zero of a fused matrix
+
+_X2 = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+_Z2 = np.diag([1, -1]).astype(np.complex128)
+
+
+def _op_roles(row, program) -> tuple[int, int]:
+    """-> (need mask, diag mask) of one op record.  A qubit is *diag* when the op is block diagonal
+    with respect to it (it never mixes amplitudes that differ in that bit): the control of a cx, both
+    qubits of cz / cp / rzz, the qubit of rz / z / s / t / p.  Such a qubit need not be in the tile of
+    the sweep that applies the op: its bit is a constant of the tile and just selects a variant
+    (qck.h: QCK_OP_U1X / QCK_OP_PHASE).  Diag uses of one qubit also commute with each other."""
+    kind, q0, q1, mat, sel = row[0], row[1], row[2], row[3], row[4]
+    if kind == _lib.OP_U1:
+        if sel < 0:
+            m = program._mat_by_off[mat]
+            if abs(m[0, 1]) < _DIAG_TOL and abs(m[1, 0]) < _DIAG_TOL:
+                return 0, 1 << q0
+        return 1 << q0, 0
+    if kind == _lib.OP_CX:
+        return 1 << q1, 1 << q0
+    if kind == _lib.OP_CZ:
+        return 0, (1 << q0) | (1 << q1)
+    m = np.abs(program._mat_by_off[mat].reshape(4, 4)) >= _DIAG_TOL
+    r, c = np.nonzero(m)
+    d0 = bool(np.all((r & 1) == (c & 1)))         # block diagonal w.r.t. q0 (index bit 0)
+    d1 = bool(np.all((r >> 1) == (c >> 1)))       # ... w.r.t. q1 (index bit 1)
+    need = (0 if d0 else 1 << q0) | (0 if d1 else 1 << q1)
+    diag = (1 << q0 if d0 else 0) | (1 << q1 if d1 else 0)
+    return need, diag
+
+
+def _cond_matrices(row, program, ext: int) -> tuple[np.ndarray, np.ndarray]:
+    """The two 2x2 matrices a two-qubit op applies to its OTHER qubit when its (diag) qubit `ext`
+    is 0 / 1."""
+    kind, q0, q1, mat = row[0], row[1], row[2], row[3]
+    if kind == _lib.OP_CX:
+        return _I2, _X2
+    if kind == _lib.OP_CZ:
+        return _I2, _Z2
+    m = program._mat_by_off[mat].reshape(4, 4)
+    if ext == q1:
+        return m[0:2, 0:2].copy(), m[2:4, 2:4].copy()
+    return m[0::2, 0::2].copy(), m[1::2, 1::2].copy()
+
+
+def _phase_scalars(row, program) -> np.ndarray:
+    """Diagonal of an op all of whose qubits are diag: 2 scalars (one qubit) or 4 (index
+    bit(q0) + 2 bit(q1))."""
+    kind, mat = row[0], row[3]
+    if kind == _lib.OP_U1:
+        return np.diag(program._mat_by_off[mat]).copy()
+    if kind == _lib.OP_CZ:
+        return np.array([1, 1, 1, -1], dtype=np.complex128)
+    return np.diag(program._mat_by_off[mat].reshape(4, 4)).copy()
+
+
+def _schedule_sweeps(ops: np.ndarray, n_state: int, tile: int, program):
+    """Greedy list scheduling: each sweep takes, in program order, every op that is not blocked by
+    an earlier unscheduled op and whose *need* qubits still fit into the tile (bit-mask sets).  Diag
+    qubits (see _op_roles) do not have to fit; when they end up outside the tile the op is emitted
+    in its tile-resolved form:
+
+    * one diag qubit outside: a one-qubit op on the other qubit whose matrix is selected by the
+      outside bit; consecutive ones on the same tile qubit are chained into ONE ``OP_U1X`` header
+      followed by ``OP_TERM`` records (the device multiplies the selected matrices once per tile);
+    * every qubit outside: a scalar per tile; all of them in a sweep are collected into one
+      ``OP_PHASE`` header + terms at the start of the sweep (they commute with everything in it).
+    """
     tile = min(tile, n_state)
     low = max(0, min(LOW_RUN, tile - 2))     # always leave room for a two-qubit gate
     rows = ops.tolist()
-    masks = [(1 << r[1]) if r[0] == _lib.OP_U1 else ((1 << r[1]) | (1 << r[2])) for r in rows]
+    roles = [_op_roles(r, program) for r in rows]
     remaining = list(range(len(rows)))
     new_ops, sweeps = [], []
     while remaining:
         tile_set = (1 << low) - 1
-        blocked = 0
+        blocked_full = blocked_diag = 0
         taken, rest = [], []
         for i in remaining:
-            m = masks[i]
-            if not (m & blocked) and bin(tile_set | m).count("1") <= tile:
-                tile_set |= m
+            need, diag = roles[i]
+            conflict = (need & (blocked_full | blocked_diag)) or (diag & blocked_full)
+            if not conflict and bin(tile_set | need).count("1") <= tile:
+                tile_set |= need
                 taken.append(i)
             else:
-                blocked |= m
+                blocked_full |= need
+                blocked_diag |= diag
                 rest.append(i)
         if not taken:
             raise NotImplementedError("an op does not fit into a tile")
@@ -443,19 +520,54 @@ def _schedule_sweeps(ops: np.ndarray, n_state: int, tile: int):
         positions = [q for q in range(n_state) if (tile_set >> q) & 1]
         local = {p: j for j, p in enumerate(positions)}
         begin = len(new_ops)
+        items: list = []                     # rows, or open chains {"q": tile qubit, "terms": [...]}
+        chain_of: dict[int, dict] = {}       # tile qubit -> its open chain
+        phase_terms: list[list[int]] = []
         for i in taken:
             r = list(rows[i])
-            r[1] = local[r[1]]
-            if r[0] != _lib.OP_U1:
-                r[2] = local[r[2]]
+            qs = _op_qubits(r)
+            outside = [q for q in qs if q not in local]
             r[6] = 0                             # n_live is meaningless inside a tile
-            new_ops.append(r)
+            if not outside:
+                for q in qs:
+                    chain_of.pop(q, None)        # anything else on the qubit closes its chain
+                r[1] = local[r[1]]
+                if r[0] != _lib.OP_U1:
+                    r[2] = local[r[2]]
+                items.append(r)
+            elif len(outside) == len(qs):        # nothing in the tile: a scalar per tile
+                sc = _phase_scalars(r, program)
+                off = program._add_matrix(sc)
+                phase_terms.append([_lib.OP_TERM, outside[0], outside[1] if len(outside) > 1 else -1, off,
+                                    -1, len(sc), 0, 1])
+            else:                                # one diag qubit outside: conditional op on the other one
+                ext = outside[0]
+                a = qs[0] if qs[1] == ext else qs[1]
+                m0, m1 = _cond_matrices(r, program, ext)
+                off = program._add_matrix(np.stack([m0, m1]))
+                ch = chain_of.get(a)
+                if ch is None or len(ch["terms"]) >= MAX_TERMS:
+                    ch = {"q": local[a], "terms": []}
+                    chain_of[a] = ch
+                    items.append(ch)
+                ch["terms"].append([_lib.OP_TERM, ext, -1, off, -1, 8, 0, 1])
+        for c0 in range(0, len(phase_terms), MAX_TERMS):
+            chunk = phase_terms[c0:c0 + MAX_TERMS]
+            new_ops.append([_lib.OP_PHASE, 0, len(chunk), 0, -1, 0, 0, 1])
+            new_ops.extend(chunk)
+        for it in items:
+            if isinstance(it, dict):
+                new_ops.append([_lib.OP_U1X, it["q"], len(it["terms"]), 0, -1, 0, 0, 0])
+                new_ops.extend(it["terms"])
+            else:
+                new_ops.append(it)
         sweeps.append((positions, begin, len(new_ops)))
         remaining = rest
     return np.asarray(new_ops, dtype=np.int32).reshape(-1, 8), sweeps
 
 
 MAX_CLUSTER_OPS = 32        # QCK_MAX_CLUSTER_OPS: a cluster must fit the staged chunk
+MAX_TERMS = 30              # terms per OP_U1X / OP_PHASE header (header + terms must fit the staged chunk)
 
 
 def _cluster_sweeps(ops: np.ndarray, sweeps: list):
@@ -596,6 +708,7 @@ class FragmentExecutor:
                 arr[i].n_tile = len(positions)
                 arr[i].op_begin = p.op_base + b
                 arr[i].op_end = p.op_base + e
+                arr[i].flags = int(np.isin(p.ops[b:e, 0], (_lib.OP_U1X, _lib.OP_PHASE)).any())
                 for j, x in enumerate(positions):
                     arr[i].pos[j] = x
             self._sweep_arrays.append(arr)

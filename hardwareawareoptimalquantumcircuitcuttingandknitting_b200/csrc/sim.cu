@@ -37,6 +37,7 @@ struct SweepDev {
     int op_begin, op_end;
     int n_low;  // pos[i] == i for i < n_low (contiguous low run)
     int init;   // 1: synthesise |0..0> instead of reading
+    int has_x;  // the op range holds tile-resolved ops (QCK_OP_U1X / QCK_OP_PHASE)
     int pos[QCK_MAX_TILE_QUBITS + 2];
 };
 
@@ -172,12 +173,17 @@ __device__ __forceinline__ void stage_ops(StagedOp* so, const qck_op* __restrict
             const double2* m = reinterpret_cast<const double2*>(mats + w0.w);
             const int n_m = w0.x == QCK_OP_U1 ? 4 : 16;
             for (int e = 0; e < n_m; ++e) so[i].m[e] = __ldg(m + e);
+        } else if (w0.x == QCK_OP_TERM) {  // the variants a tile picks from (resolve_tile)
+            const double2* m = reinterpret_cast<const double2*>(mats + w0.w);
+            for (int e = 0; e < w1.y && e < 16; ++e) so[i].m[e] = __ldg(m + e);
         }
         if (perm) {
             if (w0.x == QCK_OP_CLUSTER) {
                 w0.w = perm[w0.w];
                 w1.x = perm[w1.x];
                 w1.y = perm[w1.y];
+            } else if (w0.x == QCK_OP_U1X) {
+                w0.y = perm[w0.y];
             } else if (w1.w == 0) {
                 w0.y = perm[w0.y];
                 if (w0.x != QCK_OP_U1) w0.z = perm[w0.z];
@@ -186,6 +192,50 @@ __device__ __forceinline__ void stage_ops(StagedOp* so, const qck_op* __restrict
         so[i].w0 = w0;
         so[i].w1 = w1;
     }
+}
+
+// Tile-resolved ops: the bits of the tile's base address select, per term, one of the staged variants;
+// the header receives the product (U1X: 2x2 matrix in m[0..3]; PHASE: scalar in m[0]).  One thread per
+// header; the terms stay intact, so every tile resolves afresh.
+template <class P>
+__device__ __forceinline__ void resolve_tile(StagedOp* so, int n, unsigned long long base) {
+    for (int i = P::tid(); i < n; i += P::nth()) {
+        const int kind = so[i].w0.x;
+        if ((kind == QCK_OP_U1X || kind == QCK_OP_PHASE) && i + so[i].w0.z >= n) continue;  // terms not staged
+        if (kind == QCK_OP_U1X) {
+            const int n_terms = so[i].w0.z;
+            double2 m00 = make_double2(1.0, 0.0), m01 = make_double2(0.0, 0.0), m10 = m01, m11 = m00;
+            for (int t = 1; t <= n_terms; ++t) {
+                const StagedOp& tm = so[i + t];
+                const double2* v = tm.m + 4 * (int)((base >> tm.w0.y) & 1ull);
+                const double2 a = v[0], b = v[1], c = v[2], d = v[3];  // [[a b] [c d]] * M
+                const double2 n00 = cfma(b, m10, cmul(a, m00)), n01 = cfma(b, m11, cmul(a, m01));
+                const double2 n10 = cfma(d, m10, cmul(c, m00)), n11 = cfma(d, m11, cmul(c, m01));
+                m00 = n00; m01 = n01; m10 = n10; m11 = n11;
+            }
+            so[i].m[0] = m00; so[i].m[1] = m01; so[i].m[2] = m10; so[i].m[3] = m11;
+        } else if (kind == QCK_OP_PHASE) {
+            const int n_terms = so[i].w0.z;
+            double2 sc = make_double2(1.0, 0.0);
+            for (int t = 1; t <= n_terms; ++t) {
+                const StagedOp& tm = so[i + t];
+                int idx = (int)((base >> tm.w0.y) & 1ull);
+                if (tm.w0.z >= 0) idx |= (int)((base >> tm.w0.z) & 1ull) << 1;
+                sc = cmul(tm.m[idx], sc);
+            }
+            so[i].m[0] = sc;
+        }
+    }
+}
+
+// Whole-tile scalar (QCK_OP_PHASE after resolve_tile).
+template <class P>
+__device__ void run_phase(double2* s, int T, double2 sc) {
+    if (!(sc.x == 1.0 && sc.y == 0.0)) {  // uniform
+        const uint32_t n = 1u << T;
+        for (uint32_t j = P::tid(); j < n; j += P::nth()) s[j] = cmul(sc, s[j]);
+    }
+    P::sync();
 }
 
 // One cluster: header so[h], members so[h+1 .. h+n].  Every thread owns groups of 8 amplitudes
@@ -244,7 +294,7 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
     const int kind = op.w0.x, q0 = op.w0.y, q1 = op.w0.z;
     int nl = op.w1.z;
     if (nl <= 0 || nl > T) nl = T;
-    if (kind == QCK_OP_U1) {
+    if (kind == QCK_OP_U1 || kind == QCK_OP_U1X) {
         const double2 m00 = op.m[0], m01 = op.m[1], m10 = op.m[2], m11 = op.m[3];
         const uint32_t n = 1u << (nl - 1);
         if (m01.x == 0.0 && m01.y == 0.0 && m10.x == 0.0 && m10.y == 0.0) {
@@ -288,7 +338,21 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
 #pragma unroll
             for (int e = 0; e < 16; ++e) m[e] = op.m[e];
             const uint32_t x1 = swz(b0), x2 = swz(b1), x3 = x1 ^ x2;
-            if ((nth & (nth - 1)) == 0) {
+            bool diag = true;  // uniform: cz / cp / rzz and their fusions with one-qubit phases
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                if (e % 5 != 0) diag = diag && m[e].x == 0.0 && m[e].y == 0.0;
+            if (diag) {  // 4 complex multiplications per quad instead of 16, entries equal to 1 skipped
+                const bool t0 = !(m[0].x == 1.0 && m[0].y == 0.0), t1 = !(m[5].x == 1.0 && m[5].y == 0.0);
+                const bool t2 = !(m[10].x == 1.0 && m[10].y == 0.0), t3 = !(m[15].x == 1.0 && m[15].y == 0.0);
+                for (uint32_t p = tid; p < n; p += nth) {
+                    const uint32_t i0 = swz(insert_zero(insert_zero(p, lo), hi));
+                    if (t0) s[i0] = cmul(m[0], s[i0]);
+                    if (t1) s[i0 ^ x1] = cmul(m[5], s[i0 ^ x1]);
+                    if (t2) s[i0 ^ x2] = cmul(m[10], s[i0 ^ x2]);
+                    if (t3) s[i0 ^ x3] = cmul(m[15], s[i0 ^ x3]);
+                }
+            } else if ((nth & (nth - 1)) == 0) {
                 const uint32_t st = swz(insert_zero(insert_zero((uint32_t)tid, lo), hi));
                 if ((uint32_t)tid < n) {
 #pragma unroll 2
@@ -322,7 +386,8 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
 // CTA call this with identical arguments; the state is synchronised on return.
 template <class P>
 __device__ void apply_ops(double2* s, int T, StagedOp* so, int n_stage, const qck_op* __restrict__ ops, int begin,
-                          int end, const double* __restrict__ mats, const int* digits, bool prestaged) {
+                          int end, const double* __restrict__ mats, const int* digits, bool prestaged,
+                          bool resolve = false, unsigned long long base = 0ull) {
     int c0 = begin;
     while (c0 < end) {
         const int n = (end - c0) < n_stage ? (end - c0) : n_stage;
@@ -330,13 +395,24 @@ __device__ void apply_ops(double2* s, int T, StagedOp* so, int n_stage, const qc
             stage_ops<P>(so, ops, c0, n, mats, digits);
             P::sync();
         }
+        if (resolve) {  // headers whose terms were cut off by the chunk are resolved with the next chunk
+            resolve_tile<P>(so, n, base);
+            P::sync();
+        }
         int i = 0;
         while (i < n) {
-            if (so[i].w0.x == QCK_OP_CLUSTER) {
+            const int kind_i = so[i].w0.x;
+            if (kind_i == QCK_OP_CLUSTER) {
                 const int members = so[i].w0.y;
                 if (i + members >= n && c0 + n < end) break;  // cluster continues past the staged chunk
                 run_cluster<P>(s, T, so, i, mats);
                 i += 1 + members;
+            } else if (kind_i == QCK_OP_U1X || kind_i == QCK_OP_PHASE) {
+                const int terms = so[i].w0.z;
+                if (i + terms >= n && c0 + n < end) break;  // terms continue past the staged chunk
+                if (kind_i == QCK_OP_U1X) run_single<P>(s, T, so[i], mats);
+                else run_phase<P>(s, T, so[i].m[0]);
+                i += 1 + terms;
             } else {
                 run_single<P>(s, T, so[i], mats);
                 ++i;
@@ -503,7 +579,8 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    apply_ops<WholeCta>(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, true);
+    apply_ops<WholeCta>(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, true, sw.has_x != 0,
+                        base);
     {
         const uint32_t xr = (threadIdx.x >> 3) & 7u;  // blockDim.x == 256: bits 3-5 of j never change
 #pragma unroll 4
@@ -540,6 +617,7 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
 struct TmaSweepDev {
     int n_tile, op_begin, op_end, n_state;
     int init;                 // nothing is live yet: no loads, tile 0 starts as |0..0>
+    int has_x;                // the op range holds tile-resolved ops
     int lowc, h, k;           // low run [0, lowc), main run [h, h + k) (state bit positions)
     int n_load, n_store;      // boxes per tile
     unsigned load_bytes;      // bytes per load box
@@ -716,7 +794,9 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
                 P::sync();
                 stage_ops<P>(so, plan.ops, sw.op_begin, n_ops, plan.mats, digits, perm_s);
                 staged_inst = d.inst;
+                if (sw.has_x) P::sync();
             }
+            if (sw.has_x) resolve_tile<P>(so, n_ops, d.base);
             if (ctid == 0) dbg_step = 2;
             if (sw.init) {
                 for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS) s[j] = make_double2(j == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
@@ -729,9 +809,16 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
             P::sync();
             if (ctid == 0) dbg_step = 3;
             for (int i = 0; i < n_ops;) {
-                if (so[i].w0.x == QCK_OP_CLUSTER) {
+                const int kind_i = so[i].w0.x;
+                if (kind_i == QCK_OP_CLUSTER) {
                     run_cluster<P>(s, T, so, i, plan.mats);
                     i += 1 + so[i].w0.y;
+                } else if (kind_i == QCK_OP_U1X) {
+                    run_single<P>(s, T, so[i], plan.mats);
+                    i += 1 + so[i].w0.z;
+                } else if (kind_i == QCK_OP_PHASE) {
+                    run_phase<P>(s, T, so[i].m[0]);
+                    i += 1 + so[i].w0.z;
                 } else {
                     run_single<P>(s, T, so[i], plan.mats);
                     ++i;
@@ -816,6 +903,7 @@ static SweepDev sweep_dev(const qck_sweep& sw, bool init) {
     s.op_begin = sw.op_begin;
     s.op_end = sw.op_end;
     s.init = init ? 1 : 0;
+    s.has_x = sw.flags & 1;
     int c = 0;
     while (c < sw.n_tile && sw.pos[c] == c) ++c;
     s.n_low = c;
@@ -887,6 +975,7 @@ static bool tma_describe(const qck_sim_plan* plan, int i, unsigned long long liv
     d.op_end = sw.op_end;
     d.n_state = N;
     d.init = live_before == 0ull;
+    d.has_x = sw.flags & 1;
     d.lowc = lowc;
     d.live_before = live_before;
     // main run: the longest run of consecutive positions among the remaining tile bits (<= 8 bits: box

@@ -71,7 +71,10 @@ QCK_API int64_t qck_launch_count(const qck_handle* h);
 #define QCK_MAX_DIGITS 16
 #define QCK_MAX_OUT_BITS 40
 
-enum { QCK_OP_U1 = 0, QCK_OP_CX = 1, QCK_OP_CZ = 2, QCK_OP_U2 = 3, QCK_OP_CLUSTER = 4 };
+enum {
+    QCK_OP_U1 = 0, QCK_OP_CX = 1, QCK_OP_CZ = 2, QCK_OP_U2 = 3, QCK_OP_CLUSTER = 4,
+    QCK_OP_U1X = 5, QCK_OP_TERM = 6, QCK_OP_PHASE = 7
+};
 #define QCK_CLUSTER_QUBITS 3
 
 /* One gate application.  Qubits are TILE-LOCAL bit positions of the sweep the op
@@ -81,7 +84,18 @@ enum { QCK_OP_U1 = 0, QCK_OP_CX = 1, QCK_OP_CZ = 2, QCK_OP_U2 = 3, QCK_OP_CLUSTE
  * QCK_OP_CLUSTER is a header: the next q0 ops act only on the QCK_CLUSTER_QUBITS
  * tile positions (mat, sel_digit, sel_stride) = ascending positions p0 < p1 < p2 and
  * address them by their rank 0..2; each thread applies the whole cluster to its 8
- * amplitudes in registers (one shared-memory round trip for several gates). */
+ * amplitudes in registers (one shared-memory round trip for several gates).
+ *
+ * Tile-resolved ops (streaming sweeps only).  A qubit an op is block diagonal in (the control of a
+ * cx, both qubits of cz / cp / rzz, the qubit of rz / z / p) need not be in the tile of the sweep: its bit
+ * is a constant of the tile and only selects a variant.
+ *   QCK_OP_U1X  header: a one-qubit op on tile qubit q0 whose matrix is the ordered product of the
+ *               q1 following QCK_OP_TERM records; term j contributes mats[mat + 8 * bit(e0)]
+ *               (two 2x2 matrices), e0 = its q0 = a STATE bit position outside the tile.
+ *   QCK_OP_PHASE header: a scalar for the whole tile, the product over the q1 following terms of
+ *               mats[mat + 2 * (bit(q0) + 2 * bit(q1))] (q1 = -1: one qubit, two scalars).
+ *   QCK_OP_TERM sel_stride = number of complex values the record owns (8, 2 or 4).
+ * The device resolves them once per tile (sim.cu: resolve_tile). */
 typedef struct {
     int32_t kind;        /* QCK_OP_*                                                     */
     int32_t q0, q1;      /* U1: q0.  CX: control q0, target q1.  CZ/U2: q0 (bit0), q1     */
@@ -89,7 +103,8 @@ typedef struct {
     int32_t sel_digit;   /* -1, or the label digit that selects the variant matrix:       */
     int32_t sel_stride;  /*   offset = mat + digit[sel_digit] * sel_stride                */
     int32_t n_live;      /* ops touch only the first 2^n_live amplitudes of the tile      */
-    int32_t reserved;    /* 1 on the member ops of a cluster (q0/q1 are ranks), else 0    */
+    int32_t reserved;    /* 1 when q0/q1 are not tile positions (cluster members: ranks;   */
+                         /* TERM / PHASE records: state positions), else 0                */
 } qck_op;
 
 /* A sweep = one pass over the state: every CTA stages a 2^n_tile tile (the
@@ -98,7 +113,7 @@ typedef struct {
 typedef struct {
     int32_t n_tile;
     int32_t op_begin, op_end;
-    int32_t reserved;
+    int32_t flags;                         /* bit 0: the op range holds QCK_OP_U1X / QCK_OP_PHASE */
     int32_t pos[QCK_MAX_TILE_QUBITS + 2];  /* ascending state-bit positions of the tile bits */
 } qck_sweep;
 

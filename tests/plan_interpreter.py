@@ -41,6 +41,35 @@ def apply_op(psi, idx, kind, g0, g1, mats, moff):
     return new
 
 
+def cond_matrix(mats, terms, base):
+    """Tile-resolved matrix of an OP_U1X chain: ordered product of the term matrices the bits of
+    ``base`` select (first term applied first)."""
+    m = np.eye(2, dtype=np.complex128)
+    for t in terms:
+        e0, off = int(t[1]), int(t[3])
+        pair = mats[off:off + 16].view(np.complex128).reshape(2, 2, 2)
+        m = pair[(base >> e0) & 1] @ m
+    return m
+
+
+def phase_scalar(mats, terms, base):
+    s = 1.0 + 0j
+    for t in terms:
+        e0, e1, off, n = int(t[1]), int(t[2]), int(t[3]), int(t[5])
+        sc = mats[off:off + 2 * n].view(np.complex128)
+        s *= sc[((base >> e0) & 1) + (2 * ((base >> e1) & 1) if e1 >= 0 else 0)]
+    return s
+
+
+def apply_u1_matrix(psi, idx, g0, m, where=None):
+    lo_sel = _bits(idx, g0) == 0
+    hi_sel = _bits(idx, g0) == 1
+    partner_hi = psi[idx | (1 << g0)]
+    partner_lo = psi[idx & ~(1 << g0)]
+    new = np.where(lo_sel, m[0, 0] * psi + m[0, 1] * partner_hi, m[1, 0] * partner_lo + m[1, 1] * psi)
+    return new if where is None else np.where(where, new, psi)
+
+
 def run_plan(program, plan, label, return_state=False):
     """-> output row (1-D float64) of one instance (or the final statevector)."""
     mats = program.mats
@@ -51,8 +80,38 @@ def run_plan(program, plan, label, return_state=False):
     idx = np.arange(1 << N)
     for positions, b, e in plan.sweeps:
         cluster_pos, members_left = None, 0
-        for op in plan.ops[b:e]:
+        seg = plan.ops[b:e]
+        tile_mask = sum(1 << p for p in positions)
+        skip = 0
+        for oi, op in enumerate(seg):
             kind, q0, q1, mat, sel, stride, n_live, _ = (int(x) for x in op)
+            if skip:
+                skip -= 1
+                assert kind == _lib.OP_TERM
+                continue
+            if kind in (_lib.OP_U1X, _lib.OP_PHASE):
+                # tile-resolved forms: the outside (diag) qubits select a variant per tile
+                n_terms = q1
+                terms = seg[oi + 1:oi + 1 + n_terms]
+                skip = n_terms
+                outside = set()
+                for t in terms:
+                    assert int(t[0]) == _lib.OP_TERM
+                    for e in (int(t[1]), int(t[2])):
+                        if e >= 0:
+                            assert not (tile_mask >> e) & 1, "term qubit must be outside the tile"
+                            outside.add(e)
+                outside = sorted(outside)
+                for combo in range(1 << len(outside)):
+                    base = sum(((combo >> j) & 1) << e for j, e in enumerate(outside))
+                    sel_amp = np.ones(len(idx), dtype=bool)
+                    for j, e in enumerate(outside):
+                        sel_amp &= _bits(idx, e) == ((combo >> j) & 1)
+                    if kind == _lib.OP_PHASE:
+                        psi = np.where(sel_amp, phase_scalar(mats, terms, base) * psi, psi)
+                    else:
+                        psi = apply_u1_matrix(psi, idx, positions[q0], cond_matrix(mats, terms, base), sel_amp)
+                continue
             if kind == _lib.OP_CLUSTER:           # header: members address the 3 positions by rank
                 cluster_pos, members_left = [mat, sel, stride], q0
                 assert cluster_pos == sorted(cluster_pos) and len(set(cluster_pos)) == 3

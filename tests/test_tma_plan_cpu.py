@@ -39,6 +39,7 @@ def _plan_struct(program, plan):
         arr[i].n_tile = len(positions)
         arr[i].op_begin = b
         arr[i].op_end = e
+        arr[i].flags = int(np.isin(plan.ops[b:e, 0], (_lib.OP_U1X, _lib.OP_PHASE)).any())
         for j, x in enumerate(positions):
             arr[i].pos[j] = x
     st = _lib.QckSimPlan()
@@ -117,8 +118,20 @@ def emulate(program, plan, label):
                     stage[zf] = 0
                 assert not np.isnan(stage).any(), "tile slots neither loaded nor zero-filled"
                 cluster_pos, members_left = None, 0
-                for op in plan.ops[b:e]:
+                seg, skip = plan.ops[b:e], 0
+                for oi, op in enumerate(seg):
                     kind, q0, q1, mat, sel, stride, n_live, member = (int(x) for x in op)
+                    if skip:
+                        skip -= 1
+                        continue
+                    if kind in (_lib.OP_U1X, _lib.OP_PHASE):      # resolved once per tile from its base
+                        terms = seg[oi + 1:oi + 1 + q1]
+                        skip = q1
+                        if kind == _lib.OP_PHASE:
+                            stage = pi.phase_scalar(mats, terms, base) * stage
+                        else:
+                            stage = pi.apply_u1_matrix(stage, tidx, perm[q0], pi.cond_matrix(mats, terms, base))
+                        continue
                     if kind == _lib.OP_CLUSTER:
                         cluster_pos, members_left = [perm[mat], perm[sel], perm[stride]], q0
                         continue
@@ -208,3 +221,29 @@ def test_ineligible_sweeps_are_reported():
     assert describe(st, 0, 0, False) is not None
     # live set that does not cover the low run -> the low-run box cannot be loaded
     assert describe(st, 1, 0b1, False) is None
+
+
+@pytest.mark.parametrize("name,n,depth,onchip,tile,max_sweeps", [
+    ("qft", 10, 1, 5, 6, 3), ("aqft", 11, 1, 6, 7, 3), ("qft", 12, 1, 6, 8, 3), ("hwe", 11, 2, 6, 7, 5),
+    ("syc", 12, 3, 6, 7, 7),
+])
+def test_diag_qubits_need_no_tile_residency(name, n, depth, onchip, tile, max_sweeps):
+    """Controls of cx and the qubits of cz / cp / rz stay outside the tile (OP_U1X / OP_PHASE, resolved per
+    tile): far fewer sweeps for qft-like circuits, same probabilities as the oracle."""
+    from oracle import statevector as sv
+    prog = _uncut_program(name, n, depth, onchip_max=onchip, stream_tile=tile)
+    (plan,) = prog.plans()
+    kinds = plan.ops[:, 0].tolist()
+    assert len(plan.sweeps) <= max_sweeps
+    if name in ("qft", "aqft", "hwe"):
+        assert kinds.count(_lib.OP_U1X) > 0 and kinds.count(_lib.OP_TERM) >= kinds.count(_lib.OP_U1X)
+    # every term refers to a state bit outside its sweep's tile
+    for positions, b, e in plan.sweeps:
+        for r in plan.ops[b:e]:
+            if r[0] == _lib.OP_TERM:
+                assert r[1] not in positions and (r[2] < 0 or r[2] not in positions)
+    circ = gen.gen_circ(name, n, depth, seed=1)
+    want = sv.dense(sv.exact_distribution(circ), circ.num_clbits)
+    assert np.abs(pi.run_plan(prog, plan, 0) - want).max() < 1e-13
+    got, _, _ = emulate(prog, plan, 0)
+    assert np.abs(got - pi.run_plan(prog, plan, 0, return_state=True)).max() < 1e-14
