@@ -140,10 +140,21 @@ struct StagedOp {
 // Which threads cooperate on a tile.  WholeCta: every thread of the block, __syncthreads().
 // ConsumerWarps<N>: threads [32, 32 + N) of a warp-specialised block (warp 0 drives TMA), named
 // barrier 1 - the producer warp never takes part in it.
+// CTA barrier for the gate passes.  A pass over fewer items than a warp has lanes (16 quads of a 6-qubit
+// tile) leaves the warp diverged in front of the barrier; __syncwarp() makes the reconvergence explicit.
+// NOTE (observed on sm_100a, nvcc 12.9): no pass may leave through an early `return` that skips its
+// closing barrier, even a warp-uniform one - with the passes inlined into the op loop the lanes that had
+// skipped the previous pass's loop then ran ahead of their own warp, and the next pass's results were
+// overwritten by the lagging lanes' stores (plain sweep kernel, 64-amplitude tiles).  Every pass therefore
+// ends in exactly one barrier on every path.
+__device__ __forceinline__ void cta_sync() {
+    __syncwarp();
+    __syncthreads();
+}
 struct WholeCta {
     __device__ static __forceinline__ int tid() { return threadIdx.x; }
     __device__ static __forceinline__ int nth() { return blockDim.x; }
-    __device__ static __forceinline__ void sync() { __syncthreads(); }
+    __device__ static __forceinline__ void sync() { cta_sync(); }
 };
 template <int N>
 struct ConsumerWarps {
@@ -298,8 +309,9 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
         const double2 m00 = op.m[0], m01 = op.m[1], m10 = op.m[2], m11 = op.m[3];
         const uint32_t n = 1u << (nl - 1);
         if (m01.x == 0.0 && m01.y == 0.0 && m10.x == 0.0 && m10.y == 0.0) {
-            if (m00.x == 1.0 && m00.y == 0.0 && m11.x == 1.0 && m11.y == 0.0) return;  // uniform
-            for (uint32_t p = tid; p < n; p += nth) {
+            // identity (uniform): nothing to do, but the pass still ends in its barrier (see cta_sync)
+            const bool ident = m00.x == 1.0 && m00.y == 0.0 && m11.x == 1.0 && m11.y == 0.0;
+            for (uint32_t p = ident ? n : tid; p < n; p += nth) {
                 const uint32_t i0 = insert_zero(p, q0), i1 = i0 | (1u << q0);
                 s[swz(i0)] = cmul(m00, s[swz(i0)]);
                 s[swz(i1)] = cmul(m11, s[swz(i1)]);
@@ -458,13 +470,13 @@ __global__ void __launch_bounds__(256) sim_onchip_kernel(PlanDev plan, int op_be
     const int label = labels[blockIdx.x];
     if (threadIdx.x == 0) decode_digits(plan, label, digits);
     const uint32_t n_amp = 1u << plan.n_state;
-    __syncthreads();  // digits visible
+    cta_sync();  // digits visible
     {
         const int n0 = (op_end - op_begin) < plan.n_stage ? (op_end - op_begin) : plan.n_stage;
         stage_ops<WholeCta>(so, plan.ops, op_begin, n0, plan.mats, digits);  // global loads overlap the state init
     }
     for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
-    __syncthreads();
+    cta_sync();
     apply_ops<WholeCta>(s, plan.n_state, so, plan.n_stage, plan.ops, op_begin, op_end, plan.mats, digits, true);
     const uint64_t n_out = 1ull << plan.n_out_bits;
     double* row = out + (long long)label * row_stride;
@@ -517,14 +529,14 @@ __global__ void __launch_bounds__(256) sim_onchip_group_kernel(const __grid_cons
         plan.n_stage = G.n_stage;
         decode_digits(plan, label, digits);
     }
-    __syncthreads();
+    cta_sync();
     {
         const int n0 = (pv.op_end - pv.op_begin) < G.n_stage ? (pv.op_end - pv.op_begin) : G.n_stage;
         stage_ops<WholeCta>(so, G.ops, pv.op_begin, n0, G.mats, digits);
     }
     const uint32_t n_amp = 1u << G.n_state;
     for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
-    __syncthreads();
+    cta_sync();
     apply_ops<WholeCta>(s, G.n_state, so, G.n_stage, G.ops, pv.op_begin, pv.op_end, G.mats, digits, true);
     const uint64_t n_out = 1ull << plan.n_out_bits;
     double* row = out + (long long)label * row_stride;
@@ -555,7 +567,7 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
     unsigned long long base = blockIdx.x;
     for (int j = 0; j < T; ++j) base = insert_zero64(base, sw.pos[j]);
     double2* st = work + (unsigned long long)blockIdx.y * state_stride;
-    __syncthreads();
+    cta_sync();
     const uint32_t n_amp = 1u << T, low_mask = (1u << c) - 1u;
     if (sw.init) {
         for (uint32_t j = threadIdx.x; j < n_amp; j += blockDim.x)
@@ -578,7 +590,7 @@ __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev s
         stage_ops<WholeCta>(so, plan.ops, sw.op_begin, n0, plan.mats, digits);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    cta_sync();
     apply_ops<WholeCta>(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, true, sw.has_x != 0,
                         base);
     {
@@ -710,7 +722,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (threadIdx.x < 16) perm_s[threadIdx.x] = sw.perm[threadIdx.x];
-    __syncthreads();
+    cta_sync();
 
     if (threadIdx.x < 32) {
         if (threadIdx.x != 0) return;
