@@ -399,12 +399,12 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
 template <class P>
 __device__ void apply_ops(double2* s, int T, StagedOp* so, int n_stage, const qck_op* __restrict__ ops, int begin,
                           int end, const double* __restrict__ mats, const int* digits, bool prestaged,
-                          bool resolve = false, unsigned long long base = 0ull) {
+                          bool resolve = false, unsigned long long base = 0ull, const int* perm = nullptr) {
     int c0 = begin;
     while (c0 < end) {
         const int n = (end - c0) < n_stage ? (end - c0) : n_stage;
         if (!(prestaged && c0 == begin)) {  // the caller may have staged the first chunk already
-            stage_ops<P>(so, ops, c0, n, mats, digits);
+            stage_ops<P>(so, ops, c0, n, mats, digits, perm);
             P::sync();
         }
         if (resolve) {  // headers whose terms were cut off by the chunk are resolved with the next chunk
@@ -801,14 +801,15 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
         if (d.flags == TMA_TILE_DEAD) {
             for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS) s[j] = make_double2(0.0, 0.0);
         } else {
+            const bool chunked = n_ops > plan.n_stage;  // more records than the stage holds: restaged per tile
             if (d.inst != staged_inst) {  // uniform; the matrices depend on the instance's label digits
                 if (ctid == 0) decode_digits(plan, labels[inst_base + d.inst], digits);
                 P::sync();
-                stage_ops<P>(so, plan.ops, sw.op_begin, n_ops, plan.mats, digits, perm_s);
+                if (!chunked) stage_ops<P>(so, plan.ops, sw.op_begin, n_ops, plan.mats, digits, perm_s);
                 staged_inst = d.inst;
-                if (sw.has_x) P::sync();
+                if (sw.has_x && !chunked) P::sync();
             }
-            if (sw.has_x) resolve_tile<P>(so, n_ops, d.base);
+            if (sw.has_x && !chunked) resolve_tile<P>(so, n_ops, d.base);
             if (ctid == 0) dbg_step = 2;
             if (sw.init) {
                 for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS) s[j] = make_double2(j == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
@@ -820,7 +821,10 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
             }
             P::sync();
             if (ctid == 0) dbg_step = 3;
-            for (int i = 0; i < n_ops;) {
+            if (chunked)
+                apply_ops<P>(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, false,
+                             sw.has_x != 0, d.base, perm_s);
+            for (int i = 0; i < n_ops && !chunked;) {
                 const int kind_i = so[i].w0.x;
                 if (kind_i == QCK_OP_CLUSTER) {
                     run_cluster<P>(s, T, so, i, plan.mats);
@@ -958,8 +962,20 @@ struct TmaLaunch {
     int n_stage;
 };
 
-static size_t tma_smem_bytes(int n_tile, int n_ops) {
-    return 1024 + (size_t)TMA_STAGES * ((size_t)16 << n_tile) + sizeof(StagedOp) * (size_t)(n_ops < 1 ? 1 : n_ops);
+// records the op stage of the TMA kernel holds: everything when it fits next to the tile ring, else as
+// many as fit (the kernel then restages chunks per tile; a header and its members / terms need <= 33)
+static int tma_stage_records(int n_tile, int n_ops, int max_smem_optin) {
+    const long long room = (long long)max_smem_optin - 512 - 1024 - (long long)TMA_STAGES * ((long long)16 << n_tile);
+    long long cap = room / (long long)sizeof(StagedOp);
+    if (const char* env = getenv("QCK_TMA_STAGE_CAP")) {  // test knob: force the chunked path
+        const long long v = atoll(env);
+        if (v >= 48 && v < cap) cap = v;
+    }
+    if (cap > n_ops) cap = n_ops;
+    return (int)(cap < 1 ? 1 : cap);
+}
+static size_t tma_smem_bytes(int n_tile, int n_records) {
+    return 1024 + (size_t)TMA_STAGES * ((size_t)16 << n_tile) + sizeof(StagedOp) * (size_t)(n_records < 1 ? 1 : n_records);
 }
 
 // Can this sweep run on the TMA kernel?  (pure host logic, no CUDA calls: unit-testable)
@@ -970,7 +986,8 @@ static bool tma_describe(const qck_sim_plan* plan, int i, unsigned long long liv
     const int T = sw.n_tile, N = plan->n_state_qubits;
     const int n_ops = sw.op_end - sw.op_begin;
     if (T < 3 || T > 13 || N > 35) return false;
-    if ((int)tma_smem_bytes(T, n_ops) + 512 > max_smem_optin) return false;
+    const int n_records = tma_stage_records(T, n_ops, max_smem_optin);
+    if (n_records < n_ops && n_records < 48) return false;  // no room for a useful op stage
     int c = 0;
     while (c < T && sw.pos[c] == c) ++c;
     int lowc = c < 11 ? c : 11;
@@ -1070,8 +1087,8 @@ static bool tma_describe(const qck_sim_plan* plan, int i, unsigned long long liv
     d.enum_mask = (last ? all : live_before) & ~tile_mask;
     d.n_enum_bits = __builtin_popcountll(d.enum_mask);
     L.n_work = (unsigned long long)batch << d.n_enum_bits;
-    L.smem = tma_smem_bytes(T, n_ops);
-    L.n_stage = n_ops < 1 ? 1 : n_ops;
+    L.smem = tma_smem_bytes(T, n_records);
+    L.n_stage = n_records;
     // extents the tensor map can describe
     if (((unsigned long long)batch << (N - d.h - d.k)) > 0xffffffffull) return false;
     return true;

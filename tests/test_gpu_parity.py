@@ -212,6 +212,29 @@ def test_tma_sweep_statevector_equals_plain(dev, name, n, depth):
     assert abs(float((a * a).sum()) - 1.0) < 1e-12
 
 
+def test_tma_sweep_chunked_op_stage(dev):
+    """More op records than the shared-memory op stage holds: the TMA kernel restages chunks per tile
+    (forced with QCK_TMA_STAGE_CAP); tile-resolved ops (cp with an outside qubit) included."""
+    import os
+    circ = gen.gen_circ("qft", 17, 1, seed=0).decompose_two_qubit()
+    virt = vcm.VirtualCircuit(circ)
+    (frag,) = virt.active_fragments()
+    ex = virt.executor(frag, dev, True)
+    assert max(e - b for _, b, e in ex.plans[0].sweeps) > 48
+    kinds = ex.plans[0].ops[:, 0].tolist()
+    assert kinds.count(_lib.OP_U1X) > 0
+    h = _lib.get_handle(0)
+    full = _with_tma("1", lambda: ex.run(h).cpu().numpy())
+    os.environ["QCK_TMA_STAGE_CAP"] = "48"
+    try:
+        chunked = _with_tma("1", lambda: ex.run(h).cpu().numpy())
+    finally:
+        os.environ.pop("QCK_TMA_STAGE_CAP", None)
+    plain = _with_tma("0", lambda: ex.run(h).cpu().numpy())
+    assert np.abs(full - chunked).max() < 1e-15 and np.abs(full - plain).max() < 1e-15
+    assert np.abs(full - 2.0 ** -17).max() < 1e-12          # qft of |0..0> is uniform
+
+
 def test_b200_backend_duck_type(dev):
     """backend.run(circuits, shots).result().get_counts() -> QuasiDistr.from_counts (run.py:42-56)."""
     qc, cut = make_semcheck_circuit("cx")

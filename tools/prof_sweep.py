@@ -57,10 +57,15 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 n_sw = len(pl.sweeps)
 full_bytes = (2 * n_sw - 1) * (16 << n)
+ld, sd, used = C.c_uint64(), C.c_uint64(), C.c_int()
+h.check(h.lib.qck_sim_plan_traffic(C.byref(st), 1, C.byref(ld), C.byref(sd), C.byref(used)))
+moved = ld.value + sd.value
 norm = float((state * state).sum())
 print(f"{name}-{n} d{depth} uncut, QCK_SIM_TMA={os.environ.get('QCK_SIM_TMA', '1')}: sweeps {n_sw}, records {len(pl.ops)}, "
       f"sweeps-only {ms:.3f} ms = {full_bytes / ms / 1e6:.0f} GB/s of full-sweep traffic ({full_bytes / 1e9:.1f} GB), "
       f"norm {norm:.12f}")
+print(f"  HBM bytes moved by the sweeps ({'TMA path, live-qubit tracking' if used.value else 'plain path'}): "
+      f"{ld.value / 1e9:.2f} GB loaded + {sd.value / 1e9:.2f} GB stored = {moved / ms / 1e6:.0f} GB/s")
 del state
 t = ex.run(h)
 torch.cuda.synchronize()
