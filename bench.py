@@ -51,9 +51,11 @@ def parse_args():
     ap.add_argument("--cpu-sample-bits", type=int, default=None,
                     help="log2 of the output entries the CPU baseline knits per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--uncut-statevector", action="store_true",
+    ap.add_argument("--uncut-statevector", action="store_true", default=None,
                     help="also simulate the UNCUT circuit as one statevector on this GPU (64 GiB at 32 qubits), "
-                         "report the streaming simulator against the HBM roofline and the dense fidelity")
+                         "report the streaming simulator against the HBM roofline and the dense fidelity "
+                         "(default: on for one GPU outside --profile)")
+    ap.add_argument("--no-uncut-statevector", dest="uncut_statevector", action="store_false")
     ap.add_argument("--profile", action="store_true",
                     help="timed region only (for runs under ncu): no e2e leg, no oracle report, no CPU baseline")
     return ap.parse_args()
@@ -65,59 +67,73 @@ def metric_name(workload: str) -> str:
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region: an NVML polling thread (a few ms per sample;
+    the nvidia-smi process of the profiling recipe needs longer to start than a 100 ms timed region lasts)."""
+    REASONS = (("hw_slowdown", "HwSlowdown"), ("hw_thermal_slowdown", "HwThermalSlowdown"),
+               ("sw_thermal_slowdown", "SwThermalSlowdown"), ("sw_power_cap", "SwPowerCap"),
+               ("hw_power_brake_slowdown", "HwPowerBrakeSlowdown"))
 
-    def __init__(self, gpu_index: int, period_ms: int = 50) -> None:
-        self.proc = None
-        self.path = f"/tmp/qck_clocks_{os.getpid()}.csv"
+    def __init__(self, gpu_index: int, period_ms: int = 5) -> None:
+        import threading
+        self.rows, self.err, self.nv, self.handle = [], None, None, None
+        self._stop = threading.Event()
+        self.period = period_ms / 1e3
         try:
-            self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", str(period_ms), "-i", str(gpu_index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if visible:
+                try:
+                    phys = int(visible.split(",")[gpu_index])
+                except (ValueError, IndexError):
+                    phys = gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as exc:      # no NVML: say so in the bench line
+            self.err = repr(exc)
+
+    def _sample(self) -> None:
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
         except Exception:
-            self.proc = None
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.rows.append((time.time(), mhz, mask))
+
+    def _run(self) -> None:
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception as exc:
+                self.err = repr(exc)
+                return
+            self._stop.wait(self.period)
 
     def stop(self, t0: float, t1: float) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.fh.close()
-        from datetime import datetime
-        rows, in_region = [], []
-        for line in open(self.path):
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 10:
-                continue
-            try:
-                ts = datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                row = (ts, float(parts[2]), float(parts[3]), parts[5:10])
-            except Exception:
-                continue
-            rows.append(row)
-            if t0 - 0.05 <= ts <= t1 + 0.05:
-                in_region.append(row)
-        try:
-            os.remove(self.path)
-        except OSError:
-            pass
-        use = in_region or rows
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"NVML unavailable: {self.err}"]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        in_region = [r for r in self.rows if t0 <= r[0] <= t1]
+        use = in_region or self.rows
         if not use:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        names = ["active", "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [f"no samples ({self.err})"]}
         reasons = set()
-        for _, _, _, flags in use:
-            for n, f in zip(names[1:], flags[1:]):
-                if f.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(r[1] for r in use), "sm_max_mhz": use[0][2],
-                "reasons": sorted(reasons), "samples": len(use), "samples_in_timed_region": len(in_region)}
+        for _, _, mask in use:
+            for name, suffix in self.REASONS:
+                bit = getattr(self.nv, "nvmlClocksEventReason" + suffix, None)
+                if bit is None:
+                    bit = getattr(self.nv, "nvmlClocksThrottleReason" + suffix, 0)
+                if mask & bit:
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(r[1] for r in use), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(use), "samples_in_timed_region": len(in_region),
+                "source": "NVML polling thread"}
 
 
 # ----------------------------------------------------------------------------- CPU baseline (oracle port)
@@ -432,6 +448,8 @@ def main() -> None:
     if rank == 0 and not args.profile:
         extra = gpu_fidelity_report(virt, circ, tables_holder["t"], out, device, fid, vc, handle, K, n_out, world)
 
+    if args.uncut_statevector is None:
+        args.uncut_statevector = not args.profile
     if rank == 0 and world == 1 and args.uncut_statevector:
         extra.update(uncut_statevector_report(circ, out, device, fid, vc, handle, peaks_hbm()))
 
@@ -513,7 +531,10 @@ def peaks_hbm() -> float:
 
 def uncut_statevector_report(circ, cut_result, device, fid, vc, handle, peak) -> dict:
     """the uncut circuit as ONE statevector on this GPU (Utilities.py:39-69 runs it on
-    Aer).  Streaming regime: every sweep reads and writes the whole state once."""
+    Aer).  Streaming regime; the sweeps run on the TMA kernel with live-qubit tracking when eligible.  The
+    bytes are the exact HBM traffic of the sweeps (qck_sim_plan_traffic), not a full read + write per
+    sweep."""
+    import ctypes as C
     import torch
     rep = {}
     try:
@@ -521,25 +542,45 @@ def uncut_statevector_report(circ, cut_result, device, fid, vc, handle, peak) ->
         (frag,) = virt_u.active_fragments()
         ex = virt_u.executor(frag, device, True)
         n = ex.max_state
-        sweeps = len(ex.plans[0].sweeps)
+        plan = ex.plans[0]
+        sweeps = len(plan.sweeps)
         ex.upload()
         table = ex.run(handle)                                 # warm-up (allocates state + row)
         torch.cuda.synchronize(device)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         reps = 3
         e0.record()
         for _ in range(reps):
             ex.run(handle, out=table)
         e1.record()
-        torch.cuda.synchronize(device)
-        ms = e0.elapsed_time(e1) / reps
-        state_bytes = 16 << n
-        # first sweep synthesises |0..0> (write only), the others read + write; the fold reads the
-        # state and writes the probabilities
-        alg = state_bytes * (2 * sweeps - 1) + state_bytes + (8 << len(ex.plans[0].out_pos))
-        rep["uncut_statevector"] = {"qubits": n, "sweeps": sweeps, "ops": int(len(ex.plans[0].ops)), "ms": ms,
-                                    "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6,
-                                    "frac_of_measured_hbm_peak": alg / ms / 1e6 / peak}
+        info = {"qubits": n, "sweeps": sweeps, "ops": int(len(plan.ops))}
+        if ex.streaming:
+            st, _, _ = ex._structs[0]
+            st.d_ops = ex.d_blob.data_ptr() + ex._off_ops
+            st.d_mats = ex.d_blob.data_ptr()
+            stream = torch.cuda.current_stream(device).cuda_stream
+            for _ in range(reps):                              # the sweeps alone, into the same state buffer
+                handle.check(handle.lib.qck_sim_statevector(handle.ptr, C.byref(st), 0, ex._work.data_ptr(),
+                                                            ex._work.numel(), stream))
+            e2.record()
+            torch.cuda.synchronize(device)
+            ms, ms_sweeps = e0.elapsed_time(e1) / reps, e1.elapsed_time(e2) / reps
+            ld, sd, used = C.c_uint64(), C.c_uint64(), C.c_int()
+            handle.check(handle.lib.qck_sim_plan_traffic(C.byref(st), 1, C.byref(ld), C.byref(sd), C.byref(used)))
+            moved = ld.value + sd.value
+            fold_bytes = (16 << n) + (8 << len(plan.out_pos))  # the fold reads the state, writes the probabilities
+            ms_fold = max(ms - ms_sweeps, 1e-9)
+            info.update({"ms": ms, "sweeps_ms": ms_sweeps, "sweep_kernel": "sim_sweep_tma_kernel" if used.value
+                         else "sim_sweep_kernel", "live_qubit_tracking": bool(used.value),
+                         "sweep_bytes_loaded": ld.value, "sweep_bytes_stored": sd.value,
+                         "sweep_gbs": moved / ms_sweeps / 1e6, "sweep_frac_of_measured_hbm_peak": moved / ms_sweeps / 1e6 / peak,
+                         "full_sweep_traffic_bytes": (16 << n) * (2 * sweeps - 1),
+                         "fold_ms": ms_fold, "fold_bytes": fold_bytes, "fold_gbs": fold_bytes / ms_fold / 1e6,
+                         "fold_frac_of_measured_hbm_peak": fold_bytes / ms_fold / 1e6 / peak})
+        else:
+            torch.cuda.synchronize(device)
+            info["ms"] = e0.elapsed_time(e1) / reps
+        rep["uncut_statevector"] = info
         if cut_result.numel() == table.numel():
             rep["fidelity_cut_vs_uncut_dense_statevector"] = fid.hellinger_fidelity(cut_result, table[0])
             worst, step = 0.0, 1 << 28                         # chunked: no 32 GiB temporary

@@ -261,7 +261,14 @@ class FragmentProgram:
         def embed(t, a, b) -> np.ndarray:
             if t[0] == "u1":
                 u = self._mat_by_off[t[2]]
-                return np.kron(np.eye(2), u) if t[1] == a else np.kron(u, np.eye(2))
+                m = np.zeros((4, 4), dtype=np.complex128)
+                if t[1] == a:                       # kron(I, u): acts on index bit 0
+                    m[0:2, 0:2] = u
+                    m[2:4, 2:4] = u
+                else:                               # kron(u, I): acts on index bit 1
+                    m[0::2, 0::2] = u
+                    m[1::2, 1::2] = u
+                return m
             m = self._CX01 if t[0] == "cx" else self._CZ if t[0] == "cz" else self._mat_by_off[t[3]].reshape(4, 4)
             return m if (t[1], t[2]) == (a, b) else self._SWAP @ m @ self._SWAP
 
