@@ -81,7 +81,7 @@ extern "C" const char* qck_last_error_string(const qck_handle* h) { return h ? h
 extern "C" int64_t qck_launch_count(const qck_handle* h) { return h ? h->launches : 0; }
 
 int qck_ensure_partials(qck_handle* h, size_t count) {
-    if (count <= h->partials_count) return QCK_OK;
+    if (count + 8 <= h->partials_count) return QCK_OK;
     // partials are consumed by the kernel enqueued right after they are written, on the same
     // stream; growing here would race with in-flight work, so the size is fixed at create time
     QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "reduction scratch too small (%zu > %zu)", count, h->partials_count);
