@@ -73,7 +73,7 @@ class ClockSampler:
                ("sw_thermal_slowdown", "SwThermalSlowdown"), ("sw_power_cap", "SwPowerCap"),
                ("hw_power_brake_slowdown", "HwPowerBrakeSlowdown"))
 
-    def __init__(self, gpu_index: int, period_ms: int = 5) -> None:
+    def __init__(self, gpu_index: int, period_ms: int = 2) -> None:
         import threading
         self.rows, self.err, self.nv, self.handle = [], None, None, None
         self._stop = threading.Event()
