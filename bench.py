@@ -566,17 +566,26 @@ def uncut_statevector_report(circ, cut_result, device, fid, vc, handle, peak) ->
             torch.cuda.synchronize(device)
             ms, ms_sweeps = e0.elapsed_time(e1) / reps, e1.elapsed_time(e2) / reps
             ld, sd, used = C.c_uint64(), C.c_uint64(), C.c_int()
-            handle.check(handle.lib.qck_sim_plan_traffic(C.byref(st), 1, C.byref(ld), C.byref(sd), C.byref(used)))
+            handle.check(handle.lib.qck_sim_plan_traffic(C.byref(st), 1, 0, C.byref(ld), C.byref(sd), C.byref(used)))
             moved = ld.value + sd.value
-            fold_bytes = (16 << n) + (8 << len(plan.out_pos))  # the fold reads the state, writes the probabilities
-            ms_fold = max(ms - ms_sweeps, 1e-9)
-            info.update({"ms": ms, "sweeps_ms": ms_sweeps, "sweep_kernel": "sim_sweep_tma_kernel" if used.value
-                         else "sim_sweep_kernel", "live_qubit_tracking": bool(used.value),
-                         "sweep_bytes_loaded": ld.value, "sweep_bytes_stored": sd.value,
-                         "sweep_gbs": moved / ms_sweeps / 1e6, "sweep_frac_of_measured_hbm_peak": moved / ms_sweeps / 1e6 / peak,
-                         "full_sweep_traffic_bytes": (16 << n) * (2 * sweeps - 1),
-                         "fold_ms": ms_fold, "fold_bytes": fold_bytes, "fold_gbs": fold_bytes / ms_fold / 1e6,
-                         "fold_frac_of_measured_hbm_peak": fold_bytes / ms_fold / 1e6 / peak})
+            # the whole run: when the output row is the whole register the last sweep stores probabilities
+            # (fold fused); else a separate pass reads the state and writes the row
+            fused = bool(used.value) and not ex.program.radix and list(plan.out_pos) == list(range(n)) \
+                and plan.sum_mask == 0 and os.environ.get("QCK_FOLD_FUSION", "1") != "0"
+            ld2, sd2 = C.c_uint64(), C.c_uint64()
+            handle.check(handle.lib.qck_sim_plan_traffic(C.byref(st), 1, int(fused), C.byref(ld2), C.byref(sd2), C.byref(used)))
+            total_bytes = ld2.value + sd2.value + (0 if fused else (16 << n) + (8 << len(plan.out_pos)))
+            info.update({"ms": ms, "bytes": total_bytes, "gbs": total_bytes / ms / 1e6,
+                         "frac_of_measured_hbm_peak": total_bytes / ms / 1e6 / peak,
+                         "fold": "fused into the last sweep (probabilities stored instead of amplitudes)" if fused
+                         else "separate pass (reads the state, writes the row)",
+                         "sweep_kernel": "sim_sweep_tma_kernel" if used.value else "sim_sweep_kernel",
+                         "live_qubit_tracking": bool(used.value),
+                         "statevector_sweeps": {"ms": ms_sweeps, "bytes_loaded": ld.value, "bytes_stored": sd.value,
+                                                "gbs": moved / ms_sweeps / 1e6,
+                                                "frac_of_measured_hbm_peak": moved / ms_sweeps / 1e6 / peak,
+                                                "note": "qck_sim_statevector: the same sweeps leaving the amplitudes"},
+                         "full_sweep_traffic_bytes": (16 << n) * (2 * sweeps - 1)})
         else:
             torch.cuda.synchronize(device)
             info["ms"] = e0.elapsed_time(e1) / reps

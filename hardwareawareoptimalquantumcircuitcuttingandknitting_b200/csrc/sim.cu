@@ -630,6 +630,7 @@ struct TmaSweepDev {
     int n_tile, op_begin, op_end, n_state;
     int init;                 // nothing is live yet: no loads, tile 0 starts as |0..0>
     int has_x;                // the op range holds tile-resolved ops
+    int fold_direct;          // last sweep of a plan whose output row is the whole register: store |amp|^2
     int lowc, h, k;           // low run [0, lowc), main run [h, h + k) (state bit positions)
     int n_load, n_store;      // boxes per tile
     unsigned load_bytes;      // bytes per load box
@@ -698,7 +699,7 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
 
 __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
     sim_sweep_tma_kernel(const __grid_constant__ CUtensorMap map_st, const __grid_constant__ CUtensorMap map_ld,
-                         const __grid_constant__ TmaSweepDev sw, PlanDev plan, const int32_t* __restrict__ labels,
+                         const __grid_constant__ CUtensorMap map_pr, const __grid_constant__ TmaSweepDev sw, PlanDev plan, const int32_t* __restrict__ labels,
                          int inst_base, unsigned long long n_work, unsigned long long* __restrict__ counter) {
     typedef ConsumerWarps<TMA_CONSUMERS> P;
     const int T = sw.n_tile;
@@ -729,6 +730,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
         // ===== producer: TMA loads, TMA stores, stage recycling =====
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_st)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ld)) : "memory");
+        if (sw.fold_direct) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_pr)) : "memory");
         const int sh2 = sw.lowc, sh3 = sw.h, sh4 = sw.h + sw.k;
         const unsigned long long m2 = (1ull << (sw.h - sw.lowc)) - 1ull, m3 = (1ull << sw.k) - 1ull;
         const int inst_shift = sw.n_state - sh4;
@@ -772,9 +774,12 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
             mbar_wait(&done_bar[stg], (uint32_t)((kk / TMA_STAGES) & 1ull), 0, kk, stg, &dbg_step);
             const TmaTileDesc d = desc[stg];
             const uint32_t src0 = smem_u32(stage0 + (size_t)stg * stage_bytes);
+            // fold_direct: the consumers left the probabilities (8 bytes per amplitude, linear) in the stage
+            const CUtensorMap* mp = sw.fold_direct ? &map_pr : &map_st;
+            const uint32_t slot_bytes = sw.fold_direct ? 8u : 16u;
             for (int i = 0; i < sw.n_store; ++i) {
                 const unsigned long long idx = d.base | sw.st_off[i];
-                tma_store_5d(&map_st, src0 + sw.st_slot[i] * 16u, (int)((idx >> sh2) & m2), (int)((idx >> sh3) & m3),
+                tma_store_5d(mp, src0 + sw.st_slot[i] * slot_bytes, (int)((idx >> sh2) & m2), (int)((idx >> sh3) & m3),
                              (int)(idx >> sh4) + (d.inst << inst_shift));
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -839,6 +844,24 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
                     run_single<P>(s, T, so[i], plan.mats);
                     ++i;
                 }
+            }
+        }
+        if (sw.fold_direct) {  // |amp|^2 in place: registers first (the doubles overlap other threads' amplitudes)
+            double pr[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const uint32_t j = (uint32_t)ctid + (uint32_t)r * TMA_CONSUMERS;
+                if (j < n_amp) {
+                    const double2 a = s[swz(j)];
+                    pr[r] = fma(a.x, a.x, a.y * a.y);
+                }
+            }
+            P::sync();
+            double* ps = reinterpret_cast<double*>(s);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const uint32_t j = (uint32_t)ctid + (uint32_t)r * TMA_CONSUMERS;
+                if (j < n_amp) ps[j] = pr[r];
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
@@ -956,7 +979,7 @@ static EncodeTiledFn tensor_map_encoder() {
 
 struct TmaLaunch {
     TmaSweepDev sd;
-    CUtensorMap map_st, map_ld;
+    CUtensorMap map_st, map_ld, map_pr;
     unsigned long long n_work;
     size_t smem;
     int n_stage;
@@ -1114,6 +1137,24 @@ static int tma_encode(qck_handle* h, const TmaSweepDev& d, int batch, double2* w
     return QCK_OK;
 }
 
+// Output row as a tensor of doubles with the geometry of the state map (8 doubles = 8 amplitudes per inner
+// row, no swizzle): the fused fold stores |amp|^2 of a finished tile straight into the row.
+static int tma_encode_probs(qck_handle* h, const TmaSweepDev& d, double* row, CUtensorMap* out) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) QCK_FAIL(h, QCK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const int N = d.n_state, top = d.h + d.k;
+    cuuint64_t dims[5] = {8ull, 1ull << (d.lowc - 3), 1ull << (d.h - d.lowc), 1ull << d.k, 1ull << (N - top)};
+    cuuint64_t strides[4] = {64ull, 8ull << d.lowc, 8ull << d.h, 8ull << top};
+    cuuint32_t box[5] = {8u, 1u << (d.lowc - 3), 1u, 1u << d.k, 1u};
+    cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)row, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        QCK_FAIL(h, QCK_ERR_CUDA, "cuTensorMapEncodeTiled (probabilities) failed (%d): lowc=%d h=%d k=%d", (int)r, d.lowc, d.h, d.k);
+    return QCK_OK;
+}
+
 // Exposed for the host-logic tests (no GPU needed): describe sweep `i` of `plan` the way the TMA kernel
 // would run it.  Returns 1 and fills the arrays when the sweep is eligible, else 0.
 extern "C" int qck_debug_tma_describe(const qck_sim_plan* plan, int sweep, uint64_t live_before, int last,
@@ -1145,8 +1186,8 @@ static int tma_mode();
 // Exact HBM traffic of the sweeps of `plan` for `batch` instances (host arithmetic only): what the TMA
 // path loads and stores with live-qubit tracking, or - when a sweep is not eligible for it - the plain
 // kernel's read + write of the whole state per sweep.
-extern "C" int qck_sim_plan_traffic(const qck_sim_plan* plan, int batch, uint64_t* bytes_loaded, uint64_t* bytes_stored,
-                                    int* uses_tma) {
+extern "C" int qck_sim_plan_traffic(const qck_sim_plan* plan, int batch, int fold_fused, uint64_t* bytes_loaded,
+                                    uint64_t* bytes_stored, int* uses_tma) {
     if (!plan || !plan->sweeps || batch < 1 || !bytes_loaded || !bytes_stored) return QCK_ERR_INVALID_ARG;
     std::unique_ptr<TmaLaunch> L(new TmaLaunch);
     bool tma = tma_mode() != 0;
@@ -1158,7 +1199,8 @@ extern "C" int qck_sim_plan_traffic(const qck_sim_plan* plan, int batch, uint64_
         // live tiles: the tile number is spread over enum_mask; a tile is live iff its bits outside the live set are 0
         const unsigned long long live_tiles = (unsigned long long)batch << __builtin_popcountll(d.enum_mask & live);
         ld += live_tiles * (unsigned long long)d.n_load * d.load_bytes;
-        st += L->n_work * ((unsigned long long)16 << d.n_tile);
+        // the fused fold stores 8-byte probabilities instead of 16-byte amplitudes in the last sweep
+        st += L->n_work * ((unsigned long long)((fold_fused && i == plan->n_sweeps - 1) ? 8 : 16) << d.n_tile);
         for (int j = 0; j < plan->sweeps[i].n_tile; ++j) live |= 1ull << plan->sweeps[i].pos[j];
     }
     if (!tma) {
@@ -1172,14 +1214,22 @@ extern "C" int qck_sim_plan_traffic(const qck_sim_plan* plan, int batch, uint64_
     return QCK_OK;
 }
 
+static bool fold_fusion_enabled() {  // QCK_FOLD_FUSION=0: always run the separate fold pass (tuning / test knob)
+    const char* env = getenv("QCK_FOLD_FUSION");
+    return env ? atoi(env) != 0 : true;
+}
+
 static int tma_mode() {  // QCK_SIM_TMA: 0 = never, 1 = when eligible (default)
     const char* env = getenv("QCK_SIM_TMA");
     return env ? atoi(env) : 1;
 }
 
+// fold_row != NULL: the caller wants the probabilities of the single instance in fold_row instead of the
+// final state (only honoured - *folded = true - when the plan runs on the TMA kernels).
 static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd, const int32_t* d_labels,
                       int inst_base, int batch, double2* work, unsigned long long state_stride,
-                      cudaStream_t st) {
+                      cudaStream_t st, double* fold_row = nullptr, bool* folded = nullptr) {
+    if (folded) *folded = false;
     // The TMA kernels track live qubits, i.e. they leave memory outside the live region unwritten between
     // sweeps: a plan runs either entirely on them or entirely on the plain kernel.
     bool use_tma = tma_mode() != 0 && state_stride == (1ull << plan->n_state_qubits) && tensor_map_encoder() != nullptr;
@@ -1206,6 +1256,13 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
             const bool box_main = L->sd.zf_shift == L->sd.lowc + L->sd.k;
             rc = tma_encode(h, L->sd, batch, work, box_main, &L->map_ld);
             if (rc) return rc;
+            L->map_pr = L->map_st;
+            if (fold_row && batch == 1 && i == plan->n_sweeps - 1) {
+                rc = tma_encode_probs(h, L->sd, fold_row, &L->map_pr);
+                if (rc) return rc;
+                L->sd.fold_direct = 1;
+                if (folded) *folded = true;
+            }
             PlanDev pdl = pd;
             pdl.n_stage = L->n_stage;
             unsigned long long grid = L->n_work < (unsigned long long)h->sm_count ? L->n_work : (unsigned long long)h->sm_count;
@@ -1214,7 +1271,7 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
                 counter = reinterpret_cast<unsigned long long*>(h->d_partials + h->partials_count - 4);
                 QCK_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
             }
-            sim_sweep_tma_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(L->map_st, L->map_ld, L->sd, pdl, d_labels,
+            sim_sweep_tma_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(L->map_st, L->map_ld, L->map_pr, L->sd, pdl, d_labels,
                                                                                        inst_base, L->n_work, counter);
             QCK_CHECK_LAUNCH(h);
         }
@@ -1291,8 +1348,19 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
     if (cap > 65535) cap = 65535;
     for (int64_t done = 0; done < n_instances;) {
         int batch = (int)((n_instances - done) < cap ? (n_instances - done) : cap);
-        rc = run_sweeps(h, plan, pd, d_labels, (int)done, batch, (double2*)d_work, state_amps, st);
+        // The output row is the whole register (uncut circuit, every qubit measured into its own clbit, one
+        // instance): the last sweep stores |amp|^2 straight into the row - no final state, no fold pass.
+        const bool direct = plan->n_digits == 0 && n_instances == 1 && pd.out_ident == plan->n_out_bits &&
+                            plan->n_out_bits == plan->n_state_qubits && plan->sum_mask == 0 && plan->sign_mask == 0 &&
+                            fold_fusion_enabled();
+        bool folded = false;
+        rc = run_sweeps(h, plan, pd, d_labels, (int)done, batch, (double2*)d_work, state_amps, st,
+                        direct ? d_out : nullptr, &folded);  // one instance without digits: label 0, row 0
         if (rc) return rc;
+        if (folded) {
+            done += batch;
+            continue;
+        }
         unsigned long long n_out = 1ull << plan->n_out_bits;
         unsigned gx = (unsigned)((n_out + 255) / 256 < 148ull * 16 ? (n_out + 255) / 256 : 148ull * 16);
         fold_probs_kernel<<<dim3(gx, batch), 256, 0, st>>>(pd, d_labels, (int)done, (const double2*)d_work,

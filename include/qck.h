@@ -178,8 +178,10 @@ QCK_API int qck_debug_tma_describe(const qck_sim_plan* plan, int sweep, uint64_t
 
 /* Exact HBM bytes the sweeps of a streaming plan move for `batch` instances (host arithmetic, no
  * CUDA call): the TMA path with live-qubit tracking when every sweep is eligible (*uses_tma = 1),
- * else one read + one write of the whole state per sweep.  bench.py's roofline figures use it. */
-QCK_API int qck_sim_plan_traffic(const qck_sim_plan* plan, int batch, uint64_t* bytes_loaded,
+ * else one read + one write of the whole state per sweep.  fold_fused != 0: the last sweep stores
+ * probabilities instead of amplitudes (what qck_sim_fragments does when the output row is the
+ * whole register of a single instance).  bench.py's roofline figures use it. */
+QCK_API int qck_sim_plan_traffic(const qck_sim_plan* plan, int batch, int fold_fused, uint64_t* bytes_loaded,
                                  uint64_t* bytes_stored, int* uses_tma);
 
 /* ------------------------------------------------------------------ knitting

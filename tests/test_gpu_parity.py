@@ -212,6 +212,34 @@ def test_tma_sweep_statevector_equals_plain(dev, name, n, depth):
     assert abs(float((a * a).sum()) - 1.0) < 1e-12
 
 
+@pytest.mark.parametrize("name,n,depth", [("syc", 20, 2), ("hwe", 18, 2), ("qft", 16, 1), ("bv", 19, 1)])
+def test_fold_fused_into_last_sweep(dev, name, n, depth):
+    """Uncut circuit, every qubit measured: the last TMA sweep stores |amp|^2 straight into the row
+    (no final state, no fold pass) - identical to the separate fold pass and to the oracle."""
+    import os
+    circ = gen.gen_circ(name, n, depth, seed=5).decompose_two_qubit()
+    virt = vcm.VirtualCircuit(circ)
+    (frag,) = virt.active_fragments()
+    ex = virt.executor(frag, dev, True)
+    plan = ex.plans[0]
+    assert list(plan.out_pos) == list(range(n)) and plan.sum_mask == 0
+    h = _lib.get_handle(0)
+    l0 = h.launch_count
+    fused = _with_tma("1", lambda: ex.run(h).cpu().numpy())
+    n_fused = h.launch_count - l0
+    os.environ["QCK_FOLD_FUSION"] = "0"
+    try:
+        l0 = h.launch_count
+        separate = _with_tma("1", lambda: ex.run(h).cpu().numpy())
+        n_sep = h.launch_count - l0
+    finally:
+        os.environ.pop("QCK_FOLD_FUSION", None)
+    assert n_sep == n_fused + 1                                  # the fold pass is gone
+    assert np.abs(fused - separate).max() == 0.0
+    want = cport.simulate_probabilities(circ)
+    assert np.abs(fused[0] - want).max() < TOL_P
+
+
 def test_tma_sweep_chunked_op_stage(dev):
     """More op records than the shared-memory op stage holds: the TMA kernel restages chunks per tile
     (forced with QCK_TMA_STAGE_CAP); tile-resolved ops (cp with an outside qubit) included."""

@@ -35,6 +35,7 @@ else:
 ex.upload()
 h = _lib.get_handle(0)
 pl = ex.plans[0]
+prog_radix = list(ex.program.radix)
 st, _, _ = ex._structs[0]
 st.d_ops = ex.d_blob.data_ptr() + ex._off_ops
 st.d_mats = ex.d_blob.data_ptr()
@@ -58,7 +59,7 @@ ms = e0.elapsed_time(e1) / reps
 n_sw = len(pl.sweeps)
 full_bytes = (2 * n_sw - 1) * (16 << n)
 ld, sd, used = C.c_uint64(), C.c_uint64(), C.c_int()
-h.check(h.lib.qck_sim_plan_traffic(C.byref(st), 1, C.byref(ld), C.byref(sd), C.byref(used)))
+h.check(h.lib.qck_sim_plan_traffic(C.byref(st), 1, 0, C.byref(ld), C.byref(sd), C.byref(used)))
 moved = ld.value + sd.value
 norm = float((state * state).sum())
 print(f"{name}-{n} d{depth} uncut, QCK_SIM_TMA={os.environ.get('QCK_SIM_TMA', '1')}: sweeps {n_sw}, records {len(pl.ops)}, "
@@ -74,6 +75,12 @@ for _ in range(reps):
     ex.run(h, out=t)
 e1.record()
 torch.cuda.synchronize()
-print(f"  sweeps + fold: {e0.elapsed_time(e1) / reps:.3f} ms, sum {t.sum().item():.12f}")
+ms_all = e0.elapsed_time(e1) / reps
+fused = (used.value and os.environ.get("QCK_FOLD_FUSION", "1") != "0" and not prog_radix
+         and list(pl.out_pos) == list(range(pl.n_state)) and pl.sum_mask == 0)
+h.check(h.lib.qck_sim_plan_traffic(C.byref(st), 1, int(bool(fused)), C.byref(ld), C.byref(sd), C.byref(used)))
+tot = ld.value + sd.value + (0 if fused else (16 << n) + (8 << len(pl.out_pos)))
+print(f"  whole fragment run (sweeps + {'fused fold' if fused else 'fold pass'}): {ms_all:.3f} ms, {tot / 1e9:.2f} GB = "
+      f"{tot / ms_all / 1e6:.0f} GB/s, sum {t.sum().item():.12f}")
 for pos, b, e in pl.sweeps:
     print("  sweep tile", pos, "records", e - b)
