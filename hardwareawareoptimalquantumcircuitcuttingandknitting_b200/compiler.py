@@ -715,7 +715,8 @@ class FragmentExecutor:
                 arr[i].n_tile = len(positions)
                 arr[i].op_begin = p.op_base + b
                 arr[i].op_end = p.op_base + e
-                arr[i].flags = int(np.isin(p.ops[b:e, 0], (_lib.OP_U1X, _lib.OP_PHASE)).any())
+                arr[i].flags = (int(np.isin(p.ops[b:e, 0], (_lib.OP_U1X, _lib.OP_PHASE)).any())
+                                | 2 * int((p.ops[b:e, 0] == _lib.OP_CLUSTER).any()))
                 for j, x in enumerate(positions):
                     arr[i].pos[j] = x
             self._sweep_arrays.append(arr)

@@ -396,7 +396,7 @@ __device__ void run_single(double2* s, int T, const StagedOp& op, const double* 
 
 // Apply ops[begin, end) to the tile `s` (2^T amplitudes in shared memory).  All threads of the
 // CTA call this with identical arguments; the state is synchronised on return.
-template <class P>
+template <class P, bool CLUSTERS = true>
 __device__ void apply_ops(double2* s, int T, StagedOp* so, int n_stage, const qck_op* __restrict__ ops, int begin,
                           int end, const double* __restrict__ mats, const int* digits, bool prestaged,
                           bool resolve = false, unsigned long long base = 0ull, const int* perm = nullptr) {
@@ -414,7 +414,7 @@ __device__ void apply_ops(double2* s, int T, StagedOp* so, int n_stage, const qc
         int i = 0;
         while (i < n) {
             const int kind_i = so[i].w0.x;
-            if (kind_i == QCK_OP_CLUSTER) {
+            if (CLUSTERS && kind_i == QCK_OP_CLUSTER) {
                 const int members = so[i].w0.y;
                 if (i + members >= n && c0 + n < end) break;  // cluster continues past the staged chunk
                 run_cluster<P>(s, T, so, i, mats);
@@ -827,14 +827,11 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
             P::sync();
             if (ctid == 0) dbg_step = 3;
             if (chunked)
-                apply_ops<P>(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, false,
-                             sw.has_x != 0, d.base, perm_s);
+                apply_ops<P, false>(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, false,
+                                    sw.has_x != 0, d.base, perm_s);
             for (int i = 0; i < n_ops && !chunked;) {
                 const int kind_i = so[i].w0.x;
-                if (kind_i == QCK_OP_CLUSTER) {
-                    run_cluster<P>(s, T, so, i, plan.mats);
-                    i += 1 + so[i].w0.y;
-                } else if (kind_i == QCK_OP_U1X) {
+                if (kind_i == QCK_OP_U1X) {  // (sweeps with register clusters run on the plain kernel: flags bit 1)
                     run_single<P>(s, T, so[i], plan.mats);
                     i += 1 + so[i].w0.z;
                 } else if (kind_i == QCK_OP_PHASE) {
@@ -1009,6 +1006,7 @@ static bool tma_describe(const qck_sim_plan* plan, int i, unsigned long long liv
     const int T = sw.n_tile, N = plan->n_state_qubits;
     const int n_ops = sw.op_end - sw.op_begin;
     if (T < 3 || T > 13 || N > 35) return false;
+    if (sw.flags & 2) return false;  // register clusters: the TMA kernel carries no cluster code (plain kernel)
     const int n_records = tma_stage_records(T, n_ops, max_smem_optin);
     if (n_records < n_ops && n_records < 48) return false;  // no room for a useful op stage
     int c = 0;

@@ -113,7 +113,8 @@ typedef struct {
 typedef struct {
     int32_t n_tile;
     int32_t op_begin, op_end;
-    int32_t flags;                         /* bit 0: the op range holds QCK_OP_U1X / QCK_OP_PHASE */
+    int32_t flags;                         /* bit 0: the op range holds QCK_OP_U1X / QCK_OP_PHASE;   */
+                                           /* bit 1: it holds QCK_OP_CLUSTER (-> plain sweep kernel) */
     int32_t pos[QCK_MAX_TILE_QUBITS + 2];  /* ascending state-bit positions of the tile bits */
 } qck_sweep;
 

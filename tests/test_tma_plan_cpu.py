@@ -39,7 +39,8 @@ def _plan_struct(program, plan):
         arr[i].n_tile = len(positions)
         arr[i].op_begin = b
         arr[i].op_end = e
-        arr[i].flags = int(np.isin(plan.ops[b:e, 0], (_lib.OP_U1X, _lib.OP_PHASE)).any())
+        arr[i].flags = (int(np.isin(plan.ops[b:e, 0], (_lib.OP_U1X, _lib.OP_PHASE)).any())
+                        | 2 * int((plan.ops[b:e, 0] == _lib.OP_CLUSTER).any()))
         for j, x in enumerate(positions):
             arr[i].pos[j] = x
     st = _lib.QckSimPlan()
@@ -247,3 +248,24 @@ def test_diag_qubits_need_no_tile_residency(name, n, depth, onchip, tile, max_sw
     assert np.abs(pi.run_plan(prog, plan, 0) - want).max() < 1e-13
     got, _, _ = emulate(prog, plan, 0)
     assert np.abs(got - pi.run_plan(prog, plan, 0, return_state=True)).max() < 1e-14
+
+
+@pytest.mark.parametrize("name,n,depth,onchip,tile", [("syc", 14, 2, 8, 9), ("hwe", 11, 2, 6, 7), ("qft", 12, 1, 6, 8)])
+def test_traffic_accounting_matches_the_emulated_data_movement(name, n, depth, onchip, tile):
+    """qck_sim_plan_traffic (the bytes bench.py's roofline figures use) == what the emulated TMA path loads
+    and stores; with the fused fold the last sweep stores 8 instead of 16 bytes per amplitude."""
+    prog = _uncut_program(name, n, depth, onchip_max=onchip, stream_tile=tile)
+    (plan,) = prog.plans()
+    st, _keep = _plan_struct(prog, plan)
+    lib = _lib.load()
+    ld, sd, used = C.c_uint64(), C.c_uint64(), C.c_int()
+    assert lib.qck_sim_plan_traffic(C.byref(st), 1, 0, C.byref(ld), C.byref(sd), C.byref(used)) == 0
+    _, loaded, stored = emulate(prog, plan, 0)
+    assert used.value == 1 and (ld.value, sd.value) == (loaded, stored)
+    ld2, sd2 = C.c_uint64(), C.c_uint64()
+    assert lib.qck_sim_plan_traffic(C.byref(st), 1, 1, C.byref(ld2), C.byref(sd2), C.byref(used)) == 0
+    last_tiles = 1 << (plan.n_state - len(plan.sweeps[-1][0]))
+    assert ld2.value == loaded and sd.value - sd2.value == last_tiles * (8 << len(plan.sweeps[-1][0]))
+    # three instances move three times as much
+    assert lib.qck_sim_plan_traffic(C.byref(st), 3, 0, C.byref(ld2), C.byref(sd2), C.byref(used)) == 0
+    assert (ld2.value, sd2.value) == (3 * loaded, 3 * stored)
