@@ -240,6 +240,44 @@ def test_fold_fused_into_last_sweep(dev, name, n, depth):
     assert np.abs(fused[0] - want).max() < TOL_P
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_circuits_streaming_on_device(dev, seed):
+    """Random circuits (every gate kind) forced into the streaming regime with small tiles: TMA sweep
+    kernel == plain sweep kernel == oracle, for uncut circuits (fused fold) and for cut fragments (label
+    selected matrices, ancillas, tile-resolved ops)."""
+    import random
+    import test_random_circuits_cpu as rc
+    rng = random.Random(5000 + seed)
+    n = rng.randint(9, 12)
+    qc = rc.random_circuit(rng, n, rng.randint(30, 60))
+    tile = rng.randint(6, 8)
+    h = _lib.get_handle(0)
+    if seed % 2 == 0:
+        virt = vcm.VirtualCircuit(qc)
+        (f,) = virt.active_fragments()
+        prog = compiler.FragmentProgram(virt.fragment_circuits[f], f, qc.num_clbits, onchip_max=5, stream_tile=tile)
+        ex = compiler.FragmentExecutor(prog, dev)
+        tma = _with_tma("1", lambda: ex.run(h).cpu().numpy())
+        plain = _with_tma("0", lambda: ex.run(h).cpu().numpy())
+        want = sv.dense(sv.exact_distribution(qc), n)
+        assert np.abs(tma - plain).max() < 1e-15
+        assert np.abs(tma[0] - want).max() < TOL_P
+    else:
+        cut = cutting.apply_cuts(qc, rc.random_cut(rng, qc, max_gate_cuts=2, wire_cut=(seed % 4 == 1)))
+        virt = vcm.VirtualCircuit(cut)
+        for f in virt.active_fragments():
+            a = compiler.FragmentProgram(virt.fragment_circuits[f], f, cut.num_clbits)
+            if a.n_qubits < 5:
+                continue
+            b = compiler.FragmentProgram(virt.fragment_circuits[f], f, cut.num_clbits, onchip_max=4, stream_tile=tile)
+            ra = compiler.FragmentExecutor(a, dev).run(h).cpu().numpy()
+            eb = compiler.FragmentExecutor(b, dev)
+            r_tma = _with_tma("1", lambda: eb.run(h).cpu().numpy())
+            r_plain = _with_tma("0", lambda: eb.run(h).cpu().numpy())
+            assert np.abs(r_tma - r_plain).max() < 1e-15
+            assert np.abs(r_tma - ra).max() < 1e-12
+
+
 def test_tma_sweep_chunked_op_stage(dev):
     """More op records than the shared-memory op stage holds: the TMA kernel restages chunks per tile
     (forced with QCK_TMA_STAGE_CAP); tile-resolved ops (cp with an outside qubit) included."""

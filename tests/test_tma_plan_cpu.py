@@ -269,3 +269,47 @@ def test_traffic_accounting_matches_the_emulated_data_movement(name, n, depth, o
     # three instances move three times as much
     assert lib.qck_sim_plan_traffic(C.byref(st), 3, 0, C.byref(ld2), C.byref(sd2), C.byref(used)) == 0
     assert (ld2.value, sd2.value) == (3 * loaded, 3 * stored)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_circuits_streaming_schedule_and_tma_layout(seed):
+    """Random circuits (every gate kind, cut or uncut) forced into the streaming regime with small tiles:
+    the scheduled plans (tile-resolved ops included) reproduce the oracle, and the emulated TMA data
+    movement reproduces the plans - for every plan and a few labels of every fragment."""
+    import random
+    import test_random_circuits_cpu as rc
+    from oracle import statevector as sv
+    cutting = import_module(f"{PKG}.cutting")
+    rng = random.Random(4000 + seed)
+    n = rng.randint(6, 8)
+    qc = rc.random_circuit(rng, n, rng.randint(20, 40))
+    tile = rng.randint(5, 6)
+    if seed % 2 == 0:                                    # uncut: one fragment, compare with the oracle
+        virt = vcm.VirtualCircuit(qc)
+        (f,) = virt.active_fragments()
+        prog = compiler.FragmentProgram(virt.fragment_circuits[f], f, qc.num_clbits, onchip_max=4, stream_tile=tile)
+        (plan,) = prog.plans()
+        assert len(plan.sweeps) >= 2
+        want = sv.dense(sv.exact_distribution(qc), n)
+        assert np.abs(pi.run_plan(prog, plan, 0) - want).max() < 1e-12
+        got, _, _ = emulate(prog, plan, 0)
+        assert np.abs(got - pi.run_plan(prog, plan, 0, return_state=True)).max() < 1e-13
+    else:                                                # cut: slots, ancillas, several patterns
+        cut = cutting.apply_cuts(qc, rc.random_cut(rng, qc, max_gate_cuts=2, wire_cut=(seed % 4 == 1)))
+        virt = vcm.VirtualCircuit(cut)
+        for f in virt.active_fragments():
+            small = compiler.FragmentProgram(virt.fragment_circuits[f], f, cut.num_clbits)
+            prog = compiler.FragmentProgram(virt.fragment_circuits[f], f, cut.num_clbits, onchip_max=3, stream_tile=tile)
+            ref_rows = pi.run_program(small)
+            for plan in prog.plans():
+                if len(plan.sweeps) < 2:
+                    continue
+                for label in plan.labels[:3]:
+                    assert np.abs(pi.run_plan(prog, plan, label) - ref_rows[label]).max() < 1e-12
+                    try:
+                        got, _, _ = emulate(prog, plan, label)
+                    except AssertionError as exc:
+                        if "not eligible" in str(exc):   # e.g. a low run shorter than 3 bits: plain kernel
+                            continue
+                        raise
+                    assert np.abs(got - pi.run_plan(prog, plan, label, return_state=True)).max() < 1e-13
