@@ -161,6 +161,14 @@ QCK_API int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim_pl
 QCK_API int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t label,
                         void* d_state, size_t state_bytes, qck_stream stream);
 
+/* Host half of the program compiler (no CUDA call, re-entrant): list-schedules the ops of ONE
+ * on-chip sweep (records on tile-local qubits) into register clusters - a QCK_OP_CLUSTER header
+ * followed by its members, their qubits renamed to ranks; lone two-qubit ops and ops on fewer than
+ * QCK_CLUSTER_QUBITS live bits stay plain.  `out` needs room for 2 * n_ops records.  (compiler.py
+ * did this in Python: 64 plans per hwe-16 d5 run made it the largest part of the cold e2e time.) */
+QCK_API int qck_host_cluster_ops(const int32_t* ops, int n_ops, int n_tile, int max_cluster_ops,
+                                 int32_t* out, int* n_out);
+
 /* Host-logic probe (no CUDA call, usable without a GPU; not re-entrant): how the TMA sweep kernel
  * would run sweep `sweep` of `plan` when the state bits in `live_before` are live (some earlier
  * sweep had them in its tile; all other qubits are still |0>).  Returns 1 and fills the arrays when

@@ -132,3 +132,33 @@ def test_baseline_config_shapes():
     v = vcm.VirtualCircuit(cut)
     masks, union = v.output_masks()
     assert sorted(masks.values()) == [0x7EFF0000, 0x8100FFFF] and union == 0xFFFFFFFF
+
+
+def test_c_cluster_scheduler_equals_python_reference():
+    """qck_host_cluster_ops (C) against the Python original on every on-chip plan of the baseline configs
+    and on random op lists (n_live growth, lone two-qubit ops, clusters of every size)."""
+    import random
+    import cluster_reference as cr
+    _lib = import_module(f"{PKG}._lib")
+    cases = []
+    for cfg in ("bv16", "syc16d5", "hwe16d5"):
+        circ, cut = cutting.make_baseline(cfg)
+        virt = vcm.VirtualCircuit(cut)
+        for f in virt.active_fragments():
+            prog = compiler.FragmentProgram(virt.fragment_circuits[f], f, cut.num_clbits, cluster=False)
+            for plan in prog.plans()[::7]:
+                cases.append((plan.ops, plan.sweeps))
+    rng = random.Random(11)
+    for _ in range(60):
+        T = rng.randint(1, 9)
+        rows = []
+        for _ in range(rng.randint(1, 70)):
+            kind = rng.choice([_lib.OP_U1, _lib.OP_CX, _lib.OP_CZ, _lib.OP_U2]) if T >= 2 else _lib.OP_U1
+            q = rng.sample(range(T), 2) if kind != _lib.OP_U1 else [rng.randrange(T), 0]
+            rows.append([kind, q[0], q[1], rng.randrange(100) * 8, -1, 0, rng.choice([0, 0, 2, 3, 4, T]), 0])
+        cases.append((np.asarray(rows, dtype=np.int32), [(list(range(T)), 0, len(rows))]))
+    for ops, sweeps in cases:
+        got_ops, got_sw = compiler._cluster_sweeps(ops, sweeps)
+        want_ops, want_sw = cr.cluster_sweeps_reference(ops, sweeps)
+        assert got_sw == want_sw
+        assert np.array_equal(got_ops, want_ops)
