@@ -555,9 +555,7 @@ def uncut_statevector_report(circ, cut_result, device, fid, vc, handle, peak) ->
         e1.record()
         info = {"qubits": n, "sweeps": sweeps, "ops": int(len(plan.ops))}
         if ex.streaming:
-            st, _, _ = ex._structs[0]
-            st.d_ops = ex.d_blob.data_ptr() + ex._off_ops
-            st.d_mats = ex.d_blob.data_ptr()
+            st = ex.plan_struct(0)
             stream = torch.cuda.current_stream(device).cuda_stream
             for _ in range(reps):                              # the sweeps alone, into the same state buffer
                 handle.check(handle.lib.qck_sim_statevector(handle.ptr, C.byref(st), 0, ex._work.data_ptr(),

@@ -641,25 +641,38 @@ class FragmentExecutor:
         self.device = torch.device(device)
         self.fold = fold
         self.plans = program.plans(fold)
-        ops = np.concatenate([p.ops for p in self.plans]) if self.plans else np.zeros((0, 8), np.int32)
-        if len(ops) == 0:
-            ops = np.zeros((1, 8), np.int32)
-        labels = np.concatenate([p.labels for p in self.plans]).astype(np.int32)
-        self._labels_host = labels
-        # one host blob [mats f64 | ops i32 | labels i32] -> one H2D copy
-        mats = np.ascontiguousarray(program.mats, dtype=np.float64)
-        self._off_ops = (mats.nbytes + 255) & ~255
-        self._off_labels = (self._off_ops + ops.nbytes + 255) & ~255
-        self._blob = np.zeros(self._off_labels + labels.nbytes, dtype=np.uint8)
-        self._blob[:mats.nbytes] = mats.view(np.uint8)
-        self._blob[self._off_ops:self._off_ops + ops.nbytes] = np.ascontiguousarray(ops).view(np.uint8).reshape(-1)
-        self._blob[self._off_labels:] = labels.view(np.uint8)
+        # Host image of the program (blob + plan structs): a pure function of the program, built once and
+        # shared by every executor of it (programs are cached process-wide; run() only ever copies the
+        # struct templates, so sharing across threads is safe).
+        host = program.__dict__.setdefault("_host_images", {}).get(fold)
+        if host is None:
+            host = self._build_host_image(program, self.plans)
+            program._host_images[fold] = host
+        (self._blob, self._off_ops, self._off_labels, self._labels_host, self._sweep_arrays, self._structs) = host
         self.h2d_bytes = int(self._blob.nbytes)
         self.d_blob = None
-        self._sweep_arrays = []
-        self._structs = []
+        self.row_len = program.row_len(fold)
+        self.max_state = max(p.n_state for p in self.plans)
+        self.streaming = self.max_state > program.onchip_max
+        self._work = None
+
+    @staticmethod
+    def _build_host_image(program: FragmentProgram, plans: list):
+        ops = np.concatenate([p.ops for p in plans]) if plans else np.zeros((0, 8), np.int32)
+        if len(ops) == 0:
+            ops = np.zeros((1, 8), np.int32)
+        labels = np.concatenate([p.labels for p in plans]).astype(np.int32)
+        # one host blob [mats f64 | ops i32 | labels i32] -> one H2D copy
+        mats = np.ascontiguousarray(program.mats, dtype=np.float64)
+        off_ops = (mats.nbytes + 255) & ~255
+        off_labels = (off_ops + ops.nbytes + 255) & ~255
+        blob = np.zeros(off_labels + labels.nbytes, dtype=np.uint8)
+        blob[:mats.nbytes] = mats.view(np.uint8)
+        blob[off_ops:off_ops + ops.nbytes] = np.ascontiguousarray(ops).view(np.uint8).reshape(-1)
+        blob[off_labels:] = labels.view(np.uint8)
+        sweep_arrays, structs = [], []
         off = 0
-        for p in self.plans:
+        for p in plans:
             arr = (_lib.QckSweep * len(p.sweeps))()
             for i, (positions, b, e) in enumerate(p.sweeps):
                 arr[i].n_tile = len(positions)
@@ -669,7 +682,7 @@ class FragmentExecutor:
                                 | 2 * int((p.ops[b:e, 0] == _lib.OP_CLUSTER).any()))
                 for j, x in enumerate(positions):
                     arr[i].pos[j] = x
-            self._sweep_arrays.append(arr)
+            sweep_arrays.append(arr)
             st = _lib.QckSimPlan()
             st.n_state_qubits = p.n_state
             st.n_sweeps = len(p.sweeps)
@@ -682,12 +695,9 @@ class FragmentExecutor:
                 st.out_pos[j] = x
             st.sum_mask = p.sum_mask
             st.sign_mask = p.sign_mask
-            self._structs.append((st, off, len(p.labels)))
+            structs.append((st, off, len(p.labels)))
             off += len(p.labels)
-        self.row_len = program.row_len(fold)
-        self.max_state = max(p.n_state for p in self.plans)
-        self.streaming = self.max_state > program.onchip_max
-        self._work = None
+        return blob, off_ops, off_labels, labels, sweep_arrays, structs
 
     def upload(self) -> None:
         """Host -> device copy of matrices, ops and label lists through pinned memory (one copy;
@@ -697,6 +707,16 @@ class FragmentExecutor:
         stage[:self._blob.nbytes].numpy()[:] = self._blob
         self.d_blob = torch.empty(self._blob.nbytes, dtype=torch.uint8, device=self.device)
         self.d_blob.copy_(stage[:self._blob.nbytes], non_blocking=True)
+
+    def plan_struct(self, i: int = 0) -> "_lib.QckSimPlan":
+        """A private copy of plan i's ``qck_sim_plan`` with the device pointers of THIS executor filled in
+        (for direct C-ABI calls such as ``qck_sim_statevector``); uploads the program if necessary."""
+        if self.d_blob is None:
+            self.upload()
+        st = _lib.QckSimPlan.from_buffer_copy(self._structs[i][0])
+        st.d_ops = self.d_blob.data_ptr() + self._off_ops
+        st.d_mats = self.d_blob.data_ptr()
+        return st
 
     def run(self, handle: "_lib.Handle", out=None, label_range: tuple[int, int] | None = None):
         """-> device tensor [num_labels, row_len] float64 (rows outside label_range untouched / 0)."""
@@ -730,9 +750,9 @@ class FragmentExecutor:
                 hi = int(np.searchsorted(host, label_range[1], side="left"))
                 labels_ptr += 4 * lo
                 count = max(0, hi - lo)
-            st.d_ops = ops_ptr
-            st.d_mats = mats_ptr
-            plans[i] = st
+            plans[i] = st                    # a copy of the shared template; pointers go into the copy
+            plans[i].d_ops = ops_ptr
+            plans[i].d_mats = mats_ptr
             label_ptrs[i] = labels_ptr
             counts[i] = count
         work_ptr = self._work.data_ptr() if self._work is not None else None

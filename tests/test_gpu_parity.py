@@ -194,9 +194,7 @@ def test_tma_sweep_statevector_equals_plain(dev, name, n, depth):
     ex = virt.executor(frag, dev, True)
     ex.upload()
     h = _lib.get_handle(0)
-    (st, _off, _cnt) = ex._structs[0]
-    st.d_ops = ex.d_blob.data_ptr() + ex._off_ops
-    st.d_mats = ex.d_blob.data_ptr()
+    st = ex.plan_struct(0)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def run():

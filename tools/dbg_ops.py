@@ -20,8 +20,7 @@ f = virt.active_fragments()[0]
 b = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits, onchip_max=onchip, stream_tile=tile)
 eb = compiler.FragmentExecutor(b, dev); eb.upload()
 plan = eb.plans[0]
-st, _, _ = eb._structs[0]
-st.d_ops = eb.d_blob.data_ptr() + eb._off_ops; st.d_mats = eb.d_blob.data_ptr()
+st = eb.plan_struct(0)
 label = int(plan.labels[0])
 pos, b0, e0 = plan.sweeps[0]
 st.n_sweeps = 1

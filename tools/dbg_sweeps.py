@@ -18,8 +18,7 @@ for f in virt.active_fragments():
     b = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits, onchip_max=onchip, stream_tile=tile)
     eb = compiler.FragmentExecutor(b, dev); eb.upload()
     for pi_idx, plan in enumerate(eb.plans):
-        st, _, _ = eb._structs[pi_idx]
-        st.d_ops = eb.d_blob.data_ptr() + eb._off_ops; st.d_mats = eb.d_blob.data_ptr()
+        st = eb.plan_struct(pi_idx)
         label = int(plan.labels[0])
         n_sw = len(plan.sweeps)
         for k in range(1, n_sw + 1):

@@ -36,9 +36,7 @@ ex.upload()
 h = _lib.get_handle(0)
 pl = ex.plans[0]
 prog_radix = list(ex.program.radix)
-st, _, _ = ex._structs[0]
-st.d_ops = ex.d_blob.data_ptr() + ex._off_ops
-st.d_mats = ex.d_blob.data_ptr()
+st = ex.plan_struct(0)
 stream = torch.cuda.current_stream(dev).cuda_stream
 state = torch.empty(2 << n, dtype=torch.float64, device=dev)
 
