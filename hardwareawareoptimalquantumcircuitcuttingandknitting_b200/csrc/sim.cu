@@ -711,10 +711,12 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
     __shared__ TmaTileDesc desc[TMA_STAGES];
     __shared__ int digits[QCK_MAX_DIGITS];
     __shared__ int perm_s[16];
-    __shared__ volatile int dbg_step;  // progress of the consumers, reported by the wait watchdog
+    // consumer progress within the current tile (1 loaded, 2 staged / resolved, 3 zero-filled, 4 gates done,
+    // 5 handed to the producer, 9 finished): what the wait watchdog reports when a wait cannot complete
+    __shared__ volatile int progress;
 
     if (threadIdx.x == 0) {
-        dbg_step = 0;
+        progress = 0;
         for (int i = 0; i < TMA_STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&done_bar[i], 1);
@@ -771,7 +773,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 issue_load(kk - 1 + TMA_STAGES);
             }
-            mbar_wait(&done_bar[stg], (uint32_t)((kk / TMA_STAGES) & 1ull), 0, kk, stg, &dbg_step);
+            mbar_wait(&done_bar[stg], (uint32_t)((kk / TMA_STAGES) & 1ull), 0, kk, stg, &progress);
             const TmaTileDesc d = desc[stg];
             const uint32_t src0 = smem_u32(stage0 + (size_t)stg * stage_bytes);
             // fold_direct: the consumers left the probabilities (8 bytes per amplitude, linear) in the stage
@@ -795,11 +797,11 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
     int staged_inst = -1;
     for (unsigned long long kk = 0;; ++kk) {
         const int stg = (int)(kk % TMA_STAGES);
-        mbar_wait(&full_bar[stg], (uint32_t)((kk / TMA_STAGES) & 1ull), 1, kk, stg, &dbg_step);
-        if (ctid == 0) dbg_step = 1;
+        mbar_wait(&full_bar[stg], (uint32_t)((kk / TMA_STAGES) & 1ull), 1, kk, stg, &progress);
+        if (ctid == 0) progress = 1;
         const TmaTileDesc d = desc[stg];
         if (d.flags == TMA_TILE_DONE) {
-            if (ctid == 0) dbg_step = 9;
+            if (ctid == 0) progress = 9;
             break;
         }
         double2* s = reinterpret_cast<double2*>(stage0 + (size_t)stg * stage_bytes);
@@ -815,17 +817,15 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
                 if (sw.has_x && !chunked) P::sync();
             }
             if (sw.has_x && !chunked) resolve_tile<P>(so, n_ops, d.base);
-            if (ctid == 0) dbg_step = 2;
+            if (ctid == 0) progress = 2;
             if (sw.init) {
                 for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS) s[j] = make_double2(j == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
             } else if (sw.zf_mask) {  // boxes of non-live tile bits were not loaded: they are zeros
-                const uint32_t box_amps = 1u << sw.zf_shift;
                 for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS)
                     if ((j >> sw.zf_shift) & sw.zf_mask) s[j] = make_double2(0.0, 0.0);
-                (void)box_amps;
             }
             P::sync();
-            if (ctid == 0) dbg_step = 3;
+            if (ctid == 0) progress = 3;
             if (chunked)
                 apply_ops<P, false>(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, false,
                                     sw.has_x != 0, d.base, perm_s);
@@ -862,11 +862,11 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
-        if (ctid == 0) dbg_step = 4;
+        if (ctid == 0) progress = 4;
         P::sync();
         if (ctid == 0) {
             mbar_arrive(&done_bar[stg]);
-            dbg_step = 5;
+            progress = 5;
         }
     }
 }

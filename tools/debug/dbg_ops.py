@@ -1,6 +1,6 @@
 """Scratch: first sweep only, ops[0:m] for growing m, plain kernel vs interpreter."""
 import os, sys, copy, ctypes as C
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from importlib import import_module

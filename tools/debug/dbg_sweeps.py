@@ -1,6 +1,6 @@
 """Scratch: state after each sweep, plain kernel vs numpy interpreter (tests/plan_interpreter.py)."""
 import os, sys, copy, ctypes as C
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from importlib import import_module

@@ -1,6 +1,6 @@
 """Scratch: isolate a TMA-sweep problem on small tiles (prints progress per fragment)."""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import numpy as np, torch
 from importlib import import_module
 PKG = "hardwareawareoptimalquantumcircuitcuttingandknitting_b200"
