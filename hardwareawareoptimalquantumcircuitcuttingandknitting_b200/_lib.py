@@ -68,10 +68,17 @@ _PROTOTYPES = {
     "qck_sim_statevector": (C.c_int, [C.c_void_p, C.POINTER(QckSimPlan), C.c_int32, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
     "qck_host_cluster_ops": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
-    "qck_debug_tma_describe": (C.c_int, [C.POINTER(QckSimPlan), C.c_int, C.c_uint64, C.c_int, C.c_int,
+    "qck_debug_tma_describe": (C.c_int, [C.POINTER(QckSimPlan), C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
                                          C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
-                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "qck_sim_sweeps_sharded": (C.c_int, [C.c_void_p, C.POINTER(QckSimPlan), C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p]),
+    "qck_mem_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "qck_mem_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "qck_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
+    "qck_ipc_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "qck_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "qck_sim_plan_traffic": (C.c_int, [C.POINTER(QckSimPlan), C.c_int, C.c_int, C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "qck_knit_outer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int,

@@ -637,6 +637,8 @@ struct TmaSweepDev {
     int zf_shift;             // log2(amplitudes per load box)
     unsigned zf_mask;         // load-box index bits that belong to non-live tile bits: those boxes are zero-filled
     int n_enum_bits;          // work index = (instance << n_enum_bits) | tile number
+    int n_local;              // state bits below this index a shard; the bits above are the RANK owning it
+    unsigned long long fixed_base;   // bits of every tile base of this launch (sharded runs: rank / owner bits)
     unsigned long long enum_mask;    // state-bit positions the tile number is spread over
     unsigned long long live_before;  // state bits that are live when this sweep starts
     int perm[16];             // ascending tile-local bit -> position in the shared-memory layout
@@ -697,9 +699,15 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
                  : "memory");
 }
 
+// One store / load tensor map per shard of the state (a single-GPU run has one shard): in a sharded run the
+// rank bits of a box select the PEER buffer it lives in - the TMA unit moves it over NVLink.
+#define TMA_MAX_SHARDS 8
+struct TmaMaps {
+    CUtensorMap st[TMA_MAX_SHARDS], ld[TMA_MAX_SHARDS], pr;
+};
+
 __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
-    sim_sweep_tma_kernel(const __grid_constant__ CUtensorMap map_st, const __grid_constant__ CUtensorMap map_ld,
-                         const __grid_constant__ CUtensorMap map_pr, const __grid_constant__ TmaSweepDev sw, PlanDev plan, const int32_t* __restrict__ labels,
+    sim_sweep_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaSweepDev sw, PlanDev plan, const int32_t* __restrict__ labels,
                          int inst_base, unsigned long long n_work, unsigned long long* __restrict__ counter) {
     typedef ConsumerWarps<TMA_CONSUMERS> P;
     const int T = sw.n_tile;
@@ -730,12 +738,13 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
     if (threadIdx.x < 32) {
         if (threadIdx.x != 0) return;
         // ===== producer: TMA loads, TMA stores, stage recycling =====
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_st)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ld)) : "memory");
-        if (sw.fold_direct) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_pr)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.st[0])) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.ld[0])) : "memory");
+        if (sw.fold_direct) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.pr)) : "memory");
         const int sh2 = sw.lowc, sh3 = sw.h, sh4 = sw.h + sw.k;
+        const unsigned long long local_mask = (1ull << sw.n_local) - 1ull;
         const unsigned long long m2 = (1ull << (sw.h - sw.lowc)) - 1ull, m3 = (1ull << sw.k) - 1ull;
-        const int inst_shift = sw.n_state - sh4;
+        const int inst_shift = sw.n_local - sh4;
         const unsigned long long tile_mask = (1ull << sw.n_enum_bits) - 1ull;
         // tiles are dealt round robin, or pulled from a counter when one is given (tuning knob)
         auto issue_load = [&](unsigned long long kk) {
@@ -748,7 +757,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
                 return;
             }
             const int inst = (int)(w >> sw.n_enum_bits);
-            const unsigned long long base = soft_pdep(w & tile_mask, sw.enum_mask);
+            const unsigned long long base = sw.fixed_base | soft_pdep(w & tile_mask, sw.enum_mask);
             const bool live = (base & ~sw.live_before) == 0ull;
             d.base = base;
             d.inst = inst;
@@ -757,9 +766,9 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
                 mbar_arrive_expect_tx(&full_bar[stg], (uint32_t)sw.n_load * sw.load_bytes);
                 const uint32_t dst0 = smem_u32(stage0 + (size_t)stg * stage_bytes);
                 for (int i = 0; i < sw.n_load; ++i) {
-                    const unsigned long long idx = base | sw.ld_off[i];
-                    tma_load_5d(dst0 + sw.ld_slot[i] * 16u, &map_ld, &full_bar[stg], (int)((idx >> sh2) & m2),
-                                (int)((idx >> sh3) & m3), (int)(idx >> sh4) + (inst << inst_shift));
+                    const unsigned long long gidx = base | sw.ld_off[i], idx = gidx & local_mask;
+                    tma_load_5d(dst0 + sw.ld_slot[i] * 16u, &maps.ld[gidx >> sw.n_local], &full_bar[stg],
+                                (int)((idx >> sh2) & m2), (int)((idx >> sh3) & m3), (int)(idx >> sh4) + (inst << inst_shift));
                 }
             } else {
                 mbar_arrive(&full_bar[stg]);
@@ -777,10 +786,10 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
             const TmaTileDesc d = desc[stg];
             const uint32_t src0 = smem_u32(stage0 + (size_t)stg * stage_bytes);
             // fold_direct: the consumers left the probabilities (8 bytes per amplitude, linear) in the stage
-            const CUtensorMap* mp = sw.fold_direct ? &map_pr : &map_st;
             const uint32_t slot_bytes = sw.fold_direct ? 8u : 16u;
             for (int i = 0; i < sw.n_store; ++i) {
-                const unsigned long long idx = d.base | sw.st_off[i];
+                const unsigned long long gidx = d.base | sw.st_off[i], idx = gidx & local_mask;
+                const CUtensorMap* mp = sw.fold_direct ? &maps.pr : &maps.st[gidx >> sw.n_local];
                 tma_store_5d(mp, src0 + sw.st_slot[i] * slot_bytes, (int)((idx >> sh2) & m2), (int)((idx >> sh3) & m3),
                              (int)(idx >> sh4) + (d.inst << inst_shift));
             }
@@ -974,9 +983,13 @@ static EncodeTiledFn tensor_map_encoder() {
     return fn;
 }
 
+struct TmaShard {  // sharded run: this process holds the amplitudes whose bits >= n_local equal `rank`
+    int n_local, rank;
+};
+
 struct TmaLaunch {
     TmaSweepDev sd;
-    CUtensorMap map_st, map_ld, map_pr;
+    TmaMaps maps;
     unsigned long long n_work;
     size_t smem;
     int n_stage;
@@ -1001,11 +1014,13 @@ static size_t tma_smem_bytes(int n_tile, int n_records) {
 // Can this sweep run on the TMA kernel?  (pure host logic, no CUDA calls: unit-testable)
 // Fills everything but the tensor maps.  live_before: state bits some earlier sweep had in its tile.
 static bool tma_describe(const qck_sim_plan* plan, int i, unsigned long long live_before, bool last, int batch,
-                         int max_smem_optin, TmaLaunch& L) {
+                         int max_smem_optin, TmaLaunch& L, const TmaShard* shard = nullptr) {
     const qck_sweep& sw = plan->sweeps[i];
     const int T = sw.n_tile, N = plan->n_state_qubits;
+    const int n_loc = shard ? shard->n_local : N;  // bits a single buffer indexes
     const int n_ops = sw.op_end - sw.op_begin;
-    if (T < 3 || T > 13 || N > 35) return false;
+    if (T < 3 || T > 13 || n_loc > 35 || n_loc < T || N - n_loc > 3) return false;
+    if (shard && batch != 1) return false;
     if (sw.flags & 2) return false;  // register clusters: the TMA kernel carries no cluster code (plain kernel)
     const int n_records = tma_stage_records(T, n_ops, max_smem_optin);
     if (n_records < n_ops && n_records < 48) return false;  // no room for a useful op stage
@@ -1033,8 +1048,12 @@ static bool tma_describe(const qck_sim_plan* plan, int i, unsigned long long liv
     int best_b = -1, best_len = 0;
     bool best_live = false;
     for (int j = lowc; j < T;) {
+        if (sw.pos[j] >= n_loc) {  // a rank bit: its two values live in different buffers, never inside a box
+            ++j;
+            continue;
+        }
         int e = j;
-        while (e + 1 < T && sw.pos[e + 1] == sw.pos[e] + 1 && e + 1 - j < 8) ++e;
+        while (e + 1 < T && sw.pos[e + 1] == sw.pos[e] + 1 && e + 1 - j < 8 && sw.pos[e + 1] < n_loc) ++e;
         bool live = true;
         for (int q = j; q <= e; ++q) live = live && ((live_before >> sw.pos[q]) & 1ull);
         const int len = e - j + 1;
@@ -1105,20 +1124,43 @@ static bool tma_describe(const qck_sim_plan* plan, int i, unsigned long long liv
     unsigned long long tile_mask = 0;
     for (int j = 0; j < T; ++j) tile_mask |= 1ull << sw.pos[j];
     const unsigned long long all = N >= 64 ? ~0ull : ((1ull << N) - 1ull);
+    d.n_local = n_loc;
     d.enum_mask = (last ? all : live_before) & ~tile_mask;
+    if (shard) {
+        // Which rank works on which tile: the rank bits OUTSIDE the tile are the rank's own (its shard); for
+        // every rank bit INSIDE the tile (the tile spans the buffers of two ranks) one of the highest non-tile
+        // local positions - a live one when there is one - is pinned to the rank's bit instead, so that every
+        // tile has exactly one owner and the owners share the live tiles evenly.
+        const unsigned long long rank_mask = all & ~((1ull << n_loc) - 1ull);
+        unsigned long long fixed = ((unsigned long long)shard->rank << n_loc) & ~tile_mask, owner_mask = 0;
+        for (int b = n_loc; b < N; ++b) {
+            if (!((tile_mask >> b) & 1ull)) continue;
+            int pick = -1;
+            for (int pass = 0; pass < 2 && pick < 0; ++pass)  // first pass: live positions only
+                for (int p = n_loc - 1; p >= 0 && pick < 0; --p)
+                    if (!((tile_mask >> p) & 1ull) && !((owner_mask >> p) & 1ull) && (pass == 1 || ((live_before >> p) & 1ull)))
+                        pick = p;
+            if (pick < 0) return false;
+            owner_mask |= 1ull << pick;
+            fixed |= (unsigned long long)((shard->rank >> (b - n_loc)) & 1) << pick;
+        }
+        d.fixed_base = fixed;
+        d.enum_mask &= ~rank_mask & ~owner_mask;
+    }
     d.n_enum_bits = __builtin_popcountll(d.enum_mask);
     L.n_work = (unsigned long long)batch << d.n_enum_bits;
+    if (shard && !last && (d.fixed_base & ~live_before)) L.n_work = 0;  // every tile of this rank is still all zero
     L.smem = tma_smem_bytes(T, n_records);
     L.n_stage = n_records;
     // extents the tensor map can describe
-    if (((unsigned long long)batch << (N - d.h - d.k)) > 0xffffffffull) return false;
+    if (((unsigned long long)batch << (n_loc - d.h - d.k)) > 0xffffffffull) return false;
     return true;
 }
 
 static int tma_encode(qck_handle* h, const TmaSweepDev& d, int batch, double2* work, bool box_main, CUtensorMap* out) {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) QCK_FAIL(h, QCK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    const int N = d.n_state, top = d.h + d.k;
+    const int N = d.n_local, top = d.h + d.k;
     cuuint64_t dims[5] = {16ull, 1ull << (d.lowc - 3), 1ull << (d.h - d.lowc), 1ull << d.k,
                           (cuuint64_t)batch << (N - top)};
     cuuint64_t strides[4] = {128ull, 16ull << d.lowc, 16ull << d.h, 16ull << top};
@@ -1156,12 +1198,14 @@ static int tma_encode_probs(qck_handle* h, const TmaSweepDev& d, double* row, CU
 // Exposed for the host-logic tests (no GPU needed): describe sweep `i` of `plan` the way the TMA kernel
 // would run it.  Returns 1 and fills the arrays when the sweep is eligible, else 0.
 extern "C" int qck_debug_tma_describe(const qck_sim_plan* plan, int sweep, uint64_t live_before, int last,
-                                              int batch, int32_t* geom /*[8]: lowc,h,k,n_load,n_store,zf_shift,zf_mask,n_enum_bits*/,
+                                              int batch, int n_local, int rank,
+                                              int32_t* geom /*[8]: lowc,h,k,n_load,n_store,zf_shift,zf_mask,n_enum_bits*/,
                                               int32_t* perm /*[16]*/, uint64_t* ld_off, uint32_t* ld_slot, uint64_t* st_off,
-                                              uint32_t* st_slot, uint64_t* enum_mask, uint64_t* n_work) {
+                                              uint32_t* st_slot, uint64_t* enum_mask, uint64_t* n_work, uint64_t* fixed_base) {
     static TmaLaunch L;  // large: keep it off the stack; debug entry point, not re-entrant
     if (!plan || sweep < 0 || sweep >= plan->n_sweeps) return 0;
-    if (!tma_describe(plan, sweep, live_before, last != 0, batch, 232448, L)) return 0;
+    TmaShard sh = {n_local, rank};
+    if (!tma_describe(plan, sweep, live_before, last != 0, batch, 232448, L, n_local > 0 ? &sh : nullptr)) return 0;
     const TmaSweepDev& d = L.sd;
     const int32_t g[8] = {d.lowc, d.h, d.k, d.n_load, d.n_store, d.zf_shift, (int32_t)d.zf_mask, d.n_enum_bits};
     for (int j = 0; j < 8; ++j) geom[j] = g[j];
@@ -1176,6 +1220,7 @@ extern "C" int qck_debug_tma_describe(const qck_sim_plan* plan, int sweep, uint6
     }
     *enum_mask = d.enum_mask;
     *n_work = L.n_work;
+    if (fixed_base) *fixed_base = d.fixed_base;
     return 1;
 }
 
@@ -1249,14 +1294,14 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
         for (int i = 0; i < plan->n_sweeps; ++i) {
             tma_describe(plan, i, live, i == plan->n_sweeps - 1, batch, h->max_smem_optin, *L);
             for (int j = 0; j < plan->sweeps[i].n_tile; ++j) live |= 1ull << plan->sweeps[i].pos[j];
-            int rc = tma_encode(h, L->sd, batch, work, true, &L->map_st);
+            int rc = tma_encode(h, L->sd, batch, work, true, &L->maps.st[0]);
             if (rc) return rc;
             const bool box_main = L->sd.zf_shift == L->sd.lowc + L->sd.k;
-            rc = tma_encode(h, L->sd, batch, work, box_main, &L->map_ld);
+            rc = tma_encode(h, L->sd, batch, work, box_main, &L->maps.ld[0]);
             if (rc) return rc;
-            L->map_pr = L->map_st;
+            L->maps.pr = L->maps.st[0];
             if (fold_row && batch == 1 && i == plan->n_sweeps - 1) {
-                rc = tma_encode_probs(h, L->sd, fold_row, &L->map_pr);
+                rc = tma_encode_probs(h, L->sd, fold_row, &L->maps.pr);
                 if (rc) return rc;
                 L->sd.fold_direct = 1;
                 if (folded) *folded = true;
@@ -1269,7 +1314,7 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
                 counter = reinterpret_cast<unsigned long long*>(h->d_partials + h->partials_count - 4);
                 QCK_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
             }
-            sim_sweep_tma_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(L->map_st, L->map_ld, L->map_pr, L->sd, pdl, d_labels,
+            sim_sweep_tma_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(L->maps, L->sd, pdl, d_labels,
                                                                                        inst_base, L->n_work, counter);
             QCK_CHECK_LAUNCH(h);
         }
@@ -1518,4 +1563,105 @@ extern "C" int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int3
     QCK_CUDA(h, cudaMemcpyAsync(d_label, &label, sizeof(int32_t), cudaMemcpyHostToDevice, st));
     PlanDev pd = to_dev(plan);
     return run_sweeps(h, plan, pd, d_label, 0, 1, (double2*)d_state, state_amps, st);
+}
+
+// ------------------------------------------------------------------ sharded statevector (several GPUs)
+// The state of an uncut circuit too large for one GPU: 2^n_local amplitudes per rank, the top bits of the
+// amplitude index are the rank.  Every rank runs the same sweeps on the tiles it owns; a sweep whose tile
+// contains rank bits loads / stores the peer halves of its tiles straight from / to the peers' buffers with
+// TMA (mapped through CUDA IPC, NVLink): the exchange IS the sweep, there is no separate all-to-all.  The
+// caller synchronises the ranks between sweeps (qck.h).
+extern "C" int qck_sim_sweeps_sharded(qck_handle* h, const qck_sim_plan* plan, int sweep_begin, int sweep_end, int rank,
+                                      int world, void* const* d_shards, size_t shard_bytes, qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    int rc = validate_plan(h, plan);
+    if (rc) return rc;
+    int g = 0;
+    while ((1 << g) < world) ++g;
+    if (world < 1 || world > TMA_MAX_SHARDS || (1 << g) != world || rank < 0 || rank >= world || !d_shards)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "world=%d must be a power of two <= %d, 0 <= rank < world", world, TMA_MAX_SHARDS);
+    const int n_local = plan->n_state_qubits - g;
+    if (plan->n_digits != 0) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "sharded runs simulate one uncut circuit (no label digits)");
+    if (n_local < 14 || shard_bytes < ((size_t)16 << n_local))
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "shard of 2^%d amplitudes needs %zu bytes, got %zu", n_local, (size_t)16 << n_local,
+                 shard_bytes);
+    if (sweep_begin < 0 || sweep_end > plan->n_sweeps || sweep_begin > sweep_end)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad sweep range [%d, %d)", sweep_begin, sweep_end);
+    for (int r = 0; r < world; ++r)
+        if (!d_shards[r]) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "shard pointer of rank %d is NULL", r);
+    if (!tensor_map_encoder()) QCK_FAIL(h, QCK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    PlanDev pd = to_dev(plan);
+    int32_t* d_label = reinterpret_cast<int32_t*>(h->d_partials + h->partials_count - 8);  // reserved tail
+    QCK_CUDA(h, cudaMemsetAsync(d_label, 0, sizeof(int32_t), st));
+    std::unique_ptr<TmaLaunch> L(new TmaLaunch);
+    TmaShard sh = {n_local, rank};
+    unsigned long long live = 0;
+    for (int i = 0; i < sweep_end; ++i) {
+        if (i >= sweep_begin) {
+            if (!tma_describe(plan, i, live, i == plan->n_sweeps - 1, 1, h->max_smem_optin, *L, &sh))
+                QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "sweep %d cannot run on the TMA kernel (tile layout / op count)", i);
+            if (L->n_work > 0) {
+                const bool box_main = L->sd.zf_shift == L->sd.lowc + L->sd.k;
+                for (int r = 0; r < world; ++r) {
+                    rc = tma_encode(h, L->sd, 1, (double2*)d_shards[r], true, &L->maps.st[r]);
+                    if (rc) return rc;
+                    rc = tma_encode(h, L->sd, 1, (double2*)d_shards[r], box_main, &L->maps.ld[r]);
+                    if (rc) return rc;
+                }
+                L->maps.pr = L->maps.st[0];
+                PlanDev pdl = pd;
+                pdl.n_stage = L->n_stage;
+                const unsigned long long grid =
+                    L->n_work < (unsigned long long)h->sm_count ? L->n_work : (unsigned long long)h->sm_count;
+                sim_sweep_tma_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(L->maps, L->sd, pdl, d_label, 0,
+                                                                                           L->n_work, nullptr);
+                QCK_CHECK_LAUNCH(h);
+            }
+        }
+        for (int j = 0; j < plan->sweeps[i].n_tile; ++j) live |= 1ull << plan->sweeps[i].pos[j];
+    }
+    return QCK_OK;
+}
+
+// Plain device memory + CUDA IPC for the shards (torch's caching allocator sub-allocates, which IPC cannot
+// export directly).
+extern "C" int qck_mem_alloc(qck_handle* h, size_t bytes, void** d_ptr) {
+    if (!h || !d_ptr) return QCK_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    if (cudaMalloc(d_ptr, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        QCK_FAIL(h, QCK_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes);
+    }
+    return QCK_OK;
+}
+extern "C" int qck_mem_free(qck_handle* h, void* d_ptr) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    QCK_CUDA(h, cudaFree(d_ptr));
+    return QCK_OK;
+}
+extern "C" int qck_ipc_export(qck_handle* h, void* d_ptr, unsigned char* handle64) {
+    if (!h || !d_ptr || !handle64) return QCK_ERR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard guard(h->device);
+    cudaIpcMemHandle_t ih;
+    QCK_CUDA(h, cudaIpcGetMemHandle(&ih, d_ptr));
+    memcpy(handle64, &ih, 64);
+    return QCK_OK;
+}
+extern "C" int qck_ipc_open(qck_handle* h, const unsigned char* handle64, void** d_ptr) {
+    if (!h || !handle64 || !d_ptr) return QCK_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, handle64, 64);
+    QCK_CUDA(h, cudaIpcOpenMemHandle(d_ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    return QCK_OK;
+}
+extern "C" int qck_ipc_close(qck_handle* h, void* d_ptr) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    QCK_CUDA(h, cudaIpcCloseMemHandle(d_ptr));
+    return QCK_OK;
 }

@@ -181,9 +181,33 @@ QCK_API int qck_host_cluster_ops(const int32_t* ops, int n_ops, int n_tile, int 
  *   ld_slot / st_slot: first shared-memory amplitude slot of the box; enum_mask: the state bits a
  *   tile number is spread over; n_work = batch << popcount(enum_mask) tiles are visited. */
 QCK_API int qck_debug_tma_describe(const qck_sim_plan* plan, int sweep, uint64_t live_before, int last,
-                                   int batch, int32_t* geom, int32_t* perm, uint64_t* ld_off,
-                                   uint32_t* ld_slot, uint64_t* st_off, uint32_t* st_slot,
-                                   uint64_t* enum_mask, uint64_t* n_work);
+                                   int batch, int n_local, int rank, int32_t* geom, int32_t* perm,
+                                   uint64_t* ld_off, uint32_t* ld_slot, uint64_t* st_off,
+                                   uint32_t* st_slot, uint64_t* enum_mask, uint64_t* n_work,
+                                   uint64_t* fixed_base);
+/*   n_local > 0: sharded run (qck_sim_sweeps_sharded) - the state bits >= n_local are the rank that
+ *   holds an amplitude; `rank` is the describing rank; *fixed_base = the bits every tile base of that
+ *   rank carries (its own rank bits outside the tile, owner bits for rank bits inside it). */
+
+/* ------------------------------------------------------------------ sharded statevector
+ * Replaces: the ideal UNCUT run (Utilities.py:39-69) when the state does not fit one GPU: 2^n_local
+ * amplitudes per rank (n_local = n_state_qubits - log2(world)), the top bits of the amplitude index
+ * are the rank.  qck_sim_sweeps_sharded enqueues sweeps [sweep_begin, sweep_end) of `plan` for THIS
+ * rank (one instance, no label digits; the TMA sweep kernel with live-qubit tracking).  d_shards
+ * (HOST array of `world` device pointers valid on this device: the own buffer and the peers' buffers
+ * mapped with qck_ipc_open) - a sweep whose tile holds rank bits moves the peer halves of its tiles
+ * over NVLink with TMA, there is no separate exchange.  The caller must order the ranks: all ranks
+ * finish sweep s (e.g. a stream-ordered NCCL all-reduce of one element) before any rank starts
+ * sweep s + 1 whenever sweep s or s + 1 has a tile position >= n_local.
+ * qck_mem_alloc / qck_ipc_*: plain cudaMalloc memory and CUDA IPC handles (64 bytes) for the shards. */
+QCK_API int qck_sim_sweeps_sharded(qck_handle* h, const qck_sim_plan* plan, int sweep_begin, int sweep_end,
+                                   int rank, int world, void* const* d_shards, size_t shard_bytes,
+                                   qck_stream stream);
+QCK_API int qck_mem_alloc(qck_handle* h, size_t bytes, void** d_ptr);
+QCK_API int qck_mem_free(qck_handle* h, void* d_ptr);
+QCK_API int qck_ipc_export(qck_handle* h, void* d_ptr, unsigned char* handle64);
+QCK_API int qck_ipc_open(qck_handle* h, const unsigned char* handle64, void** d_ptr);
+QCK_API int qck_ipc_close(qck_handle* h, void* d_ptr);
 
 /* Exact HBM bytes the sweeps of a streaming plan move for `batch` instances (host arithmetic, no
  * CUDA call): the TMA path with live-qubit tracking when every sweep is eligible (*uses_tma = 1),

@@ -276,6 +276,34 @@ def test_random_circuits_streaming_on_device(dev, seed):
             assert np.abs(r_tma - ra).max() < 1e-12
 
 
+@pytest.mark.parametrize("name,n,depth,world", [("syc", 20, 2, 2), ("syc", 21, 3, 4), ("qft", 18, 1, 2), ("hwe", 20, 2, 8),
+                                                ("bv", 19, 1, 4)])
+def test_sharded_statevector_emulated_on_one_device(dev, name, n, depth, world):
+    """qck_sim_sweeps_sharded with every shard on this GPU (ranks run one after the other; same kernels and
+    per-shard tensor maps as the multi-GPU run, no IPC): the concatenated shards == the single-buffer
+    statevector, amplitude by amplitude."""
+    sharded = import_module(f"{PKG}.sharded")
+    circ = gen.gen_circ(name, n, depth, seed=2).decompose_two_qubit()
+    sv_sh = sharded.ShardedStatevector(circ, dev, world=world, emulate=True)
+    for b in sv_sh._own:
+        b.fill_(float("nan"))
+    sv_sh.run()
+    torch.cuda.synchronize()
+    got = torch.cat([sv_sh.local_shard(r) for r in range(world)])
+    ex = sv_sh.ex
+    st = ex.plan_struct(0)
+    h = _lib.get_handle(0)
+    ref = torch.full((2 << n,), float("nan"), dtype=torch.float64, device=dev)
+    h.check(h.lib.qck_sim_statevector(h.ptr, C.byref(st), 0, ref.data_ptr(), ref.numel() * 8,
+                                      torch.cuda.current_stream(dev).cuda_stream))
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any()
+    assert float((got - ref).abs().max()) < 1e-15
+    assert abs(sv_sh.norm() - 1.0) < 1e-12
+    tr = sv_sh.traffic()
+    assert tr["bytes"] > 0 and 0 <= tr["peer_bytes"] <= tr["bytes"]
+
+
 def test_tma_sweep_chunked_op_stage(dev):
     """More op records than the shared-memory op stage holds: the TMA kernel restages chunks per tile
     (forced with QCK_TMA_STAGE_CAP); tile-resolved ops (cp with an outside qubit) included."""

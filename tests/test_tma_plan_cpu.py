@@ -50,22 +50,22 @@ def _plan_struct(program, plan):
     return st, arr
 
 
-def describe(st, i, live, last, batch=1):
+def describe(st, i, live, last, batch=1, n_local=0, rank=0):
     lib = _lib.load()
     geom = (C.c_int32 * 8)()
     perm = (C.c_int32 * 16)()
     ld_off, st_off = (C.c_uint64 * 128)(), (C.c_uint64 * 128)()
     ld_slot, st_slot = (C.c_uint32 * 128)(), (C.c_uint32 * 128)()
-    enum_mask, n_work = C.c_uint64(), C.c_uint64()
-    ok = lib.qck_debug_tma_describe(C.byref(st), i, live, int(last), batch, geom, perm, ld_off, ld_slot, st_off,
-                                    st_slot, C.byref(enum_mask), C.byref(n_work))
+    enum_mask, n_work, fixed = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    ok = lib.qck_debug_tma_describe(C.byref(st), i, live, int(last), batch, n_local, rank, geom, perm, ld_off, ld_slot,
+                                    st_off, st_slot, C.byref(enum_mask), C.byref(n_work), C.byref(fixed))
     if not ok:
         return None
     lowc, h, k, n_load, n_store, zf_shift, zf_mask, n_enum = list(geom)
     return dict(lowc=lowc, h=h, k=k, zf_shift=zf_shift, zf_mask=zf_mask, n_enum=n_enum, perm=list(perm),
                 ld=[(ld_off[j], ld_slot[j]) for j in range(n_load)],
                 st=[(st_off[j], st_slot[j]) for j in range(n_store)],
-                enum_mask=enum_mask.value, n_work=n_work.value)
+                enum_mask=enum_mask.value, n_work=n_work.value, fixed_base=fixed.value)
 
 
 def emulate(program, plan, label):
@@ -313,3 +313,100 @@ def test_random_circuits_streaming_schedule_and_tma_layout(seed):
                             continue
                         raise
                     assert np.abs(got - pi.run_plan(prog, plan, label, return_state=True)).max() < 1e-13
+
+
+def emulate_sharded(program, plan, world):
+    """The data movement of qck_sim_sweeps_sharded on `world` ranks (shards = separate NaN-filled buffers; a box
+    whose rank bits differ from the working rank's is a peer access) -> (concatenated final state, bytes a rank
+    moved from / to PEER buffers)."""
+    st, _keep = _plan_struct(program, plan)
+    mats = program.mats
+    N = plan.n_state
+    g = world.bit_length() - 1
+    n_local = N - g
+    shards = [np.full(1 << n_local, np.nan + 1j * np.nan, dtype=np.complex128) for _ in range(world)]
+    lmask = (1 << n_local) - 1
+    live, peer_bytes = 0, 0
+    for i, (positions, b, e) in enumerate(plan.sweeps):
+        T = len(positions)
+        last = i == len(plan.sweeps) - 1
+        written = [np.zeros(1 << n_local, dtype=bool) for _ in range(world)]
+        for rank in range(world):
+            d = describe(st, i, live, last, n_local=n_local, rank=rank)
+            assert d is not None, f"sweep {i} not eligible on rank {rank}"
+            lowc, h, k, perm = d["lowc"], d["h"], d["k"], d["perm"]
+
+            def box_offsets(bits):
+                j = np.arange(1 << bits)
+                off = j & ((1 << lowc) - 1)
+                for t in range(lowc, bits):
+                    off = off | (((j >> t) & 1) << (h + t - lowc))
+                return off
+
+            ld_box, st_box = box_offsets(d["zf_shift"]), box_offsets(lowc + k)
+            assert h + k <= n_local, "a box must not span two shards"
+            tidx = np.arange(1 << T)
+            for w in range(d["n_work"]):
+                base = d["fixed_base"] | _pdep(w, d["enum_mask"])
+                tile_live = (base & ~live) == 0
+                stage = np.full(1 << T, np.nan + 1j * np.nan, dtype=np.complex128)
+                if not tile_live:
+                    assert last
+                    stage[:] = 0
+                else:
+                    if live == 0:
+                        stage[:] = 0
+                        stage[0] = 1
+                    else:
+                        for off, slot in d["ld"]:
+                            gidx = base | off
+                            src = shards[gidx >> n_local][(gidx & lmask) | ld_box]
+                            assert not np.isnan(src).any(), "load of memory that was never written"
+                            stage[slot:slot + len(ld_box)] = src
+                            peer_bytes += 16 * len(ld_box) * ((gidx >> n_local) != rank)
+                        stage[((tidx >> d["zf_shift"]) & d["zf_mask"]) != 0] = 0
+                    assert not np.isnan(stage).any()
+                    seg, skip = plan.ops[b:e], 0
+                    for oi, op in enumerate(seg):
+                        kind, q0, q1, mat, sel, stride, n_live, member = (int(x) for x in op)
+                        if skip:
+                            skip -= 1
+                            continue
+                        if kind in (_lib.OP_U1X, _lib.OP_PHASE):
+                            terms = seg[oi + 1:oi + 1 + q1]
+                            skip = q1
+                            if kind == _lib.OP_PHASE:
+                                stage = pi.phase_scalar(mats, terms, base) * stage
+                            else:
+                                stage = pi.apply_u1_matrix(stage, tidx, perm[q0], pi.cond_matrix(mats, terms, base))
+                            continue
+                        stage = pi.apply_op(stage, tidx, kind, perm[q0], perm[q1] if kind != _lib.OP_U1 else 0, mats, mat)
+                for off, slot in d["st"]:
+                    gidx = base | off
+                    r, l = gidx >> n_local, (gidx & lmask) | st_box
+                    assert not written[r][l].any(), "two tiles of one sweep store the same amplitude"
+                    written[r][l] = True
+                    shards[r][l] = stage[slot:slot + len(st_box)]
+                    peer_bytes += 16 * len(st_box) * (r != rank)
+        for p in positions:
+            live |= 1 << p
+    return np.concatenate(shards), peer_bytes
+
+
+@pytest.mark.parametrize("name,n,depth,world,onchip,tile", [
+    ("syc", 12, 2, 2, 6, 7), ("syc", 12, 2, 4, 6, 7), ("qft", 11, 1, 2, 5, 6), ("hwe", 12, 2, 4, 6, 7), ("bv", 12, 1, 2, 6, 6),
+    ("syc", 13, 3, 8, 6, 7),
+])
+def test_sharded_sweeps_move_peer_halves_through_the_tiles(name, n, depth, world, onchip, tile):
+    """Several ranks, each owning the amplitudes whose top bits equal its rank: every tile has exactly one
+    owner, sweeps whose tile holds rank bits read / write the peers' buffers, nothing unwritten is ever read
+    and the concatenated shards equal the single-buffer result."""
+    prog = _uncut_program(name, n, depth, onchip_max=onchip, stream_tile=tile)
+    (plan,) = prog.plans()
+    want = pi.run_plan(prog, plan, 0, return_state=True)
+    got, peer_bytes = emulate_sharded(prog, plan, world)
+    assert not np.isnan(got).any(), "the last sweep must leave every shard completely written"
+    assert np.abs(got - want).max() < 1e-14
+    n_local = n - (world.bit_length() - 1)
+    touches = any(p >= n_local for pos, _, _ in plan.sweeps for p in pos)
+    assert (peer_bytes > 0) == touches
