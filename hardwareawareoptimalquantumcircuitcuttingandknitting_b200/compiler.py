@@ -85,7 +85,7 @@ class FragmentProgram:
 
     def __init__(self, frag_circuit: QuantumCircuit, fragment: QuantumRegister, num_clbits: int,
                  onchip_max: int = ONCHIP_MAX_QUBITS, stream_tile: int = STREAM_TILE,
-                 cluster: bool = True, fuse: bool = True) -> None:
+                 cluster: bool = True, fuse: bool = True, early_bits: int = 0) -> None:
         self.fragment = fragment
         self.n_qubits = len(fragment)
         self.num_clbits = num_clbits
@@ -93,6 +93,9 @@ class FragmentProgram:
         self.stream_tile = stream_tile
         self.cluster = cluster
         self.fuse = fuse
+        # state bits the FIRST sweep of a streaming plan should take into its tile (sharded runs: the rank
+        # bits - they then go live while the state is one tile, and the big expansion sweeps stay local)
+        self.early_bits = int(early_bits)
         self._pool: list[np.ndarray] = []
         self._pool_len = 0
         self._mat_by_off: dict[int, np.ndarray] = {}
@@ -508,6 +511,8 @@ def _schedule_sweeps(ops: np.ndarray, n_state: int, tile: int, program):
     new_ops, sweeps = [], []
     while remaining:
         tile_set = (1 << low) - 1
+        if not sweeps and bin(tile_set | program.early_bits).count("1") <= tile - 2:
+            tile_set |= program.early_bits & ((1 << n_state) - 1)
         blocked_full = blocked_diag = 0
         taken, rest = [], []
         for i in remaining:

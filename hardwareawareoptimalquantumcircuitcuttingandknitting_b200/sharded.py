@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 
 from . import _lib
+from .compiler import FragmentExecutor, FragmentProgram
 from .virtual_circuit import VirtualCircuit
 
 
@@ -52,15 +53,31 @@ class ShardedStatevector:
             raise ValueError("world must be a power of two <= 8")
         self.virt = VirtualCircuit(circ)
         (frag,) = self.virt.active_fragments()
-        self.ex = self.virt.executor(frag, self.device, True)
-        if self.ex.program.radix:
-            raise ValueError("sharded runs simulate one uncut circuit (no virtual gates)")
-        self.plan = self.ex.plans[0]
-        self.n = self.plan.n_state
         self.g = self.world.bit_length() - 1
-        self.n_local = self.n - self.g
+        n = len(frag)
+        self.n = n
+        self.n_local = n - self.g
         if self.n_local < 14:
             raise ValueError(f"{self.n} qubits over {self.world} ranks leaves fewer than 14 local qubits")
+        # Two schedules: the plain one, and one whose FIRST sweep takes the rank bits into its tile - they then
+        # go live while the state is a single tile and the large expansion sweeps of a shallow circuit write
+        # local memory only (syc-33 d1 on 2 GPUs: 68.7 GB -> 0 GB over NVLink); deeper circuits can be better
+        # off with the plain one.  The one that moves fewer bytes between shards wins (host arithmetic).
+        early = ((1 << n) - 1) & ~((1 << self.n_local) - 1)
+        best = None
+        for bits in ((early, 0) if self.world > 1 else (0,)):
+            prog = FragmentProgram(self.virt.fragment_circuits[frag], frag, self.virt.num_clbits, early_bits=bits)
+            if prog.radix:
+                raise ValueError("sharded runs simulate one uncut circuit (no virtual gates)")
+            ex = FragmentExecutor(prog, self.device, True)
+            if len(ex.plans) != 1 or ex.plans[0].n_state != n:
+                raise ValueError("sharded runs need a measurement-terminal circuit (no ancilla bits)")
+            self.ex, self.plan = ex, ex.plans[0]
+            tr = self.traffic()
+            key = (tr["peer_bytes"], tr["bytes"])
+            if best is None or key < best[0]:
+                best = (key, ex)
+        self.ex, self.plan = best[1], best[1].plans[0]
         self.handle = _lib.get_handle(self.device.index or 0)
         self.shard_bytes = 16 << self.n_local
         self._own: list = []          # buffers this process allocated (raw or torch)
@@ -166,10 +183,7 @@ class ShardedStatevector:
         """Exact bytes this configuration moves (host arithmetic over the sweep descriptions): total and the
         part that crosses between shards."""
         lib = _lib.load()
-        st = self.ex.plan_struct(0) if self.ex.d_blob is not None else None
-        if st is None:
-            self.ex.upload()
-            st = self.ex.plan_struct(0)
+        st = _lib.QckSimPlan.from_buffer_copy(self.ex._structs[0][0])      # host fields only: no device pointers needed
         geom, perm = (C.c_int32 * 8)(), (C.c_int32 * 16)()
         ld_off, st_off = (C.c_uint64 * 128)(), (C.c_uint64 * 128)()
         ld_slot, st_slot = (C.c_uint32 * 128)(), (C.c_uint32 * 128)()
