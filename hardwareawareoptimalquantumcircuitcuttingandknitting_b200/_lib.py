@@ -115,7 +115,7 @@ _lib_lock = threading.Lock()
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile ``libqck.so`` in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inc"))]
     srcs.append(os.path.join(_HERE, "..", "include", "qck.h"))
     if not force and os.path.exists(LIB_PATH):
         newest = max(os.path.getmtime(s) for s in srcs)

@@ -156,7 +156,9 @@ struct WholeCta {
     __device__ static __forceinline__ int nth() { return blockDim.x; }
     __device__ static __forceinline__ void sync() { cta_sync(); }
 };
-template <int N>
+// TAG only makes the instantiations of the gate passes distinct per kernel: a pass shared by several kernel
+// instantiations is no longer inlined into them (measured: 13.3 -> 14.9 ms on the syc-32 d1 expansion sweep).
+template <int N, int TAG = 0>
 struct ConsumerWarps {
     __device__ static __forceinline__ int tid() { return (int)threadIdx.x - 32; }
     __device__ static __forceinline__ int nth() { return N; }
@@ -701,184 +703,58 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
 
 // One store / load tensor map per shard of the state (a single-GPU run has one shard): in a sharded run the
 // rank bits of a box select the PEER buffer it lives in - the TMA unit moves it over NVLink.
+#ifndef TMA_MAX_SHARDS
 #define TMA_MAX_SHARDS 8
-struct TmaMaps {
-    CUtensorMap st[TMA_MAX_SHARDS], ld[TMA_MAX_SHARDS], pr;
+#endif
+struct TmaShardMaps {
+    CUtensorMap st, ld;
+};
+struct TmaMaps {  // the maps one tile uses sit next to each other (store, load of shard 0, probabilities)
+    TmaShardMaps sh0;
+    CUtensorMap pr;
+    TmaShardMaps peer[TMA_MAX_SHARDS - 1];  // shards 1 ..
+    __host__ __device__ const CUtensorMap* st(int r) const { return r == 0 ? &sh0.st : &peer[r - 1].st; }
+    __host__ __device__ const CUtensorMap* ld(int r) const { return r == 0 ? &sh0.ld : &peer[r - 1].ld; }
+    __host__ CUtensorMap* st_mut(int r) { return r == 0 ? &sh0.st : &peer[r - 1].st; }
+    __host__ CUtensorMap* ld_mut(int r) { return r == 0 ? &sh0.ld : &peer[r - 1].ld; }
 };
 
-__global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
-    sim_sweep_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaSweepDev sw, PlanDev plan, const int32_t* __restrict__ labels,
-                         int inst_base, unsigned long long n_work, unsigned long long* __restrict__ counter) {
-    typedef ConsumerWarps<TMA_CONSUMERS> P;
-    const int T = sw.n_tile;
-    const uint32_t stage_bytes = 16u << T;
-    // SWIZZLE_128B repeats every 1024 bytes: the stages must be 1024-byte aligned
-    unsigned char* stage0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    StagedOp* so = reinterpret_cast<StagedOp*>(stage0 + TMA_STAGES * stage_bytes);
-    __shared__ __align__(8) uint64_t full_bar[TMA_STAGES], done_bar[TMA_STAGES];
-    __shared__ TmaTileDesc desc[TMA_STAGES];
-    __shared__ int digits[QCK_MAX_DIGITS];
-    __shared__ int perm_s[16];
-    // consumer progress within the current tile (1 loaded, 2 staged / resolved, 3 zero-filled, 4 gates done,
-    // 5 handed to the producer, 9 finished): what the wait watchdog reports when a wait cannot complete
-    __shared__ volatile int progress;
-
-    if (threadIdx.x == 0) {
-        progress = 0;
-        for (int i = 0; i < TMA_STAGES; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&done_bar[i], 1);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (threadIdx.x < 16) perm_s[threadIdx.x] = sw.perm[threadIdx.x];
-    cta_sync();
-
-    if (threadIdx.x < 32) {
-        if (threadIdx.x != 0) return;
-        // ===== producer: TMA loads, TMA stores, stage recycling =====
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.st[0])) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.ld[0])) : "memory");
-        if (sw.fold_direct) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.pr)) : "memory");
-        const int sh2 = sw.lowc, sh3 = sw.h, sh4 = sw.h + sw.k;
-        const unsigned long long local_mask = (1ull << sw.n_local) - 1ull;
-        const unsigned long long m2 = (1ull << (sw.h - sw.lowc)) - 1ull, m3 = (1ull << sw.k) - 1ull;
-        const int inst_shift = sw.n_local - sh4;
-        const unsigned long long tile_mask = (1ull << sw.n_enum_bits) - 1ull;
-        // tiles are dealt round robin, or pulled from a counter when one is given (tuning knob)
-        auto issue_load = [&](unsigned long long kk) {
-            const int stg = (int)(kk % TMA_STAGES);
-            const unsigned long long w = counter ? atomicAdd(counter, 1ull) : blockIdx.x + kk * gridDim.x;
-            TmaTileDesc& d = desc[stg];
-            if (w >= n_work) {
-                d.flags = TMA_TILE_DONE;
-                mbar_arrive(&full_bar[stg]);
-                return;
-            }
-            const int inst = (int)(w >> sw.n_enum_bits);
-            const unsigned long long base = sw.fixed_base | soft_pdep(w & tile_mask, sw.enum_mask);
-            const bool live = (base & ~sw.live_before) == 0ull;
-            d.base = base;
-            d.inst = inst;
-            d.flags = live ? TMA_TILE_LIVE : TMA_TILE_DEAD;
-            if (live && sw.n_load > 0) {
-                mbar_arrive_expect_tx(&full_bar[stg], (uint32_t)sw.n_load * sw.load_bytes);
-                const uint32_t dst0 = smem_u32(stage0 + (size_t)stg * stage_bytes);
-                for (int i = 0; i < sw.n_load; ++i) {
-                    const unsigned long long gidx = base | sw.ld_off[i], idx = gidx & local_mask;
-                    tma_load_5d(dst0 + sw.ld_slot[i] * 16u, &maps.ld[gidx >> sw.n_local], &full_bar[stg],
-                                (int)((idx >> sh2) & m2), (int)((idx >> sh3) & m3), (int)(idx >> sh4) + (inst << inst_shift));
-                }
-            } else {
-                mbar_arrive(&full_bar[stg]);
-            }
-        };
-        for (int kk = 0; kk < TMA_STAGES; ++kk) issue_load(kk);
-        for (unsigned long long kk = 0;; ++kk) {
-            const int stg = (int)(kk % TMA_STAGES);
-            if (desc[stg].flags == TMA_TILE_DONE) break;  // claims are monotone: nothing later either
-            if (kk >= 1) {  // the store of tile kk-1 has finished reading its stage: reload it
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                issue_load(kk - 1 + TMA_STAGES);
-            }
-            mbar_wait(&done_bar[stg], (uint32_t)((kk / TMA_STAGES) & 1ull), 0, kk, stg, &progress);
-            const TmaTileDesc d = desc[stg];
-            const uint32_t src0 = smem_u32(stage0 + (size_t)stg * stage_bytes);
-            // fold_direct: the consumers left the probabilities (8 bytes per amplitude, linear) in the stage
-            const uint32_t slot_bytes = sw.fold_direct ? 8u : 16u;
-            for (int i = 0; i < sw.n_store; ++i) {
-                const unsigned long long gidx = d.base | sw.st_off[i], idx = gidx & local_mask;
-                const CUtensorMap* mp = sw.fold_direct ? &maps.pr : &maps.st[gidx >> sw.n_local];
-                tma_store_5d(mp, src0 + sw.st_slot[i] * slot_bytes, (int)((idx >> sh2) & m2), (int)((idx >> sh3) & m3),
-                             (int)(idx >> sh4) + (d.inst << inst_shift));
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        return;
-    }
-
-    // ===== consumers: gates on the resident tile =====
-    const int ctid = P::tid();
-    const uint32_t n_amp = 1u << T;
-    const int n_ops = sw.op_end - sw.op_begin;
-    int staged_inst = -1;
-    for (unsigned long long kk = 0;; ++kk) {
-        const int stg = (int)(kk % TMA_STAGES);
-        mbar_wait(&full_bar[stg], (uint32_t)((kk / TMA_STAGES) & 1ull), 1, kk, stg, &progress);
-        if (ctid == 0) progress = 1;
-        const TmaTileDesc d = desc[stg];
-        if (d.flags == TMA_TILE_DONE) {
-            if (ctid == 0) progress = 9;
-            break;
-        }
-        double2* s = reinterpret_cast<double2*>(stage0 + (size_t)stg * stage_bytes);
-        if (d.flags == TMA_TILE_DEAD) {
-            for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS) s[j] = make_double2(0.0, 0.0);
-        } else {
-            const bool chunked = n_ops > plan.n_stage;  // more records than the stage holds: restaged per tile
-            if (d.inst != staged_inst) {  // uniform; the matrices depend on the instance's label digits
-                if (ctid == 0) decode_digits(plan, labels[inst_base + d.inst], digits);
-                P::sync();
-                if (!chunked) stage_ops<P>(so, plan.ops, sw.op_begin, n_ops, plan.mats, digits, perm_s);
-                staged_inst = d.inst;
-                if (sw.has_x && !chunked) P::sync();
-            }
-            if (sw.has_x && !chunked) resolve_tile<P>(so, n_ops, d.base);
-            if (ctid == 0) progress = 2;
-            if (sw.init) {
-                for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS) s[j] = make_double2(j == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
-            } else if (sw.zf_mask) {  // boxes of non-live tile bits were not loaded: they are zeros
-                for (uint32_t j = ctid; j < n_amp; j += TMA_CONSUMERS)
-                    if ((j >> sw.zf_shift) & sw.zf_mask) s[j] = make_double2(0.0, 0.0);
-            }
-            P::sync();
-            if (ctid == 0) progress = 3;
-            if (chunked)
-                apply_ops<P, false>(s, T, so, plan.n_stage, plan.ops, sw.op_begin, sw.op_end, plan.mats, digits, false,
-                                    sw.has_x != 0, d.base, perm_s);
-            for (int i = 0; i < n_ops && !chunked;) {
-                const int kind_i = so[i].w0.x;
-                if (kind_i == QCK_OP_U1X) {  // (sweeps with register clusters run on the plain kernel: flags bit 1)
-                    run_single<P>(s, T, so[i], plan.mats);
-                    i += 1 + so[i].w0.z;
-                } else if (kind_i == QCK_OP_PHASE) {
-                    run_phase<P>(s, T, so[i].m[0]);
-                    i += 1 + so[i].w0.z;
-                } else {
-                    run_single<P>(s, T, so[i], plan.mats);
-                    ++i;
-                }
-            }
-        }
-        if (sw.fold_direct) {  // |amp|^2 in place: registers first (the doubles overlap other threads' amplitudes)
-            double pr[16];
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const uint32_t j = (uint32_t)ctid + (uint32_t)r * TMA_CONSUMERS;
-                if (j < n_amp) {
-                    const double2 a = s[swz(j)];
-                    pr[r] = fma(a.x, a.x, a.y * a.y);
-                }
-            }
-            P::sync();
-            double* ps = reinterpret_cast<double*>(s);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const uint32_t j = (uint32_t)ctid + (uint32_t)r * TMA_CONSUMERS;
-                if (j < n_amp) ps[j] = pr[r];
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
-        if (ctid == 0) progress = 4;
-        P::sync();
-        if (ctid == 0) {
-            mbar_arrive(&done_bar[stg]);
-            progress = 5;
-        }
-    }
-}
+// WIDE: every lane of the producer warp issues boxes (tiles of many small boxes: 32 boxes of 2 KiB issued by one
+// lane took as long as the gate passes); the narrow instantiation keeps the whole producer on one lane, which
+// is 12 % faster when a tile is a few large boxes (measured: syc-32 d1, 13.3 vs 15.1 ms).
+// SHARDED: the rank bits of a box pick its tensor map at run time; with a single shard the map addresses
+// stay compile-time constants of the parameter space (a run-time map address cost the single-GPU
+// expansion sweep 13 %: 13.3 -> 15.1 ms).
+// The four variants are PLAIN kernels generated from one body (sim_tma_kernel.inc), not template instantiations:
+// as instantiations of one template the narrow single-shard kernel ran 12 % slower (14.9 vs 13.3 ms, syc-32 d1).
+#define QCK_TMA_KERNEL_NAME sim_sweep_tma_kernel
+#define QCK_TMA_WIDE false
+#define QCK_TMA_SHARDED false
+#include "sim_tma_kernel.inc"
+#undef QCK_TMA_KERNEL_NAME
+#undef QCK_TMA_WIDE
+#undef QCK_TMA_SHARDED
+#define QCK_TMA_KERNEL_NAME sim_sweep_tma_wide_kernel
+#define QCK_TMA_WIDE true
+#define QCK_TMA_SHARDED false
+#include "sim_tma_kernel.inc"
+#undef QCK_TMA_KERNEL_NAME
+#undef QCK_TMA_WIDE
+#undef QCK_TMA_SHARDED
+#define QCK_TMA_KERNEL_NAME sim_sweep_tma_sharded_kernel
+#define QCK_TMA_WIDE false
+#define QCK_TMA_SHARDED true
+#include "sim_tma_kernel.inc"
+#undef QCK_TMA_KERNEL_NAME
+#undef QCK_TMA_WIDE
+#undef QCK_TMA_SHARDED
+#define QCK_TMA_KERNEL_NAME sim_sweep_tma_sharded_wide_kernel
+#define QCK_TMA_WIDE true
+#define QCK_TMA_SHARDED true
+#include "sim_tma_kernel.inc"
+#undef QCK_TMA_KERNEL_NAME
+#undef QCK_TMA_WIDE
+#undef QCK_TMA_SHARDED
 
 __global__ void __launch_bounds__(256) fold_probs_kernel(PlanDev plan, const int32_t* __restrict__ labels,
                                                          int inst_base, const double2* __restrict__ work,
@@ -1294,12 +1170,12 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
         for (int i = 0; i < plan->n_sweeps; ++i) {
             tma_describe(plan, i, live, i == plan->n_sweeps - 1, batch, h->max_smem_optin, *L);
             for (int j = 0; j < plan->sweeps[i].n_tile; ++j) live |= 1ull << plan->sweeps[i].pos[j];
-            int rc = tma_encode(h, L->sd, batch, work, true, &L->maps.st[0]);
+            int rc = tma_encode(h, L->sd, batch, work, true, &L->maps.sh0.st);
             if (rc) return rc;
             const bool box_main = L->sd.zf_shift == L->sd.lowc + L->sd.k;
-            rc = tma_encode(h, L->sd, batch, work, box_main, &L->maps.ld[0]);
+            rc = tma_encode(h, L->sd, batch, work, box_main, &L->maps.sh0.ld);
             if (rc) return rc;
-            L->maps.pr = L->maps.st[0];
+            L->maps.pr = L->maps.sh0.st;
             if (fold_row && batch == 1 && i == plan->n_sweeps - 1) {
                 rc = tma_encode_probs(h, L->sd, fold_row, &L->maps.pr);
                 if (rc) return rc;
@@ -1314,8 +1190,12 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
                 counter = reinterpret_cast<unsigned long long*>(h->d_partials + h->partials_count - 4);
                 QCK_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
             }
-            sim_sweep_tma_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(L->maps, L->sd, pdl, d_labels,
-                                                                                       inst_base, L->n_work, counter);
+            if (L->sd.n_store >= 16 || L->sd.n_load >= 16)  // measured: 8 boxes of 8 KiB are still faster from one lane
+                sim_sweep_tma_wide_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(
+                    L->maps, L->sd, pdl, d_labels, inst_base, L->n_work, counter);
+            else
+                sim_sweep_tma_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(
+                    L->maps, L->sd, pdl, d_labels, inst_base, L->n_work, counter);
             QCK_CHECK_LAUNCH(h);
         }
         return QCK_OK;
@@ -1421,6 +1301,9 @@ int qck_sim_init(qck_handle* h) {
     QCK_CUDA(h, qck_allow_max_smem(sim_onchip_group_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_kernel, h->max_smem_optin));
+    QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_wide_kernel, h->max_smem_optin));
+    QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_sharded_kernel, h->max_smem_optin));
+    QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_sharded_wide_kernel, h->max_smem_optin));
     return QCK_OK;
 }
 
@@ -1605,18 +1488,22 @@ extern "C" int qck_sim_sweeps_sharded(qck_handle* h, const qck_sim_plan* plan, i
             if (L->n_work > 0) {
                 const bool box_main = L->sd.zf_shift == L->sd.lowc + L->sd.k;
                 for (int r = 0; r < world; ++r) {
-                    rc = tma_encode(h, L->sd, 1, (double2*)d_shards[r], true, &L->maps.st[r]);
+                    rc = tma_encode(h, L->sd, 1, (double2*)d_shards[r], true, L->maps.st_mut(r));
                     if (rc) return rc;
-                    rc = tma_encode(h, L->sd, 1, (double2*)d_shards[r], box_main, &L->maps.ld[r]);
+                    rc = tma_encode(h, L->sd, 1, (double2*)d_shards[r], box_main, L->maps.ld_mut(r));
                     if (rc) return rc;
                 }
-                L->maps.pr = L->maps.st[0];
+                L->maps.pr = L->maps.sh0.st;
                 PlanDev pdl = pd;
                 pdl.n_stage = L->n_stage;
                 const unsigned long long grid =
                     L->n_work < (unsigned long long)h->sm_count ? L->n_work : (unsigned long long)h->sm_count;
-                sim_sweep_tma_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(L->maps, L->sd, pdl, d_label, 0,
-                                                                                           L->n_work, nullptr);
+                if (L->sd.n_store >= 16 || L->sd.n_load >= 16)  // measured: 8 boxes of 8 KiB are still faster from one lane
+                    sim_sweep_tma_sharded_wide_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(
+                        L->maps, L->sd, pdl, d_label, 0, L->n_work, nullptr);
+                else
+                    sim_sweep_tma_sharded_kernel<<<(unsigned)grid, TMA_CONSUMERS + 32, L->smem, st>>>(
+                        L->maps, L->sd, pdl, d_label, 0, L->n_work, nullptr);
                 QCK_CHECK_LAUNCH(h);
             }
         }

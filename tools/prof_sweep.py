@@ -17,6 +17,8 @@ PKG = "hardwareawareoptimalquantumcircuitcuttingandknitting_b200"
 gen = import_module(PKG + ".generators")
 vcm = import_module(PKG + ".virtual_circuit")
 _lib = import_module(PKG + "._lib")
+if os.environ.get("QCK_LIB_VARIANT"):            # A/B experiments: load libqck_<variant>.so instead
+    _lib.LIB_PATH = _lib.LIB_PATH.replace("libqck.so", "libqck_" + os.environ["QCK_LIB_VARIANT"] + ".so")
 
 name = sys.argv[1] if len(sys.argv) > 1 else "syc"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 28
