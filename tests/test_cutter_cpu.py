@@ -1,0 +1,200 @@
+"""Qiskit-free cutter - host side, CPU only.
+
+The reference has no tests for ``Cutter.py``; what pins the restatement here is (1) an exhaustive search over every
+vertex assignment / teleport choice of small circuits that evaluates the reference's constraints and objectives
+(``Cutter.py:383-567``) directly, (2) the cut shapes SURVEY Appendix B / C.4 records for the BASELINE configs, and
+(3) the end-to-end property that the cut circuit knits back to the uncut distribution (oracle on both sides).
+"""
+import itertools
+from importlib import import_module
+
+import numpy as np
+import pytest
+
+from conftest import oracle_knit
+from oracle import statevector as sv
+
+PKG = "hardwareawareoptimalquantumcircuitcuttingandknitting_b200"
+cutter_mod = import_module(f"{PKG}.cutter")
+cutting = import_module(f"{PKG}.cutting")
+circuit = import_module(f"{PKG}.circuit")
+generators = import_module(f"{PKG}.generators")
+z3 = pytest.importorskip("z3")
+
+Cutter = cutter_mod.Cutter
+
+
+def _brute_force(cu, max_cuts=None, max_qpd=None, max_cuts_per_part=None):
+    """Lexicographic optimum (soft, Q, S, A, L, C) by enumeration; None if infeasible."""
+    P, nv = cu.maxNPartitions, len(cu.V)
+    best = None
+    for assign in itertools.product(range(P), repeat=nv):
+        cut_edges = [i for i, (u, v, _t) in enumerate(cu.edges) if assign[u] != assign[v]]
+        if max_cuts is not None and len(cut_edges) > max_cuts:
+            continue
+        for tele in itertools.product((False, True), repeat=len(cut_edges)):
+            tele_set = {e for e, b in zip(cut_edges, tele) if b}
+            qpd_set = [e for e in cut_edges if e not in tele_set]
+            if max_qpd is not None:
+                if len(qpd_set) > max_qpd or (tele_set and len(qpd_set) != max_qpd):
+                    continue
+            Qp, Cp = [], []
+            for p in range(P):
+                q = sum(1 for v in cu.I if assign[v.idx] == p)
+                q += sum(1 for e in cut_edges if cu.edges[e][2] == "W" and assign[cu.edges[e][1]] == p)
+                q += sum(1 for e in tele_set if p in (assign[cu.edges[e][0]], assign[cu.edges[e][1]]))
+                Qp.append(q)
+                Cp.append(sum(1 for e in qpd_set if p in (assign[cu.edges[e][0]], assign[cu.edges[e][1]])))
+            if any(q > m for q, m in zip(Qp, cu.maxNQubitsPerPartition)):
+                continue
+            if max_cuts_per_part is not None and max(Cp) > max_cuts_per_part:
+                continue
+            S, A, L = 1, 0, 0
+            for e in cut_edges:
+                gate = cu.edges[e][2] == "G"
+                if e in tele_set:
+                    A += 2; L += 10
+                else:
+                    S *= 6 if gate else 8
+                    A += 0 if gate else 1
+            A *= S
+            mx = max([cu.edges[e][1] for e in qpd_set], default=-1)
+            mn = min([cu.edges[e][0] for e in tele_set], default=nv)
+            key = (0 if mx < mn else 1, max(Qp), S, A, L, max(Cp))
+            if best is None or key < best:
+                best = key
+    return best
+
+
+def _small_circuits():
+    QC, QR = circuit.QuantumCircuit, circuit.QuantumRegister
+    out = {}
+    c = QC(QR(4, "q"))
+    c.h(0); c.cx(0, 1); c.cx(1, 2); c.cx(2, 3); c.cx(0, 1)
+    out["chain4"] = c
+    c = QC(QR(4, "q"))
+    c.cx(0, 1); c.cz(1, 2); c.cx(2, 3); c.cz(3, 0)
+    out["ring4"] = c
+    c = QC(QR(3, "q"))
+    c.cx(0, 2); c.cx(1, 2); c.cx(0, 2); c.cx(1, 2)
+    out["star3"] = c
+    c = QC(QR(5, "q"))
+    for i in range(4):
+        c.cx(i, 4)
+    out["bv5like"] = c
+    return out
+
+
+@pytest.mark.parametrize("name,P,q,limits", [
+    ("chain4", 2, 2, dict(maxNCuts=3, maxNQpdCuts=3)),
+    ("chain4", 2, 3, dict()),
+    ("ring4", 2, 2, dict(maxNCuts=4, maxNQpdCuts=4)),
+    ("ring4", 2, 3, dict(maxNCuts=2, maxNQpdCuts=1)),          # teleport cuts become possible
+    ("star3", 2, 2, dict(maxNCuts=4, maxNQpdCuts=4, maxCutsPerPartitions=4)),
+    ("bv5like", 2, 3, dict(maxNCuts=5, maxNQpdCuts=5, maxCutsPerPartitions=5)),
+    ("chain4", 3, 2, dict(maxNCuts=3)),
+])
+def test_optimum_equals_exhaustive_search(name, P, q, limits):
+    c = _small_circuits()[name]
+    cu = Cutter(c, P, q, **limits)
+    want = _brute_force(cu, limits.get("maxNCuts"), limits.get("maxNQpdCuts"), limits.get("maxCutsPerPartitions"))
+    ok = cu.solve()
+    if want is None:
+        assert not ok
+        return
+    assert ok
+    S, A, L, n_w, n_g, Q, Q_p, C, C_p = cu.getModelKeyResults()
+    assert (Q, S, A, L, C) == want[1:]
+    assert Q == max(Q_p) and C == max(C_p)
+    assert all(qp <= m for qp, m in zip(Q_p, cu.maxNQubitsPerPartition))
+
+
+def test_infeasible_returns_false():
+    c = _small_circuits()["ring4"]
+    cu = Cutter(c, 2, 2, maxNCuts=1, maxNQpdCuts=1)
+    assert _brute_force(cu, 1, 1) is None
+    assert cu.solve() is False
+    with pytest.raises(RuntimeError):
+        cu.getModelKeyResults()
+
+
+def test_graph_of_bv5():
+    # Cutter.py:212-275: two vertices per two-qubit gate, wire edges between consecutive vertices of a qubit
+    c = generators.gen_circ("bv", 5, 1)
+    cu = Cutter(c, 2, 10)
+    assert len(cu.V) == 8 and len(cu.G) == 4 and len(cu.W) == 3 and len(cu.I) == 5
+    assert [v.qubit for v in cu.I] == [0, 4, 1, 2, 3]
+
+
+def _knits_back(cut_circ, uncut, tol=1e-12):
+    res, ov = oracle_knit(cut_circ)
+    want = sv.exact_distribution(uncut)
+    keys = set(res) | set(want)
+    assert max(abs(res.get(k, 0.0) - want.get(k, 0.0)) for k in keys) < tol
+
+
+def test_bv5_wire_cut_and_round_trip():
+    # README.md:27-28 / SURVEY C.4: BV(5) results in one wire cut, Q = 3, S = 8
+    c = generators.gen_circ("bv", 5, 1)
+    cu = Cutter(c, 2, 10, maxNQpdCuts=5, maxNCuts=5, maxCutsPerPartitions=5)
+    assert cu.solve()
+    S, A, L, n_w, n_g, Q, Q_p, C, C_p = cu.getModelKeyResults()
+    assert (S, A, L, n_w, n_g, Q, sorted(Q_p), C) == (8, 8, 0, 1, 0, 3, [3, 3], 1)
+    spec = cu.cut_spec()
+    assert spec.wire_cuts and spec.wire_cuts[0][0] == 4 and not spec.gate_cuts
+    again = cutter_mod.cut_spec_from_json(cutter_mod.cut_spec_to_json(spec))
+    assert again == spec
+    cut = cu.getCutCirc()
+    assert sorted(len(r) for r in cut.qregs) == [3, 3]
+    _knits_back(cut, cu.decomposedCirc)
+
+
+def test_gate_cut_circuit_knits_back():
+    QC, QR = circuit.QuantumCircuit, circuit.QuantumRegister
+    c = QC(QR(4, "q"))
+    for q in range(4):
+        c.ry(0.3 + 0.2 * q, q)
+    c.cx(0, 1); c.cx(2, 3); c.cz(1, 2); c.rx(0.4, 1); c.ry(0.9, 2); c.cx(0, 1); c.cx(2, 3)
+    c.measure_all()
+    cu = Cutter(c, 2, 2, maxNCuts=2, maxNQpdCuts=2)
+    assert cu.solve()
+    S, A, L, n_w, n_g, Q, Q_p, C, C_p = cu.getModelKeyResults()
+    assert (S, n_w, n_g, Q) == (6, 0, 1, 2)
+    _knits_back(cu.getCutCirc(), cu.decomposedCirc)
+
+
+def test_bv16_matches_survey_shape():
+    # Q = 9, one wire cut on q15, S = 8, fragments of 9 and 8 qubits
+    c = generators.gen_circ("bv", 16, 1)
+    cu = Cutter(c, 2, 10, maxNQpdCuts=5, maxNCuts=5, maxCutsPerPartitions=5)
+    assert cu.solve()
+    S, A, L, n_w, n_g, Q, Q_p, C, C_p = cu.getModelKeyResults()
+    assert (S, n_w, n_g, Q, sorted(Q_p)) == (8, 1, 0, 9, [8, 9])
+    spec = cu.cut_spec()
+    assert [w[0] for w in spec.wire_cuts] == [15]
+    cut = cu.getCutCirc()
+    assert sorted(len(r) for r in cut.qregs) == [8, 9]
+
+
+def test_syc32d1_needs_no_cut():
+    # already a tensor product - Q = 14, S = 1, leftovers go to the first partition: 18 | 14
+    c = generators.gen_circ("syc", 32, 1, seed=0)
+    cu = Cutter(c, 2, 50, maxNQpdCuts=5, maxNCuts=5, maxCutsPerPartitions=5)
+    assert cu.solve()
+    S, A, L, n_w, n_g, Q, Q_p, C, C_p = cu.getModelKeyResults()
+    assert (S, A, L, n_w, n_g, Q, Q_p, C) == (1, 0, 0, 0, 0, 14, [14, 14], 0)
+    spec = cu.cut_spec()
+    assert [len(p) for p in spec.partitions] == [18, 14]
+    assert sorted(q for p in spec.partitions for q in p) == list(range(32))
+    cut = cu.getCutCirc()
+    assert [len(r) for r in cut.qregs] == [18, 14]
+
+
+def test_constructor_checks_follow_the_reference():
+    c = _small_circuits()["chain4"]
+    with pytest.raises(AssertionError):
+        Cutter(c, 2, 1)                          # 4 qubits do not fit 2 x 1 (Cutter.py:62)
+    with pytest.raises(RuntimeError):
+        Cutter(c, 2, "10")
+    with pytest.raises(AssertionError):
+        Cutter(c, 2, [3, 3, 3])
