@@ -34,7 +34,7 @@ import itertools
 import numpy as np
 
 from . import _lib
-from .circuit import Barrier, ClassicalRegister, QuantumCircuit, QuantumRegister as Fragment
+from .circuit import Barrier, ClassicalRegister, Gate, QuantumCircuit, QuantumRegister as Fragment
 from .compiler import FragmentExecutor, FragmentProgram
 from .quasi_distr import QuasiDistr, default_device
 from .virtual_gates import VirtualBinaryGate, VirtualGateEndpoint, VirtualMove
@@ -108,28 +108,31 @@ class VirtualCircuit:
     def _replace_vgates_with_endpoints(circuit: QuantumCircuit) -> QuantumCircuit:
         new_circuit = QuantumCircuit(*circuit.qregs, *circuit.cregs, name=circuit.name)
         vgate_index = 0
-        for instr in circuit:
-            op, qubits, clbits = instr.operation, instr.qubits, instr.clbits
+        data = new_circuit.data
+        for instr in circuit.data:
+            op = instr.operation
             if isinstance(op, VirtualBinaryGate):
                 for i in range(2):
-                    new_circuit.append(VirtualGateEndpoint(op, vgate_idx=vgate_index, qubit_idx=i), [qubits[i]], [])
+                    new_circuit.append(VirtualGateEndpoint(op, vgate_idx=vgate_index, qubit_idx=i),
+                                       [instr.qubits[i]], [])
                 vgate_index += 1
                 continue
-            new_circuit.append(op, qubits, clbits)
+            data.append(instr)          # instructions are never modified in place: shared, not copied
         return new_circuit
 
     @staticmethod
     def _circuit_on_fragment(circuit: QuantumCircuit, fragment: Fragment) -> QuantumCircuit:
         new_circuit = QuantumCircuit(fragment, *circuit.cregs)
-        fq = set(fragment)
+        data = new_circuit.data
         for instr in circuit.data:
-            op, qubits, clbits = instr.operation, instr.qubits, instr.clbits
-            if set(qubits) <= fq:
-                new_circuit.append(op, qubits, clbits)
+            inside = sum(1 for q in instr.qubits if q.register is fragment)
+            if inside == len(instr.qubits):
+                data.append(instr)
                 continue
-            elif isinstance(op, Barrier) and not isinstance(op, VirtualGateEndpoint):
+            op = instr.operation
+            if isinstance(op, Barrier) and not isinstance(op, VirtualGateEndpoint):
                 continue
-            elif set(qubits) & fq:
+            elif inside:
                 raise ValueError(f"Circuit contains gates that act on multiple fragments. {op}")
         return new_circuit
 
@@ -345,17 +348,24 @@ def _structure_key(circ: QuantumCircuit, fragment: Fragment):
     qpos = {q: i for i, q in enumerate(fragment)}
     cpos = {c: i for i, c in enumerate(circ.clbits)}
     items = [len(fragment), len(cpos)]
+    add = items.append
     for ins in circ.data:
         op = ins.operation
-        if isinstance(op, VirtualGateEndpoint):
+        kind = type(op)
+        if kind is Gate:                                   # the common case first
+            m = op._matrix
+            qs = ins.qubits
+            add((op.name, tuple(op.params), None if m is None else m.tobytes(),
+                 (qpos[qs[0]],) if len(qs) == 1 else tuple([qpos[q] for q in qs]), ()))
+        elif isinstance(op, VirtualGateEndpoint):
             vg = op.virtual_gate
-            items.append(("ep", type(vg).__name__, tuple(vg.params), op.vgate_idx, op.qubit_idx, qpos[ins.qubits[0]]))
+            add(("ep", type(vg).__name__, tuple(vg.params), op.vgate_idx, op.qubit_idx, qpos[ins.qubits[0]]))
         elif isinstance(op, Barrier):
             continue
         else:
             m = getattr(op, "_matrix", None)
-            items.append((op.name, tuple(getattr(op, "params", ())), None if m is None else m.tobytes(),
-                          tuple(qpos[q] for q in ins.qubits), tuple(cpos[c] for c in ins.clbits)))
+            add((op.name, tuple(getattr(op, "params", ())), None if m is None else m.tobytes(),
+                 tuple([qpos[q] for q in ins.qubits]), tuple([cpos[c] for c in ins.clbits])))
     return tuple(items)
 
 
