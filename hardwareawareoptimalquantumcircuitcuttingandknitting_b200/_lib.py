@@ -170,6 +170,21 @@ class Handle:
             msg = self.lib.qck_last_error_string(self.ptr).decode(errors="replace")
             raise _EXC.get(rc, RuntimeError)(f"{self.lib.qck_status_string(rc).decode()}: {msg}")
 
+    SCRATCH_CACHE_MAX = 256 << 20
+
+    def scratch(self, torch, nbytes: int, device, stream: int):
+        """Device scratch of at least ``nbytes`` for work enqueued on ``stream``.  Buffers up to
+        ``SCRATCH_CACHE_MAX`` are kept per (device, stream) and grow only - the handle is thread-local and
+        work on one stream is ordered, so consecutive runs can share them; larger ones belong to the caller."""
+        if nbytes > self.SCRATCH_CACHE_MAX:
+            return torch.empty(nbytes, dtype=torch.uint8, device=device)
+        cache = self.__dict__.setdefault("_scratch", {})
+        key = (str(device), int(stream))
+        buf = cache.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return buf
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.qck_launch_count(self.ptr))
