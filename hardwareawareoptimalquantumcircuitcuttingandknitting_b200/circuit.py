@@ -34,7 +34,9 @@ __all__ = [
 
 
 # --------------------------------------------------------------------------- bits / registers
-@dataclass(frozen=True)
+# Bits are created once, by their register, and compared by identity (eq=False keeps object.__hash__: the
+# host compiler hashes qubits tens of thousands of times per circuit).
+@dataclass(frozen=True, eq=False)
 class Qubit:
     register: "QuantumRegister"
     index: int
@@ -43,7 +45,7 @@ class Qubit:
         return f"{self.register.name}[{self.index}]"
 
 
-@dataclass(frozen=True)
+@dataclass(frozen=True, eq=False)
 class Clbit:
     register: "ClassicalRegister"
     index: int
