@@ -10,8 +10,12 @@ Differences from the reference, both forced by the environment (SURVEY.md C.1, A
 
 * the reference solves with ``z3.Optimize`` and five ``minimize`` objectives; z3 4.15.4 (this image) returns
   constraint-violating models for exactly this pattern, so the same lexicographic optimum (soft constraint
-  first, then Q, S, A, L, C - the order the objectives are added, ``Cutter.py:553-567``) is found with a plain
-  ``z3.Solver`` and iterative tightening;
+  first, then Q, S, A, L, C - the order the objectives are added, ``Cutter.py:553-567``) is found by iterative
+  tightening on z3's finite-domain solver.  Every integer of the reference's model is a sum of 0/1 terms, so the
+  model is stated over Booleans with pseudo-Boolean cardinality constraints; S = 6^a 8^b is never multiplied out
+  but searched over the (a, b) pairs in ascending order of their product.  Solve times (this container, one
+  core): bv-16 0.5 s, hwe-16 d5 1.4 s, syc-16 d5 0.8 s, qft-16 -q 10 proved infeasible in 3.3 s (the same
+  search over ``Int`` sums took 16 min for hwe-16 d5; the reference reports up to 12 min, SURVEY section 6);
 * teleportation cuts (``b_e``) are part of the model as in the reference, but - as there (``Cutter.py:574``
   FIXME) - cannot be turned into a circuit: ``cut_spec()`` raises if the optimum uses one.
 
@@ -74,7 +78,7 @@ class Cutter:
         self.V, self.W, self.G, self.I = self._read_circ(self.decomposedCirc)
         self.model = None
         self.nWireCuts = self.nGateCuts = 0
-        self.s = z3.Solver()
+        self.s = z3.SolverFor("QF_FD")
         self._build_model()
 
     # ------------------------------------------------------------------ graph (Cutter.py:212-294)
@@ -106,6 +110,10 @@ class Cutter:
 
     # ------------------------------------------------------------------ model (Cutter.py:297-567)
     def _build_model(self) -> None:
+        """The reference's constraints over Booleans only: every integer of its model (Q_p, C_p, the cut counts, A, L)
+        is a sum of 0/1 terms, so ``Q_p <= cap`` etc. become pseudo-Boolean constraints (``PbLe`` / ``PbEq``) and the
+        objectives are minimised by tightening such bounds.  (With ``Int`` sums the same search took 16 min for
+        hwe-16 d5; the finite-domain solver needs seconds.)"""
         z3, s, P = self.z3, self.s, self.maxNPartitions
         assert P <= max(len(self.V), 1)
         self.o = [[z3.Bool(f"o_{v}_{p}") for p in range(P)] for v in range(len(self.V))]
@@ -121,117 +129,110 @@ class Cutter:
             self.c_e.append(z3.Bool(f"c_{e}[G]_{u}_{v}"))
             self.b_e.append(z3.Bool(f"b_{e}[G]_{u}_{v}"))
             self.edges.append((u, v, "G"))
-        self.Q_p = [z3.Int(f"Q_p{p}") for p in range(P)]
-        self.C_p = [z3.Int(f"C_p{p}") for p in range(P)]
-        self.Q, self.S, self.A, self.L, self.C = (z3.Int(n) for n in "QSALC")
-        o, c_e, b_e = self.o, self.c_e, self.b_e
-        for i, (u, v, _t) in enumerate(self.edges):
+        o, c_e, b_e, edges = self.o, self.c_e, self.b_e, self.edges
+        n_aux = [0]
+
+        def lit(expr):
+            """A fresh Boolean equal to ``expr`` (pseudo-Boolean constraints count literals)."""
+            n_aux[0] += 1
+            x = z3.Bool(f"aux_{n_aux[0]}")
+            s.add(x == expr)
+            return x
+
+        for i, (u, v, _t) in enumerate(edges):
             s.add(c_e[i] == z3.Or([o[u][p] != o[v][p] for p in range(P)]))
             s.add(z3.Implies(b_e[i], c_e[i]))
-        for v in range(len(self.V)):                      # exactly one partition per vertex
-            for i in range(P):
-                for j in range(P):
-                    if i != j:
-                        s.add(z3.Implies(o[v][i], z3.Not(o[v][j])))
-            s.add(z3.Or(o[v]))
-            # redundant, for the arithmetic solver only: it cannot see "exactly one" through the implications
-            s.add(z3.Sum([z3.If(o[v][p], 1, 0) for p in range(P)]) == 1)
-        if self.I:                                        # every wire starts in exactly one partition (pigeonhole bound)
-            s.add(self.Q >= -(-len(self.I) // P))
+        for v in range(len(self.V)):                      # exactly one partition per vertex (Cutter.py:396-410)
+            s.add(z3.PbEq([(x, 1) for x in o[v]], 1))
+        # partitions of equal capacity are interchangeable: pin the first vertex to partition 0, and let vertex v
+        # use partition p only if an earlier vertex uses p - 1 (halves the search at P = 2; the optimum is unchanged)
+        if self.V and len(set(self.maxNQubitsPerPartition)) == 1:
+            s.add(o[0][0])
+            for v in range(1, len(self.V)):
+                for p in range(1, P):
+                    if p > v:
+                        s.add(z3.Not(o[v][p]))
+                    elif p >= 2:
+                        s.add(z3.Implies(o[v][p], z3.Or([o[u][p - 1] for u in range(v)])))
+        # teleportation needs exactly maxNQpdCuts QPD cuts besides itself (Cutter.py:536-540): impossible when that
+        # already exhausts maxNCuts (the limits of benchmarks/benchmark.py:41)
+        self.teleport_possible = not (self.maxNQpdCuts is not None and self.maxNCuts is not None
+                                      and self.maxNQpdCuts >= self.maxNCuts)
+        if not self.teleport_possible:
+            s.add([z3.Not(b) for b in b_e])
+        self.qpd = [lit(z3.And(c, z3.Not(b))) if self.teleport_possible else c for c, b in zip(c_e, b_e)]
+        self.gate_qpd = [x for x, e in zip(self.qpd, edges) if e[2] == "G"]
+        self.wire_qpd = [x for x, e in zip(self.qpd, edges) if e[2] == "W"]
+        # Q_p (Cutter.py:412-439) and C_p (:441-451) as lists of literals
+        self.Qp_terms, self.Cp_terms = [], []
         for p in range(P):
-            terms = [z3.If(o[v.idx][p], 1, 0) for v in self.I]
-            terms += [z3.If(z3.And(c_e[i], o[v][p]), 1, 0) for i, (u, v, t) in enumerate(self.edges) if t == "W"]
-            terms += [z3.If(z3.And(b_e[i], z3.Or(o[u][p], o[v][p])), 1, 0) for i, (u, v, t) in enumerate(self.edges)]
-            s.add(self.Q_p[p] == z3.Sum(terms) if terms else self.Q_p[p] == 0)
-            cuts = [z3.If(z3.And(c_e[i], z3.Or(o[u][p], o[v][p]), z3.Not(b_e[i])), 1, 0)
-                    for i, (u, v, t) in enumerate(self.edges)]
-            s.add(self.C_p[p] == z3.Sum(cuts) if cuts else self.C_p[p] == 0)
-        total_s, total_a, total_l = z3.IntVal(1), z3.IntVal(0), z3.IntVal(0)
-        for i, (_u, _v, t) in enumerate(self.edges):
-            qpd, tele = (_GATE_QPD, _GATE_TELE) if t == "G" else (_WIRE_QPD, _WIRE_TELE)
-            total_s = total_s * z3.If(c_e[i], z3.If(b_e[i], tele[0], qpd[0]), 1)
-            total_a = total_a + z3.If(c_e[i], z3.If(b_e[i], tele[1], qpd[1]), 0)
-            total_l = total_l + z3.If(c_e[i], z3.If(b_e[i], tele[2], qpd[2]), 0)
-        # S (a product) is NOT asserted here: the definitions of S, A and L do not restrict the cuts, and the
-        # non-linear product makes every check slow.  solve() minimises Q on the linear part first and then
-        # walks the possible values of S = 6^a 8^b in ascending order (see _minimise_S).
-        self._total_s, self._total_a, self._total_l = total_s, total_a, total_l
-        self._n_gate_qpd = z3.Sum([z3.If(z3.And(c, z3.Not(b)), 1, 0) for c, b, (_u, _v, t) in zip(c_e, b_e, self.edges)
-                                   if t == "G"] or [z3.IntVal(0)])
-        self._n_wire_qpd = z3.Sum([z3.If(z3.And(c, z3.Not(b)), 1, 0) for c, b, (_u, _v, t) in zip(c_e, b_e, self.edges)
-                                   if t == "W"] or [z3.IntVal(0)])
-        for p in range(P):
-            s.add(self.Q >= self.Q_p[p], self.Q_p[p] <= self.maxNQubitsPerPartition[p], self.C >= self.C_p[p])
-            if self.maxCutsPerPartitions is not None:
-                s.add(self.C_p[p] <= self.maxCutsPerPartitions)
-        wire = [z3.If(c, 1, 0) for c, (_u, _v, t) in zip(c_e, self.edges) if t == "W"]
-        gate = [z3.If(c, 1, 0) for c, (_u, _v, t) in zip(c_e, self.edges) if t == "G"]
-        n_wire = z3.Sum(wire) if wire else z3.IntVal(0)
-        n_gate = z3.Sum(gate) if gate else z3.IntVal(0)
+            terms = [o[v.idx][p] for v in self.I]
+            terms += [lit(z3.And(c_e[i], o[v][p])) for i, (u, v, t) in enumerate(edges) if t == "W"]
+            if self.teleport_possible:
+                terms += [lit(z3.And(b_e[i], z3.Or(o[u][p], o[v][p]))) for i, (u, v, t) in enumerate(edges)]
+            self.Qp_terms.append(terms)
+            self.Cp_terms.append([lit(z3.And(self.qpd[i], z3.Or(o[u][p], o[v][p]))) for i, (u, v, t) in enumerate(edges)])
+            if terms:
+                s.add(z3.PbLe([(x, 1) for x in terms], self.maxNQubitsPerPartition[p]))
+            if self.maxCutsPerPartitions is not None and self.Cp_terms[p]:
+                s.add(z3.PbLe([(x, 1) for x in self.Cp_terms[p]], self.maxCutsPerPartitions))
+        wire = [(c, 1) for c, e in zip(c_e, edges) if e[2] == "W"]
+        gate = [(c, 1) for c, e in zip(c_e, edges) if e[2] == "G"]
         if self.forceNWireCuts is not None:
-            s.add(n_wire == self.forceNWireCuts)
+            s.add(z3.PbEq(wire, self.forceNWireCuts) if wire else z3.BoolVal(self.forceNWireCuts == 0))
         if self.forceNGateCuts is not None:
-            s.add(n_gate == self.forceNGateCuts)
-        if self.maxNCuts is not None:
-            s.add(n_wire + n_gate <= self.maxNCuts)
-        if self.maxNQpdCuts is not None:
-            qpd = [z3.If(z3.And(c, z3.Not(b)), 1, 0) for c, b in zip(c_e, b_e)]
-            n_qpd = z3.Sum(qpd) if qpd else z3.IntVal(0)
-            s.add([z3.Implies(b, n_qpd == self.maxNQpdCuts) for b in b_e])
-            s.add(n_qpd <= self.maxNQpdCuts)
-        # soft constraint (Cutter.py:545-551): every QPD cut lies before every teleport cut
-        n_v = len(self.V)
-        if self.edges:
-            qpd_idx = [z3.If(z3.And(c, z3.Not(b)), v, -1) for c, b, (_u, v, _t) in zip(c_e, b_e, self.edges)]
-            tele_idx = [z3.If(b, u, n_v) for b, (u, _v, _t) in zip(b_e, self.edges)]
-            mx, mn = qpd_idx[0], tele_idx[0]
-            for x in qpd_idx[1:]:
-                mx = z3.If(x > mx, x, mx)
-            for x in tele_idx[1:]:
-                mn = z3.If(x < mn, x, mn)
-            self.soft = mx < mn
+            s.add(z3.PbEq(gate, self.forceNGateCuts) if gate else z3.BoolVal(self.forceNGateCuts == 0))
+        if self.maxNCuts is not None and wire + gate:
+            s.add(z3.PbLe(wire + gate, self.maxNCuts))
+        if self.maxNQpdCuts is not None and self.qpd:
+            s.add(z3.PbLe([(x, 1) for x in self.qpd], self.maxNQpdCuts))
+            if self.teleport_possible:
+                full = lit(z3.PbEq([(x, 1) for x in self.qpd], self.maxNQpdCuts))
+                s.add([z3.Implies(b, full) for b in b_e])
+        # ancilla and latency sums (Cutter.py:453-510): A = S * (2 per teleport cut + 1 per QPD wire cut), L = 10 per
+        # teleport cut
+        self.A_terms = [(x, _WIRE_QPD[1]) for x in self.wire_qpd]
+        self.L_terms = []
+        if self.teleport_possible:
+            self.A_terms += [(b, _GATE_TELE[1]) for b in b_e]
+            self.L_terms = [(b, _GATE_TELE[2]) for b in b_e]
+        # soft constraint (Cutter.py:545-551): every QPD cut lies before every teleport cut, i.e. no pair
+        # (QPD cut i, teleport cut j) with v_i >= u_j
+        if self.teleport_possible and edges:
+            self.soft = z3.And([z3.Not(z3.And(self.qpd[i], b_e[j]))
+                                for i in range(len(edges)) for j in range(len(edges)) if edges[i][1] >= edges[j][0]]
+                               or [z3.BoolVal(True)])
         else:
             self.soft = z3.BoolVal(True)
 
     # ------------------------------------------------------------------ solving
-    def _minimise(self, expr) -> None:
-        """Fix ``expr`` to its minimum under the current constraints (which must be satisfiable)."""
-        z3, s = self.z3, self.s
-        best = s.model().eval(expr, model_completion=True).as_long()
-        while True:
-            s.push()
-            s.add(expr < best)
-            if s.check() == z3.sat:
-                best = s.model().eval(expr, model_completion=True).as_long()
-                s.pop()
-            else:
-                s.pop()
-                break
-        s.add(expr == best)
-        assert s.check() == z3.sat
+    def _true(self, x) -> bool:
+        return self.z3.is_true(self._m.eval(x, model_completion=True))
 
-    def _minimise_S(self) -> None:
-        """S = 6^(gate QPD cuts) * 8^(wire QPD cuts) (teleport cuts cost 1): the smallest feasible value is found by
-        trying the (a, b) pairs in ascending order of 6^a 8^b - linear constraints only."""
+    def _count(self, terms) -> int:
+        return sum(1 for x in terms if self._true(x))
+
+    def _weight(self, terms) -> int:
+        return sum(w for x, w in terms if self._true(x))
+
+    def _tighten(self, value, bound, lower: int = 0) -> int:
+        """Smallest value of an objective: ``value()`` reads it off the current model ``self._m``, ``bound(k)`` is the
+        constraint "objective <= k".  The optimum is asserted and returned; ``self._m`` stays a model of everything
+        asserted so far, so no re-check is needed."""
         z3, s = self.z3, self.s
-        n_g = sum(1 for e in self.edges if e[2] == "G")
-        n_w = len(self.edges) - n_g
-        bound = min(x for x in (self.maxNQpdCuts, self.maxNCuts, n_g + n_w) if x is not None)
-        values = sorted({6 ** a * 8 ** b for a in range(min(n_g, bound) + 1) for b in range(min(n_w, bound) + 1)
-                         if a + b <= bound})
-        for v in values:
-            pairs = [(a, b) for a in range(min(n_g, bound) + 1) for b in range(min(n_w, bound) + 1)
-                     if a + b <= bound and 6 ** a * 8 ** b == v]
+        best = value()
+        while best > lower:                               # ``lower``: a bound known without search
             s.push()
-            s.add(z3.Or([z3.And(self._n_gate_qpd == a, self._n_wire_qpd == b) for a, b in pairs]))
-            if s.check() == z3.sat:
-                s.pop()
-                s.add(z3.Or([z3.And(self._n_gate_qpd == a, self._n_wire_qpd == b) for a, b in pairs]))
-                s.add(self.S == v)
-                assert s.check() == z3.sat
-                return
+            s.add(bound(best - 1))
+            sat = s.check() == z3.sat
+            if sat:
+                self._m = s.model()
+                best = value()
             s.pop()
-        raise RuntimeError("no feasible sampling overhead")   # cannot happen: the constraints were satisfiable
+            if not sat:
+                break
+        s.add(bound(best))
+        return best
 
     def solve(self) -> bool:
         z3, s = self.z3, self.s
@@ -239,34 +240,93 @@ class Cutter:
         self.nWireCuts = self.nGateCuts = 0
         if s.check() != z3.sat:
             return False
-        s.push()                                          # the soft constraint comes first in the lexicographic order
-        s.add(self.soft)
-        if s.check() != z3.sat:
-            s.pop()
-            s.check()
-        self._minimise(self.Q)
-        self._minimise_S()
-        s_val = s.model().eval(self.S, model_completion=True).as_long()
-        s.add(self.A == self._total_a * s_val, self.L == self._total_l)     # linear now that S is a constant
-        assert s.check() == z3.sat
-        for obj in (self.A, self.L, self.C):
-            self._minimise(obj)
-        self.model = s.model()
+        self._m = s.model()
+        if self.teleport_possible:                        # the soft constraint comes first in the lexicographic order
+            s.push()
+            s.add(self.soft)
+            if s.check() == z3.sat:
+                self._m = s.model()
+            else:
+                s.pop()
+        P = self.maxNPartitions
+        # Q = max_p Q_p (Cutter.py:512-514, objective :567)
+        # (every wire starts in exactly one partition: Q >= ceil(|I| / P) needs no proof by search)
+        self._Q = self._tighten(lambda: max(self._count(t) for t in self.Qp_terms),
+                                lambda k: z3.And([z3.PbLe([(x, 1) for x in t], k) for t in self.Qp_terms if t]),
+                                lower=-(-len(self.I) // P))
+        # S (objective :568)
+        self._S = self._solve_S()
+        # A = S * ancillas (:569), L (:570), C = max_p C_p (:571)
+        if self.A_terms:
+            self._A = self._S * self._tighten(lambda: self._weight(self.A_terms), lambda k: z3.PbLe(self.A_terms, k))
+        else:
+            self._A = 0
+        self._L = self._tighten(lambda: self._weight(self.L_terms), lambda k: z3.PbLe(self.L_terms, k)) \
+            if self.L_terms else 0
+        self._C = self._tighten(lambda: max(self._count(t) for t in self.Cp_terms),
+                                lambda k: z3.And([z3.PbLe([(x, 1) for x in t], k) for t in self.Cp_terms if t])) \
+            if any(self.Cp_terms) else 0
+        self.model = self._m
         for c, (_u, _v, t) in zip(self.c_e, self.edges):
-            if z3.is_true(self.model.eval(c, model_completion=True)):
+            if self._true(c):
                 if t == "W":
                     self.nWireCuts += 1
                 else:
                     self.nGateCuts += 1
         return True
 
+    def _solve_S(self) -> int:
+        z3, s = self.z3, self.s
+        if not self.qpd:
+            return 1
+        ones = [(x, 1) for x in self.qpd]
+        # the lower bound on the number of cuts is a consequence, not an objective: prove it, keep it, but do not
+        # fix the count (a larger count can have a smaller S: one wire cut = 8 < two gate cuts = 36)
+        t_min = self._count(self.qpd)
+        model = self._m
+        while t_min > 0:
+            s.push()
+            s.add(z3.PbLe(ones, t_min - 1))
+            sat = s.check() == z3.sat
+            if sat:
+                model = s.model()
+                t_min = sum(1 for x in self.qpd if z3.is_true(model.eval(x, model_completion=True)))
+            s.pop()
+            if not sat:
+                break
+        s.add(z3.PbGe(ones, t_min))
+        n_g, n_w = len(self.gate_qpd), len(self.wire_qpd)
+        bound = min(x for x in (self.maxNQpdCuts, self.maxNCuts, n_g + n_w) if x is not None)
+        all_pairs = [(a, b) for a in range(min(n_g, bound) + 1) for b in range(min(n_w, bound) + 1)
+                     if t_min <= a + b <= bound]
+
+        def exactly(a, b):
+            cs = []
+            if self.gate_qpd:
+                cs.append(z3.PbEq([(x, 1) for x in self.gate_qpd], a))
+            if self.wire_qpd:
+                cs.append(z3.PbEq([(x, 1) for x in self.wire_qpd], b))
+            return z3.And(cs)
+
+        for v in sorted({6 ** a * 8 ** b for a, b in all_pairs}):
+            choice = z3.Or([exactly(a, b) for a, b in all_pairs if 6 ** a * 8 ** b == v])
+            s.push()
+            s.add(choice)
+            sat = s.check() == z3.sat
+            if sat:
+                self._m = s.model()
+            s.pop()
+            if sat:
+                s.add(choice)
+                return v
+        raise RuntimeError("no feasible sampling overhead")   # cannot happen: the constraints were satisfiable
+
     def getModelKeyResults(self):
         """-> S, A, L, nWireCuts, nGateCuts, Q, [Q_p], C, [C_p] (Cutter.py:162-178)."""
         if self.model is None:
             raise RuntimeError("no model exists")
-        val = lambda x: self.model.eval(x, model_completion=True).as_long()
-        return (val(self.S), val(self.A), val(self.L), self.nWireCuts, self.nGateCuts, val(self.Q),
-                [val(q) for q in self.Q_p], val(self.C), [val(c) for c in self.C_p])
+        return (self._S, self._A, self._L, self.nWireCuts, self.nGateCuts, self._Q,
+                [self._count(t) for t in self.Qp_terms], self._C, [self._count(t) for t in self.Cp_terms])
 
     # ------------------------------------------------------------------ results
     def cut_spec(self) -> CutSpec:

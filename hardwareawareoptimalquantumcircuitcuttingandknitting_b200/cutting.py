@@ -168,10 +168,20 @@ def baseline_cut_spec(config: str, circuit: QuantumCircuit) -> CutSpec:
     raise KeyError(config)
 
 
-def make_baseline(config: str, seed: int = 0) -> tuple[QuantumCircuit, QuantumCircuit]:
+def make_baseline(config: str, seed: int = 0, cut: str = "table") -> tuple[QuantumCircuit, QuantumCircuit]:
     """-> (decomposed input circuit, cut circuit) of a BASELINE.json config, i.e. the two
-    arguments of ``compareOriginalCircWithCutCirc`` (``benchmarks/benchmark.py:99``)."""
+    arguments of ``compareOriginalCircWithCutCirc`` (``benchmarks/benchmark.py:99``).
+    ``cut="table"`` applies the recorded cut shape (``baseline_cut_spec``); ``cut="solver"`` runs the
+    cutter (``cutter.Cutter``, needs z3) with the limits of ``benchmarks/benchmark.py:41``."""
     from .generators import gen_circ
-    name, n, depth, _p, _q = BASELINE_CONFIGS[config]
+    name, n, depth, p, q = BASELINE_CONFIGS[config]
     circ = gen_circ(name, n, depth, seed=seed).decompose_two_qubit()
+    if cut == "solver":
+        from .cutter import Cutter
+        cutter = Cutter(circ, p, q, maxNQpdCuts=5, maxNCuts=5, maxCutsPerPartitions=5)
+        if not cutter.solve():
+            raise ValueError(f"{config}: no cut satisfies -p {p} -q {q}")
+        return cutter.decomposedCirc, cutter.getCutCirc()
+    if cut != "table":
+        raise ValueError(f"unknown cut source {cut!r}")
     return circ, apply_cuts(circ, baseline_cut_spec(config, circ))

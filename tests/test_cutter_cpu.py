@@ -198,3 +198,57 @@ def test_constructor_checks_follow_the_reference():
         Cutter(c, 2, "10")
     with pytest.raises(AssertionError):
         Cutter(c, 2, [3, 3, 3])
+
+
+# ---------------------------------------------------------------------- BASELINE.json configs
+def _solve_config(config):
+    name, n, depth, P, q = cutting.BASELINE_CONFIGS[config]
+    circ = generators.gen_circ(name, n, depth, seed=0)
+    cu = Cutter(circ, P, q, maxNQpdCuts=5, maxNCuts=5, maxCutsPerPartitions=5)      # benchmarks/benchmark.py:41
+    return cu, cu.solve()
+
+
+@pytest.mark.parametrize("config,S,n_wire,n_gate,Q", [
+    ("bv16", 8, 1, 0, 9), ("hwe16d5", 7776, 0, 5, 8), ("syc16d5", 1296, 0, 4, 8)])
+def test_solver_reproduces_the_recorded_cut_shapes(config, S, n_wire, n_gate, Q, golden):
+    cu, ok = _solve_config(config)
+    assert ok
+    res = cu.getModelKeyResults()
+    assert (res[0], res[3], res[4], res[5]) == (S, n_wire, n_gate, Q)
+    spec = cu.cut_spec()
+    want = cutting.baseline_cut_spec(config, cu.decomposedCirc)       # the shapes bench.py and the GPU tests use
+    assert sorted(spec.gate_cuts) == sorted(want.gate_cuts)
+    assert [q for q, _ in spec.wire_cuts] == [q for q, _ in want.wire_cuts]
+    # the cut circuit has the fragment sizes of Appendix B, whichever of the equivalent optima the solver returns
+    sizes = sorted(len(r) for r in cu.getCutCirc().qregs)
+    assert sizes == sorted(len(r) for r in cutting.apply_cuts(cu.decomposedCirc, want).qregs)
+    # fixture written by tests/golden/make_cut_specs.py from this solver (the z3 search is cached)
+    fixture = golden("cut_specs.json")[config]
+    assert fixture["key_results"][:6] == list(res[:6])
+    assert sorted(fixture["spec"]["gate_cuts"]) == sorted(spec.gate_cuts)
+
+
+@pytest.mark.parametrize("config", ["qft16", "aqft16"])
+def test_qft_family_is_infeasible_at_q10(config):
+    # the reference itself exits at benchmarks/benchmark.py:53-54 for -q 10
+    name, n, depth, P, _q = cutting.BASELINE_CONFIGS[config]
+    cu = Cutter(generators.gen_circ(name, n, depth, seed=0), P, 10, maxNQpdCuts=5, maxNCuts=5, maxCutsPerPartitions=5)
+    assert cu.solve() is False
+
+
+def test_make_baseline_with_the_solver():
+    circ, cut = cutting.make_baseline("hwe16d5", cut="solver")
+    _circ, cut_table = cutting.make_baseline("hwe16d5")
+    assert sorted(len(r) for r in cut.qregs) == sorted(len(r) for r in cut_table.qregs) == [8, 8]
+    names = lambda c: sorted(type(i.operation).__name__ for i in c.data if len(i.qubits) == 2)
+    assert names(cut) == names(cut_table)
+
+
+def test_add6_solver_cut_knits_back():
+    # Q is minimised before S (Cutter.py:567-568): even at -q 50 the 6-qubit adder is cut (two wire cuts on q2, 3 | 3
+    # original qubits) - the resulting circuit must still reproduce the uncut distribution
+    cu, ok = _solve_config("add6")
+    assert ok
+    S, A, L, n_w, n_g, Q, Q_p, C, C_p = cu.getModelKeyResults()
+    assert (S, n_w, n_g, Q) == (64, 2, 0, 4)
+    _knits_back(cu.getCutCirc(), cu.decomposedCirc, tol=1e-10)
