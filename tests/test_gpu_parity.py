@@ -130,6 +130,35 @@ def test_baseline_16q_configs(dev, cfg):
     assert abs(f_gpu - f_or) < TOL_F and f_gpu > 1 - 1e-9
 
 
+@pytest.mark.parametrize("cfg", ["add6", "aqft16"])
+def test_solver_made_wire_cuts(dev, cfg):
+    """The cutter's own optimum at -q 50 (Q is minimised before S, Cutter.py:567-568): add-6 gets two wire cuts,
+    aqft-16 five (K = 5 VirtualMoves, 8^5 = 32 768 labels, fragments of 10 and 11 qubits).  cut == uncut."""
+    pytest.importorskip("z3")
+    circ, cut = cutting.make_baseline(cfg, cut="solver")
+    virt = vcm.VirtualCircuit(cut)
+    assert all(type(vg).__name__ == "VirtualMove" for vg in virt.vgates)
+    assert len(virt.vgates) == {"add6": 2, "aqft16": 5}[cfg]
+    dense_res, _ = runm.run_virtual_circuit_dense(virt, device=dev, nearest=False)
+    got = dense_res.values.cpu().numpy()
+    uncut = sv.dense(sv.exact_distribution(circ), circ.num_clbits)
+    assert np.abs(got - uncut).max() < TOL_P
+    assert abs(dense_res.total - 1.0) < 1e-9
+    # label enumeration bit-exact, a sample of instances against the oracle simulator
+    ov = oi.OracleVirtualCircuit(cut)
+    tables = virt.simulate_fragments(dev)
+    rng = np.random.default_rng(1)
+    K = len(virt.vgates)
+    for f in virt.active_fragments():
+        labels = ov.instance_labels(f)
+        assert labels == virt.get_instance_labels(f)
+        prog = virt.program(f)
+        host = tables[f].cpu().numpy()
+        for li in rng.choice(len(labels), size=min(8, len(labels)), replace=False):
+            want = od.signed_fold(sv.exact_distribution(ov.instance(f, labels[li])), ov.n_clbits, K, prog.out_mask)
+            assert np.abs(want - host[li]).max() < TOL_P
+
+
 @pytest.mark.parametrize("cfg", ["qft16", "aqft16", "add6"])
 def test_uncut_configs_streaming_regime(dev, cfg):
     circ, cut = cutting.make_baseline(cfg)
