@@ -46,7 +46,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="syc32d1")
+    ap.add_argument("--workload", default="syc32d1",
+                    help="a BASELINE config (cutting.BASELINE_CONFIGS); 'NAME:solver' cuts it with the z3 cutter "
+                         "instead of applying the recorded cut shape (e.g. aqft16:solver: five wire cuts)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-sample-bits", type=int, default=None,
                     help="log2 of the output entries the CPU baseline knits per step")

@@ -174,6 +174,8 @@ def make_baseline(config: str, seed: int = 0, cut: str = "table") -> tuple[Quant
     ``cut="table"`` applies the recorded cut shape (``baseline_cut_spec``); ``cut="solver"`` runs the
     cutter (``cutter.Cutter``, needs z3) with the limits of ``benchmarks/benchmark.py:41``."""
     from .generators import gen_circ
+    if config.endswith(":solver"):                     # "aqft16:solver" == make_baseline("aqft16", cut="solver")
+        config, cut = config[:-len(":solver")], "solver"
     name, n, depth, p, q = BASELINE_CONFIGS[config]
     circ = gen_circ(name, n, depth, seed=seed).decompose_two_qubit()
     if cut == "solver":
