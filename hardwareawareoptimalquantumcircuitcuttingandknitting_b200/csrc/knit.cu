@@ -503,7 +503,8 @@ __global__ void __launch_bounds__(256) contract_generic_kernel(const __grid_cons
 #define GT 64
 #define GK 16
 __global__ void __launch_bounds__(256) contract_gemm_kernel(const __grid_constant__ ContractParams P, int n_split,
-                                                            double* __restrict__ partial, int M, int N) {
+                                                            double* __restrict__ partial, int M, int N, int Mr,
+                                                            int Nr) {
     __shared__ double As[GK][GT + 4];
     __shared__ double Bs[GK][GT + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -523,9 +524,10 @@ __global__ void __launch_bounds__(256) contract_gemm_kernel(const __grid_constan
             int e = tid + 256 * k, rr = e / GT, cc = e % GT;
             long long l = l0 + rr;
             double a = 0.0, b = 0.0;
-            if (l < le) {
-                a = __ldg(P.w + l) * __ldg(P.table[0] + (long long)__ldg(rowA + l) * P.row_stride[0] + i0 + cc);
-                b = __ldg(P.table[1] + (long long)__ldg(rowB + l) * P.row_stride[1] + j0 + cc);
+            if (l < le) {  // Mr / Nr: real row lengths (a fragment with fewer than 6 output bits fills part of a tile)
+                if (i0 + cc < Mr)
+                    a = __ldg(P.w + l) * __ldg(P.table[0] + (long long)__ldg(rowA + l) * P.row_stride[0] + i0 + cc);
+                if (j0 + cc < Nr) b = __ldg(P.table[1] + (long long)__ldg(rowB + l) * P.row_stride[1] + j0 + cc);
             }
             As[rr][cc] = a;
             Bs[rr][cc] = b;
@@ -567,7 +569,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 }
 
 __global__ void __launch_bounds__(256) contract_dmma_kernel(const __grid_constant__ ContractParams P, int n_split,
-                                                            double* __restrict__ partial, int M, int N) {
+                                                            double* __restrict__ partial, int M, int N, int Mr,
+                                                            int Nr) {
     __shared__ double As[GK][GP];
     __shared__ double Bs[GK][GP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -589,9 +592,10 @@ __global__ void __launch_bounds__(256) contract_dmma_kernel(const __grid_constan
             const int e = tid + 256 * k, rr = e / GT, cc = e % GT;
             const long long l = l0 + rr;
             double a = 0.0, b = 0.0;
-            if (l < le) {
-                a = __ldg(P.w + l) * __ldg(P.table[0] + (long long)__ldg(rowA + l) * P.row_stride[0] + i0 + cc);
-                b = __ldg(P.table[1] + (long long)__ldg(rowB + l) * P.row_stride[1] + j0 + cc);
+            if (l < le) {  // Mr / Nr: real row lengths (a fragment with fewer than 6 output bits fills part of a tile)
+                if (i0 + cc < Mr)
+                    a = __ldg(P.w + l) * __ldg(P.table[0] + (long long)__ldg(rowA + l) * P.row_stride[0] + i0 + cc);
+                if (j0 + cc < Nr) b = __ldg(P.table[1] + (long long)__ldg(rowB + l) * P.row_stride[1] + j0 + cc);
             }
             As[rr][cc] = a;
             Bs[rr][cc] = b;
@@ -670,17 +674,21 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
     // scratch: w[count] + rows[n_frag][count] (+ split partials for the GEMM path)
     const int mA = __builtin_popcountll(masks[0]);
     const int mB = n_frag >= 2 ? __builtin_popcountll(masks[1]) : 0;
-    const bool gemm = (n_frag == 2) && mA >= 6 && mB >= 6;
+    // two fragments always take the tile kernels: rows shorter than a tile (a fragment with fewer than 6 output
+    // bits, e.g. the 5-bit side of aqft-16 with five wire cuts) are padded with zeros inside the tile - the
+    // per-output generic kernel walks all labels serially (19.5 ms against 0.3 ms for those 32 768 labels)
+    const bool gemm = (n_frag == 2);
+    const int mAp = mA < 6 ? 6 : mA, mBp = mB < 6 ? 6 : mB;
     int n_split = 1;
     size_t partial_bytes = 0;
     if (gemm) {
-        long long tiles = (1ll << (mA - 6)) * (1ll << (mB - 6));
+        long long tiles = (1ll << (mAp - 6)) * (1ll << (mBp - 6));
         long long want = (4ll * h->sm_count + tiles - 1) / tiles;
         long long maxs = (count + 4 * GK - 1) / (4 * GK);
         n_split = (int)(want < maxs ? want : maxs);
         if (n_split < 1) n_split = 1;
         if (n_split > 64) n_split = 64;
-        partial_bytes = (size_t)n_split * sizeof(double) << (mA + mB);
+        partial_bytes = (size_t)n_split * sizeof(double) << (mAp + mBp);
     }
     size_t w_bytes = ((size_t)count * sizeof(double) + 255) & ~(size_t)255;
     size_t r_bytes = ((size_t)count * n_frag * sizeof(int) + 255) & ~(size_t)255;
@@ -726,14 +734,14 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
     int ggrid = (int)((n + 255) / 256 < (unsigned long long)h->sm_count * 8 ? (n + 255) / 256
                                                                            : (unsigned long long)h->sm_count * 8);
     if (gemm && (seen == (n_out_bits >= 64 ? ~0ull : (1ull << n_out_bits) - 1ull))) {
-        const int M = 1 << mA, N = 1 << mB;
+        const int M = 1 << mAp, N = 1 << mBp, Mr = 1 << mA, Nr = 1 << mB;
         dim3 grid(M / GT, N / GT, n_split);
         // FP64 tensor cores (DMMA) by default; QCK_CONTRACT_FMA=1 selects the FMA-pipe tile kernel
         const char* fma_env = getenv("QCK_CONTRACT_FMA");
         if (fma_env && atoi(fma_env) == 1)
-            contract_gemm_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N);
+            contract_gemm_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N, Mr, Nr);
         else
-            contract_dmma_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N);
+            contract_dmma_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N, Mr, Nr);
         QCK_CHECK_LAUNCH(h);
         contract_scatter_kernel<<<ggrid, 256, 0, st>>>(d_partial, n_split, M, N, masks[0], masks[1], n_out_bits,
                                                         d_out, accumulate);
