@@ -252,3 +252,44 @@ def test_add6_solver_cut_knits_back():
     S, A, L, n_w, n_g, Q, Q_p, C, C_p = cu.getModelKeyResults()
     assert (S, n_w, n_g, Q) == (64, 2, 0, 4)
     _knits_back(cu.getCutCirc(), cu.decomposedCirc, tol=1e-10)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_small_circuits_against_exhaustive_search(seed):
+    """Random circuits of 3-5 qubits (cx / cz / rzz; the cutter decomposes them to cx first, Cutter.py:84), random
+    limits, 2 or 3 partitions: the optimum equals the exhaustive one."""
+    import random
+    rnd = random.Random(1000 + seed)
+    n = rnd.randint(3, 5)
+    P = rnd.choice([2, 2, 3])
+    budget = 10 if P == 2 else 8                  # vertices the exhaustive search can afford
+    c = circuit.QuantumCircuit(circuit.QuantumRegister(n, "q"))
+    used = 0
+    while True:
+        kind = rnd.choice(["cx", "cx", "cz", "rzz"])
+        cost = 4 if kind == "rzz" else 2          # rzz -> two cx
+        if used + cost > budget:
+            break
+        a, b = rnd.sample(range(n), 2)
+        if kind == "rzz":
+            c.rzz(0.3, a, b)
+        else:
+            getattr(c, kind)(a, b)
+        c.h(rnd.randrange(n))
+        used += cost
+    q = max(rnd.randint(2, n), -(-n // P))
+    limits = {}
+    if rnd.random() < 0.7:
+        limits["maxNCuts"] = rnd.randint(1, 4)
+        if rnd.random() < 0.7:
+            limits["maxNQpdCuts"] = rnd.randint(0, limits["maxNCuts"])
+    if rnd.random() < 0.4:
+        limits["maxCutsPerPartitions"] = rnd.randint(1, 3)
+    cu = Cutter(c, P, q, **limits)
+    assert len(cu.V) <= budget
+    want = _brute_force(cu, limits.get("maxNCuts"), limits.get("maxNQpdCuts"), limits.get("maxCutsPerPartitions"))
+    ok = cu.solve()
+    assert ok == (want is not None)
+    if ok:
+        S, A, L, n_w, n_g, Q, Q_p, C, C_p = cu.getModelKeyResults()
+        assert (Q, S, A, L, C) == want[1:], (limits, P, q)
