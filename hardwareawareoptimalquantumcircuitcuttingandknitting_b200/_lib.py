@@ -27,6 +27,7 @@ MAX_OUT_BITS = 40
 MAX_FRAGMENTS = 8
 MAX_VARIANTS = 8
 OP_U1, OP_CX, OP_CZ, OP_U2, OP_CLUSTER, OP_U1X, OP_TERM, OP_PHASE = 0, 1, 2, 3, 4, 5, 6, 7
+SWEEP_SHARED = 4            # qck_sweep.flags: QCK_SWEEP_SHARED
 CLUSTER_QUBITS = 3
 
 

@@ -45,6 +45,15 @@ import os as _os
 
 STREAM_TILE = int(_os.environ.get("QCK_STREAM_TILE", "12"))   # 64 KiB tiles; env override = tuning knob
 LOW_RUN = 5                 # tiles always hold qubits 0..4: 32 amplitudes = 512 contiguous bytes
+# Prefix sharing (first level): the ops of an on-chip program that precede its first label-dependent
+# op are the same for every instance; they run once per program and the instances start from that state.
+# "auto": only where instances, not latency, are the bound - many instances and a prefix that is most of the
+# program (the sending side of wire cuts: basis change + measurement at the END of the fragment);
+# QCK_SHARE_PREFIX=1 / 0 forces it on (whenever a prefix exists) / off.
+SHARE_PREFIX = {"1": True, "0": False}.get(_os.environ.get("QCK_SHARE_PREFIX", ""), "auto")
+SHARE_PREFIX_MIN_INSTANCES = 1024       # instances of the fragment
+SHARE_PREFIX_MIN_PLAN = 64              # instances of the program (measurement pattern)
+SHARE_PREFIX_MIN_FRACTION = 0.5
 
 _I2 = np.eye(2, dtype=np.complex128)
 
@@ -78,6 +87,7 @@ class PlanHost:
     sum_mask: int
     sign_mask: int
     op_base: int = 0                    # offset of this plan's ops in the fragment's device op array
+    shared_prefix: bool = False         # on-chip: sweeps[0] holds no label-dependent op and runs once per plan
 
 
 class FragmentProgram:
@@ -85,7 +95,8 @@ class FragmentProgram:
 
     def __init__(self, frag_circuit: QuantumCircuit, fragment: QuantumRegister, num_clbits: int,
                  onchip_max: int = ONCHIP_MAX_QUBITS, stream_tile: int = STREAM_TILE,
-                 cluster: bool = True, fuse: bool = True, early_bits: int = 0) -> None:
+                 cluster: bool = True, fuse: bool = True, early_bits: int = 0, share_prefix=None) -> None:
+        self.share_prefix = SHARE_PREFIX if share_prefix is None else share_prefix      # True / False / "auto"
         self.fragment = fragment
         self.n_qubits = len(fragment)
         self.num_clbits = num_clbits
@@ -410,15 +421,23 @@ class FragmentProgram:
             for p in cfg_pos.values():
                 sign_mask |= 1 << p
         ops_arr = np.asarray(ops, dtype=np.int32).reshape(-1, 8)
+        shared = False
         if n_state <= self.onchip_max:
             sweeps = [(list(range(n_state)), 0, len(ops_arr))]
+            dep = np.nonzero(ops_arr[:, 4] >= 0)[0]       # ops that select their matrix by a label digit
+            split = int(dep[0]) if len(dep) else 0
+            if split > 0 and (self.share_prefix is True or (
+                    self.share_prefix == "auto" and self.num_labels >= SHARE_PREFIX_MIN_INSTANCES
+                    and len(labels) >= SHARE_PREFIX_MIN_PLAN and split >= SHARE_PREFIX_MIN_FRACTION * len(ops_arr))):
+                shared = True
+                sweeps = [(list(range(n_state)), 0, split), (list(range(n_state)), split, len(ops_arr))]
         else:
             ops_arr, sweeps = _schedule_sweeps(ops_arr, n_state, self.stream_tile, self)
         # register clusters pay in the latency-bound on-chip kernel; in the streaming kernel the plain
         # passes (matrix in registers, no per-op dispatch) measured faster (hwe-30 d3: 62 -> 45 ms)
         if self.cluster and n_state <= self.onchip_max:
             ops_arr, sweeps = _cluster_sweeps(ops_arr, sweeps)
-        return PlanHost(pattern, labels, n_state, ops_arr, sweeps, out_pos, sum_mask, sign_mask)
+        return PlanHost(pattern, labels, n_state, ops_arr, sweeps, out_pos, sum_mask, sign_mask, shared_prefix=shared)
 
     @property
     def row_bits(self) -> int:
@@ -686,7 +705,8 @@ class FragmentExecutor:
                 arr[i].op_begin = p.op_base + b
                 arr[i].op_end = p.op_base + e
                 arr[i].flags = (int(np.isin(p.ops[b:e, 0], (_lib.OP_U1X, _lib.OP_PHASE)).any())
-                                | 2 * int((p.ops[b:e, 0] == _lib.OP_CLUSTER).any()))
+                                | 2 * int((p.ops[b:e, 0] == _lib.OP_CLUSTER).any())
+                                | (_lib.SWEEP_SHARED if p.shared_prefix and i == 0 else 0))
                 for j, x in enumerate(positions):
                     arr[i].pos[j] = x
             sweep_arrays.append(arr)
@@ -735,6 +755,10 @@ class FragmentExecutor:
             alloc = torch.zeros if label_range is not None else torch.empty
             out = alloc((prog.num_labels, self.row_len), dtype=torch.float64, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if not self.streaming and self._work is None:
+            snap = sum(16 << p.n_state for p in self.plans if p.shared_prefix)   # one state per shared prefix
+            if snap:
+                self._work = handle.scratch(torch, snap, self.device, stream)
         if self.streaming and self._work is None:
             per = 16 << self.max_state
             n = 1

@@ -463,9 +463,30 @@ __device__ __forceinline__ double fold_entry(const PlanDev& plan, uint64_t o, Lo
 // ------------------------------------------------------------------ on-chip regime
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
+// Label-independent prefix of an on-chip program (qck_sweep flag QCK_SWEEP_SHARED): run ONCE, the state is left
+// in global memory (`snap`, the shared-memory image as it is) and every instance starts from it instead of |0>.
+__global__ void __launch_bounds__(256) sim_onchip_prefix_kernel(PlanDev plan, int op_begin, int op_end,
+                                                                double2* __restrict__ snap) {
+    double2* s = reinterpret_cast<double2*>(smem_raw);
+    StagedOp* so = reinterpret_cast<StagedOp*>(smem_raw + ((size_t)16 << plan.n_state));
+    __shared__ int digits[QCK_MAX_DIGITS];
+    if (threadIdx.x < QCK_MAX_DIGITS) digits[threadIdx.x] = 0;  // no op of a shared prefix selects by digit
+    const uint32_t n_amp = 1u << plan.n_state;
+    cta_sync();
+    {
+        const int n0 = (op_end - op_begin) < plan.n_stage ? (op_end - op_begin) : plan.n_stage;
+        stage_ops<WholeCta>(so, plan.ops, op_begin, n0, plan.mats, digits);
+    }
+    for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
+    cta_sync();
+    apply_ops<WholeCta>(s, plan.n_state, so, plan.n_stage, plan.ops, op_begin, op_end, plan.mats, digits, true);
+    for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) snap[i] = s[i];
+}
+
 __global__ void __launch_bounds__(256) sim_onchip_kernel(PlanDev plan, int op_begin, int op_end,
                                                          const int32_t* __restrict__ labels,
-                                                         double* __restrict__ out, long long row_stride) {
+                                                         double* __restrict__ out, long long row_stride,
+                                                         const double2* __restrict__ init) {
     double2* s = reinterpret_cast<double2*>(smem_raw);
     StagedOp* so = reinterpret_cast<StagedOp*>(smem_raw + ((size_t)16 << plan.n_state));
     __shared__ int digits[QCK_MAX_DIGITS];
@@ -477,7 +498,11 @@ __global__ void __launch_bounds__(256) sim_onchip_kernel(PlanDev plan, int op_be
         const int n0 = (op_end - op_begin) < plan.n_stage ? (op_end - op_begin) : plan.n_stage;
         stage_ops<WholeCta>(so, plan.ops, op_begin, n0, plan.mats, digits);  // global loads overlap the state init
     }
-    for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
+    if (init) {
+        for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = __ldg(init + i);
+    } else {
+        for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
+    }
     cta_sync();
     apply_ops<WholeCta>(s, plan.n_state, so, plan.n_stage, plan.ops, op_begin, op_end, plan.mats, digits, true);
     const uint64_t n_out = 1ull << plan.n_out_bits;
@@ -497,6 +522,7 @@ struct PlanVarDev {
     signed char out_pos[QCK_MAX_OUT_BITS];
     unsigned long long sum_mask, sign_mask;
     const int32_t* labels;
+    const double2* init;  // state after the shared prefix (sim_onchip_prefix_kernel), or nullptr: start from |0>
     int cta_begin, n_stage_unused;
 };
 struct GroupDev {
@@ -537,7 +563,11 @@ __global__ void __launch_bounds__(256) sim_onchip_group_kernel(const __grid_cons
         stage_ops<WholeCta>(so, G.ops, pv.op_begin, n0, G.mats, digits);
     }
     const uint32_t n_amp = 1u << G.n_state;
-    for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
+    if (pv.init) {
+        for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = __ldg(pv.init + i);
+    } else {
+        for (uint32_t i = threadIdx.x; i < n_amp; i += blockDim.x) s[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // swz(0) == 0
+    }
     cta_sync();
     apply_ops<WholeCta>(s, G.n_state, so, G.n_stage, G.ops, pv.op_begin, pv.op_end, G.mats, digits, true);
     const uint64_t n_out = 1ull << plan.n_out_bits;
@@ -839,8 +869,31 @@ static int stage_records(int n_ops) {
     return n < 1 ? 1 : n;
 }
 
+// On-chip: the whole state is one tile.  Two such sweeps with QCK_SWEEP_SHARED on the first = a label-independent
+// prefix (run once per plan, sim_onchip_prefix_kernel) followed by the per-instance rest.
+static bool has_shared_prefix(const qck_sim_plan* plan) {
+    return plan->n_sweeps == 2 && plan->sweeps[0].n_tile == plan->n_state_qubits &&
+           plan->sweeps[1].n_tile == plan->n_state_qubits && (plan->sweeps[0].flags & QCK_SWEEP_SHARED);
+}
 static bool is_onchip(const qck_sim_plan* plan) {
-    return plan->n_sweeps == 1 && plan->sweeps[0].n_tile == plan->n_state_qubits;
+    return (plan->n_sweeps == 1 && plan->sweeps[0].n_tile == plan->n_state_qubits) || has_shared_prefix(plan);
+}
+
+// Runs the shared prefix of an on-chip plan into `snap` (16 << n_state bytes) on `st`.
+static int launch_prefix(qck_handle* h, const qck_sim_plan* plan, double2* snap, cudaStream_t st) {
+    PlanDev pd = to_dev(plan);
+    const qck_sweep& sw = plan->sweeps[0];
+    const int N = plan->n_state_qubits;
+    pd.n_stage = stage_records(sw.op_end - sw.op_begin);
+    size_t smem = ((size_t)16 << N) + sizeof(StagedOp) * pd.n_stage;
+    if ((int)smem + 2048 > h->max_smem_optin)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "on-chip plan with %d qubits does not fit shared memory", N);
+    int threads = 1 << (N > 3 ? N - 3 : 0);
+    if (threads < 32) threads = 32;
+    if (threads > 256) threads = 256;
+    sim_onchip_prefix_kernel<<<1, threads, smem, st>>>(pd, sw.op_begin, sw.op_end, snap);
+    QCK_CHECK_LAUNCH(h);
+    return QCK_OK;
 }
 
 // ---- TMA sweep: host-side description of one sweep ------------------------------------------
@@ -1250,12 +1303,25 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
         int threads = 1 << (N > 3 ? N - 3 : 0);  // one thread per group of 8 amplitudes
         if (threads < 32) threads = 32;
         if (threads > 256) threads = 256;
-        const qck_sweep& sw = plan->sweeps[0];
+        const bool shared = has_shared_prefix(plan);
+        const qck_sweep& sw = plan->sweeps[shared ? 1 : 0];
+        const double2* init = nullptr;
+        if (shared) {
+            if (!d_work || work_bytes < ((size_t)16 << N))
+                QCK_FAIL(h, QCK_ERR_INVALID_ARG, "a plan with a shared prefix needs %zu bytes of work space, got %zu",
+                         (size_t)16 << N, work_bytes);
+            rc = launch_prefix(h, plan, (double2*)d_work, st);
+            if (rc) return rc;
+            init = (const double2*)d_work;
+            const int st1 = stage_records(sw.op_end - sw.op_begin);
+            if (st1 > pd.n_stage) pd.n_stage = st1;
+            smem = ((size_t)16 << N) + sizeof(StagedOp) * pd.n_stage;
+        }
         for (int64_t done = 0; done < n_instances;) {
             int64_t batch = n_instances - done;
             if (batch > (1ll << 30)) batch = 1ll << 30;
             sim_onchip_kernel<<<(unsigned)batch, threads, smem, st>>>(pd, sw.op_begin, sw.op_end, d_labels + done,
-                                                                       d_out, (long long)out_row_stride);
+                                                                       d_out, (long long)out_row_stride, init);
             QCK_CHECK_LAUNCH(h);
             done += batch;
         }
@@ -1298,6 +1364,7 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
 // (at handle creation) - setting them per launch races between host threads.
 int qck_sim_init(qck_handle* h) {
     QCK_CUDA(h, qck_allow_max_smem(sim_onchip_kernel, h->max_smem_optin));
+    QCK_CUDA(h, qck_allow_max_smem(sim_onchip_prefix_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_onchip_group_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_kernel, h->max_smem_optin));
@@ -1319,7 +1386,8 @@ static int ensure_side_streams(qck_handle* h) {
 }
 
 static int launch_group(qck_handle* h, const qck_sim_plan* plans, const int* idx, int n, const int32_t* const* d_labels,
-                        const int64_t* n_instances, double* d_out, int64_t out_row_stride, cudaStream_t st) {
+                        const int64_t* n_instances, double* d_out, int64_t out_row_stride, cudaStream_t st,
+                        char* d_work, size_t work_bytes, size_t* work_used) {
     GroupDev G;
     memset(&G, 0, sizeof(G));
     const qck_sim_plan& p0 = plans[idx[0]];
@@ -1341,6 +1409,21 @@ static int launch_group(qck_handle* h, const qck_sim_plan* plans, const int* idx
         PlanVarDev& v = G.var[i];
         v.op_begin = p.sweeps[0].op_begin;
         v.op_end = p.sweeps[0].op_end;
+        v.init = nullptr;
+        if (has_shared_prefix(&p)) {  // prefix once (same stream, so ordered before the group launch), then the rest
+            const size_t need = (size_t)16 << p.n_state_qubits;
+            if (!d_work || *work_used + need > work_bytes)
+                QCK_FAIL(h, QCK_ERR_INVALID_ARG,
+                         "plans with a shared prefix need 16 << n_state bytes of work space each (%zu of %zu used)",
+                         *work_used, work_bytes);
+            double2* snap = reinterpret_cast<double2*>(d_work + *work_used);
+            *work_used += need;
+            int rc = launch_prefix(h, &p, snap, st);
+            if (rc) return rc;
+            v.init = snap;
+            v.op_begin = p.sweeps[1].op_begin;
+            v.op_end = p.sweeps[1].op_end;
+        }
         v.n_out_bits = pd.n_out_bits;
         v.out_ident = pd.out_ident;
         for (int j = 0; j < QCK_MAX_OUT_BITS; ++j) v.out_pos[j] = (signed char)pd.out_pos[j];
@@ -1388,6 +1471,7 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
     }
     const bool fan = n_groups >= 2;
     int used = 0, k = 0;
+    size_t work_used = 0;  // snapshots of shared prefixes: disjoint slices of d_work (groups run concurrently)
     if (fan) {
         int rc = ensure_side_streams(h);
         if (rc) return rc;
@@ -1408,7 +1492,8 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
                         used = slot + 1;
                     }
                 }
-                int rc = launch_group(h, plans, idx, cnt, d_labels, n_instances, d_out, out_row_stride, st);
+                int rc = launch_group(h, plans, idx, cnt, d_labels, n_instances, d_out, out_row_stride, st,
+                                      (char*)d_work, work_bytes, &work_used);
                 if (rc) return rc;
                 cnt = 0;
             }

@@ -110,11 +110,15 @@ typedef struct {
 /* A sweep = one pass over the state: every CTA stages a 2^n_tile tile (the
  * amplitudes that differ only in the listed bit positions) in shared memory,
  * applies ops[op_begin, op_end) there and writes it back. */
+#define QCK_SWEEP_SHARED 4
 typedef struct {
     int32_t n_tile;
     int32_t op_begin, op_end;
     int32_t flags;                         /* bit 0: the op range holds QCK_OP_U1X / QCK_OP_PHASE;   */
                                            /* bit 1: it holds QCK_OP_CLUSTER (-> plain sweep kernel) */
+                                           /* bit 2 (QCK_SWEEP_SHARED): no op of the range selects by */
+                                           /* label digit - on-chip plans only, first of two sweeps:  */
+                                           /* run once per plan, every instance starts from its state */
     int32_t pos[QCK_MAX_TILE_QUBITS + 2];  /* ascending state-bit positions of the tile bits */
 } qck_sweep;
 
@@ -142,7 +146,8 @@ typedef struct {
  * virtual gates, last fastest: virtual_circuit.py:39-48); its row is written at
  * d_out + d_labels[i] * out_row_stride.  d_work: scratch for the streaming
  * regime (>= 16 << n_state_qubits bytes, more = more instances in flight);
- * ignored in the on-chip regime. */
+ * in the on-chip regime only plans with a QCK_SWEEP_SHARED prefix use it
+ * (16 << n_state_qubits bytes per such plan: the state after the prefix). */
 QCK_API int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const int32_t* d_labels,
                       int64_t n_instances, double* d_out, int64_t out_row_stride,
                       void* d_work, size_t work_bytes, qck_stream stream);

@@ -78,9 +78,14 @@ def run_plan(program, plan, label, return_state=False):
     psi = np.zeros(1 << N, dtype=np.complex128)
     psi[0] = 1.0
     idx = np.arange(1 << N)
-    for positions, b, e in plan.sweeps:
+    for si, (positions, b, e) in enumerate(plan.sweeps):
         cluster_pos, members_left = None, 0
         seg = plan.ops[b:e]
+        if getattr(plan, "shared_prefix", False):
+            assert len(plan.sweeps) == 2 and len(positions) == N
+            if si == 0:       # runs once for all instances: nothing in it may depend on the label
+                assert all(int(op[4]) < 0 for op in seg if int(op[0]) != _lib.OP_CLUSTER), \
+                    "label-dependent op inside a shared prefix"       # (cluster headers keep a position there)
         tile_mask = sum(1 << p for p in positions)
         skip = 0
         for oi, op in enumerate(seg):

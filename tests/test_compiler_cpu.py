@@ -162,3 +162,35 @@ def test_c_cluster_scheduler_equals_python_reference():
         want_ops, want_sw = cr.cluster_sweeps_reference(ops, sweeps)
         assert got_sw == want_sw
         assert np.array_equal(got_ops, want_ops)
+
+
+@pytest.mark.parametrize("gname,theta", [("cx", None), ("rzz", 0.83)])
+def test_shared_prefix_split_does_not_change_rows(gname, theta):
+    """On-chip programs split into a label-independent prefix (run once) and the per-instance rest
+    (compiler.SHARE_PREFIX, qck.h QCK_SWEEP_SHARED): same rows as the unsplit program, and the prefix holds no
+    label-dependent op (asserted by the interpreter)."""
+    qc, cut = make_semcheck_circuit(gname, theta)
+    virt = vcm.VirtualCircuit(cut)
+    n_split = 0
+    for f in virt.active_fragments():
+        circ = virt.fragment_circuits[f]
+        plain = compiler.FragmentProgram(circ, f, virt.num_clbits, share_prefix=False)
+        split = compiler.FragmentProgram(circ, f, virt.num_clbits, share_prefix=True)
+        for fold in (True, False):
+            assert all(len(p.sweeps) == 1 and not p.shared_prefix for p in plain.plans(fold))
+            n_split += sum(p.shared_prefix for p in split.plans(fold))
+            for p in split.plans(fold):
+                if p.shared_prefix:
+                    (pos0, b0, e0), (pos1, b1, e1) = p.sweeps
+                    assert b0 == 0 and e0 == b1 and e1 == len(p.ops) and e0 > 0
+            assert np.abs(pi.run_program(plain, fold=fold) - pi.run_program(split, fold=fold)).max() < 1e-14
+    assert n_split > 0
+
+
+def test_shared_prefix_auto_policy():
+    # auto: only with many instances and a prefix that is most of the program - never for the semcheck circuit
+    qc, cut = make_semcheck_circuit("cx")
+    virt = vcm.VirtualCircuit(cut)
+    for f in virt.active_fragments():
+        prog = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits, share_prefix="auto")
+        assert not any(p.shared_prefix for p in prog.plans())
