@@ -50,6 +50,14 @@ LOW_RUN = 5                 # tiles always hold qubits 0..4: 32 amplitudes = 512
 # "auto": only where instances, not latency, are the bound - many instances and a prefix that is most of the
 # program (the sending side of wire cuts: basis change + measurement at the END of the fragment);
 # QCK_SHARE_PREFIX=1 / 0 forces it on (whenever a prefix exists) / off.
+# Instance de-duplication: label digits that select identical variants in every slot of their gate inside this
+# fragment give identical instances; one representative per class is simulated and its row copied to the others
+# (qck_rows_broadcast).  The copy is one more dependent launch per fragment: measured on one box, syc-16 d5 (671 of
+# 1 296 instances saved per fragment) 0.265 -> 0.284 ms and bv-16 0.143 -> 0.165 ms, but hwe-16 d5 (4 651 of 7 776
+# saved) 0.75 -> 0.41 ms and aqft-16 with five wire cuts (31 744 and 24 992 of 32 768 saved) 7.7 -> 3.0 ms.  Hence
+# "auto": only when at least DEDUPE_MIN_SAVED instances are saved; QCK_DEDUPE=1 / 0 forces it on / off.
+DEDUPE = {"1": True, "0": False}.get(_os.environ.get("QCK_DEDUPE", ""), "auto")
+DEDUPE_MIN_SAVED = 2048
 SHARE_PREFIX = {"1": True, "0": False}.get(_os.environ.get("QCK_SHARE_PREFIX", ""), "auto")
 SHARE_PREFIX_MIN_INSTANCES = 1024       # instances of the fragment
 SHARE_PREFIX_MIN_PLAN = 64              # instances of the program (measurement pattern)
@@ -334,6 +342,32 @@ class FragmentProgram:
         for q in list(pending):
             flush_pending(q)
         return out
+
+    # ------------------------------------------------------------------ identical instances
+    def canonical_labels(self) -> np.ndarray:
+        """int32 [num_labels]: the smallest label whose instance is identical to this one (itself for a
+        representative).  Two variants of a gate are identical in this fragment when every slot of that gate here has
+        bit-identical pre / post matrices and the same measure flag for both."""
+        cached = getattr(self, "_canon", None)
+        if cached is not None:
+            return cached
+        n_dig = len(self.radix)
+        maps = []
+        for d in range(n_dig):
+            first: dict = {}
+            m = np.zeros(self.radix[d], dtype=np.int64)
+            for v in range(self.radix[d]):
+                key = tuple(((s.pre[v] + 0.0).tobytes(), bool(s.meas[v]), (s.post[v] + 0.0).tobytes())
+                            for s in self.slots if s.digit == d)
+                m[v] = first.setdefault(key, v)
+            maps.append(m)
+        labels = np.arange(self.num_labels, dtype=np.int64)
+        if n_dig:
+            digits = self.label_digits(labels)
+            canon = np.stack([maps[d][digits[:, d]] for d in range(n_dig)], axis=0)
+            labels = np.ravel_multi_index(tuple(canon), self.radix)
+        self._canon = labels.astype(np.int32)
+        return self._canon
 
     # ------------------------------------------------------------------ patterns
     def label_digits(self, labels: np.ndarray) -> np.ndarray:
@@ -674,7 +708,8 @@ class FragmentExecutor:
         if host is None:
             host = self._build_host_image(program, self.plans)
             program._host_images[fold] = host
-        (self._blob, self._off_ops, self._off_labels, self._labels_host, self._sweep_arrays, self._structs) = host
+        (self._blob, self._off_ops, self._off_labels, self._labels_host, self._sweep_arrays, self._structs,
+         self._dedupe) = host
         self.h2d_bytes = int(self._blob.nbytes)
         self.d_blob = None
         self.row_len = program.row_len(fold)
@@ -688,14 +723,28 @@ class FragmentExecutor:
         if len(ops) == 0:
             ops = np.zeros((1, 8), np.int32)
         labels = np.concatenate([p.labels for p in plans]).astype(np.int32)
-        # one host blob [mats f64 | ops i32 | labels i32] -> one H2D copy
+        # representatives only (per plan, same order) + the source row of every label: used when the whole
+        # label range is simulated and some instances are identical (qck_rows_broadcast)
+        src = program.canonical_labels()
+        saved = int((src != np.arange(len(src))).sum())
+        dedupe = saved > 0 and (DEDUPE is True or (DEDUPE == "auto" and saved >= DEDUPE_MIN_SAVED))
+        reps = [p.labels[src[p.labels] == p.labels] for p in plans] if dedupe else []
+        extra = np.concatenate(reps + [src]).astype(np.int32) if dedupe else np.zeros(0, np.int32)
+        # one host blob [mats f64 | ops i32 | labels i32 | representatives i32 | sources i32] -> one H2D copy
         mats = np.ascontiguousarray(program.mats, dtype=np.float64)
         off_ops = (mats.nbytes + 255) & ~255
         off_labels = (off_ops + ops.nbytes + 255) & ~255
-        blob = np.zeros(off_labels + labels.nbytes, dtype=np.uint8)
+        off_extra = (off_labels + labels.nbytes + 255) & ~255
+        blob = np.zeros(off_extra + extra.nbytes, dtype=np.uint8)
         blob[:mats.nbytes] = mats.view(np.uint8)
         blob[off_ops:off_ops + ops.nbytes] = np.ascontiguousarray(ops).view(np.uint8).reshape(-1)
-        blob[off_labels:] = labels.view(np.uint8)
+        blob[off_labels:off_labels + labels.nbytes] = labels.view(np.uint8)
+        blob[off_extra:] = extra.view(np.uint8)
+        rep_ranges, w = [], 0
+        for r in reps:
+            rep_ranges.append((w, len(r)))
+            w += len(r)
+        dedupe_info = (off_extra, rep_ranges, off_extra + 4 * w) if dedupe else None
         sweep_arrays, structs = [], []
         off = 0
         for p in plans:
@@ -724,7 +773,7 @@ class FragmentExecutor:
             st.sign_mask = p.sign_mask
             structs.append((st, off, len(p.labels)))
             off += len(p.labels)
-        return blob, off_ops, off_labels, labels, sweep_arrays, structs
+        return blob, off_ops, off_labels, labels, sweep_arrays, structs, dedupe_info
 
     def upload(self) -> None:
         """Host -> device copy of matrices, ops and label lists through pinned memory (one copy;
@@ -774,8 +823,12 @@ class FragmentExecutor:
         counts = (C.c_int64 * n)()
         ops_ptr = self.d_blob.data_ptr() + self._off_ops
         mats_ptr = self.d_blob.data_ptr()
+        dedupe = self._dedupe if label_range is None else None      # a clipped range may miss its representatives
         for i, (st, off, count) in enumerate(self._structs):
             labels_ptr = self.d_blob.data_ptr() + self._off_labels + 4 * off
+            if dedupe is not None:
+                rep_off, count = dedupe[1][i]
+                labels_ptr = self.d_blob.data_ptr() + dedupe[0] + 4 * rep_off
             if label_range is not None:
                 # label lists are ascending inside a plan: clip to the requested range
                 host = self._labels_host[off:off + count]
@@ -792,4 +845,7 @@ class FragmentExecutor:
         work_bytes = self._work.numel() if self._work is not None else 0
         handle.check(handle.lib.qck_sim_fragments_batch(handle.ptr, n, plans, label_ptrs, counts, out.data_ptr(),
                                                         self.row_len, work_ptr, work_bytes, stream))
+        if dedupe is not None:
+            handle.check(handle.lib.qck_rows_broadcast(handle.ptr, out.data_ptr(), self.row_len, self.row_len,
+                                                       self.d_blob.data_ptr() + dedupe[2], prog.num_labels, stream))
         return out

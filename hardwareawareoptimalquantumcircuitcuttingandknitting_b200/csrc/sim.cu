@@ -1513,6 +1513,42 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
     return QCK_OK;
 }
 
+// Instances of a fragment whose label digits select identical variants (several instantiations of a virtual gate
+// look the same from one side: virtual_gates.py:62-103 measures Z for both the I and the Z term) have identical
+// rows: the caller simulates one representative per class and copies its row to the others.
+__global__ void __launch_bounds__(256) rows_broadcast_kernel(double* __restrict__ table, long long row_stride,
+                                                             long long row_len, const int32_t* __restrict__ src,
+                                                             long long n_rows) {
+    for (long long r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const long long from = __ldg(src + r);
+        if (from == r) continue;  // uniform per CTA
+        const double* a = table + from * row_stride;
+        double* b = table + r * row_stride;
+        if (((row_stride | row_len) & 1) == 0 && (reinterpret_cast<uintptr_t>(table) & 15) == 0) {
+            const double2* a2 = reinterpret_cast<const double2*>(a);
+            double2* b2 = reinterpret_cast<double2*>(b);
+            for (long long i = threadIdx.x; i < row_len / 2; i += blockDim.x) b2[i] = a2[i];
+        } else {
+            for (long long i = threadIdx.x; i < row_len; i += blockDim.x) b[i] = a[i];
+        }
+    }
+}
+
+extern "C" int qck_rows_broadcast(qck_handle* h, double* d_table, int64_t row_stride, int64_t row_len,
+                                  const int32_t* d_src, int64_t n_rows, qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    if (n_rows == 0) return QCK_OK;
+    if (!d_table || !d_src || n_rows < 0 || row_len < 1 || row_stride < row_len)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad table / source list");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    long long grid = n_rows < 16ll * h->sm_count ? n_rows : 16ll * h->sm_count;
+    rows_broadcast_kernel<<<(unsigned)grid, 256, 0, st>>>(d_table, (long long)row_stride, (long long)row_len, d_src,
+                                                           (long long)n_rows);
+    QCK_CHECK_LAUNCH(h);
+    return QCK_OK;
+}
+
 extern "C" int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t label, void* d_state,
                                    size_t state_bytes, qck_stream stream) {
     if (!h) return QCK_ERR_INVALID_ARG;

@@ -152,6 +152,14 @@ QCK_API int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const int
                       int64_t n_instances, double* d_out, int64_t out_row_stride,
                       void* d_work, size_t work_bytes, qck_stream stream);
 
+/* d_table[r][0..row_len) = d_table[d_src[r]][0..row_len) for every row r with d_src[r] != r (sources are rows
+ * with d_src[s] == s).  Several instantiations of a virtual gate look the same from one side of the cut
+ * (virtual_gates.py:62-103: the I and the Z term both measure Z), so instances whose label digits select
+ * identical variants have identical rows: one representative per class is simulated
+ * (virtual_circuit.py:39-48 still enumerates all of them) and its row is copied to the others. */
+QCK_API int qck_rows_broadcast(qck_handle* h, double* d_table, int64_t row_stride, int64_t row_len,
+                               const int32_t* d_src, int64_t n_rows, qck_stream stream);
+
 /* Several programs of one fragment in one call (one per measurement pattern).  On-chip
  * programs are independent small launches: they are fanned out over internal side streams
  * (forked from and joined back into `stream` with events) so that they overlap on the GPU;

@@ -173,3 +173,12 @@ def run_program(program, fold=True, labels=None):
                 continue
             out[label] = run_plan(program, plan, label)
     return out
+
+
+def run_program_deduped(program, fold=True):
+    """What FragmentExecutor.run does with instance de-duplication: only the representatives of
+    ``program.canonical_labels()`` are simulated, every other row is a copy of its representative's."""
+    src = program.canonical_labels()
+    reps = set(int(x) for x in np.unique(src))
+    out = run_program(program, fold, labels=reps)
+    return out[src]

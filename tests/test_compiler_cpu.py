@@ -194,3 +194,21 @@ def test_shared_prefix_auto_policy():
     for f in virt.active_fragments():
         prog = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits, share_prefix="auto")
         assert not any(p.shared_prefix for p in prog.plans())
+
+
+def test_identical_instances_are_found_and_bit_identical():
+    """Several instantiations of a virtual gate look the same from one side (the I and the Z term of a wire cut
+    both measure Z; virtual_gates.py:62-103): bv-16's sender side needs 4 of its 8 instances, the receiver 6."""
+    circ, cut = cutting.make_baseline("bv16")
+    virt = vcm.VirtualCircuit(cut)
+    uniq = sorted(len(np.unique(virt.program(f).canonical_labels())) for f in virt.active_fragments())
+    assert uniq == [4, 6]
+    for f in virt.active_fragments():
+        prog = virt.program(f)
+        assert np.array_equal(pi.run_program(prog), pi.run_program_deduped(prog))
+    # gate cuts: 5 of the 6 instantiations of a cut cx differ on either side
+    circ, cut = cutting.make_baseline("syc16d5")
+    virt = vcm.VirtualCircuit(cut)
+    for f in virt.active_fragments():
+        prog = virt.program(f)
+        assert len(np.unique(prog.canonical_labels())) == 5 ** 4 and prog.num_labels == 6 ** 4

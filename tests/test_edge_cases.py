@@ -103,6 +103,8 @@ def test_edge_case_host_compiler(name):
     virt = vcm.VirtualCircuit(cut)
     want = _expected(qc, cut)
     tables = {f: pi.run_program(virt.program(f)) for f in virt.active_fragments()}
+    for f in virt.active_fragments():       # instance de-duplication: copies equal their representatives' rows
+        assert np.array_equal(tables[f], pi.run_program_deduped(virt.program(f)))
     masks, union = virt.output_masks()
     frags = list(tables)
     coeffs = [[c[0] for c in vg.knit_coefficients()] for vg in virt.vgates]

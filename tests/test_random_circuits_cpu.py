@@ -86,6 +86,15 @@ def test_random_cut_circuit(seed):
     # labels bit-exact per fragment
     for f in virt.fragment_circuits:
         assert virt.get_instance_labels(f) == ov.instance_labels(f)
+    # instance de-duplication: a row equals the row of its representative BIT FOR BIT, and representatives are
+    # fixed points of the map
+    for f in virt.active_fragments():
+        prog = virt.program(f)
+        src = prog.canonical_labels()
+        assert np.array_equal(src[src], src) and np.all(src <= np.arange(len(src)))
+        full = pi.run_program(prog)
+        assert np.array_equal(full, pi.run_program_deduped(prog))
+        assert np.array_equal(pi.run_program(prog, fold=False), pi.run_program_deduped(prog, fold=False))
     has_cp = any(type(v).__name__ == "VirtualCPhase" for v in virt.vgates)
     if not has_cp:      # every decomposition except the reference's CPhase reproduces the uncut circuit
         uncut = sv.dense(sv.exact_distribution(qc), n)
