@@ -372,6 +372,49 @@ class Cutter:
         return CutSpec(gate_cuts=sorted(gate_cuts), wire_cuts=sorted(wire_cuts, key=lambda t: (t[1], t[0])),
                        partitions=[sorted(p) for p in parts if p])
 
+    def getResultCircs(self, getInstantiations: bool = False):
+        """-> (decomposed circuit, cut-marked circuit, cut-marked circuit with VirtualMoves, cut circuit,
+        instantiated circuits) as ``Cutter.getResultCircs`` (``Cutter.py:128-160``).  The two marked circuits are for
+        display there: here the first carries the virtual gates and a ``WireCut`` marker after every cut position
+        on the original register, the second is the cut circuit before its qubits are renamed into ``frag*``
+        registers (one register ``q`` plus ``vmove``).  Instantiations: one list per fragment, in
+        ``get_instance_labels`` order (``Cutter.py:702-707``)."""
+        from .circuit import CircuitInstruction, QuantumRegister
+        from .virtual_gates import VirtualMove, WireCut
+        spec = self.cut_spec()
+        circ = self.decomposedCirc
+        gate_cuts = set(spec.gate_cuts)
+        wire_after: dict[int, list[int]] = {}
+        for q, idx in spec.wire_cuts:
+            wire_after.setdefault(idx, []).append(q)
+        marked = QuantumCircuit(*circ.qregs, *circ.cregs, name=circ.name)
+        moves_reg = QuantumRegister(len(spec.wire_cuts), "vmove")
+        with_moves = QuantumCircuit(*circ.qregs, moves_reg, *circ.cregs, name=circ.name)
+        current = {q: q for q in circ.qubits}
+        n_moves = 0
+        for idx, ins in enumerate(circ.data):
+            op = ins.operation
+            if idx in gate_cuts:
+                op = VIRTUAL_GATE_TYPES[op.name](op, f"{op.name} {getattr(op, 'label', None)}")
+            marked.data.append(CircuitInstruction(op, ins.qubits, ins.clbits))
+            with_moves.data.append(CircuitInstruction(op, tuple(current[q] for q in ins.qubits), ins.clbits))
+            for qi in wire_after.get(idx, ()):
+                q = circ.qubits[qi]
+                marked.data.append(CircuitInstruction(WireCut(1, f"{idx}_{qi}"), (q,), ()))
+                target = moves_reg[n_moves]
+                with_moves.data.append(CircuitInstruction(VirtualMove(Gate("swap", 2, (), label=f"{idx}_{qi}")),
+                                                          (current[q], target), ()))
+                current[q] = target
+                n_moves += 1
+        cut = apply_cuts(circ, spec)
+        instantiations = []
+        if getInstantiations:
+            from .virtual_circuit import VirtualCircuit, generate_instantiations
+            virt = VirtualCircuit(cut.copy())
+            for frag, frag_circ in virt.fragment_circuits.items():
+                instantiations.append(generate_instantiations(frag_circ, virt.get_instance_labels(frag)))
+        return circ, marked, with_moves, cut, instantiations
+
     def getCutCirc(self) -> QuantumCircuit:
         """The circuit ``Cutter.getResultCircs`` hands to qvm: ``frag*`` registers, virtual gates, VirtualMoves."""
         return apply_cuts(self.decomposedCirc, self.cut_spec())

@@ -293,3 +293,31 @@ def test_random_small_circuits_against_exhaustive_search(seed):
     if ok:
         S, A, L, n_w, n_g, Q, Q_p, C, C_p = cu.getModelKeyResults()
         assert (Q, S, A, L, C) == want[1:], (limits, P, q)
+
+
+def test_get_result_circs_shapes():
+    # Cutter.getResultCircs (Cutter.py:128-160): decomposed, marked, marked with moves, cut, instantiations
+    c = generators.gen_circ("bv", 5, 1)
+    cu = Cutter(c, 2, 10, maxNQpdCuts=5, maxNCuts=5, maxCutsPerPartitions=5)
+    with pytest.raises(RuntimeError):
+        cu.getResultCircs()
+    assert cu.solve()
+    dec, marked, with_moves, cut, inst = cu.getResultCircs(True)
+    assert dec is cu.decomposedCirc
+    names = lambda circ: [type(i.operation).__name__ for i in circ.data]
+    assert names(marked).count("WireCut") == 1 and len(marked.data) == len(dec.data) + 1
+    assert names(with_moves).count("VirtualMove") == 1 and with_moves.num_qubits == dec.num_qubits + 1
+    assert names(cut) == names(with_moves)                      # same ops, qubits renamed into frag registers
+    assert sorted(len(r) for r in cut.qregs) == [3, 3]
+    assert sorted(len(x) for x in inst) == [8, 8]               # one VirtualMove: 8 instantiations on either side
+    assert cu.getResultCircs()[4] == []
+    # a gate cut: the virtual gate sits where the cx was
+    QC, QR = circuit.QuantumCircuit, circuit.QuantumRegister
+    c = QC(QR(4, "q"))
+    c.cx(0, 1); c.cx(2, 3); c.cz(1, 2); c.cx(0, 1); c.cx(2, 3)
+    c.measure_all()
+    cu = Cutter(c, 2, 2, maxNCuts=2, maxNQpdCuts=2)
+    assert cu.solve()
+    dec, marked, with_moves, cut, inst = cu.getResultCircs(True)
+    assert [n for n in names(marked) if n.startswith("Virtual")] == ["VirtualCX"]      # cz decomposes to h cx h
+    assert sorted(len(x) for x in inst) == [6, 6]
