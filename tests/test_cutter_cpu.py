@@ -321,3 +321,20 @@ def test_get_result_circs_shapes():
     dec, marked, with_moves, cut, inst = cu.getResultCircs(True)
     assert [n for n in names(marked) if n.startswith("Virtual")] == ["VirtualCX"]      # cz decomposes to h cx h
     assert sorted(len(x) for x in inst) == [6, 6]
+
+
+def test_benchmark_driver_cut_only(tmp_path):
+    # tools/benchmark.py keeps the reference's command line (benchmarks/benchmark.py:22-29)
+    import importlib.util, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("qck_benchmark_driver", os.path.join(root, "tools", "benchmark.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(["-p", "2", "-q", "10", "bv", "5", "1", "--cut-only", "--out", str(tmp_path)]) == 0
+    (run_dir,) = list(tmp_path.iterdir())
+    cut = json.loads((run_dir / "cut_spec.json").read_text())
+    assert cut["gate_cuts"] == [] and [w[0] for w in cut["wire_cuts"]] == [4]
+    log = (run_dir / "run.log").read_text()
+    assert "S: 8" in log and "nWireCuts: 1" in log and "success => True" in log
+    # an infeasible request ends like the reference (benchmarks/benchmark.py:53-54): logged, exit code 0
+    assert mod.main(["-p", "2", "-q", "10", "qft", "16", "1", "--cut-only", "--out", str(tmp_path)]) == 0
