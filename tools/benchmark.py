@@ -35,9 +35,15 @@ def main(argv=None) -> int:
     out_dir = pathlib.Path(args.out) / (f"{args.name}_{args.n_qubits}_{args.depth}_{args.p}_{args.q}_"
                                         f"{datetime.datetime.now():%Y%m%d_%H%M%S}")
     out_dir.mkdir(parents=True, exist_ok=True)
-    logging.basicConfig(level=logging.INFO, format="%(asctime)s %(message)s",
-                        handlers=[logging.StreamHandler(), logging.FileHandler(out_dir / "run.log")])
-    log = logging.getLogger("benchmark")
+    log = logging.getLogger("benchmark")            # stream INFO + run.log, as the reference's Logger.py:24-59
+    log.setLevel(logging.INFO)
+    log.propagate = False
+    for h in list(log.handlers):
+        log.removeHandler(h)
+        h.close()
+    for h in (logging.StreamHandler(), logging.FileHandler(out_dir / "run.log")):
+        h.setFormatter(logging.Formatter("%(asctime)s %(message)s"))
+        log.addHandler(h)
 
     circ = generators.gen_circ(args.name.lower(), args.n_qubits, args.depth, seed=args.seed)
     cutter = cutter_mod.Cutter(circ, args.p, args.q, maxNQpdCuts=5, maxNCuts=5, maxCutsPerPartitions=5)
