@@ -1,11 +1,12 @@
 """Small end-to-end runs for compute-sanitizer (memcheck / racecheck): every kernel family once, at sizes a
-sanitizer finishes in a minute.  `compute-sanitizer --tool memcheck python tools/sanitize_small.py`."""
+sanitizer finishes in a minute.  `compute-sanitizer --tool memcheck python tests/sanitize_small.py`
+(lives under tests/ because it checks against the oracle)."""
 import os
 import sys
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 import torch
 from importlib import import_module
