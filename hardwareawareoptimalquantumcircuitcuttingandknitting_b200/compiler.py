@@ -67,7 +67,8 @@ _I2 = np.eye(2, dtype=np.complex128)
 
 
 def _is_identity(m: np.ndarray) -> bool:
-    return bool(np.array_equal(m, _I2))
+    # exact comparison with the 2x2 identity (np.array_equal costs ~10 us per call; this runs per gate)
+    return m.shape == (2, 2) and m[0, 0] == 1 and m[1, 1] == 1 and m[0, 1] == 0 and m[1, 0] == 0
 
 
 @dataclass
@@ -133,11 +134,14 @@ class FragmentProgram:
     def _lower(self, circ: QuantumCircuit) -> None:
         frag_qubits = list(self.fragment)
         qset = set(frag_qubits)
-        instrs = [ins for ins in circ.data if not (isinstance(ins.operation, Barrier)
-                                                   and not isinstance(ins.operation, VirtualGateEndpoint))]
+        # (plain gates are the common case: `type(op) is Gate` spares them the abstract-base-class checks)
+        instrs = [ins for ins in circ.data
+                  if type(ins.operation) is Gate or not (isinstance(ins.operation, Barrier)
+                                                         and not isinstance(ins.operation, VirtualGateEndpoint))]
         for ins in instrs:
-            if not set(ins.qubits) <= qset:
-                raise ValueError("Circuit contains gates that act on multiple fragments.")
+            for q in ins.qubits:
+                if q not in qset:
+                    raise ValueError("Circuit contains gates that act on multiple fragments.")
         last_use = {}
         for i, ins in enumerate(instrs):
             for q in ins.qubits:
@@ -145,7 +149,7 @@ class FragmentProgram:
         # finally-measured clbits (terminal measurements) define the output row
         terminal = []                    # (clbit index, qubit)
         for i, ins in enumerate(instrs):
-            if isinstance(ins.operation, Measure) and last_use[ins.qubits[0]] == i:
+            if type(ins.operation) is not Gate and isinstance(ins.operation, Measure) and last_use[ins.qubits[0]] == i:
                 terminal.append((circ.clbit_index(ins.clbits[0]), ins.qubits[0]))
         terminal.sort(key=lambda t: t[0])
         if len({c for c, _ in terminal}) != len(terminal):
@@ -175,7 +179,7 @@ class FragmentProgram:
         for i, ins in enumerate(instrs):
             op = ins.operation
             qs = [pos[q] for q in ins.qubits]
-            if isinstance(op, VirtualGateEndpoint):
+            if type(op) is not Gate and isinstance(op, VirtualGateEndpoint):
                 vg: VirtualBinaryGate = op.virtual_gate
                 table = vg._table()
                 d = digit_of[op.vgate_idx]
@@ -210,7 +214,7 @@ class FragmentProgram:
                     slot.post_off = self._add_matrix(np.stack(post))
                 tops.append(("slot", len(slots)))
                 slots.append(slot)
-            elif isinstance(op, Measure):
+            elif type(op) is not Gate and isinstance(op, Measure):
                 flush(qs[0])
                 if last_use[ins.qubits[0]] != i:          # mid-circuit measurement of the input circuit
                     tops.append(("mmeas", qs[0], circ.clbit_index(ins.clbits[0])))
