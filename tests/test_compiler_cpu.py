@@ -212,3 +212,41 @@ def test_identical_instances_are_found_and_bit_identical():
     for f in virt.active_fragments():
         prog = virt.program(f)
         assert len(np.unique(prog.canonical_labels())) == 5 ** 4 and prog.num_labels == 6 ** 4
+
+
+def _all_cut_circuits():
+    import random
+    import test_edge_cases as tec
+    import test_random_circuits_cpu as trc
+    for gname, theta in [("cx", None), ("cz", None), ("cy", None), ("rzz", 0.83), ("cp", 0.83)]:
+        yield make_semcheck_circuit(gname, theta)[1]
+    for cfg in ("bv16", "syc16d5", "hwe16d5"):
+        yield cutting.make_baseline(cfg)[1]
+    for name in sorted(tec.CASES):
+        yield tec.CASES[name]()[1]
+    for seed in range(12):
+        rng = random.Random(1000 + seed)
+        qc = trc.random_circuit(rng, rng.randint(4, 6), rng.randint(10, 22))
+        yield cutting.apply_cuts(qc, trc.random_cut(rng, qc, max_gate_cuts=2, wire_cut=(seed % 3 == 0)))
+
+
+def test_template_build_plan_equals_the_emit_loop():
+    """compiler._build_plan (rows built once per program, selected and renumbered per pattern) against the original
+    per-pattern emit loop (tests/build_plan_reference.py): identical op arrays, masks and output positions."""
+    import build_plan_reference as ref
+    n_plans = 0
+    for cut in _all_cut_circuits():
+        virt = vcm.VirtualCircuit(cut)
+        for f in virt.fragment_circuits:
+            prog = compiler.FragmentProgram(virt.fragment_circuits[f], f, virt.num_clbits, cluster=False,
+                                            share_prefix=False)
+            for fold in (True, False):
+                for plan in prog.plans(fold):
+                    if plan.n_state > prog.onchip_max:
+                        continue
+                    ops, n_state, out_pos, sum_mask, sign_mask = ref.emit_ops(prog, plan.pattern, fold)
+                    assert np.array_equal(plan.ops, ops)
+                    assert (plan.n_state, plan.out_pos, plan.sum_mask, plan.sign_mask) == \
+                        (n_state, out_pos, sum_mask, sign_mask)
+                    n_plans += 1
+    assert n_plans > 200
