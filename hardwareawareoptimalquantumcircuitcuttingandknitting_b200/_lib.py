@@ -29,6 +29,9 @@ MAX_VARIANTS = 8
 OP_U1, OP_CX, OP_CZ, OP_U2, OP_CLUSTER, OP_U1X, OP_TERM, OP_PHASE = 0, 1, 2, 3, 4, 5, 6, 7
 SWEEP_SHARED = 4            # qck_sweep.flags: QCK_SWEEP_SHARED
 CLUSTER_QUBITS = 3
+NPD_STATS, NPD_PLAN, NPD_LEVEL, NPD_SELECT, NPD_APPLY = 0, 1, 2, 3, 4      # qck_npd_stage stages
+NPD_STATE_SLOTS, NPD_BINS, NPD_LEVEL_PASSES = 32, 8192, 6
+NPD_ST_SEARCH, NPD_ST_IDENTITY, NPD_ST_SOLVED, NPD_ST_NEGATIVE_TOTAL, NPD_ST_LOCATED = 0, 1, 2, 3, 4
 
 
 class QckSweep(C.Structure):
@@ -96,6 +99,10 @@ _PROTOTYPES = {
     "qck_hellinger": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "qck_npd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.POINTER(C.c_double),
                           C.POINTER(C.c_double), C.c_void_p]),
+    "qck_npd_workspace_bytes": (C.c_size_t, []),
+    "qck_npd_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_void_p]),
+    "qck_npd_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_int,
+                                C.c_void_p]),
     "qck_rows_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "qck_qd_prune": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p]),
     "qck_qd_sqrt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
@@ -186,6 +193,16 @@ class Handle:
         if buf is None or buf.numel() < nbytes:
             buf = cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
         return buf
+
+    def npd_workspace(self, torch, device):
+        """Zeroed int64 device workspace of qck_npd_async / qck_npd_stage (one per handle and device: the
+        handle is thread-local and the stages of one call are stream ordered)."""
+        cache = self.__dict__.setdefault("_npd_ws", {})
+        ws = cache.get(str(device))
+        if ws is None:
+            ws = cache[str(device)] = torch.zeros(int(self.lib.qck_npd_workspace_bytes()) // 8, dtype=torch.int64,
+                                                  device=device)
+        return ws
 
     @property
     def launch_count(self) -> int:

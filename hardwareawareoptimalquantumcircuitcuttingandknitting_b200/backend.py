@@ -71,7 +71,7 @@ class B200Backend:
         if not prog.measures_anything:
             return {}
         row = FragmentExecutor(prog, device).run(handle)[0].cpu().numpy()
-        clbits = sorted(prog.out_clbits + [t[2] for t in prog.tops if t[0] == "mmeas"])
+        clbits = prog.out_clbits                         # every written clbit, ascending (mid-circuit ones too)
         out = {}
         for i in np.nonzero(row)[0]:
             key = 0

@@ -241,7 +241,10 @@ class FragmentProgram:
         self.slots = slots
         self.tops = self._fuse_pairs(tops) if self.fuse else tops
         self.out_bits = out_bits
-        self.out_clbits = [c for c, _ in out_bits]
+        # the row of an instance has one bit per WRITTEN clbit, in ascending clbit order: the terminal
+        # measurements and the mid-circuit measurements of the input circuit (their outcome lives on an
+        # ancilla, see _build_plan) - masks, key_mask and row_bits all follow this list
+        self.out_clbits = sorted([c for c, _ in out_bits] + [t[2] for t in self.tops if t[0] == "mmeas"])
         self.has_mid_measure = mid_measures > 0
         self.out_mask = 0
         for c in self.out_clbits:
@@ -746,6 +749,7 @@ class FragmentExecutor:
         self.max_state = max(p.n_state for p in self.plans)
         self.streaming = self.max_state > program.onchip_max
         self._work = None
+        self._work_bytes = None
 
     @staticmethod
     def _build_host_image(program: FragmentProgram, plans: list):
@@ -834,19 +838,20 @@ class FragmentExecutor:
             alloc = torch.zeros if label_range is not None else torch.empty
             out = alloc((prog.num_labels, self.row_len), dtype=torch.float64, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        if not self.streaming and self._work is None:
-            snap = sum(16 << p.n_state for p in self.plans if p.shared_prefix)   # one state per shared prefix
-            if snap:
-                self._work = handle.scratch(torch, snap, self.device, stream)
-        if self.streaming and self._work is None:
-            per = 16 << self.max_state
-            n = 1
-            if prog.num_labels > 1:          # several instances in flight: bounded by free memory
-                free, _ = torch.cuda.mem_get_info(self.device)
-                n = max(1, min(prog.num_labels, int(free * 0.5) // per, 64))
-            # small state buffers come from the (thread-local) handle's scratch cache: a fresh executor per
-            # run must not cost a cudaMalloc per run (0.3-0.8 ms each: 1.6 ms of a 6.8 ms syc-32 d1 call)
-            self._work = handle.scratch(torch, n * per, self.device, stream)
+        # Scratch comes from the handle's cache, keyed by (device, stream): it is fetched on EVERY run for the
+        # stream this run is enqueued on (work on one stream is ordered; another stream gets its own buffer).
+        # Only the size is remembered: the shared-prefix snapshots, or as many streaming states as fit.
+        if self._work_bytes is None:
+            if not self.streaming:
+                self._work_bytes = sum(16 << p.n_state for p in self.plans if p.shared_prefix)
+            else:
+                per = 16 << self.max_state
+                n = 1
+                if prog.num_labels > 1:          # several instances in flight: bounded by free memory
+                    free, _ = torch.cuda.mem_get_info(self.device)
+                    n = max(1, min(prog.num_labels, int(free * 0.5) // per, 64))
+                self._work_bytes = n * per
+        self._work = handle.scratch(torch, self._work_bytes, self.device, stream) if self._work_bytes else None
         n = len(self._structs)
         plans = (_lib.QckSimPlan * n)()
         label_ptrs = (C.c_void_p * n)()

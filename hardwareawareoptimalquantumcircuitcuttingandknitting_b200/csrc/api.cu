@@ -5,6 +5,7 @@
 
 int qck_sim_init(qck_handle* h);   // sim.cu
 int qck_knit_init(qck_handle* h);  // knit.cu
+int qck_npd_init(qck_handle* h);   // npd.cu
 
 extern "C" int qck_abi_version(void) { return QCK_ABI_VERSION; }
 
@@ -49,7 +50,8 @@ extern "C" int qck_create(int device, qck_handle** out) {
         delete full;
         return QCK_ERR_NOMEM;
     }
-    if (qck_sim_init(h) != QCK_OK || qck_knit_init(h) != QCK_OK) {
+    if (qck_sim_init(h) != QCK_OK || qck_knit_init(h) != QCK_OK || qck_npd_init(h) != QCK_OK) {
+        if (h->npd_ws) cudaFree(h->npd_ws);
         cudaFree(h->d_partials);
         cudaFreeHost(h->h_pinned);
         delete full;
@@ -65,6 +67,7 @@ extern "C" int qck_destroy(qck_handle* h) {
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->scratch) cudaFree(h->scratch);
+    if (h->npd_ws) cudaFree(h->npd_ws);
     if (h->side_ready) {
         for (int i = 0; i < QCK_SIDE_STREAMS; ++i) {
             cudaStreamDestroy(h->side[i]);

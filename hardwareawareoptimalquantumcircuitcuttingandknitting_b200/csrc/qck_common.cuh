@@ -29,6 +29,8 @@ struct qck_handle {
     cudaEvent_t side_done[QCK_SIDE_STREAMS];
     cudaEvent_t fork;
     int side_ready;
+    // workspace of nearest_probability_distribution (npd.cu): state, bins, per-CTA partials
+    void* npd_ws;
 };
 
 #define QCK_FAIL(h, code, ...)                                    \

@@ -1,13 +1,5 @@
-// Reductions over dense distributions (sm_100a): statistics, Hellinger sums and
-// QuasiDistr.nearest_probability_distribution (third_party/qvm/qvm/quasi_distr.py:28-43).
-//
-// nearest_probability_distribution without sorting.  The reference sorts ascending and
-// drops the j-th smallest value while  v_(j) + (sum of the j-1 smaller ones) / (N - j + 1) < 0,
-// i.e. while  g(j) = v_(j) (N - j + 1) + S_(j-1) < 0.  g(j) = sum_i min(v_i, v_(j)) and is
-// non-decreasing in j, so an entry with value t is dropped  <=>  G(t) = sum_i min(v_i, t) < 0.
-// G is monotone in t: the drop threshold is found by bisection on the (order-preserving)
-// integer image of the doubles with one streaming reduction per step, then one pass
-// applies  v -> v + beta / num  to the survivors (beta = sum of dropped, num = #survivors).
+// Reductions over dense distributions (sm_100a): statistics and Hellinger sums
+// (nearest_probability_distribution lives in npd.cu).
 #include "qck_common.cuh"
 
 int qck_ensure_partials(qck_handle* h, size_t count);
@@ -161,134 +153,5 @@ extern "C" int qck_hellinger(qck_handle* h, const double* d_p, const double* d_q
     QCK_CHECK_LAUNCH(h);
     sum3_final_kernel<<<1, 32, 0, st>>>(h->d_partials, grid, d_result3);
     QCK_CHECK_LAUNCH(h);
-    return QCK_OK;
-}
-
-// ---- nearest_probability_distribution
-// G(t) = sum over alive entries of min(v, t); also counts / sums the entries with v < t
-__global__ void __launch_bounds__(256) npd_probe_kernel(const double* __restrict__ p, unsigned long long n, double acc,
-                                                        double t, double* __restrict__ partials) {
-    double g = 0.0, below_sum = 0.0, below_cnt = 0.0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        double v = p[i];
-        if (fabs(v) > acc) {
-            g += fmin(v, t);
-            if (v < t) {
-                below_sum += v;
-                below_cnt += 1.0;
-            }
-        }
-    }
-    __shared__ double red[3][8];
-    g = warp_sum(g);
-    below_sum = warp_sum(below_sum);
-    below_cnt = warp_sum(below_cnt);
-    if ((threadIdx.x & 31) == 0) {
-        int w = threadIdx.x >> 5;
-        red[0][w] = g;
-        red[1][w] = below_sum;
-        red[2][w] = below_cnt;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0, c = 0.0;
-        for (int w = 0; w < 8; ++w) {
-            a += red[0][w];
-            b += red[1][w];
-            c += red[2][w];
-        }
-        partials[3 * blockIdx.x + 0] = a;
-        partials[3 * blockIdx.x + 1] = b;
-        partials[3 * blockIdx.x + 2] = c;
-    }
-}
-
-__global__ void __launch_bounds__(256) npd_apply_kernel(double* __restrict__ p, unsigned long long n, double acc,
-                                                        double t, double shift) {
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        double v = p[i];
-        p[i] = (fabs(v) > acc && !(v < t)) ? v + shift : 0.0;
-    }
-}
-
-static inline long long ordered_of(double d) {
-    long long b;
-    memcpy(&b, &d, 8);
-    return b < 0 ? (long long)(0x8000000000000000ull - (unsigned long long)b) : b;
-}
-static inline double double_of(long long o) {
-    long long b = o < 0 ? (long long)(0x8000000000000000ull - (unsigned long long)o) : o;
-    double d;
-    memcpy(&d, &b, 8);
-    return d;
-}
-
-extern "C" int qck_npd(qck_handle* h, double* d_p, uint64_t n, double acc, double* host_beta, double* host_num,
-                       qck_stream stream) {
-    if (!h) return QCK_ERR_INVALID_ARG;
-    if (!d_p) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "NULL argument");
-    DeviceGuard guard(h->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    int grid = reduce_grid(h, n);
-    int rc = qck_ensure_partials(h, (size_t)grid * 4 + 8);
-    if (rc) return rc;
-    double* d_res = h->d_partials + (size_t)grid * 4;  // 4 doubles of results after the partials
-    // pass 1: statistics
-    stats_kernel<<<grid, 256, 0, st>>>(d_p, n, acc, h->d_partials);
-    QCK_CHECK_LAUNCH(h);
-    stats_final_kernel<<<1, 32, 0, st>>>(h->d_partials, grid, reinterpret_cast<qck_stats*>(d_res));
-    QCK_CHECK_LAUNCH(h);
-    QCK_CUDA(h, cudaMemcpyAsync(h->h_pinned, d_res, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    QCK_CUDA(h, cudaStreamSynchronize(st));
-    const double vmin = h->h_pinned[1], alive = h->h_pinned[3];
-    double beta = 0.0, num = alive;
-    if (alive > 0.0 && vmin < 0.0) {
-        // bisection for t0 = inf{t : G(t) >= 0};  G(vmin) = N * vmin < 0.  If the total is
-        // negative everything but (at most) the top is dropped; the reference then divides
-        // by zero - we report that as an error instead of reproducing the exception.
-        auto probe = [&](double t, double* out3) -> int {
-            npd_probe_kernel<<<grid, 256, 0, st>>>(d_p, n, acc, t, h->d_partials);
-            QCK_CHECK_LAUNCH(h);
-            sum3_final_kernel<<<1, 32, 0, st>>>(h->d_partials, grid, d_res);
-            QCK_CHECK_LAUNCH(h);
-            QCK_CUDA(h, cudaMemcpyAsync(h->h_pinned, d_res, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-            QCK_CUDA(h, cudaStreamSynchronize(st));
-            out3[0] = h->h_pinned[0];
-            out3[1] = h->h_pinned[1];
-            out3[2] = h->h_pinned[2];
-            return QCK_OK;
-        };
-        double r[3];
-        rc = probe(INFINITY, r);  // G(inf) = total sum
-        if (rc) return rc;
-        if (r[0] < 0.0)
-            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "nearest_probability_distribution: total mass %.3e is negative", r[0]);
-        long long lo = ordered_of(vmin);       // G(lo) < 0
-        long long hi = ordered_of(INFINITY);   // G(hi) >= 0
-        // hi - lo can exceed 2^63 (lo < 0 < hi): overflow-free floor average
-        while ((unsigned long long)hi - (unsigned long long)lo > 1ull) {
-            long long mid = (lo >> 1) + (hi >> 1) + (lo & hi & 1);
-            rc = probe(double_of(mid), r);
-            if (rc) return rc;
-            if (r[0] < 0.0)
-                lo = mid;
-            else
-                hi = mid;
-        }
-        const double t0 = double_of(hi);  // entries with v < t0 are dropped
-        rc = probe(t0, r);
-        if (rc) return rc;
-        beta = r[1];
-        num = alive - r[2];
-        npd_apply_kernel<<<grid, 256, 0, st>>>(d_p, n, acc, t0, beta / num);
-        QCK_CHECK_LAUNCH(h);
-    } else if (acc > 0.0) {
-        npd_apply_kernel<<<grid, 256, 0, st>>>(d_p, n, acc, -INFINITY, 0.0);  // only removes pruned entries
-        QCK_CHECK_LAUNCH(h);
-    }
-    if (host_beta) *host_beta = beta;
-    if (host_num) *host_num = num;
     return QCK_OK;
 }

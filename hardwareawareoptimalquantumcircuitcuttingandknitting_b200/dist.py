@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import os
 
-__all__ = ["shard_range", "shard_pow2", "init_from_env", "allreduce_stats", "allreduce_sum_", "world"]
+__all__ = ["shard_range", "shard_pow2", "init_from_env", "allreduce_stats", "allreduce_sum_", "npd_sharded", "world"]
 
 
 def shard_range(total: int, rank: int, world_size: int, align: int = 1) -> tuple[int, int]:
@@ -74,11 +74,43 @@ def allreduce_stats(stats, group=None):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return stats
-    mn = stats[1:2].clone()
-    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
-    stats[1:2] = mn
+    # ONE collective: every rank gathers all ranks' four scalars and combines them itself, in rank order
+    # (deterministic) - a SUM and a MIN all-reduce would be two launch-latency-bound collectives
+    world_size = dist.get_world_size(group)
+    gathered = stats.new_empty((world_size, stats.numel()))
+    dist.all_gather_into_tensor(gathered, stats.reshape(1, -1), group=group)
+    mn = gathered[:, 1].min()
+    stats.copy_(gathered.sum(dim=0))
+    stats[1] = mn
     return stats
+
+
+def npd_sharded(handle, values, acc: float, ws, group=None, stream: int = 0):
+    """``nearest_probability_distribution`` (``quasi_distr.py:28-43``) of a result SHARDED over the ranks by
+    output index.  The ranks exchange five scalars, then per refinement level two
+    scalars and one 128 KiB histogram - never the distribution; no host round trip.  ``ws``: this rank's
+    int64 workspace (``Handle.npd_workspace``); its first slots hold the global state afterwards."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    lib, n, ptr = handle.lib, values.numel(), values.data_ptr()
+    f64 = ws.view(torch.float64)
+    world_size = dist.get_world_size(group)
+    handle.check(lib.qck_npd_stage(handle.ptr, _lib.NPD_STATS, ptr, n, acc, ws.data_ptr(), 0, stream))
+    gathered = f64.new_empty((world_size, 5))
+    dist.all_gather_into_tensor(gathered, f64[0:5].reshape(1, 5), group=group)
+    mn = gathered[:, 1].min()
+    f64[0:5] = gathered.sum(dim=0)              # sum, (min), negative sum, alive, negative count
+    f64[1] = mn
+    handle.check(lib.qck_npd_stage(handle.ptr, _lib.NPD_PLAN, None, 0, acc, ws.data_ptr(), 0, stream))
+    bins = ws[_lib.NPD_STATE_SLOTS:_lib.NPD_STATE_SLOTS + 2 * _lib.NPD_BINS]
+    for _ in range(_lib.NPD_LEVEL_PASSES):      # enqueued unconditionally: finished searches return at once
+        handle.check(lib.qck_npd_stage(handle.ptr, _lib.NPD_LEVEL, ptr, n, acc, ws.data_ptr(), 0, stream))
+        dist.all_reduce(f64[10:12], op=dist.ReduceOp.SUM, group=group)      # (sum, count) at or below the range
+        dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=group)            # integer bins: order independent
+        handle.check(lib.qck_npd_stage(handle.ptr, _lib.NPD_SELECT, None, 0, acc, ws.data_ptr(), 0, stream))
+    handle.check(lib.qck_npd_stage(handle.ptr, _lib.NPD_APPLY, ptr, n, acc, ws.data_ptr(), 0, stream))
+    return ws
 
 
 def allreduce_sum_(tensor, group=None):

@@ -144,10 +144,19 @@ class QuasiDistr:
         return f"QuasiDistr(num_bits={self.num_bits}, accuracy={self.accuracy})"
 
     def support_mask(self) -> int:
-        m = 0
-        for k in self.to_dict():
-            m |= k
-        return m
+        """OR of the keys with a non-zero value, computed on the device (one small read-back instead of a
+        full device -> host copy and a Python loop per merge operand)."""
+        import torch
+        if self._dict is not None:
+            m = 0
+            for k in self._dict:
+                m |= k
+            return m
+        if self.num_bits == 0:
+            return 0
+        idx = torch.nonzero(self.values).reshape(-1, 1)
+        bits = ((idx >> torch.arange(self.num_bits, device=self.device)) & 1).any(dim=0).cpu().tolist()
+        return sum(1 << b for b, on in enumerate(bits) if on)
 
     # ---------------------------------------------------------------- algebra (quasi_distr.py:45-86)
     def nearest_probability_distribution(self) -> dict[int, float]:

@@ -203,10 +203,54 @@ class VirtualCircuit:
             return (0, prog.num_labels if l_end > l_begin else 0)
         radices = self.global_radices()
         strides = self._fragment_strides(fragment)
-        idx = np.arange(l_begin, l_end, dtype=np.int64)
-        digits = np.stack(np.unravel_index(idx, radices), axis=1)
-        lf = digits @ np.asarray(strides, dtype=np.int64)
-        return int(lf.min()), int(lf.max()) + 1
+        K = len(radices)
+        # min / max of lf over the global labels in [l_begin, l_end), from the digits of the two ends only
+        # (enumerating the range costs gigabytes of host memory at 6^10 labels)
+        full = [0] * (K + 1)                       # full[p]: largest contribution of the digits p..K-1
+        for p in reversed(range(K)):
+            full[p] = full[p + 1] + (radices[p] - 1) * strides[p]
+
+        def digits_of(l):
+            out = [0] * K
+            for p in reversed(range(K)):
+                out[p] = l % radices[p]
+                l //= radices[p]
+            return out
+
+        def upward(d, p):                          # suffixes >= d[p:]
+            if p == K:
+                return 0, 0
+            a, b = upward(d, p + 1)
+            lo, hi = d[p] * strides[p] + a, d[p] * strides[p] + b
+            if d[p] < radices[p] - 1:
+                lo, hi = min(lo, (d[p] + 1) * strides[p]), max(hi, (radices[p] - 1) * strides[p] + full[p + 1])
+            return lo, hi
+
+        def downward(d, p):                        # suffixes <= d[p:]
+            if p == K:
+                return 0, 0
+            a, b = downward(d, p + 1)
+            lo, hi = d[p] * strides[p] + a, d[p] * strides[p] + b
+            if d[p] > 0:
+                lo, hi = min(lo, 0), max(hi, (d[p] - 1) * strides[p] + full[p + 1])
+            return lo, hi
+
+        def between(a, b, p):                      # a[:p] == b[:p]
+            if p == K:
+                return 0, 0
+            if a[p] == b[p]:
+                lo, hi = between(a, b, p + 1)
+                return a[p] * strides[p] + lo, a[p] * strides[p] + hi
+            l1, h1 = upward(a, p + 1)
+            l2, h2 = downward(b, p + 1)
+            lo = min(a[p] * strides[p] + l1, b[p] * strides[p] + l2)
+            hi = max(a[p] * strides[p] + h1, b[p] * strides[p] + h2)
+            if b[p] - a[p] >= 2:
+                lo, hi = min(lo, (a[p] + 1) * strides[p]), max(hi, (b[p] - 1) * strides[p] + full[p + 1])
+            return lo, hi
+
+        lo, hi = between(digits_of(l_begin), digits_of(l_end - 1), 0)
+        return int(lo), int(hi) + 1
 
     def _fragment_strides(self, fragment: Fragment) -> list[int]:
         """lf = sum_k digit_k * stride_k maps a global label to the fragment's label index."""
@@ -235,10 +279,11 @@ class VirtualCircuit:
             tables[frag] = ex.run(handle, label_range=rng)
         return tables
 
-    def output_masks(self) -> tuple[dict, int]:
+    def output_masks(self, fragments=None) -> tuple[dict, int]:
         """-> ({fragment: clbit mask of its output row}, union).  The dense result lives on the
-        union's bits (compacted when some clbit is never written)."""
-        masks = {f: self.program(f).out_mask for f in self.active_fragments()}
+        union's bits (compacted when some clbit is never written).  ``fragments``: the fragments that
+        delivered results (default: every fragment that measures anything)."""
+        masks = {f: self.program(f).out_mask for f in (self.active_fragments() if fragments is None else fragments)}
         union = 0
         for f, m in masks.items():
             if m & union:
@@ -254,8 +299,8 @@ class VirtualCircuit:
         device = default_device() if device is None else device
         handle = _lib.get_handle(getattr(device, "index", None) or 0)
         stream = torch.cuda.current_stream(device).cuda_stream
-        masks, union = self.output_masks()
         frags = list(tables.keys())
+        masks, union = self.output_masks(frags)
         n_out = bin(union).count("1")
         cmask = [_compress_mask(masks[f], union) for f in frags]
         ptrs = (C.c_void_p * len(frags))(*[tables[f].data_ptr() for f in frags])
@@ -270,6 +315,7 @@ class VirtualCircuit:
             return out
         if y_range is not None:
             raise NotImplementedError("output sharding is only available without virtual gates")
+        self._check_limits(len(frags), K)
         radices = self.global_radices()
         coef = (C.c_double * (K * _lib.MAX_VARIANTS))()
         for k, vg in enumerate(self.vgates):
@@ -291,6 +337,18 @@ class VirtualCircuit:
                                                     stats.data_ptr(), stream))
         return out
 
+    def _check_limits(self, n_frag: int, K: int) -> None:
+        """The C ABI's fixed-size arrays (qck.h: QCK_MAX_FRAGMENTS, QCK_MAX_DIGITS, QCK_MAX_VARIANTS, int32
+        strides) - checked before anything is written into them."""
+        if n_frag > _lib.MAX_FRAGMENTS:
+            raise NotImplementedError(f"{n_frag} fragments: the knit kernels take at most {_lib.MAX_FRAGMENTS}")
+        if K > _lib.MAX_DIGITS:
+            raise NotImplementedError(f"{K} virtual gates: the knit kernels take at most {_lib.MAX_DIGITS}")
+        if any(r > _lib.MAX_VARIANTS for r in self.global_radices()):
+            raise NotImplementedError("a virtual gate has more instantiations than QCK_MAX_VARIANTS")
+        if any(self.program(f).num_labels >= 2 ** 31 for f in self.active_fragments()):
+            raise NotImplementedError("a fragment has 2^31 or more instances: label strides are int32")
+
     def knit_tables_faithful(self, tables: dict, accuracy: float, device=None, out=None, stats=None):
         """Reference-faithful knit (``ACCURACY = accuracy`` pruning after every operation, reference
         order) of UNFOLDED fragment tables (``simulate_fragments(fold=False)``), fused per output
@@ -299,13 +357,14 @@ class VirtualCircuit:
         device = default_device() if device is None else device
         handle = _lib.get_handle(getattr(device, "index", None) or 0)
         stream = torch.cuda.current_stream(device).cuda_stream
-        masks, union = self.output_masks()
         frags = list(tables.keys())
+        masks, union = self.output_masks(frags)
         n_out = bin(union).count("1")
         K = len(self._vgate_instrs)
         ptrs = (C.c_void_p * len(frags))(*[tables[f].data_ptr() for f in frags])
         cm = (C.c_uint64 * len(frags))(*[_compress_mask(masks[f], union) for f in frags])
         row_strides = (C.c_int64 * len(frags))(*[tables[f].shape[1] for f in frags])
+        self._check_limits(len(frags), K)
         gates = (_lib.QckFaithfulGate * max(K, 1))(*[_faithful_gate(vg) for vg in self.vgates])
         strides = (C.c_int32 * (len(frags) * _lib.MAX_DIGITS))()
         cfg_bit = (C.c_int32 * (len(frags) * _lib.MAX_DIGITS))(*([-1] * (len(frags) * _lib.MAX_DIGITS)))

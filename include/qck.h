@@ -295,13 +295,46 @@ QCK_API int qck_knit_faithful(qck_handle* h, int n_frag, const double* const* d_
  * qck_hellinger: result[0..2] = sum p, sum q, sum sqrt(p q) over max(.,0) entries; the
  *   fidelity (Utilities.py:224, qiskit hellinger_fidelity) is (r2 / sqrt(r0 r1))^2.
  * qck_npd: QuasiDistr.nearest_probability_distribution (quasi_distr.py:28-43) on a dense
- *   vector, in place.  Synchronises the stream (the threshold search is host-driven). */
+ *   vector, in place; returns beta (sum of the dropped entries) and num (survivors) on the host, so it
+ *   synchronises the stream ONCE at the end (qck_npd_async + one 256-byte read-back). */
 QCK_API int qck_stats_dense(qck_handle* h, const double* d_p, uint64_t n, double acc, qck_stats* d_stats,
                     qck_stream stream);
 QCK_API int qck_hellinger(qck_handle* h, const double* d_p, const double* d_q, uint64_t n, double* d_result3,
                   qck_stream stream);
 QCK_API int qck_npd(qck_handle* h, double* d_p, uint64_t n, double acc, double* host_beta, double* host_num,
             qck_stream stream);
+
+/* The same without any host round trip: 8 launches enqueued on `stream` (statistics, <= 5 radix
+ * refinement levels of 13 bits each on the ordered integer image of the doubles + one summation pass,
+ * apply), each looking at the state the previous one left in the workspace; launches with nothing
+ * left to do return at once.  d_ws: qck_npd_workspace_bytes() bytes of device memory, ZEROED once by
+ * the caller (NULL: the handle's own - one npd in flight per handle).  After the stream has passed the
+ * call the first QCK_NPD_STATE_SLOTS 8-byte slots of the workspace hold (doubles unless noted):
+ *   0 sum, 1 min, 2 sum of negative entries, 3 alive entries (|v| > acc), 4 negative entries,
+ *   5 status (int64: QCK_NPD_ST_*), 6 / 7 lo / hi (int64 keys: the dropped set is {key <= lo}),
+ *   10 / 11 sum / count of the entries with key <= lo, 13 t0, 14 beta / num, 15 beta, 16 num. */
+#define QCK_NPD_STATE_SLOTS 32
+enum { QCK_NPD_ST_SEARCH = 0, QCK_NPD_ST_IDENTITY = 1, QCK_NPD_ST_SOLVED = 2, QCK_NPD_ST_NEGATIVE_TOTAL = 3,
+       QCK_NPD_ST_LOCATED = 4 };
+QCK_API size_t qck_npd_workspace_bytes(void);
+QCK_API int qck_npd_async(qck_handle* h, double* d_p, uint64_t n, double acc, void* d_ws, qck_stream stream);
+
+/* One stage of the above, for results SHARDED over ranks by output index (the ranks
+ * exchange scalars and one 128 KiB histogram per level, never the distribution).  Per rank:
+ *   QCK_NPD_STATS (fuse_tail = 0)  local statistics -> slots 0-4; the caller reduces them over the ranks
+ *                                  (sum, min, sum, sum, sum), writes them back, then
+ *   QCK_NPD_PLAN                   identity / error / first key range;
+ *   repeat 6 times:
+ *   QCK_NPD_LEVEL (fuse_tail = 0)  local histogram of the range: slots 10-11 (doubles) and the bins
+ *                                  (2 x 8192 int64 right after the state slots); the caller sum-reduces
+ *                                  both over the ranks, then
+ *   QCK_NPD_SELECT                 narrows the range or finishes;
+ *   QCK_NPD_APPLY                  rewrites the local shard.
+ * With fuse_tail = 1 the last CTA of STATS / LEVEL runs PLAN / SELECT itself (single-rank form). */
+enum { QCK_NPD_STATS = 0, QCK_NPD_PLAN = 1, QCK_NPD_LEVEL = 2, QCK_NPD_SELECT = 3, QCK_NPD_APPLY = 4 };
+#define QCK_NPD_BINS 8192
+QCK_API int qck_npd_stage(qck_handle* h, int stage, double* d_p, uint64_t n, double acc, void* d_ws, int fuse_tail,
+                  qck_stream stream);
 
 /* ------------------------------------------------------------------ dense QuasiDistr algebra
  * Device forms of quasi_distr.py:45-86 on dense vectors of 2^n_bits doubles with

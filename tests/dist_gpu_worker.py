@@ -1,0 +1,88 @@
+"""One rank of the multi-GPU parity run (launched by tests/test_gpu_multi.py through torchrun, one process
+per GPU, NCCL).  Every rank checks ITS OWN results against the oracle; any mismatch is a non-zero exit."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = "hardwareawareoptimalquantumcircuitcuttingandknitting_b200"
+
+
+def main() -> None:
+    import torch
+    import torch.distributed as dist
+    from importlib import import_module
+    qdist = import_module(f"{PKG}.dist")
+    cutting = import_module(f"{PKG}.cutting")
+    vcm = import_module(f"{PKG}.virtual_circuit")
+    runm = import_module(f"{PKG}.run")
+    gen = import_module(f"{PKG}.generators")
+    lib = import_module(f"{PKG}._lib")
+    from oracle import cport, dense as od, tables as otab
+    rank, local_rank, world = qdist.init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    worst = 0.0
+
+    # (1) virtual gates: label shard + all-reduce, then nearest_probability_distribution on every rank
+    for cfg in ("bv16", "syc16d5", "hwe16d5"):
+        circ, cut = cutting.make_baseline(cfg, seed=1)
+        uncut = cport.simulate_probabilities(circ)
+        res, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=False,
+                                                rank=rank, world_size=world)
+        got = res.values.cpu().numpy()
+        err = float(np.abs(got - uncut).max())
+        assert err < 1e-10, (cfg, rank, err)
+        res2, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=True,
+                                                 rank=rank, world_size=world)
+        want = od.nearest_probability_distribution(got)
+        err2 = float(np.abs(res2.values.cpu().numpy() - want).max())
+        assert err2 < 1e-13, (cfg, rank, err2)
+        assert abs(res2.total - 1.0) < 1e-9
+        worst = max(worst, err, err2)
+
+    # (2) no virtual gate: output index sharded by its top bits, nothing gathered
+    c20 = gen.gen_circ("syc", 20, 1, seed=0).decompose_two_qubit()
+    cut20 = cutting.apply_cuts(c20, cutting.CutSpec(partitions=[list(range(10)), list(range(10, 20))]))
+    res, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut20), device=dev, rank=rank, world_size=world)
+    o_tabs, o_masks = otab.all_tables_k0(cut20)
+    span = (1 << 20) // world
+    assert res.y_begin == rank * span and res.values.numel() == span
+    want, _, _ = cport.knit_outer(o_tabs, o_masks, res.y_begin, res.y_begin + span)
+    err = float(np.abs(res.values.cpu().numpy() - want).max())
+    assert err < 1e-10, (rank, err)
+    assert abs(res.total - 1.0) < 1e-9          # the statistics are global (one collective)
+    worst = max(worst, err)
+
+    # (3) nearest_probability_distribution of an output-SHARDED vector with negative entries
+    rng = np.random.default_rng(11)
+    for n, make in ((1 << 16, "noise"), (1 << 18, "bulk"), (1 << 12, "ties")):
+        if make == "noise":
+            v = np.zeros(n); v[n - 1] = 1.0; v += rng.normal(0, 1e-17, n)
+        elif make == "bulk":
+            v = rng.random(n); v /= v.sum(); v[rng.choice(n, 3000, replace=False)] -= 8e-6
+        else:
+            v = np.full(n, -1e-17); v[-1] = 1.0; v[77] = 3e-17
+        want = od.nearest_probability_distribution(v)
+        lo, hi = rank * (n // world), (rank + 1) * (n // world)
+        mine = torch.from_numpy(v[lo:hi].copy()).to(dev)
+        h = lib.get_handle(local_rank)
+        ws = h.npd_workspace(torch, dev)
+        qdist.npd_sharded(h, mine, 0.0, ws, None, torch.cuda.current_stream(dev).cuda_stream)
+        state = runm._check_npd_state(ws)
+        err = float(np.abs(mine.cpu().numpy() - want[lo:hi]).max())
+        assert err < 1e-13, (make, rank, err)
+        worst = max(worst, err)
+
+    t = torch.tensor([worst], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"MULTI_GPU_PARITY_OK world={world} max_abs_err_vs_oracle={float(t.item()):.3e}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -90,3 +90,32 @@ def test_qft_output_is_uniform_and_bv_is_delta():
     assert list(d) == [63] and abs(d[63] - 1) < 1e-14
     d = sv.exact_distribution(gen.gen_circ("add", 6))
     assert list(d) == [0]
+
+
+def test_fragment_label_range_matches_enumeration():
+    """fragment_label_range from the digits of the two ends == brute-force enumeration of the global labels
+    (three fragments, one gate untouched by each: zero strides in the middle of the digit list)."""
+    import itertools
+    import random
+    from hardwareawareoptimalquantumcircuitcuttingandknitting_b200 import circuit, cutting, virtual_circuit as vcm
+    qc = circuit.QuantumCircuit(circuit.QuantumRegister(6, "q"))
+    for q in range(6):
+        qc.ry(0.1 + 0.2 * q, q)
+    qc.cx(0, 1); qc.cx(1, 2); qc.cx(2, 3); qc.cz(3, 4); qc.cx(4, 5); qc.cx(1, 2); qc.cx(3, 4)
+    qc.measure_all()
+    two = [i for i, ins in enumerate(qc.data) if ins.operation.num_qubits == 2 and ins.operation.name in ("cx", "cz")]
+    cut = cutting.apply_cuts(qc, cutting.CutSpec(gate_cuts=[two[1], two[3], two[5], two[6]]))
+    virt = vcm.VirtualCircuit(cut)
+    radices = virt.global_radices()
+    L = virt.num_global_labels()
+    assert len(radices) == 4 and len(virt.fragment_circuits) == 3
+    rng = random.Random(0)
+    labels = list(itertools.product(*[range(r) for r in radices]))
+    assert sum(0 in virt._fragment_strides(f) for f in virt.fragment_circuits) == 2
+    for frag in virt.fragment_circuits:
+        strides = virt._fragment_strides(frag)
+        lf = [sum(d * s for d, s in zip(lab, strides)) for lab in labels]
+        for _ in range(300):
+            a = rng.randrange(L)
+            b = rng.randrange(a + 1, L + 1)
+            assert virt.fragment_label_range(frag, a, b) == (min(lf[a:b]), max(lf[a:b]) + 1)

@@ -105,6 +105,19 @@ def test_mid_circuit_measurement_of_input_circuit():
     row = pi.run_program(virt.program(f))[0]
     want = sv.dense(sv.exact_distribution(qc), 3)
     assert np.abs(row - want).max() < 1e-14
+    # the masks the knit and DenseResult.key_mask use cover EVERY written clbit, the mid-circuit one included
+    prog = virt.program(f)
+    assert prog.out_mask == 0b111 and prog.out_clbits == [0, 1, 2] and prog.row_len() == 8
+    masks, union = virt.output_masks()
+    assert union == 0b111
+    # mid-circuit outcome on the HIGHEST clbit, terminal ones below it
+    qc2 = circuit.QuantumCircuit(circuit.QuantumRegister(2, "q"), circuit.ClassicalRegister(3, "c"))
+    qc2.h(0); qc2.measure(0, 2); qc2.h(0); qc2.cx(0, 1); qc2.measure(0, 0); qc2.measure(1, 1)
+    v2 = vcm.VirtualCircuit(qc2)
+    (f2,) = v2.active_fragments()
+    p2 = v2.program(f2)
+    assert p2.out_mask == 0b111 and p2.row_len() == 8
+    assert np.abs(pi.run_program(p2)[0] - sv.dense(sv.exact_distribution(qc2), 3)).max() < 1e-14
 
 
 def test_errors_mirror_reference():

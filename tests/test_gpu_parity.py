@@ -237,6 +237,12 @@ def test_tma_sweep_statevector_equals_plain(dev, name, n, depth):
     assert not torch.isnan(a).any()
     assert float((a - b).abs().max()) < 1e-15
     assert abs(float((a * a).sum()) - 1.0) < 1e-12
+    # ... and against the ORACLE (C statevector, independent gate matrices), not only CUDA vs CUDA
+    assert ex.program.qubit_order == list(circ.qubits)
+    want = cport.simulate_probabilities(circ)
+    for buf in (a, b):
+        got = (buf.view(-1, 2) ** 2).sum(dim=1).cpu().numpy()
+        assert np.abs(got - want).max() < TOL_P
 
 
 @pytest.mark.parametrize("name,n,depth", [("syc", 20, 2), ("hwe", 18, 2), ("qft", 16, 1), ("bv", 19, 1)])
@@ -329,6 +335,11 @@ def test_sharded_statevector_emulated_on_one_device(dev, name, n, depth, world):
     assert not torch.isnan(got).any()
     assert float((got - ref).abs().max()) < 1e-15
     assert abs(sv_sh.norm() - 1.0) < 1e-12
+    # the shards against the ORACLE (C statevector), not only against the single-GPU CUDA run
+    assert ex.program.qubit_order == list(circ.qubits)
+    want = cport.simulate_probabilities(circ)
+    probs = (got.view(-1, 2) ** 2).sum(dim=1).cpu().numpy()
+    assert np.abs(probs - want).max() < TOL_P
     tr = sv_sh.traffic()
     assert tr["bytes"] > 0 and 0 <= tr["peer_bytes"] <= tr["bytes"]
 
@@ -420,8 +431,76 @@ def test_foreign_backend_and_reference_order_knit(dev, acc):
             want = {int(k): v for k, v in case["npd"]}
             assert set(res) == set(want)
             assert max(abs(res[k] - want[k]) for k in want) < 1e-12
+            # the literal flow on the operator API: from_counts per instance, virt.knit level by level
+            width = virt.num_clbits + len(virt.vgates)
+            results = {}
+            for frag, fc in virt.fragment_circuits.items():
+                insts = vcm.generate_instantiations(fc, virt.get_instance_labels(frag))
+                counts = _OracleBackend().run(insts, shots=1000).result().get_counts()
+                counts = [counts] if isinstance(counts, dict) else counts
+                results[frag] = [qdm.QuasiDistr.from_counts(c, num_bits=width) for c in counts]
+            lit = virt.knit(results, None).to_dict()
+            want_knit = {int(k): v for k, v in case["knit"]}
+            assert set(lit) == set(want_knit)
+            assert max(abs(lit[k] - want_knit[k]) for k in want_knit) < 1e-12
+            # mixed: one fragment on the B200 backend, the other on the foreign one
+            mixed = vcm.VirtualCircuit(cut)
+            mixed.set_backend(list(mixed.fragment_circuits)[0], _OracleBackend())
+            res_m, _ = runm.run_virtual_circuit(mixed, shots=1000)
+            assert set(res_m) == set(want)
+            assert max(abs(res_m[k] - want[k]) for k in want) < 1e-12
     finally:
         qdm.ACCURACY = old
+
+
+class _StrictBackend(_OracleBackend):
+    """Like Qiskit: get_counts() raises as soon as one experiment has no measurement; get_counts(i) works
+    for the experiments that have one."""
+
+    def run(self, circuits, shots=1024):
+        dists = [sv.exact_distribution(c) if any(i.operation.name == "measure" for i in c.data) else None
+                 for c in circuits]
+        width = [len(c.clbits) for c in circuits]
+
+        def fmt(i):
+            if dists[i] is None:
+                raise RuntimeError(f'No counts for experiment "{i}"')
+            return {format(k, f"0{width[i]}b"): v * shots for k, v in dists[i].items()}
+
+        class _R:
+            def get_counts(self_inner, experiment=None):
+                if experiment is not None:
+                    return fmt(experiment)
+                out = [fmt(i) for i in range(len(dists))]
+                return out[0] if len(out) == 1 else out
+
+        class _J:
+            def result(self_inner):
+                return _R()
+        return _J()
+
+
+def test_fragment_whose_instances_do_not_all_measure(dev):
+    """The sending end of a wire cut on a one-qubit fragment: the I / X instances of the VirtualMove do not
+    measure at all (virtual_gates.py:62-103), so Qiskit's get_counts() raises and the reference DROPS the
+    fragment (run.py:49-58) - and with it the cut's coefficients.  Chosen behaviour here, on the B200 path
+    and on foreign backends alike: a fragment is kept when ANY of its instances measures; instances without
+    a measurement have the empty outcome with probability 1.  cut == uncut pins it."""
+    qc = circuit.QuantumCircuit(circuit.QuantumRegister(2, "q"))
+    qc.ry(0.7, 0); qc.ry(0.4, 1); qc.cx(0, 1); qc.rx(0.3, 0)
+    qc.measure_all()
+    first = [i for i, ins in enumerate(qc.data) if ins.operation.name == "ry"][0]
+    cut = cutting.apply_cuts(qc, cutting.CutSpec(wire_cuts=[(0, first)]))
+    virt = vcm.VirtualCircuit(cut)
+    sizes = sorted(len(f) for f in virt.fragment_circuits)
+    assert sizes == [1, 2] and len(virt.vgates) == 1
+    want = sv.exact_distribution(qc)
+    res, _ = runm.run_virtual_circuit(virt)
+    assert max(abs(res.get(k, 0.0) - want.get(k, 0.0)) for k in set(res) | set(want)) < TOL_P
+    for_b = vcm.VirtualCircuit(cut)
+    for_b.set_backend_for_all(_StrictBackend())
+    res_f, _ = runm.run_virtual_circuit(for_b, shots=1000)
+    assert max(abs(res_f.get(k, 0.0) - want.get(k, 0.0)) for k in set(res_f) | set(want)) < TOL_P
 
 
 # ------------------------------------------------------------------ QuasiDistr algebra on device
@@ -492,6 +571,83 @@ def test_npd_properties_large(dev):
     # idempotent
     q2 = qdm.QuasiDistr(torch.from_numpy(out).to(dev), accuracy=0.0, _pruned=True)
     assert np.abs(q2.nearest_probability_distribution_dense().cpu().numpy() - out).max() == 0.0
+
+
+def _npd_async(dev, v, acc=0.0, shards=1):
+    """qck_npd_async (shards == 1) or the staged multi-rank flow emulated on one device: every 'rank' owns a
+    slice and its own workspace, the statistics / bins are combined exactly as dist.npd_sharded does."""
+    h = _lib.get_handle(0)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    full = torch.from_numpy(np.asarray(v, dtype=np.float64)).to(dev)
+    n_ws = h.lib.qck_npd_workspace_bytes() // 8
+    if shards == 1:
+        ws = torch.zeros(n_ws, dtype=torch.int64, device=dev)
+        l0 = h.launch_count
+        h.check(h.lib.qck_npd_async(h.ptr, full.data_ptr(), full.numel(), acc, ws.data_ptr(), stream))
+        assert h.launch_count - l0 == 8                 # statistics + 6 level passes + apply, no round trip
+        return full.cpu().numpy(), ws[:32].cpu()
+    parts = list(torch.tensor_split(full, shards))
+    wss = [torch.zeros(n_ws, dtype=torch.int64, device=dev) for _ in parts]
+    S, B = _lib.NPD_STATE_SLOTS, _lib.NPD_BINS
+
+    def stage(which, fuse=0):
+        for p_, w in zip(parts, wss):
+            h.check(h.lib.qck_npd_stage(h.ptr, which, p_.data_ptr(), p_.numel(), acc, w.data_ptr(), fuse, stream))
+
+    stage(_lib.NPD_STATS)
+    g = torch.stack([w.view(torch.float64)[0:5] for w in wss])
+    red = g.sum(dim=0)
+    red[1] = g[:, 1].min()
+    for w in wss:
+        w.view(torch.float64)[0:5] = red
+    stage(_lib.NPD_PLAN)
+    for _ in range(_lib.NPD_LEVEL_PASSES):
+        stage(_lib.NPD_LEVEL)
+        under = torch.stack([w.view(torch.float64)[10:12] for w in wss]).sum(dim=0)
+        bins = torch.stack([w[S:S + 2 * B] for w in wss]).sum(dim=0)
+        for w in wss:
+            w.view(torch.float64)[10:12] = under
+            w[S:S + 2 * B] = bins
+        stage(_lib.NPD_SELECT)
+    stage(_lib.NPD_APPLY)
+    return torch.cat(parts).cpu().numpy(), wss[0][:32].cpu()
+
+
+@pytest.mark.parametrize("shards", [1, 2, 8])
+def test_npd_async_no_host_round_trip(dev, shards):
+    """Radix-refinement npd (csrc/npd.cu) against the oracle (quasi_distr.py:28-43 restated): golden cases,
+    rounding-noise vectors like the 16-bit knit results, exact ties at the threshold, extreme ranges; the
+    single-rank form in 8 launches, and the multi-rank staged form on slices."""
+    for c in load_golden("knit_cases.json")["npd"]:
+        dense = np.zeros(1 << c["nbits"])
+        for k, v in c["raw"]:
+            dense[int(k)] = v
+        want = np.zeros_like(dense)
+        for k, v in c["out"]:
+            want[int(k)] = v
+        got, st = _npd_async(dev, dense, c["acc"], shards)
+        assert np.abs(got - want).max() < 1e-13
+    rng = np.random.default_rng(7)
+    cases = []
+    v = np.zeros(1 << 16); v[0xFFFF] = 1.0; v += rng.normal(0, 1e-17, v.size); cases.append((v, 1e-15))
+    v = np.full(1 << 14, -1e-17); v[-1] = 1.0; v[77] = 3e-17; cases.append((v, 1e-15))      # ties
+    v = rng.choice([-2e-17, -1e-17, 1e-17, 5e-17, 0.0, 0.25], 1 << 12); v[0] = 1.0; cases.append((v, 1e-15))
+    v = np.array([-1e-300, 1e-300, 1.0, 5e-301] + [0.0] * 60); cases.append((v, 1e-15))
+    v = rng.normal(0, 1, 5000); v[0] += abs(v.sum()) + 1; cases.append((v, 1e-11))
+    v = rng.random(1 << 18); v /= v.sum(); v[rng.choice(v.size, 3000, replace=False)] -= 8e-6; cases.append((v, 1e-13))
+    for v, tol in cases:
+        want = od.nearest_probability_distribution(v)
+        got, st = _npd_async(dev, v, 0.0, shards)
+        assert int(st[5]) == _lib.NPD_ST_SOLVED
+        assert np.abs(got - want).max() < tol
+        assert got.min() >= 0.0
+        # bit-reproducible: integer bins and fixed-order sums
+        again, _ = _npd_async(dev, v, 0.0, shards)
+        assert np.array_equal(got, again)
+    got, st = _npd_async(dev, np.array([0.25, 0.75, 0.0, 0.0]), 0.0, shards)
+    assert int(st[5]) == _lib.NPD_ST_IDENTITY and np.array_equal(got, [0.25, 0.75, 0.0, 0.0])
+    _, st = _npd_async(dev, np.array([-1.0, 0.5, 0.0, 0.0]), 0.0, shards)
+    assert int(st[5]) == _lib.NPD_ST_NEGATIVE_TOTAL
 
 
 def test_hellinger_identities_and_random(dev):
@@ -785,3 +941,71 @@ def test_random_cut_circuits_on_device(dev, seed):
     want5 = _dense(want5_d, n)
     got5 = res5.values.cpu().numpy()
     assert all(_near_threshold(got5[i], want5[i], 1e-5) for i in range(1 << n)), seed
+
+
+# ------------------------------------------------------------------ the metric config itself
+def test_syc32d1_full(dev):
+    """BASELINE.json's metric config (syc-32 d1, -p 2 -q 50: fragments of 18 and 14 qubits, no virtual gate,
+    a 2^32-entry result) through the public entry point: fragment tables against the oracle, the knitted
+    result against the oracle's outer product of ITS OWN tables on windows at the start, in the middle and at
+    the end of the output (bit-exact: one IEEE product per entry), and the whole-vector statistics."""
+    from oracle import tables as otab
+    free, _ = torch.cuda.mem_get_info(dev)
+    if free < 40 << 30:
+        pytest.skip("needs 32 GiB for the dense 2^32 result")
+    circ, cut = cutting.make_baseline("syc32d1", seed=0)
+    virt = vcm.VirtualCircuit(cut)
+    res, info = runm.run_virtual_circuit_dense(virt, device=dev)
+    assert res.values.numel() == 1 << 32 and res.key_mask == (1 << 32) - 1 and res.y_begin == 0
+    o_tabs, o_masks = otab.all_tables_k0(cut)
+    masks, union = virt.output_masks()
+    tabs = virt.simulate_fragments(dev)
+    by_mask = {masks[f]: tabs[f][0].cpu().numpy() for f in tabs}
+    assert sorted(by_mask) == sorted(o_masks)                   # index maps: bit-exact
+    for t, m in zip(o_tabs, o_masks):
+        assert np.abs(by_mask[m] - t).max() < TOL_P
+    win = 1 << 20
+    for y0 in (0, (1 << 31) - win // 2, (1 << 32) - win, 0x5A5A5A5A00000 >> 20 << 20):
+        y0 = int(y0) % ((1 << 32) - win + 1)
+        want, _, _ = cport.knit_outer(o_tabs, o_masks, y0, y0 + win)
+        got = res.values[y0:y0 + win].cpu().numpy()
+        assert np.abs(got - want).max() < TOL_P
+        # the device's own tables multiplied on the host: the knit itself is bit-exact
+        own, _, _ = cport.knit_outer([by_mask[m] for m in o_masks], o_masks, y0, y0 + win)
+        assert np.array_equal(got, own)
+    assert abs(res.total - 1.0) < 1e-9 and res.minimum >= 0.0
+    # sum of the whole vector in 2^28-entry pieces (no 32 GiB temporary) == reported total
+    tot = sum(float(res.values[a:a + (1 << 28)].sum()) for a in range(0, 1 << 32, 1 << 28))
+    assert abs(tot - res.total) < 1e-9
+    del res
+    torch.cuda.empty_cache()
+
+
+def test_mid_circuit_measurement_end_to_end(dev):
+    """A mid-circuit measurement of the INPUT circuit adds a row bit (its outcome lives on an ancilla):
+    run_virtual_circuit must return the distribution over every written clbit - uncut, and with a gate cut
+    next to it - equal to the oracle's."""
+    qc = circuit.QuantumCircuit(circuit.QuantumRegister(2, "q"), circuit.ClassicalRegister(3, "c"))
+    qc.h(0); qc.measure(0, 2); qc.h(0); qc.cx(0, 1); qc.ry(0.3, 1); qc.measure(0, 0); qc.measure(1, 1)
+    res, _ = runm.run_virtual_circuit(vcm.VirtualCircuit(qc))
+    want = sv.exact_distribution(qc)
+    assert abs(sum(res.values()) - 1.0) < 1e-12
+    assert max(abs(res.get(k, 0.0) - want.get(k, 0.0)) for k in set(res) | set(want)) < TOL_P
+    # 4 qubits, mid-circuit measurement in the first fragment, cx(1, 2) cut
+    q4 = circuit.QuantumCircuit(circuit.QuantumRegister(4, "q"), circuit.ClassicalRegister(5, "c"))
+    for q in range(4):
+        q4.ry(0.3 + 0.2 * q, q)
+    q4.cx(0, 1); q4.measure(0, 4); q4.h(0); q4.cx(2, 3); q4.cx(1, 2); q4.rx(0.4, 1); q4.cx(0, 1); q4.ry(0.2, 2)
+    for q in range(4):
+        q4.measure(q, q)
+    gidx = [i for i, ins in enumerate(q4.data) if ins.operation.name == "cx"][2]
+    cut = cutting.apply_cuts(q4, cutting.CutSpec(gate_cuts=[gidx]))
+    virt = vcm.VirtualCircuit(cut)
+    assert len(virt.vgates) == 1
+    dense_res, _ = runm.run_virtual_circuit_dense(virt, device=dev, nearest=False)
+    assert dense_res.key_mask == 0b11111
+    want = sv.dense(sv.exact_distribution(q4), 5)
+    assert np.abs(dense_res.values.cpu().numpy() - want).max() < TOL_P
+    ref, _ = oracle_knit(cut, 0.0)
+    got = dense_res.to_dict()
+    assert max(abs(got.get(k, 0.0) - ref.get(k, 0.0)) for k in set(got) | set(ref)) < TOL_P
