@@ -1,27 +1,29 @@
 #!/usr/bin/env python
 """bench.py - BASELINE.json metric: syc-32 d1 fragment simulation + knit wall time.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload syc32d1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload syc32d1|all|NAME[:solver]]
+                    [--accuracy 1e-5] [--impl ours|reference]
 
-One "step" = one pass of the hot path over the workload: simulate every fragment
-instance, knit the fragment tables into the dense full-circuit distribution and
-reduce its (sum, min).  Default workload = ``syc32d1`` (``benchmark.py -p 2 -q 50
-syc 32 1``, seeded): 18- and 14-qubit fragments, no virtual gates, a 2^32-entry
-(32 GiB) float64 result - it fits one B200.  Under torchrun (N > 1) the output
-index is sharded by its top bits (total work fixed -> "strong" scaling); the
-16-qubit configs shard the label range instead and all-reduce the result.
+One "step" = one pass of the hot path (third_party/qvm/qvm/run.py:23-71) over the workload: simulate every
+fragment instance, knit the fragment tables into the dense full-circuit distribution, take its statistics
+and apply nearest_probability_distribution.  Default workload = ``syc32d1`` (``benchmark.py -p 2 -q 50 syc
+32 1``, seeded): 18- and 14-qubit fragments, no virtual gate, a 2^32-entry (32 GiB) float64 result - it fits
+one B200.  Under torchrun (N > 1) the output index is sharded by its top bits (total work fixed -> "strong"
+scaling); configs with virtual gates shard the label range and all-reduce the result when that pays, else
+every rank runs the whole (sub-millisecond) job.
 
-JSON line (rank 0): ``value`` = seconds per step with programs resident in HBM
-(CUDA events, max over ranks); ``e2e`` = the same through the public API
-``run_virtual_circuit_dense`` on a fresh ``VirtualCircuit`` each step (host
-compile, pinned H2D of programs, kernels, D2H of the statistics);
-``roofline`` = the knit kernel's algorithmic bytes / its own CUDA-event time
-against the measured HBM copy peak (MEASURED_PEAKS.json); ``cpu_baseline`` = the
-oracle port (C + OpenMP, all host cores) on a bounded sample, extrapolated.
+JSON line (rank 0): ``value`` = seconds per step with the programs resident in HBM (CUDA events, max over
+ranks); ``e2e`` = the same through the public API ``run_virtual_circuit_dense`` on a fresh ``VirtualCircuit``
+each step (host compile, pinned H2D of the programs, kernels, D2H of the statistics); ``roofline`` = the
+dominant kernel family's algorithmic bytes (flops) / its own CUDA-event time against the measured peak
+(MEASURED_PEAKS.json for HBM; the FP64 / shared-memory peaks are measured here with qck_measure_peaks);
+``cpu_baseline`` = the oracle port on the host cores; ``oracle`` = this run's GPU results against the
+oracle, checked on EVERY rank and max-reduced.  ``other_workloads`` holds the same figures, compact, for
+the other BASELINE circuits (bv / hwe / syc-16 / qft / aqft / add), measured in the same process.
 
-``--impl reference`` times that CPU path alone (the reference's own CPU
-implementation - qiskit-aer + multiprocessing - cannot be installed in this
-image) and prints the same line with ``"impl": "reference"``.
+``--impl reference`` times the CPU path alone (the reference's own CPU implementation - qiskit-aer +
+multiprocessing - cannot be installed in this image) and prints the same line with
+``"impl": "reference"``.
 """
 from __future__ import annotations
 
@@ -29,7 +31,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import time
 
@@ -38,6 +39,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "syc-32 d1 sim+knit wall time (s) at 1/2/4/8 B200; HBM GB/s; fidelity delta vs ref"
 PKG = "hardwareawareoptimalquantumcircuitcuttingandknitting_b200"
+OTHER_WORKLOADS = ("bv16", "hwe16d5", "syc16d5", "qft16", "aqft16", "add6")
 
 
 def parse_args():
@@ -48,11 +50,17 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="syc32d1",
                     help="a BASELINE config (cutting.BASELINE_CONFIGS); 'NAME:solver' cuts it with the z3 cutter "
-                         "instead of applying the recorded cut shape (e.g. aqft16:solver: five wire cuts)")
+                         "instead of applying the recorded cut shape (e.g. aqft16:solver: five wire cuts); "
+                         "'all' = syc32d1 as the line plus every other circuit under other_workloads, each with "
+                         "its own CPU baseline")
+    ap.add_argument("--accuracy", type=float, default=0.0,
+                    help="quasi_distr.ACCURACY of the run: 0 = exact closed-form knit (default), 1e-5 = the "
+                         "reference's pruning after every operation (qck_knit_faithful)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-sample-bits", type=int, default=None,
-                    help="log2 of the output entries the CPU baseline knits per step")
+                    help="log2 of the output entries the CPU baseline knits per sampled step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the compact other_workloads section")
     ap.add_argument("--uncut-statevector", action="store_true", default=None,
                     help="also simulate the UNCUT circuit as one statevector on this GPU (64 GiB at 32 qubits), "
                          "report the streaming simulator against the HBM roofline and the dense fidelity "
@@ -63,8 +71,10 @@ def parse_args():
     return ap.parse_args()
 
 
-def metric_name(workload: str) -> str:
-    return METRIC if workload == "syc32d1" else f"{workload} sim+knit wall time (s)"
+def metric_name(workload: str, accuracy: float = 0.0) -> str:
+    if workload == "syc32d1" and accuracy == 0.0:
+        return METRIC
+    return f"{workload} sim+knit wall time (s)" + (f" at ACCURACY={accuracy:g}" if accuracy else "")
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -138,99 +148,89 @@ class ClockSampler:
                 "source": "NVML polling thread"}
 
 
+
 # ----------------------------------------------------------------------------- CPU baseline (oracle port)
-def _fragment_out_mask(ov, frag) -> int:
-    """clbits the fragment's own (final) measurements write (bit i = clbit i)."""
-    cidx = {c: i for i, c in enumerate(ov.circuit.clbits)}
-    mask = 0
-    for op in ov.frag_ops[frag]:
-        if op.operation is not None and getattr(op.operation, "name", "") == "measure":
-            mask |= 1 << cidx[op.clbits[0]]
-    return mask
+def _sim_instance(job):
+    """Pool worker: exact folded row of one fragment instance with the numpy oracle."""
+    from oracle import dense as od, statevector as sv
+    inst, n_cl, K, mask = job
+    return od.signed_fold(sv.exact_distribution(inst), n_cl, K, mask)
 
 
-def cpu_fragment_table_k0(ov, frag):
-    """Exact table of a fragment without virtual gates: C oracle statevector, |amp|^2 compacted
-    to the measured clbits in ascending order.  -> (table, clbit mask)"""
-    import numpy as np
-    from oracle import cport
-    inst = ov.instance(frag, ())
-    qidx = {q: i for i, q in enumerate(inst.qubits)}
-    cidx = {c: i for i, c in enumerate(inst.clbits)}
-    last = {}
-    for i, d in enumerate(inst.data):
-        for q in d.qubits:
-            last[q] = i
-    pairs = []
-    for i, d in enumerate(inst.data):
-        if getattr(d.operation, "name", "") == "measure":
-            assert last[d.qubits[0]] == i, "C-oracle fast path needs terminal measurements"
-            pairs.append((cidx[d.clbits[0]], qidx[d.qubits[0]]))
-    pairs.sort()
-    mask = 0
-    for c, _ in pairs:
-        mask |= 1 << c
-    prob = cport.simulate_probabilities(inst)
-    if [q for _, q in pairs] == list(range(len(inst.qubits))):
-        return prob, mask
-    idx = np.arange(1 << len(inst.qubits), dtype=np.uint64)
-    comp = np.zeros_like(idx)
-    for j, (_, q) in enumerate(pairs):
-        comp |= ((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(j)
-    return np.bincount(comp.astype(np.int64), weights=prob, minlength=1 << len(pairs)), mask
+def cpu_reference_step(workload: str, seed: int, sample_bits: int | None, full_pass: bool = False,
+                       window: int = 0, sim_budget_s: float = 6.0, ctx: dict | None = None):
+    """One bounded CPU step of the workload with the oracle port on every host core.  Returns
+    (seconds for the whole job, description of the sample, cores, details).
 
-
-def cpu_reference_step(workload: str, seed: int, sample_bits: int | None):
-    """One bounded CPU step of the workload with the oracle port.  Returns
-    (extrapolated seconds for the whole job, description of the sample, cores)."""
+    No virtual gate (syc-32): full fragment simulation (C statevector) + the outer-product knit of a 2^sb
+    window (window number ``window``: successive steps sample different parts of the output) scaled to the
+    2^n_out entries - or, with ``full_pass``, ALL windows one after the other: measured, not scaled.
+    Virtual gates: as many fragment instances as fit ``sim_budget_s`` of wall time on a process pool (numpy
+    exact-branching simulator), scaled to all of them, + the full dense contraction (C/OpenMP)."""
     import numpy as np
     from math import cos, sin
     from importlib import import_module
-    from oracle import cport, dense as od, instantiate as oi, qpd_tables as qt, statevector as sv
+    from oracle import cport, instantiate as oi, qpd_tables as qt, tables as otab
     cutting = import_module(f"{PKG}.cutting")
-    cores = cport.num_threads()
-    circ, cut = cutting.make_baseline(workload, seed)
-    ov = oi.OracleVirtualCircuit(cut)
+    cores = cport.set_num_threads()
+    ctx = ctx if ctx is not None else {}
+    if "cut" not in ctx:
+        ctx["circ"], ctx["cut"] = cutting.make_baseline(workload, seed)
+        ctx["ov"] = oi.OracleVirtualCircuit(ctx["cut"])
+    cut, ov = ctx["cut"], ctx["ov"]
     frags = [f for f in ov.fragments if any(ov.has_measurement(f, l) for l in ov.instance_labels(f))]
     K = len(ov.vgates)
     n_cl = ov.n_clbits
     t0 = time.perf_counter()
     if K == 0:
-        pairs = [cpu_fragment_table_k0(ov, f) for f in frags]
+        pairs = [otab.fragment_table_k0(ov, f) for f in frags]
         tabs, masks = [p[0] for p in pairs], [p[1] for p in pairs]
         t_sim = time.perf_counter() - t0
         n_out = bin(sum(masks)).count("1")
         sb = min(n_out, sample_bits if sample_bits is not None else 26)
+        n_win = 1 << (n_out - sb)
+        buf = ctx.get("buf")
+        if buf is None or len(buf) != (1 << sb):
+            buf = ctx["buf"] = np.empty(1 << sb)
+        wins = range(n_win) if full_pass else [window % n_win]
         t1 = time.perf_counter()
-        cport.knit_outer(tabs, masks, 0, 1 << sb, want_output=True)
+        for w in wins:
+            cport.knit_outer(tabs, masks, w << sb, (w + 1) << sb, out=buf)
         t_knit = time.perf_counter() - t1
-        scale = float(1 << (n_out - sb))
-        total = t_sim + t_knit * scale
-        sample = (f"full simulation of {len(frags)} fragments ({t_sim:.3f} s) + outer-product knit of the first "
-                  f"2^{sb} of 2^{n_out} output entries ({t_knit:.3f} s), knit time scaled x{scale:.0f}")
-        return total, sample, cores
-    # virtual gates: a time-bounded number of instances per fragment, then the full contraction
+        if full_pass:
+            total = t_sim + t_knit
+            sample = (f"MEASURED, not scaled: full simulation of {len(frags)} fragments ({t_sim:.3f} s) + outer-product "
+                      f"knit of all 2^{n_out} output entries in {n_win} windows of 2^{sb} ({t_knit:.2f} s)")
+        else:
+            total = t_sim + t_knit * n_win
+            sample = (f"full simulation of {len(frags)} fragments ({t_sim:.3f} s) + outer-product knit of window "
+                      f"{window % n_win} of {n_win} (2^{sb} of 2^{n_out} output entries, {t_knit:.3f} s), knit "
+                      f"time scaled x{n_win}")
+        return total, sample, cores, {"sim_s": t_sim, "knit_s": t_knit * (1 if full_pass else n_win)}
+    # virtual gates: a time-bounded number of instances per fragment on a process pool, then the full contraction
+    import multiprocessing as mp
     folded, masks, touches = [], [], []
     t_sim, n_done, n_total = 0.0, 0, 0
-    budget_s = 6.0
+    pool = ctx.get("pool")
+    if pool is None:
+        pool = ctx["pool"] = mp.get_context("fork").Pool(cores)
     for frag in frags:
         labels = ov.instance_labels(frag)
         n_total += len(labels)
-        mask = _fragment_out_mask(ov, frag)
+        mask = otab.fragment_out_mask(ov, frag)
         full = np.zeros((len(labels), 1 << bin(mask).count("1")))
-        spent = 0.0
-        for i, lab in enumerate(labels):
-            if spent > budget_s:
-                break
-            ts = time.perf_counter()
-            full[i] = od.signed_fold(sv.exact_distribution(ov.instance(frag, lab)), n_cl, K, mask)
-            spent += time.perf_counter() - ts
-            n_done += 1
-        t_sim += spent
+        ts = time.perf_counter()
+        done, chunk = 0, 4 * cores
+        while done < len(labels) and time.perf_counter() - ts < sim_budget_s / len(frags):
+            jobs = [(ov.instance(frag, lab), n_cl, K, mask) for lab in labels[done:done + chunk]]
+            rows = pool.map(_sim_instance, jobs)
+            full[done:done + len(rows)] = rows
+            done += len(rows)
+        t_sim += (time.perf_counter() - ts) * (len(labels) / max(done, 1))
+        n_done += done
         folded.append(full)
         masks.append(mask)
         touches.append(ov.touches(frag))
-    sim_scale = n_total / max(n_done, 1)
     radices = ov.radices
     coeffs = []
     for (kind, theta, _), r in zip(ov.vgates, radices):
@@ -257,33 +257,48 @@ def cpu_reference_step(workload: str, seed: int, sample_bits: int | None):
     t1 = time.perf_counter()
     cport.knit_contract(folded, masks, n_out, w, np.stack(rows_idx))
     t_knit = time.perf_counter() - t1
-    total = t_sim * sim_scale + t_knit
-    sample = (f"{n_done} of {n_total} fragment instances simulated (numpy oracle, {t_sim:.2f} s, scaled "
-              f"x{sim_scale:.1f}) + full dense contraction over {L} labels (C oracle, {t_knit:.2f} s)")
-    return total, sample, cores
+    total = t_sim + t_knit
+    sample = (f"{n_done} of {n_total} fragment instances simulated on a pool of {cores} processes (numpy oracle; "
+              f"time scaled x{n_total / max(n_done, 1):.1f} -> {t_sim:.2f} s) + full dense contraction over {L} labels "
+              f"(C oracle, {cores} OpenMP threads, {t_knit:.2f} s)")
+    return total, sample, cores, {"sim_s": t_sim, "knit_s": t_knit}
 
 
 def reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    times, sample, cores = [], "", 1
+    workload = "syc32d1" if args.workload == "all" else args.workload
+    times, sample, cores, ctx = [], "", 1, {}
+    extra = {}
+    from oracle import cport
+    cores = cport.set_num_threads()          # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
+    # one FULL pass first (every output window, nothing scaled) when it fits the budget; the K timed steps are
+    # bounded samples - a different window each - so that the run ends within minutes
+    t_probe, _, _, _ = cpu_reference_step(workload, args.seed, args.cpu_sample_bits, ctx=ctx)
+    if t_probe < 90.0 and not ctx["ov"].vgates:
+        t_full, s_full, _, det = cpu_reference_step(workload, args.seed, args.cpu_sample_bits, full_pass=True, ctx=ctx)
+        extra["full_pass"] = {"value": t_full, "unit": "s", "sample": s_full, **det}
     for i in range(args.warmup + args.steps):
-        t, sample, cores = cpu_reference_step(args.workload, args.seed, args.cpu_sample_bits)
+        t, sample, cores, _ = cpu_reference_step(workload, args.seed, args.cpu_sample_bits, window=7 * i + 1, ctx=ctx)
         if i >= args.warmup:
             times.append(t)
         if sum(times) > 240:
             break
+    if ctx.get("pool") is not None:
+        ctx["pool"].close()
     val = statistics.mean(times)
+    if "full_pass" in extra:
+        extra["full_pass"]["sampled_over_full"] = val / extra["full_pass"]["value"]
     line = {
-        "impl": "reference", "metric": metric_name(args.workload), "value": val, "unit": "s",
+        "impl": "reference", "metric": metric_name(workload), "value": val, "unit": "s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": val * 1e3,
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": args.workload, "seed": args.seed},
-        "cpu_baseline": {"value": val, "unit": "s", "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": {"workload": workload, "seed": args.seed},
+        "cpu_baseline": {"value": val, "unit": "s", "cores": cores, "kind": "port", "sample": sample, **extra},
         "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference CPU path (qiskit-aer + multiprocessing) is not installable here; this is the "
-                "oracle port (C/OpenMP + numpy) on all host cores",
+                "oracle port (C/OpenMP + numpy on a process pool) on all host cores",
     }
     emit(line)
 
@@ -308,220 +323,449 @@ def emit(line: dict) -> None:
     out.flush()
 
 
-def main() -> None:
-    args = parse_args()
-    _quiet_stdout()
-    if args.impl == "reference":
-        reference_arm(args)
-        return
+def load_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def sim_work(virt, frags, device, fold: bool = True) -> dict:
+    """Work of the fragment simulation.  ``flops_algorithmic`` follows SURVEY.md 8(d): every instance the
+    reference enumerates (virtual_circuit.py:39-48) x every gate of its fragment circuit, 14 flop per
+    amplitude for a one-qubit gate on complex128 (28 per amplitude pair), 30 for a general two-qubit gate,
+    0 for cx / cz, on 2^n_f amplitudes.  ``flops_executed`` / ``smem_bytes_executed`` count what the compiled
+    programs really do (fused gates, ancilla-enlarged states, live-amplitude limits, identical instances
+    simulated once): one shared-memory read + write of the live state per pass."""
+    from importlib import import_module
+    import numpy as np
+    lib = import_module(f"{PKG}._lib")
+    vgm = import_module(f"{PKG}.virtual_gates")
+    circm = import_module(f"{PKG}.circuit")
+    alg = 0.0
+    execd, smem, runs, inst_total, passes = 0.0, 0.0, 0, 0, 0
+    for f in frags:
+        prog = virt.program(f)
+        nq = prog.n_qubits
+        per_inst = 0.0
+        for ins in virt.fragment_circuits[f].data:
+            op = ins.operation
+            if isinstance(op, vgm.VirtualGateEndpoint):
+                per_inst += 14.0 * (1 << nq)
+            elif isinstance(op, circm.Gate) and not isinstance(op, circm.Barrier):
+                if op.num_qubits == 1:
+                    per_inst += 14.0 * (1 << nq)
+                elif op.num_qubits == 2 and not (op._matrix is None and op.name in ("cx", "cz")):
+                    per_inst += 30.0 * (1 << nq)
+        alg += per_inst * prog.num_labels
+        inst_total += prog.num_labels
+        canon = prog.canonical_labels()
+        dedupe = virt.executor(f, device, fold)._dedupe is not None
+        for plan in prog.plans(fold):
+            n_inst = int((canon[plan.labels] == plan.labels).sum()) if dedupe else len(plan.labels)
+            runs += n_inst
+            fl, sm, np_ = 0.0, 0.0, 0
+            in_cluster = 0
+            for row in plan.ops.tolist():
+                kind, nl = row[0], row[6]
+                amps = float(1 << (nl if 0 < nl <= plan.n_state else plan.n_state))
+                if kind == lib.OP_CLUSTER:
+                    in_cluster = row[1]
+                    sm += 32.0 * amps
+                    np_ += 1
+                    continue
+                if kind == lib.OP_U1:
+                    m = prog._mat_by_off.get(row[3])
+                    diag = m is not None and m.shape == (2, 2) and m[0, 1] == 0 and m[1, 0] == 0
+                    fl += (6.0 if diag else 14.0) * amps
+                elif kind == lib.OP_U2:
+                    fl += 30.0 * amps
+                elif kind in (lib.OP_U1X,):
+                    fl += 14.0 * amps
+                if in_cluster > 0:
+                    in_cluster -= 1
+                elif kind not in (lib.OP_TERM, lib.OP_PHASE):
+                    sm += 32.0 * amps
+                    np_ += 1
+            fl += 4.0 * (1 << plan.n_state)                      # |amp|^2 and the signed fold
+            execd += fl * n_inst
+            smem += sm * n_inst
+            passes += np_ * n_inst
+    return {"flops_algorithmic": alg, "flops_executed": execd, "smem_bytes_executed": smem,
+            "instances": inst_total, "instances_simulated": runs, "passes_executed": passes}
+
+
+def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0, cpu: bool = False) -> dict:
+    """Everything bench.py reports for one workload (one JSON object)."""
     import numpy as np
     import torch
-    from importlib import import_module
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
-    qdist = import_module(f"{PKG}.dist")
-    cutting = import_module(f"{PKG}.cutting")
-    vc = import_module(f"{PKG}.virtual_circuit")
-    runm = import_module(f"{PKG}.run")
-    fid = import_module(f"{PKG}.fidelity")
-    lib = import_module(f"{PKG}._lib")
     import torch.distributed as dist
+    qdist, cutting, vc, runm, fid, lib = (env[k] for k in ("qdist", "cutting", "vc", "runm", "fid", "lib"))
+    rank, world, device, handle = env["rank"], env["world"], env["device"], env["handle"]
+    steps, warmup = (args.steps, max(args.warmup, 3)) if primary else (min(args.steps, 10), 3)
+    stream = torch.cuda.current_stream(device).cuda_stream
 
-    rank, local_rank, world = qdist.init_from_env("nccl")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    handle = lib.get_handle(local_rank)
-
-    circ, cut = cutting.make_baseline(args.workload, args.seed)
+    name, _, how = workload.partition(":")
+    circ, cut = cutting.make_baseline(name, args.seed, cut=how or "table")
     virt = vc.VirtualCircuit(cut)
     K = len(virt.vgates)
     masks, union = virt.output_masks()
     n_out = bin(union).count("1")
     frags = virt.active_fragments()
     L = virt.num_global_labels()
+    faithful = accuracy > 0.0
 
+    # partition over the ranks
+    mode = "single"
+    if world > 1:
+        mode = "output index by top bits" if K == 0 else qdist.partition_mode(virt, world, faithful)
     if K == 0:
         y0, y1 = qdist.shard_pow2(n_out, rank, world) if world > 1 else (0, 1 << n_out)
         label_range = None
-        out = torch.empty(y1 - y0, dtype=torch.float64, device=device)
     else:
         y0, y1 = 0, 1 << n_out
-        label_range = qdist.shard_range(L, rank, world, align=virt.global_radices()[-1]) if world > 1 else None
-        out = torch.empty(1 << n_out, dtype=torch.float64, device=device)
+        label_range = (qdist.shard_range(L, rank, world, align=virt.global_radices()[-1])
+                       if mode == "label range + all-reduce" else None)
+    out = torch.empty(y1 - y0, dtype=torch.float64, device=device)
     stats = torch.zeros(4, dtype=torch.float64, device=device)
-    # programs resident in HBM before the timed region
-    for f in frags:
-        virt.executor(f, device, True).upload()
-    tables_holder = {}
-    knit_events = []
+    ws = handle.npd_workspace(torch, device)
+    for f in frags:                                  # programs resident in HBM before the timed region
+        virt.executor(f, device, not faithful).upload()
+    holder, ev_log = {}, []
 
     def step_resident(record: bool) -> None:
-        tables = virt.simulate_fragments(device, label_range=label_range)
-        tables_holder["t"] = tables
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
         if record:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        if K == 0:
+            ev[0].record()
+        tables = virt.simulate_fragments(device, label_range=label_range, fold=not faithful)
+        holder["t"] = tables
+        if record:
+            ev[1].record()
+        if faithful:
+            virt.knit_tables_faithful(tables, accuracy, device, out=out)
+        elif K == 0:
             virt.knit_tables(tables, device, stats=stats, y_range=(y0, y1) if world > 1 else None, out=out)
         else:
-            virt.knit_tables(tables, device, label_range=label_range, out=out,
-                             stats=None if world > 1 else stats)
+            virt.knit_tables(tables, device, label_range=label_range, out=out)
         if record:
-            e1.record()
-            knit_events.append((e0, e1))
-        if world > 1:
-            if K == 0:
-                qdist.allreduce_stats(stats)
-            else:
+            ev[2].record()
+        if K == 0:
+            if world > 1:
+                qdist.allreduce_stats(stats)         # min >= 0 by construction: no npd pass over 2^32 entries
+        else:
+            if label_range is not None:
                 qdist.allreduce_sum_(out)
+            # statistics + nearest_probability_distribution (run.py:71), enqueued: no host round trip
+            handle.check(handle.lib.qck_npd_async(handle.ptr, out.data_ptr(), out.numel(), accuracy,
+                                                  ws.data_ptr(), stream))
+        if record:
+            ev[3].record()
+            ev_log.append(ev)
 
     def barrier() -> None:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    for _ in range(max(args.warmup, 3)):
+    def reduce_max(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(warmup):
         step_resident(False)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(env["local_rank"]) if (rank == 0 and primary) else None
     time.sleep(0.15 if sampler else 0.0)
     barrier()
     launches0 = handle.launch_count
     t_wall0 = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
         step_resident(True)
-    ev1.record()
+    e1.record()
     barrier()
     t_wall1 = time.time()
     launches = handle.launch_count - launches0
-    elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
-    knit_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in knit_events) / len(knit_events)],
-                           dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(knit_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(elapsed_ms.item()) / args.steps
-    knit_ms = float(knit_ms.item())
-    host_stats = stats.cpu().numpy().copy()
-    if K > 0 and world > 1:
-        handle.check(handle.lib.qck_stats_dense(handle.ptr, out.data_ptr(), out.numel(), 0.0, stats.data_ptr(),
-                                                torch.cuda.current_stream(device).cuda_stream))
+    ms_per_step = reduce_max(e0.elapsed_time(e1)) / steps
+    sim_ms = reduce_max(sum(e[0].elapsed_time(e[1]) for e in ev_log) / len(ev_log))
+    knit_ms = reduce_max(sum(e[1].elapsed_time(e[2]) for e in ev_log) / len(ev_log))
+    post_ms = reduce_max(sum(e[2].elapsed_time(e[3]) for e in ev_log) / len(ev_log))
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if K == 0:
         host_stats = stats.cpu().numpy().copy()
+        r_sum, r_min = float(host_stats[0]), float(host_stats[1])
+    else:
+        st = runm._check_npd_state(ws)
+        r_sum, r_min = float(st[0]), float(st[1])
+    result_after = out.clone() if out.numel() <= (1 << 26) else out       # e2e reuses `out`
 
     # ---- e2e: public API, fresh VirtualCircuit per step (host compile + H2D + kernels + D2H)
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    e2e_s, e2e_warm_s, h2d = None, None, 0
+    e2e = None
     if not args.profile:
-        e2e_virts = [vc.VirtualCircuit(cut) for _ in range(args.steps + 1)]
-        runm.run_virtual_circuit_dense(e2e_virts[0], device=device, rank=rank, world_size=world, out=out,
-                                       nearest=False)
+        def call(v):
+            return runm.run_virtual_circuit_dense(v, device=device, rank=rank, world_size=world, out=out,
+                                                  nearest=True, accuracy=accuracy)
+        cold = [vc.VirtualCircuit(cut) for _ in range(steps + 1)]
+        call(cold[0])
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        for v in e2e_virts[1:]:
-            vc.clear_program_cache()            # e2e is the COLD path: every step compiles its programs
-            runm.run_virtual_circuit_dense(v, device=device, rank=rank, world_size=world, out=out, nearest=False)
+        for v in cold[1:]:
+            vc.clear_program_cache()                 # the COLD path: every step compiles its programs
+            call(v)
         g1.record()
         barrier()
-        # same call with the process-wide program cache warm (what a second run of the same cut
-        # circuit costs, e.g. the reference's ideal + noisy pair)
-        warm_virts = [vc.VirtualCircuit(cut) for _ in range(args.steps)]
+        warm = [vc.VirtualCircuit(cut) for _ in range(steps)]
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0.record()
-        for v in warm_virts:
-            runm.run_virtual_circuit_dense(v, device=device, rank=rank, world_size=world, out=out, nearest=False)
+        for v in warm:                               # process-wide program cache warm (a second run of the
+            call(v)                                  # same cut circuit, e.g. the reference's ideal + noisy pair)
         w1.record()
         barrier()
-        warm_ms = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(warm_ms, op=dist.ReduceOp.MAX)
-        e2e_warm_s = float(warm_ms.item()) / args.steps / 1e3
-        for f in e2e_virts[1].active_fragments():
-            h2d += e2e_virts[1].executor(f, device, True).h2d_bytes
-        e2e_ms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        e2e_s = float(e2e_ms.item()) / args.steps / 1e3
+        h2d = sum(cold[1].executor(f, device, not faithful).h2d_bytes for f in cold[1].active_fragments())
+        e2e = {"value": reduce_max(g0.elapsed_time(g1)) / steps / 1e3, "unit": "s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 32 if K == 0 else 8 * lib.NPD_STATE_SLOTS,
+               "program_cache": "cold (cleared every step)",
+               "value_program_cache_warm": reduce_max(w0.elapsed_time(w1)) / steps / 1e3,
+               "api": "run_virtual_circuit_dense(VirtualCircuit(cut), nearest=True)"}
 
-    # ---- fidelity against the uncut circuit and parity against the oracle (outside the timed region)
+    # ---- this run's GPU results against the ORACLE, on every rank (max-reduced); fidelity vs the uncut circuit
     extra = {}
-    if rank == 0 and not args.profile:
-        extra = gpu_fidelity_report(virt, circ, tables_holder["t"], out, device, fid, vc, handle, K, n_out, world)
-
+    if not args.profile:
+        rep = oracle_parity(virt, circ, cut, holder["t"], result_after, y0, y1, K, n_out, faithful)
+        oracle = {k: reduce_max(v) for k, v in sorted(rep.items()) if isinstance(v, float)}
+        oracle["ranks_checked"] = world
+        oracle.update({k: v for k, v in rep.items() if not isinstance(v, float)})
+        extra["oracle"] = oracle
+        if rank == 0:
+            extra.update(gpu_fidelity_report(virt, circ, holder["t"], result_after, device, fid, vc, handle, K, n_out,
+                                             world, faithful))
+            if "fidelity_oracle" in rep and "fidelity_cut_vs_uncut" in extra:
+                extra["fidelity_delta_vs_oracle"] = abs(extra["fidelity_cut_vs_uncut"] - rep["fidelity_oracle"])
     if args.uncut_statevector is None:
         args.uncut_statevector = not args.profile
-    if rank == 0 and world == 1 and args.uncut_statevector:
-        extra.update(uncut_statevector_report(circ, out, device, fid, vc, handle, peaks_hbm()))
+    if rank == 0 and world == 1 and primary and name == "syc32d1" and args.uncut_statevector:
+        extra.update(uncut_statevector_report(circ, out, device, fid, vc, handle, env["hbm_peak"]))
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-        return
-    # ---- roofline of the dominant kernel
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    if K == 0:
-        table_bytes = sum(8 * (1 << bin(m).count("1")) for m in masks.values())
-        alg_bytes = 8 * (y1 - y0) + table_bytes
-        kernel = "knit_outer_kernel"
+    # ---- roofline of the dominant kernel family
+    peaks = env["peaks"]
+    share = {"simulation": sim_ms / ms_per_step, "knit": knit_ms / ms_per_step, "npd+collective": post_ms / ms_per_step}
+    work = sim_work(virt, frags, device, not faithful)
+    if K == 0 or knit_ms >= sim_ms:
+        if K == 0:
+            alg = 8 * (y1 - y0) + sum(8 * (1 << bin(m).count("1")) for m in masks.values())
+            kernel, bound, unit, peak, src = "knit_outer_kernel", "hbm", "GB/s", env["hbm_peak"], env["hbm_src"]
+            achieved = alg / (knit_ms * 1e-3) / 1e9
+            key = "algorithmic_bytes_per_launch"
+        else:
+            Ls = (label_range[1] - label_range[0]) if label_range is not None else L
+            alg = 2.0 * Ls * float(np.prod([t.shape[1] for t in holder["t"].values()]))
+            kernel = "qck_knit_faithful" if faithful else "contract_dmma_kernel+contract_scatter_kernel"
+            bound, unit, peak, src = "tensor", "TFLOP/s", peaks.get("dmma_tflops"), "qck_measure_peaks (FP64 DMMA m8n8k4, this run)"
+            achieved = alg / (knit_ms * 1e-3) / 1e12
+            key = "algorithmic_flops_per_step"
+        kernel_ms = knit_ms
     else:
-        alg_bytes = 8 * (1 << n_out) + sum(int(t.numel()) * 8 for t in tables_holder["t"].values())
-        kernel = "contract_gemm_kernel+contract_scatter_kernel"
-    achieved = alg_bytes / (knit_ms * 1e-3) / 1e9
+        alg = work["flops_algorithmic"] * ((label_range[1] - label_range[0]) / L if label_range is not None else 1.0)
+        kernel, bound, unit = "sim_onchip_*_kernel (all programs of all fragments)", "fp64", "TFLOP/s"
+        peak, src = peaks.get("fp64_fma_tflops"), "qck_measure_peaks (FP64 FMA issue rate, this run)"
+        achieved = alg / (sim_ms * 1e-3) / 1e12
+        kernel_ms, key = sim_ms, "algorithmic_flops_per_step"
     traffic = None
     try:        # per-launch DRAM bytes of the same kernel from the committed ncu --set full capture
         if world == 1:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload][kernel]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[name][kernel.split("+")[0]]
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": knit_ms,
-                "kernel_share_of_step": knit_ms / ms_per_step}
+    roofline = {"bound": bound, "kernel": kernel, "achieved": achieved, "peak": peak, "unit": unit,
+                "frac": (achieved / peak) if peak else None, "traffic": traffic, "peak_source": src,
+                key: alg, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
+                "share_of_step": share}
+    if K > 0:
+        roofline["simulation"] = {
+            "ms": sim_ms, "instances": work["instances"], "instances_simulated": work["instances_simulated"],
+            "instances_per_s": work["instances"] / (sim_ms * 1e-3),
+            "flops_algorithmic": work["flops_algorithmic"], "flops_executed": work["flops_executed"],
+            "executed_tflops": work["flops_executed"] / (sim_ms * 1e-3) / 1e12,
+            "frac_of_fp64_fma_peak_executed": (work["flops_executed"] / (sim_ms * 1e-3) / 1e12 / peaks["fp64_fma_tflops"])
+            if peaks.get("fp64_fma_tflops") else None,
+            "smem_tbs_executed": work["smem_bytes_executed"] / (sim_ms * 1e-3) / 1e12,
+            "frac_of_smem_peak_executed": (work["smem_bytes_executed"] / (sim_ms * 1e-3) / 1e12 / peaks["smem_ld_tbs"])
+            if peaks.get("smem_ld_tbs") else None,
+            "amplitude_passes_per_s": work["smem_bytes_executed"] / 32.0 / (sim_ms * 1e-3)}
 
-    # ---- CPU-baseline leg (rank 0, N = 1): the oracle port timed on the host cores, and the parity
-    #      of this run's GPU results against the oracle.  The only place oracle/ is touched.
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline and not args.profile:
+    cpu_rep = None
+    if cpu and rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile and not faithful:
         try:
-            val, sample, cores = cpu_reference_step(args.workload, args.seed, args.cpu_sample_bits)
-            cpu = {"value": val, "unit": "s", "cores": cores, "kind": "port", "sample": sample}
+            ctx = {}
+            val, sample, cores, det = cpu_reference_step(name, args.seed, args.cpu_sample_bits, ctx=ctx,
+                                                         sim_budget_s=6.0 if primary else 3.0)
+            if ctx.get("pool") is not None:
+                ctx["pool"].close()
+            cpu_rep = {"value": val, "unit": "s", "cores": cores, "kind": "port", "sample": sample, **det}
         except Exception as exc:  # the baseline must never take the bench line down
-            cpu = {"value": None, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
-        extra.update(oracle_parity_report(virt, circ, cut, tables_holder["t"], out, y0, y1, device, K, n_out,
-                                          extra.get("fidelity_cut_vs_uncut")))
+            cpu_rep = {"value": None, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
 
     line = {
-        "metric": metric_name(args.workload), "value": ms_per_step / 1e3, "unit": "s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "metric": metric_name(name if not how else workload, accuracy), "value": ms_per_step / 1e3, "unit": "s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": args.workload, "seed": args.seed, "n_out_bits": n_out,
+        "config": {"workload": workload, "seed": args.seed, "accuracy": accuracy, "n_out_bits": n_out,
                    "fragments": [len(f) for f in frags], "virtual_gates": K, "global_labels": L,
-                   "partition": ("output index by top bits" if K == 0 else "label range + all-reduce"),
+                   "partition": mode, "nearest_probability_distribution": "in the timed region" if K else
+                   "skipped by its own statistics (a product of probabilities has min >= 0)",
                    "l2": (f"every step rewrites the {8 * (y1 - y0) / 2**30:.2f} GiB result (>> 126 MB L2): "
                           "no flush needed" if 8 * (y1 - y0) > (1 << 28) else
                           "working set fits L2; small config, launch/latency bound")},
         "clocks": clocks,
-        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
-                "program_cache": "cold (cleared every step)", "value_program_cache_warm": e2e_warm_s},
+        "e2e": e2e,
         "gpu_launches": launches,
         "roofline": roofline,
-        "cpu_baseline": cpu,
-        "hbm_gbs": achieved,
-        "result_sum": float(host_stats[0]), "result_min": float(host_stats[1]),
+        "cpu_baseline": cpu_rep,
+        "result_sum": r_sum, "result_min": r_min,
     }
+    if K == 0:
+        line["hbm_gbs"] = roofline["achieved"]
     line.update(extra)
-    emit(line)
+    del out
+    return line
+
+
+def compact(line: dict) -> dict:
+    """The figures of a secondary workload that go under other_workloads."""
+    keep = ("value", "ms_per_step", "steps", "gpu_launches", "result_sum", "result_min", "oracle",
+            "fidelity_cut_vs_uncut", "fidelity_delta_vs_oracle", "max_abs_err_cut_vs_uncut_gpu", "cpu_baseline")
+    out = {k: line[k] for k in keep if k in line and line[k] is not None}
+    out["config"] = {k: line["config"][k] for k in ("fragments", "virtual_gates", "global_labels", "partition", "accuracy")}
+    if line.get("e2e"):
+        out["e2e"] = {k: line["e2e"][k] for k in ("value", "value_program_cache_warm", "h2d_bytes_per_step",
+                                                   "d2h_bytes_per_step")}
+    r = line["roofline"]
+    out["roofline"] = {k: r[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "kernel_ms",
+                                         "share_of_step") if k in r}
+    if "simulation" in r:
+        out["roofline"]["simulation"] = {k: r["simulation"][k] for k in (
+            "ms", "instances", "instances_simulated", "instances_per_s", "executed_tflops",
+            "frac_of_fp64_fma_peak_executed", "smem_tbs_executed", "frac_of_smem_peak_executed")}
+    return out
+
+
+def main() -> None:
+    args = parse_args()
+    _quiet_stdout()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+    from importlib import import_module
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
+    env = {k: import_module(f"{PKG}.{m}") for k, m in (("qdist", "dist"), ("cutting", "cutting"),
+                                                        ("vc", "virtual_circuit"), ("runm", "run"),
+                                                        ("fid", "fidelity"), ("lib", "_lib"))}
+    import ctypes as C
+    import torch.distributed as dist
+    rank, local_rank, world = env["qdist"].init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    handle = env["lib"].get_handle(local_rank)
+    mp = load_peaks()
+    env.update(rank=rank, local_rank=local_rank, world=world, device=device, handle=handle,
+               hbm_peak=float(mp.get("hbm_gbs", 6650.0)),
+               hbm_src="measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in mp else "fallback 6650 GB/s")
+    # FP64 / DMMA / shared-memory peaks of this device (SURVEY 8d: not in MEASURED_PEAKS.json), measured now
+    peaks = {}
+    if not args.profile:
+        buf = (C.c_double * 4)()
+        handle.check(handle.lib.qck_measure_peaks(handle.ptr, buf))
+        peaks = {"fp64_fma_tflops": buf[0], "dmma_tflops": buf[1], "smem_ld_tbs": buf[2], "sm_count": int(buf[3]),
+                 "how": "qck_measure_peaks (csrc/peaks.cu): DFMA chains, mma.sync.m8n8k4.f64 chains, LDS.128 streams; "
+                        "best of 3 after a warm-up, CUDA events"}
+    env["peaks"] = peaks
+
+    primary = "syc32d1" if args.workload == "all" else args.workload
+    line = measure(primary, args, env, primary=True, accuracy=args.accuracy, cpu=True)
+    line["measured_peaks"] = peaks or None
+    others = {}
+    if args.workload == "all" or (args.workload == "syc32d1" and not args.no_others and not args.profile
+                                  and args.accuracy == 0.0):
+        torch.cuda.empty_cache()
+        for w in OTHER_WORKLOADS:
+            try:
+                others[w] = compact(measure(w, args, env, primary=False, cpu=args.workload == "all"))
+            except Exception as exc:                  # a secondary workload must never take the line down
+                others[w] = {"error": repr(exc)}
+        for w in ("hwe16d5", "syc16d5"):              # the reference's default mode: ACCURACY = 1e-5 pruning
+            try:
+                others[f"{w}@1e-5"] = compact(measure(w, args, env, primary=False, accuracy=1e-5))
+            except Exception as exc:
+                others[f"{w}@1e-5"] = {"error": repr(exc)}
+    if rank == 0:
+        if others:
+            line["other_workloads"] = others
+        emit(line)
     if world > 1:
         dist.barrier()
+
+
+def oracle_parity(virt, circ, cut, tables, out, y0, y1, K, n_out, faithful) -> dict:
+    """This rank's GPU results against the oracle, on what the oracle finishes in seconds (every rank runs
+    it on ITS slice / copy; bench.py max-reduces the errors).  The checker, outside every timed region."""
+    import numpy as np
+    from importlib import import_module
+    from oracle import cport, dense as od, instantiate as oi, tables as otab
+    rep = {}
+    try:
+        masks, union = virt.output_masks()
+        frags = list(tables.keys())
+        if K == 0:
+            o_tabs, o_masks = otab.all_tables_k0(cut)
+            worst = 0.0
+            by_mask = {masks[f]: tables[f][0].cpu().numpy() for f in frags}
+            for t, m in zip(o_tabs, o_masks):
+                worst = max(worst, float(np.abs(by_mask[m] - t).max()))
+            rep["max_abs_err_fragment_tables_vs_oracle"] = worst
+            # knit: windows at the start, in the middle and at the end of THIS RANK'S slice vs the oracle's
+            # outer product of ITS OWN tables
+            span = y1 - y0
+            win = min(1 << 20, span)
+            worst, wins = 0.0, []
+            for off in sorted({0, (span - win) // 2, span - win}):
+                ref, _, _ = cport.knit_outer(o_tabs, o_masks, y0 + off, y0 + off + win)
+                got = out[off:off + win].cpu().numpy()
+                worst = max(worst, float(np.abs(got - ref).max()))
+                wins.append([int(y0 + off), int(y0 + off + win)])
+            rep["max_abs_err_knit_windows_vs_oracle"] = worst
+            rep["knit_windows_rank0"] = wins
+            # oracle fidelity, independent of every GPU table: both sides factorise over the connected
+            # components of the uncut circuit
+            cutting = import_module(f"{PKG}.cutting")
+            ovc = oi.OracleVirtualCircuit(cutting.apply_cuts(circ, cutting.CutSpec()))
+            f_or = 1.0
+            for cfrag in ovc.fragments:
+                if not ovc.has_measurement(cfrag, ()):
+                    continue
+                q_c, m_c = otab.fragment_table_k0(ovc, cfrag)
+                (t_f, m_f), = [(t, m) for t, m in zip(o_tabs, o_masks) if m & m_c]
+                assert (m_c & ~m_f) == 0
+                local = int(od.pext(np.uint64(m_c), m_f))
+                idx = od.pext(np.arange(len(t_f), dtype=np.uint64), local).astype(np.int64)
+                p_c = np.bincount(idx, weights=t_f, minlength=len(q_c))
+                f_or *= float(np.sum(np.sqrt(p_c * q_c)) / np.sqrt(p_c.sum() * q_c.sum()))
+            rep["fidelity_oracle"] = f_or ** 2
+        else:
+            uncut = cport.simulate_probabilities(circ)
+            got = out.cpu().numpy()
+            key = "max_abs_err_vs_uncut_oracle" + ("_pruned_1e-5_mode" if faithful else "")
+            rep[key] = float(np.abs(got - uncut).max())
+            rep["fidelity_oracle"] = float(od.hellinger_fidelity_dense(np.maximum(got, 0.0), uncut))
+    except Exception as exc:
+        rep["oracle_parity_error"] = repr(exc)
+    return rep
 
 
 def peaks_hbm() -> float:
@@ -601,7 +845,7 @@ def uncut_statevector_report(circ, cut_result, device, fid, vc, handle, peak) ->
     return rep
 
 
-def gpu_fidelity_report(virt, circ, tables, out, device, fid, vc, handle, K, n_out, world) -> dict:
+def gpu_fidelity_report(virt, circ, tables, out, device, fid, vc, handle, K, n_out, world, faithful=False) -> dict:
     """Hellinger fidelity of the cut result to the UNCUT circuit, both computed on the GPU by the
     product path only (Utilities.py:224 compares the ideal uncut run with the knitted one)."""
     import torch
@@ -609,6 +853,8 @@ def gpu_fidelity_report(virt, circ, tables, out, device, fid, vc, handle, K, n_o
     try:
         masks, union = virt.output_masks()
         frags = list(tables.keys())
+        if faithful:
+            tables = virt.simulate_fragments(device)             # folded tables for the factorised comparison
         if K == 0:
             # uncut circuit simulated per connected component, compared in factorised form
             comp_tabs, comp_masks = uncut_component_tables(circ, device)
@@ -618,68 +864,10 @@ def gpu_fidelity_report(virt, circ, tables, out, device, fid, vc, handle, K, n_o
         else:
             uncut_virt = vc.VirtualCircuit(circ)
             q = uncut_virt.knit_tables(uncut_virt.simulate_fragments(device), device)
-            p = out.clone()
-            stream = torch.cuda.current_stream(device).cuda_stream
-            handle.check(handle.lib.qck_npd(handle.ptr, p.data_ptr(), p.numel(), 0.0, None, None, stream))
-            rep["fidelity_cut_vs_uncut"] = fid.hellinger_fidelity(p, q)
+            rep["fidelity_cut_vs_uncut"] = fid.hellinger_fidelity(out, q)   # `out` went through npd in the step
             rep["max_abs_err_cut_vs_uncut_gpu"] = float((out - q).abs().max().item())
     except Exception as exc:
         rep["fidelity_report_error"] = repr(exc)
-    return rep
-
-
-def oracle_parity_report(virt, circ, cut, tables, out, y0, y1, device, K, n_out, f_gpu) -> dict:
-    """Part of the CPU-baseline leg (the only place bench.py touches oracle/): the GPU results of
-    this run against the oracle, on what the oracle finishes in seconds."""
-    import numpy as np
-    from importlib import import_module
-    from oracle import cport, dense as od, instantiate as oi, statevector as sv
-    rep = {}
-    try:
-        masks, union = virt.output_masks()
-        frags = list(tables.keys())
-        if K == 0:
-            ov = oi.OracleVirtualCircuit(cut)
-            pairs = [cpu_fragment_table_k0(ov, f) for f in ov.fragments
-                     if ov.has_measurement(f, ())]
-            o_tabs, o_masks = [p[0] for p in pairs], [p[1] for p in pairs]
-            worst = 0.0
-            by_mask = {masks[f]: tables[f][0].cpu().numpy() for f in frags}
-            for t, m in zip(o_tabs, o_masks):
-                worst = max(worst, float(np.abs(by_mask[m] - t).max()))
-            rep["max_abs_err_fragment_tables_vs_oracle"] = worst
-            # knit: a window of the output vs the oracle's outer product of ITS OWN tables
-            win = min(1 << 20, y1 - y0)
-            ref, _, _ = cport.knit_outer(o_tabs, o_masks, y0, y0 + win)
-            got = out[:win].cpu().numpy()
-            rep["max_abs_err_knit_window_vs_oracle"] = float(np.abs(got - ref).max())
-            rep["knit_window"] = [int(y0), int(y0 + win)]
-            # oracle fidelity, independent of every GPU table: both sides factorise over the connected
-            # components of the uncut circuit, so BC = prod_c sum_x sqrt(p_c(x) q_c(x)) with q_c the
-            # oracle's own simulation of component c and p_c the marginal of the oracle's fragment table
-            cutting = import_module(f"{PKG}.cutting")
-            ovc = oi.OracleVirtualCircuit(cutting.apply_cuts(circ, cutting.CutSpec()))
-            f_or = 1.0
-            for cfrag in ovc.fragments:
-                if not ovc.has_measurement(cfrag, ()):
-                    continue
-                q_c, m_c = cpu_fragment_table_k0(ovc, cfrag)
-                (t_f, m_f), = [(t, m) for t, m in zip(o_tabs, o_masks) if m & m_c]
-                assert (m_c & ~m_f) == 0
-                local = int(od.pext(np.uint64(m_c), m_f))
-                idx = od.pext(np.arange(len(t_f), dtype=np.uint64), local).astype(np.int64)
-                p_c = np.bincount(idx, weights=t_f, minlength=len(q_c))
-                f_or *= float(np.sum(np.sqrt(p_c * q_c)) / np.sqrt(p_c.sum() * q_c.sum()))
-            rep["fidelity_oracle"] = f_or ** 2
-        else:
-            uncut = sv.dense(sv.exact_distribution(circ), circ.num_clbits)
-            got = out.cpu().numpy()
-            rep["max_abs_err_vs_uncut_oracle"] = float(np.abs(got - uncut).max())
-            rep["fidelity_oracle"] = od.hellinger_fidelity_dense(od.nearest_probability_distribution(got), uncut)
-        if f_gpu is not None:
-            rep["fidelity_delta_vs_oracle"] = abs(f_gpu - rep["fidelity_oracle"])
-    except Exception as exc:
-        rep["oracle_parity_error"] = repr(exc)
     return rep
 
 

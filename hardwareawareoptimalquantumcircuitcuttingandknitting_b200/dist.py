@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import os
 
-__all__ = ["shard_range", "shard_pow2", "init_from_env", "allreduce_stats", "allreduce_sum_", "npd_sharded", "world"]
+__all__ = ["shard_range", "shard_pow2", "init_from_env", "allreduce_stats", "allreduce_sum_", "npd_sharded", "partition_mode", "simulation_work", "world"]
 
 
 def shard_range(total: int, rank: int, world_size: int, align: int = 1) -> tuple[int, int]:
@@ -44,6 +44,34 @@ def shard_pow2(n_bits: int, rank: int, world_size: int) -> tuple[int, int]:
         raise ValueError("more ranks than output entries")
     span = (1 << n_bits) // world_size
     return rank * span, (rank + 1) * span
+
+
+# Below this much simulation work (instances x amplitudes x op records, over all fragments) a cut with virtual
+# gates is NOT sharded: the whole job is a few hundred microseconds of latency-bound launches, and sharding
+# the labels adds a 2^n_out-entry all-reduce (512 KiB at 16 bits, ~30 us over NVLink) plus the row clipping
+# of every program - measured in round 1: hwe-16 d5 0.72 ms on one GPU, 0.88 ms label-sharded over two.
+# Every rank then computes the full result itself (identical bits, no collective): never slower than one GPU.
+SHARD_MIN_WORK = float(os.environ.get("QCK_SHARD_MIN_WORK", 4e9))
+
+
+def simulation_work(virt) -> float:
+    """Cost estimate of the fragment simulation: sum over programs of instances x 2^n_state x op records."""
+    work = 0.0
+    for f in virt.active_fragments():
+        for plan in virt.program(f).plans(True):
+            work += float(len(plan.labels)) * float(1 << plan.n_state) * max(len(plan.ops), 1)
+    return work
+
+
+def partition_mode(virt, world_size: int, faithful: bool = False) -> str:
+    """How a cut WITH virtual gates is spread over ``world_size`` ranks: "label range + all-reduce" or
+    "replicated (below the sharding threshold)".  The reference-faithful knit (one expression tree per output
+    entry over ALL labels) is never label-sharded."""
+    if world_size <= 1:
+        return "single"
+    if faithful or simulation_work(virt) < SHARD_MIN_WORK:
+        return "replicated (below the sharding threshold)"
+    return "label range + all-reduce"
 
 
 def world() -> tuple[int, int, int]:

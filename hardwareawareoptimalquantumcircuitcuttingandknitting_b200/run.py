@@ -106,7 +106,7 @@ def run_virtual_circuit_dense(virt: VirtualCircuit, shots: int = 20000, device=N
     if accuracy > 0.0:
         return _run_faithful(virt, device, handle, nearest, accuracy, world_size, out)
     label_range = None
-    if K > 0 and world_size > 1:
+    if K > 0 and world_size > 1 and qdist.partition_mode(virt, world_size) == "label range + all-reduce":
         label_range = qdist.shard_range(virt.num_global_labels(), rank, world_size,
                                         align=virt.global_radices()[-1])
     stream = torch.cuda.current_stream(device).cuda_stream
@@ -141,7 +141,7 @@ def run_virtual_circuit_dense(virt: VirtualCircuit, shots: int = 20000, device=N
             _check_npd_state(ws)
     else:
         values = virt.knit_tables(tables, device, label_range=label_range, out=out)
-        if world_size > 1:
+        if label_range is not None:
             qdist.allreduce_sum_(values, group)
         if nearest:
             # statistics, threshold search and shift are all enqueued (qck_npd_async: no host round

@@ -336,6 +336,12 @@ enum { QCK_NPD_STATS = 0, QCK_NPD_PLAN = 1, QCK_NPD_LEVEL = 2, QCK_NPD_SELECT = 
 QCK_API int qck_npd_stage(qck_handle* h, int stage, double* d_p, uint64_t n, double acc, void* d_ws, int fuse_tail,
                   qck_stream stream);
 
+/* Roofline denominators MEASURED_PEAKS.json does not hold, measured on this device:
+ * out4 = { FP64 FMA TFLOP/s, FP64 tensor-core (DMMA m8n8k4) TFLOP/s, shared-memory load TB/s (LDS.128,
+ * whole device), SM count }.  A measurement utility (bench.py records it next to its roofline figures);
+ * synchronises the device, ~50 ms. */
+QCK_API int qck_measure_peaks(qck_handle* h, double* out4);
+
 /* ------------------------------------------------------------------ dense QuasiDistr algebra
  * Device forms of quasi_distr.py:45-86 on dense vectors of 2^n_bits doubles with
  * the reference's pruning (v = |v| > acc ? v : 0 after every operation).  They

@@ -47,6 +47,15 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the timed CPU baseline sets its thread count itself */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* returns sum of the produced entries through *sum_out and their minimum through *min_out */
 void oracle_knit_outer(int n_frag, const double* const* tables, const uint64_t* masks, uint64_t y_begin,
                        uint64_t y_end, double* out, double* sum_out, double* min_out) {

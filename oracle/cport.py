@@ -51,12 +51,23 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
-def knit_outer(tables, masks, y_begin, y_end, want_output=True):
+def set_num_threads(n=None):
+    """Use ``n`` OpenMP threads (default: every host core) whatever OMP_NUM_THREADS says - torchrun sets it
+    to 1 for its workers, which made the multi-GPU reference arm run on one core."""
+    import os
+    lib().oracle_set_num_threads(int(n or os.cpu_count() or 1))
+    return num_threads()
+
+
+def knit_outer(tables, masks, y_begin, y_end, want_output=True, out=None):
     L = lib()
     tabs = [np.ascontiguousarray(t, dtype=np.float64) for t in tables]
     ptrs = (C.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
     cm = (C.c_uint64 * len(tabs))(*masks)
-    out = np.empty(y_end - y_begin) if want_output else None
+    if out is not None:
+        assert out.dtype == np.float64 and out.flags.c_contiguous and len(out) == y_end - y_begin
+    elif want_output:
+        out = np.empty(y_end - y_begin)
     s, m = C.c_double(), C.c_double()
     L.oracle_knit_outer(len(tabs), ptrs, cm, y_begin, y_end, out.ctypes.data if out is not None else None,
                         C.byref(s), C.byref(m))

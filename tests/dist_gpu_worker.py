@@ -27,8 +27,14 @@ def main() -> None:
     worst = 0.0
 
     # (1) virtual gates: label shard + all-reduce, then nearest_probability_distribution on every rank
-    for cfg in ("bv16", "syc16d5", "hwe16d5"):
+    default_min_work = qdist.SHARD_MIN_WORK
+    for cfg, min_work in (("bv16", 0.0), ("syc16d5", 0.0), ("hwe16d5", 0.0), ("hwe16d5", default_min_work)):
+        # min_work 0: the label range is ALWAYS sharded and the partial results all-reduced; default: these
+        # small configs run replicated (dist.partition_mode)
+        qdist.SHARD_MIN_WORK = min_work
         circ, cut = cutting.make_baseline(cfg, seed=1)
+        want_mode = "label range + all-reduce" if min_work == 0.0 else "replicated (below the sharding threshold)"
+        assert qdist.partition_mode(vcm.VirtualCircuit(cut), world) == want_mode
         uncut = cport.simulate_probabilities(circ)
         res, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=False,
                                                 rank=rank, world_size=world)
@@ -42,6 +48,8 @@ def main() -> None:
         assert err2 < 1e-13, (cfg, rank, err2)
         assert abs(res2.total - 1.0) < 1e-9
         worst = max(worst, err, err2)
+
+    qdist.SHARD_MIN_WORK = default_min_work
 
     # (2) no virtual gate: output index sharded by its top bits, nothing gathered
     c20 = gen.gen_circ("syc", 20, 1, seed=0).decompose_two_qubit()
