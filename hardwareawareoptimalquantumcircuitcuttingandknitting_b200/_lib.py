@@ -28,6 +28,7 @@ MAX_FRAGMENTS = 8
 MAX_VARIANTS = 8
 OP_U1, OP_CX, OP_CZ, OP_U2, OP_CLUSTER, OP_U1X, OP_TERM, OP_PHASE = 0, 1, 2, 3, 4, 5, 6, 7
 SWEEP_SHARED = 4            # qck_sweep.flags: QCK_SWEEP_SHARED
+SWEEP_WARP = 8              # qck_sweep.flags: QCK_SWEEP_WARP (bits 8-15: fragment qubits held in registers)
 CLUSTER_QUBITS = 3
 NPD_STATS, NPD_PLAN, NPD_LEVEL, NPD_SELECT, NPD_APPLY = 0, 1, 2, 3, 4      # qck_npd_stage stages
 NPD_STATE_SLOTS, NPD_BINS, NPD_LEVEL_PASSES = 32, 8192, 6

@@ -43,6 +43,15 @@ from .virtual_gates import VirtualBinaryGate, VirtualGateEndpoint
 ONCHIP_MAX_QUBITS = 13      # 2^13 complex128 = 128 KiB of the 227 KiB shared memory
 import os as _os
 
+# Register-resident regime (csrc/sim_warp_kernel.inc): fragments of <= WARP_MAX_QUBITS qubits whose programs hold
+# only one-qubit gates, cx and cz run ONE WARP PER INSTANCE with the state in registers (lane bits = qubits 0-4:
+# shuffle butterflies) and a depth-first walk over the outcomes of mid-circuit measurements instead of ancilla
+# bits.  Pair fusion is off for them (a fused 4x4 would need all four amplitudes of a quad in one lane).
+# QCK_SIM_WARP=0 keeps them on the shared-memory kernel.
+WARP_MAX_QUBITS = 10
+WARP_MAX_DEPTH = 8          # QCK_WARP_MAX_DEPTH: measurements whose qubit lives on, per program
+WARP = _os.environ.get("QCK_SIM_WARP", "1") != "0"
+
 STREAM_TILE = int(_os.environ.get("QCK_STREAM_TILE", "12"))   # 64 KiB tiles; env override = tuning knob
 LOW_RUN = 5                 # tiles always hold qubits 0..4: 32 amplitudes = 512 contiguous bytes
 # Prefix sharing (first level): the ops of an on-chip program that precede its first label-dependent
@@ -97,6 +106,8 @@ class PlanHost:
     sign_mask: int
     op_base: int = 0                    # offset of this plan's ops in the fragment's device op array
     shared_prefix: bool = False         # on-chip: sweeps[0] holds no label-dependent op and runs once per plan
+    warp_base: int = 0                  # > 0: register-resident plan of that many fragment qubits (the state bits
+    #                                     above are branch outcomes, not amplitudes the kernel holds)
 
 
 class FragmentProgram:
@@ -104,8 +115,12 @@ class FragmentProgram:
 
     def __init__(self, frag_circuit: QuantumCircuit, fragment: QuantumRegister, num_clbits: int,
                  onchip_max: int = ONCHIP_MAX_QUBITS, stream_tile: int = STREAM_TILE,
-                 cluster: bool = True, fuse: bool = True, early_bits: int = 0, share_prefix=None) -> None:
+                 cluster: bool = True, fuse: bool = True, early_bits: int = 0, share_prefix=None,
+                 warp=None) -> None:
         self.share_prefix = SHARE_PREFIX if share_prefix is None else share_prefix      # True / False / "auto"
+        # register-resident regime wanted?  (only default-shaped programs: the knobs below select other kernels)
+        self.warp_wanted = (WARP if warp is None else bool(warp)) and onchip_max == ONCHIP_MAX_QUBITS \
+            and self.share_prefix is not True and cluster and fuse and not early_bits
         self.fragment = fragment
         self.n_qubits = len(fragment)
         self.num_clbits = num_clbits
@@ -239,7 +254,10 @@ class FragmentProgram:
         # cannot change any probability and are dropped
         pending.clear()
         self.slots = slots
-        self.tops = self._fuse_pairs(tops) if self.fuse else tops
+        branch_points = mid_measures + sum(1 for sl in slots if not sl.terminal and any(sl.meas))
+        self.warp = (self.warp_wanted and self.n_qubits <= WARP_MAX_QUBITS and branch_points <= WARP_MAX_DEPTH
+                     and not any(t[0] == "u2" for t in tops) and len(tops) + 2 * len(slots) < 60000)
+        self.tops = tops if self.warp or not self.fuse else self._fuse_pairs(tops)
         self.out_bits = out_bits
         # the row of an instance has one bit per WRITTEN clbit, in ascending clbit order: the terminal
         # measurements and the mid-circuit measurements of the input circuit (their outcome lives on an
@@ -489,6 +507,11 @@ class FragmentProgram:
             for p in cfg_pos.values():
                 sign_mask |= 1 << p
         shared = False
+        if self.warp:
+            # one "sweep" over the whole program; the kernel holds the n fragment qubits and walks the outcomes
+            # of the n_anc branch points depth first (positions listed for the plan interpreter: all n_state bits)
+            return PlanHost(pattern, labels, n_state, ops_arr, [(list(range(n_state)), 0, len(ops_arr))], out_pos,
+                            sum_mask, sign_mask, warp_base=n)
         if n_state <= self.onchip_max:
             sweeps = [(list(range(n_state)), 0, len(ops_arr))]
             dep = np.nonzero(ops_arr[:, 4] >= 0)[0]       # ops that select their matrix by a label digit
@@ -747,7 +770,7 @@ class FragmentExecutor:
         self.d_blob = None
         self.row_len = program.row_len(fold)
         self.max_state = max(p.n_state for p in self.plans)
-        self.streaming = self.max_state > program.onchip_max
+        self.streaming = self.max_state > program.onchip_max and not program.warp
         self._work = None
         self._work_bytes = None
 
@@ -784,12 +807,15 @@ class FragmentExecutor:
         for p in plans:
             arr = (_lib.QckSweep * len(p.sweeps))()
             for i, (positions, b, e) in enumerate(p.sweeps):
+                if p.warp_base:
+                    positions = positions[:p.warp_base]
                 arr[i].n_tile = len(positions)
                 arr[i].op_begin = p.op_base + b
                 arr[i].op_end = p.op_base + e
                 arr[i].flags = (int(np.isin(p.ops[b:e, 0], (_lib.OP_U1X, _lib.OP_PHASE)).any())
                                 | 2 * int((p.ops[b:e, 0] == _lib.OP_CLUSTER).any())
-                                | (_lib.SWEEP_SHARED if p.shared_prefix and i == 0 else 0))
+                                | (_lib.SWEEP_SHARED if p.shared_prefix and i == 0 else 0)
+                                | ((_lib.SWEEP_WARP | (p.warp_base << 8)) if p.warp_base else 0))
                 for j, x in enumerate(positions):
                     arr[i].pos[j] = x
             sweep_arrays.append(arr)

@@ -407,7 +407,7 @@ extern "C" size_t qck_npd_workspace_bytes(void) { return NPD_WS_BYTES; }
 extern "C" int qck_npd_stage(qck_handle* h, int stage, double* d_p, uint64_t n, double acc, void* d_ws, int fuse_tail,
                              qck_stream stream) {
     if (!h) return QCK_ERR_INVALID_ARG;
-    if (!d_p && (stage == QCK_NPD_STATS || stage == QCK_NPD_LEVEL || stage == QCK_NPD_APPLY))
+    if (!d_p && n > 0 && (stage == QCK_NPD_STATS || stage == QCK_NPD_LEVEL || stage == QCK_NPD_APPLY))
         QCK_FAIL(h, QCK_ERR_INVALID_ARG, "NULL argument");
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;

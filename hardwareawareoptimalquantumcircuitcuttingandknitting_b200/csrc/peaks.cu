@@ -47,7 +47,10 @@ __global__ void __launch_bounds__(256) peak_smem_kernel(double* out, int iters) 
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {  // 16-byte loads, consecutive lanes -> consecutive 16-byte words
-            const double2 v = s[(idx + u * 256) & (n - 1)];
+            double2 v;  // volatile: the loads must not be hoisted out of the loop (the buffer is never written)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                         : "=d"(v.x), "=d"(v.y)
+                         : "r"((unsigned)__cvta_generic_to_shared(s + ((idx + u * 256) & (n - 1)))));
             acc.x += v.x;
             acc.y += v.y;
         }

@@ -31,6 +31,10 @@ struct qck_handle {
     int side_ready;
     // workspace of nearest_probability_distribution (npd.cu): state, bins, per-CTA partials
     void* npd_ws;
+    // register-resident simulator (sim_warp_kernel.inc): branch stash (grows only) and CTAs per SM per variant
+    void* warp_stash;
+    size_t warp_stash_bytes;
+    int warp_occ[6];
 };
 
 #define QCK_FAIL(h, code, ...)                                    \

@@ -576,6 +576,8 @@ __global__ void __launch_bounds__(256) sim_onchip_group_kernel(const __grid_cons
         row[o] = fold_entry(plan, o, [&](uint64_t idx) { return s[swz((uint32_t)idx)]; });
 }
 
+#include "sim_warp_kernel.inc"
+
 // ------------------------------------------------------------------ streaming regime
 __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev sw,
                                                         const int32_t* __restrict__ labels, int inst_base,
@@ -875,7 +877,14 @@ static bool has_shared_prefix(const qck_sim_plan* plan) {
     return plan->n_sweeps == 2 && plan->sweeps[0].n_tile == plan->n_state_qubits &&
            plan->sweeps[1].n_tile == plan->n_state_qubits && (plan->sweeps[0].flags & QCK_SWEEP_SHARED);
 }
+// Register-resident plans (one warp per instance): one sweep flagged QCK_SWEEP_WARP whose tile is the
+// fragment's own qubits; the state bits above them are branch outcomes.
+static bool is_warp_plan(const qck_sim_plan* plan) {
+    return plan->n_sweeps == 1 && (plan->sweeps[0].flags & QCK_SWEEP_WARP);
+}
+static int warp_base(const qck_sim_plan* plan) { return (plan->sweeps[0].flags >> 8) & 0xff; }
 static bool is_onchip(const qck_sim_plan* plan) {
+    if (is_warp_plan(plan)) return false;
     return (plan->n_sweeps == 1 && plan->sweeps[0].n_tile == plan->n_state_qubits) || has_shared_prefix(plan);
 }
 
@@ -1280,6 +1289,11 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
     return QCK_OK;
 }
 
+static int qck_warp_init(qck_handle* h);
+static int launch_warp_group(qck_handle* h, const qck_sim_plan* plans, const int* idx, int n,
+                             const int32_t* const* d_labels, const int64_t* n_instances, double* d_out,
+                             int64_t out_row_stride, cudaStream_t st, int slot, int n_slots);
+
 extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const int32_t* d_labels,
                                  int64_t n_instances, double* d_out, int64_t out_row_stride, void* d_work,
                                  size_t work_bytes, qck_stream stream) {
@@ -1292,6 +1306,12 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
         QCK_FAIL(h, QCK_ERR_INVALID_ARG, "out_row_stride smaller than the row (2^%d)", plan->n_out_bits);
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (is_warp_plan(plan)) {
+        const int one = 0;
+        const int32_t* labs[1] = {d_labels};
+        const int64_t cnt[1] = {n_instances};
+        return launch_warp_group(h, plan, &one, 1, labs, cnt, d_out, out_row_stride, st, 0, 1);
+    }
     PlanDev pd = to_dev(plan);
     if (is_onchip(plan)) {
         const int N = plan->n_state_qubits;
@@ -1371,6 +1391,101 @@ int qck_sim_init(qck_handle* h) {
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_wide_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_sharded_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_sharded_wide_kernel, h->max_smem_optin));
+    return qck_warp_init(h);
+}
+
+typedef void (*WarpKernelFn)(const WarpGroupDev, double*, long long);
+static WarpKernelFn warp_kernel(int log_r) {
+    switch (log_r) {
+        case 0: return sim_warp_kernel<0>;
+        case 1: return sim_warp_kernel<1>;
+        case 2: return sim_warp_kernel<2>;
+        case 3: return sim_warp_kernel<3>;
+        case 4: return sim_warp_kernel<4>;
+        default: return sim_warp_kernel<5>;
+    }
+}
+
+static int qck_warp_init(qck_handle* h) {
+    for (int r = 0; r <= 5; ++r) {
+        const int smem = QCK_WARP_PER_CTA * (8 << (r + 5));
+        QCK_CUDA(h, cudaFuncSetAttribute(warp_kernel(r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 0;
+        QCK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, warp_kernel(r), 32 * QCK_WARP_PER_CTA, smem));
+        h->warp_occ[r] = occ < 1 ? 1 : occ;
+    }
+    return QCK_OK;
+}
+
+// Groups of register-resident plans (same fragment qubit count) -> one launch; `slot` picks a private slice
+// of the handle's stash (groups of one call run concurrently on side streams).
+static int launch_warp_group(qck_handle* h, const qck_sim_plan* plans, const int* idx, int n,
+                             const int32_t* const* d_labels, const int64_t* n_instances, double* d_out,
+                             int64_t out_row_stride, cudaStream_t st, int slot, int n_slots) {
+    WarpGroupDev G;
+    memset(&G, 0, sizeof(G));
+    const qck_sim_plan& p0 = plans[idx[0]];
+    G.n_base = warp_base(&p0);
+    G.n_vars = n;
+    G.n_digits = p0.n_digits;
+    G.ops = p0.d_ops;
+    G.mats = p0.d_mats;
+    long long div = 1;
+    for (int k = QCK_MAX_DIGITS - 1; k >= 0; --k) {
+        G.radix[k] = k < p0.n_digits ? p0.radix[k] : 1;
+        G.div[k] = (int)div;
+        if (k < p0.n_digits) div *= p0.radix[k];
+        if (div > 0x7fffffffll) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "fragment label space exceeds 2^31");
+    }
+    long long total = 0;
+    int max_anc = 0;
+    for (int i = 0; i < n; ++i) {
+        const qck_sim_plan& p = plans[idx[i]];
+        if (p.d_ops != p0.d_ops || p.d_mats != p0.d_mats || p.n_digits != p0.n_digits || warp_base(&p) != G.n_base)
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "plans of one batch must share the program blob and the label radices");
+        if (out_row_stride < (1ll << p.n_out_bits))
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "out_row_stride smaller than the row (2^%d)", p.n_out_bits);
+        const int n_anc = p.n_state_qubits - G.n_base;
+        if (n_anc < 0 || n_anc > QCK_WARP_MAX_DEPTH || G.n_base < 1 || G.n_base > 10 || p.n_out_bits > 30 ||
+            p.sweeps[0].op_end - p.sweeps[0].op_begin > 60000)
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "register-resident plan out of range (%d qubits, %d branch points)",
+                     G.n_base, n_anc);
+        WarpVarDev& v = G.var[i];
+        v.op_begin = p.sweeps[0].op_begin;
+        v.op_end = p.sweeps[0].op_end;
+        v.n_out_bits = p.n_out_bits;
+        v.n_anc = n_anc;
+        for (int j = 0; j < QCK_MAX_OUT_BITS; ++j) v.out_pos[j] = (signed char)(j < p.n_out_bits ? p.out_pos[j] : -1);
+        v.sum_mask = p.sum_mask;
+        v.sign_mask = p.sign_mask;
+        v.labels = d_labels[idx[i]];
+        v.inst_begin = (int)total;
+        total += n_instances[idx[i]];
+        if (n_anc > max_anc) max_anc = n_anc;
+    }
+    if (total > 0x7fffffffll) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "too many instances in one group");
+    G.total = (int)total;
+    const int log_r = G.n_base > 5 ? G.n_base - 5 : 0;
+    long long ctas = (total + QCK_WARP_PER_CTA - 1) / QCK_WARP_PER_CTA;
+    const long long cap = (long long)h->sm_count * h->warp_occ[log_r];
+    if (ctas > cap) ctas = cap;
+    // stash: [slot][warp of the grid][QCK_WARP_MAX_DEPTH][R][32] double2
+    const size_t per_slot = (size_t)cap * QCK_WARP_PER_CTA * QCK_WARP_MAX_DEPTH * (32u << log_r) * sizeof(double2);
+    if (max_anc > 0) {
+        const size_t need = per_slot * (size_t)n_slots;
+        if (need > h->warp_stash_bytes) {  // grows only; synchronous, first use of a larger shape only
+            if (h->warp_stash) QCK_CUDA(h, cudaFree(h->warp_stash));
+            h->warp_stash = nullptr;
+            h->warp_stash_bytes = 0;
+            cudaError_t e = cudaMalloc(&h->warp_stash, need);
+            if (e != cudaSuccess) QCK_FAIL(h, QCK_ERR_NOMEM, "cudaMalloc(%zu bytes of branch stash): %s", need, cudaGetErrorString(e));
+            h->warp_stash_bytes = need;
+        }
+        G.stash = reinterpret_cast<double2*>(reinterpret_cast<char*>(h->warp_stash) + per_slot * (size_t)slot);
+    }
+    const int smem = QCK_WARP_PER_CTA * (8 << (log_r + 5));
+    warp_kernel(log_r)<<<(unsigned)ctas, 32 * QCK_WARP_PER_CTA, smem, st>>>(G, d_out, (long long)out_row_stride);
+    QCK_CHECK_LAUNCH(h);
     return QCK_OK;
 }
 
@@ -1469,6 +1584,14 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
             if (n_instances[i] > 0 && is_onchip(&plans[i]) && plans[i].n_state_qubits == N) ++cnt;
         n_groups += (cnt + QCK_GROUP_MAX - 1) / QCK_GROUP_MAX;
     }
+    int n_warp_groups = 0;
+    for (int N = 1; N <= 10; ++N) {
+        int cnt = 0;
+        for (int i = 0; i < n_plans; ++i)
+            if (n_instances[i] > 0 && is_warp_plan(&plans[i]) && warp_base(&plans[i]) == N) ++cnt;
+        n_warp_groups += (cnt + QCK_GROUP_MAX - 1) / QCK_GROUP_MAX;
+    }
+    n_groups += n_warp_groups;
     const bool fan = n_groups >= 2;
     int used = 0, k = 0;
     size_t work_used = 0;  // snapshots of shared prefixes: disjoint slices of d_work (groups run concurrently)
@@ -1499,13 +1622,38 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
             }
         }
     }
+    // register-resident plans: most branch points first (they run longest), one launch per QCK_GROUP_MAX plans
+    int warp_slot = 0;
+    for (int N = 10; N >= 1 && n_warp_groups > 0; --N) {
+        int order[1024], n_sel = 0;
+        for (int a = QCK_WARP_MAX_DEPTH; a >= 0; --a)
+            for (int i = 0; i < n_plans && n_sel < 1024; ++i)
+                if (n_instances[i] > 0 && is_warp_plan(&plans[i]) && warp_base(&plans[i]) == N &&
+                    plans[i].n_state_qubits - N == a)
+                    order[n_sel++] = i;
+        for (int b = 0; b < n_sel; b += QCK_GROUP_MAX) {
+            const int cnt = n_sel - b < QCK_GROUP_MAX ? n_sel - b : QCK_GROUP_MAX;
+            cudaStream_t st = main_st;
+            if (fan) {
+                const int slot = k++ % QCK_SIDE_STREAMS;
+                st = h->side[slot];
+                if (slot >= used) {
+                    QCK_CUDA(h, cudaStreamWaitEvent(st, h->fork, 0));
+                    used = slot + 1;
+                }
+            }
+            int rc = launch_warp_group(h, plans, order + b, cnt, d_labels, n_instances, d_out, out_row_stride, st,
+                                       warp_slot++, n_warp_groups);
+            if (rc) return rc;
+        }
+    }
     for (int s = 0; s < used; ++s) {  // join
         QCK_CUDA(h, cudaEventRecord(h->side_done[s], h->side[s]));
         QCK_CUDA(h, cudaStreamWaitEvent(main_st, h->side_done[s], 0));
     }
     // streaming plans: one after the other on the caller's stream, sharing d_work
     for (int i = 0; i < n_plans; ++i) {
-        if (n_instances[i] <= 0 || is_onchip(&plans[i])) continue;
+        if (n_instances[i] <= 0 || is_onchip(&plans[i]) || is_warp_plan(&plans[i])) continue;
         int rc = qck_sim_fragments(h, &plans[i], d_labels[i], n_instances[i], d_out, out_row_stride, d_work, work_bytes,
                                    (qck_stream)main_st);
         if (rc) return rc;

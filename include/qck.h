@@ -111,6 +111,13 @@ typedef struct {
  * amplitudes that differ only in the listed bit positions) in shared memory,
  * applies ops[op_begin, op_end) there and writes it back. */
 #define QCK_SWEEP_SHARED 4
+/* QCK_SWEEP_WARP (bit 3): register-resident plan - ONE sweep whose tile is the n_base = (flags >> 8) & 0xff
+ * qubits of the fragment itself (n_base <= 10), ops restricted to QCK_OP_U1 / CX / CZ on state bit positions.
+ * One warp simulates one instance with the 2^n_base amplitudes in its registers; a QCK_OP_CX onto a state bit
+ * >= n_base is a mid-circuit measurement of q0 whose qubit lives on: the warp walks both outcomes depth first
+ * (n_state_qubits - n_base <= 8 of them) instead of widening the state.  out_pos / sum_mask / sign_mask address
+ * those outcome bits exactly as they address ancilla bits in the other regimes. */
+#define QCK_SWEEP_WARP 8
 typedef struct {
     int32_t n_tile;
     int32_t op_begin, op_end;

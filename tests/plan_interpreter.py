@@ -182,3 +182,80 @@ def run_program_deduped(program, fold=True):
     reps = set(int(x) for x in np.unique(src))
     out = run_program(program, fold, labels=reps)
     return out[src]
+
+
+def run_plan_warp(program, plan, label):
+    """The register-resident kernel (csrc/sim_warp_kernel.inc) step for step: the state holds only the
+    ``plan.warp_base`` fragment qubits, a CX onto a state bit >= warp_base is a branch point walked depth
+    first (stash, project onto 0, run to the end, fold the leaf, restore, project onto 1), the leaf fold
+    takes the outcome bits as the virtual state bits above warp_base.  Must equal ``run_plan`` (the same
+    ops on the ancilla-enlarged state) bit for bit in exact arithmetic, to rounding in floating point."""
+    nb = plan.warp_base
+    assert nb > 0 and len(plan.sweeps) == 1
+    mats = program.mats
+    digits = list(np.unravel_index(int(label), program.radix)) if program.radix else []
+    idx = np.arange(1 << nb)
+    psi = np.zeros(1 << nb, dtype=np.complex128)
+    psi[0] = 1.0
+    _, b, e = plan.sweeps[0]
+    ops = plan.ops[b:e]
+    n_out = len(plan.out_pos)
+    row = np.zeros(1 << n_out)
+    base_mask = (1 << nb) - 1
+    base_sum, base_sign = plan.sum_mask & base_mask, plan.sign_mask & base_mask
+    free = [(j, p) for j, p in enumerate(plan.out_pos) if 0 <= p < nb]
+    pc, outcomes, stack = 0, 0, []                 # stack: (return pc, saved state, qubit, outcome bit)
+    while True:
+        if pc < len(ops):
+            kind, q0, q1, mat, sel, stride, _, _ = (int(x) for x in ops[pc])
+            if kind == _lib.OP_U1:
+                moff = mat + (digits[sel] * stride if sel >= 0 else 0)
+                psi = apply_op(psi, idx, kind, q0, 0, mats, moff)
+            elif kind == _lib.OP_CX and q1 >= nb:  # branch point
+                stack.append((pc, psi.copy(), q0, q1 - nb))
+                outcomes &= ~(1 << (q1 - nb))
+                psi = np.where(_bits(idx, q0) == 1, 0.0, psi)
+            elif kind in (_lib.OP_CX, _lib.OP_CZ):
+                assert q0 < nb and q1 < nb
+                psi = apply_op(psi, idx, kind, q0, q1, mats, 0)
+            else:
+                raise AssertionError(f"op kind {kind} in a register-resident program")
+            pc += 1
+            continue
+        # leaf
+        prob = psi.real ** 2 + psi.imag ** 2
+        P = np.where(np.array([bin(int(i) & base_sign).count("1") & 1 for i in idx]) == 1, -prob, prob)
+        virt = outcomes << nb
+        leaf_sign = -1.0 if bin(virt & plan.sign_mask).count("1") & 1 else 1.0
+        col_fixed = 0
+        for j, p in enumerate(plan.out_pos):
+            if p >= nb and (virt >> p) & 1:
+                col_fixed |= 1 << j
+        for o in range(1 << len(free)):
+            base, col = 0, col_fixed
+            for r, (j, p) in enumerate(free):
+                if (o >> r) & 1:
+                    base |= 1 << p
+                    col |= 1 << j
+            sub, acc = 0, 0.0
+            while True:
+                acc += P[base | sub]
+                sub = (sub - base_sum) & base_sum
+                if sub == 0:
+                    break
+            row[col] += leaf_sign * acc
+        # backtrack
+        resumed = False
+        while stack:
+            rpc, saved, q, bit = stack[-1]
+            if (outcomes >> bit) & 1:
+                stack.pop()
+                continue
+            outcomes |= 1 << bit
+            psi = np.where(_bits(idx, q) == 1, saved, 0.0)
+            pc = rpc + 1
+            resumed = True
+            break
+        if not resumed:
+            break
+    return row
