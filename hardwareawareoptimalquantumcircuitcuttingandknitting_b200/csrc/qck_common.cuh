@@ -34,6 +34,7 @@ struct qck_handle {
     // register-resident simulator (sim_warp_kernel.inc): branch stash (grows only) and CTAs per SM per variant
     void* warp_stash;
     size_t warp_stash_bytes;
+    size_t warp_cnt_bytes;  // leading bytes of warp_stash that hold arrival counters (kept zero between launches)
     int warp_occ[6];
 };
 

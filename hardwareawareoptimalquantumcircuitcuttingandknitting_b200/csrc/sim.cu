@@ -1290,9 +1290,8 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
 }
 
 static int qck_warp_init(qck_handle* h);
-static int launch_warp_group(qck_handle* h, const qck_sim_plan* plans, const int* idx, int n,
-                             const int32_t* const* d_labels, const int64_t* n_instances, double* d_out,
-                             int64_t out_row_stride, cudaStream_t st, int slot, int n_slots);
+static int warp_single_plan(qck_handle* h, const qck_sim_plan* plan, const int32_t* d_labels, int64_t n_instances,
+                            double* d_out, int64_t out_row_stride, cudaStream_t st);
 
 extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const int32_t* d_labels,
                                  int64_t n_instances, double* d_out, int64_t out_row_stride, void* d_work,
@@ -1306,12 +1305,7 @@ extern "C" int qck_sim_fragments(qck_handle* h, const qck_sim_plan* plan, const 
         QCK_FAIL(h, QCK_ERR_INVALID_ARG, "out_row_stride smaller than the row (2^%d)", plan->n_out_bits);
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_warp_plan(plan)) {
-        const int one = 0;
-        const int32_t* labs[1] = {d_labels};
-        const int64_t cnt[1] = {n_instances};
-        return launch_warp_group(h, plan, &one, 1, labs, cnt, d_out, out_row_stride, st, 0, 1);
-    }
+    if (is_warp_plan(plan)) return warp_single_plan(h, plan, d_labels, n_instances, d_out, out_row_stride, st);
     PlanDev pd = to_dev(plan);
     if (is_onchip(plan)) {
         const int N = plan->n_state_qubits;
@@ -1408,7 +1402,7 @@ static WarpKernelFn warp_kernel(int log_r) {
 
 static int qck_warp_init(qck_handle* h) {
     for (int r = 0; r <= 5; ++r) {
-        const int smem = QCK_WARP_PER_CTA * (8 << (r + 5));
+        const int smem = QCK_WARP_PER_CTA * (48 << (r + 5));
         QCK_CUDA(h, cudaFuncSetAttribute(warp_kernel(r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
         QCK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, warp_kernel(r), 32 * QCK_WARP_PER_CTA, smem));
@@ -1417,13 +1411,32 @@ static int qck_warp_init(qck_handle* h) {
     return QCK_OK;
 }
 
-// Groups of register-resident plans (same fragment qubit count) -> one launch; `slot` picks a private slice
-// of the handle's stash (groups of one call run concurrently on side streams).
-static int launch_warp_group(qck_handle* h, const qck_sim_plan* plans, const int* idx, int n,
-                             const int32_t* const* d_labels, const int64_t* n_instances, double* d_out,
-                             int64_t out_row_stride, cudaStream_t st, int slot, int n_slots) {
+static int warp_dfs_levels() {  // QCK_WARP_DFS_LEVELS: outcome levels one warp walks itself (tuning knob)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("QCK_WARP_DFS_LEVELS");
+        v = e ? atoi(e) : 2;
+        if (v < 0) v = 0;
+        if (v > QCK_WARP_MAX_DEPTH) v = QCK_WARP_MAX_DEPTH;
+    }
+    return v;
+}
+
+// A group of register-resident plans (same fragment qubit count) = one launch.  warp_group_layout fills the
+// kernel parameters and says how much scratch the launch needs ([global stash | partial rows | counters]);
+// warp_group_launch binds the scratch and launches.
+struct WarpGroupHost {
     WarpGroupDev G;
-    memset(&G, 0, sizeof(G));
+    int log_r;
+    long long ctas;
+    size_t stash_bytes, part_bytes, cnt_bytes;
+};
+
+static int warp_group_layout(qck_handle* h, const qck_sim_plan* plans, const int* idx, int n,
+                             const int32_t* const* d_labels, const int64_t* n_instances, int64_t out_row_stride,
+                             WarpGroupHost* W) {
+    WarpGroupDev& G = W->G;
+    memset(W, 0, sizeof(*W));
     const qck_sim_plan& p0 = plans[idx[0]];
     G.n_base = warp_base(&p0);
     G.n_vars = n;
@@ -1437,8 +1450,8 @@ static int launch_warp_group(qck_handle* h, const qck_sim_plan* plans, const int
         if (k < p0.n_digits) div *= p0.radix[k];
         if (div > 0x7fffffffll) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "fragment label space exceeds 2^31");
     }
-    long long total = 0;
-    int max_anc = 0;
+    long long items = 0, parts = 0, cnts = 0;
+    int max_walk = 0;
     for (int i = 0; i < n; ++i) {
         const qck_sim_plan& p = plans[idx[i]];
         if (p.d_ops != p0.d_ops || p.d_mats != p0.d_mats || p.n_digits != p0.n_digits || warp_base(&p) != G.n_base)
@@ -1455,38 +1468,94 @@ static int launch_warp_group(qck_handle* h, const qck_sim_plan* plans, const int
         v.op_end = p.sweeps[0].op_end;
         v.n_out_bits = p.n_out_bits;
         v.n_anc = n_anc;
-        for (int j = 0; j < QCK_MAX_OUT_BITS; ++j) v.out_pos[j] = (signed char)(j < p.n_out_bits ? p.out_pos[j] : -1);
+        int n_free = 0;
+        v.mode = QCK_WARP_MODE_ACC;
+        for (int j = 0; j < QCK_MAX_OUT_BITS; ++j) {
+            v.out_pos[j] = (signed char)(j < p.n_out_bits ? p.out_pos[j] : -1);
+            if (j < p.n_out_bits && p.out_pos[j] >= G.n_base) v.mode = QCK_WARP_MODE_RMW;  // an outcome is a column bit
+            if (j < p.n_out_bits && p.out_pos[j] >= 0 && p.out_pos[j] < G.n_base) ++n_free;
+        }
         v.sum_mask = p.sum_mask;
         v.sign_mask = p.sign_mask;
         v.labels = d_labels[idx[i]];
-        v.inst_begin = (int)total;
-        total += n_instances[idx[i]];
-        if (n_anc > max_anc) max_anc = n_anc;
-    }
-    if (total > 0x7fffffffll) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "too many instances in one group");
-    G.total = (int)total;
-    const int log_r = G.n_base > 5 ? G.n_base - 5 : 0;
-    long long ctas = (total + QCK_WARP_PER_CTA - 1) / QCK_WARP_PER_CTA;
-    const long long cap = (long long)h->sm_count * h->warp_occ[log_r];
-    if (ctas > cap) ctas = cap;
-    // stash: [slot][warp of the grid][QCK_WARP_MAX_DEPTH][R][32] double2
-    const size_t per_slot = (size_t)cap * QCK_WARP_PER_CTA * QCK_WARP_MAX_DEPTH * (32u << log_r) * sizeof(double2);
-    if (max_anc > 0) {
-        const size_t need = per_slot * (size_t)n_slots;
-        if (need > h->warp_stash_bytes) {  // grows only; synchronous, first use of a larger shape only
-            if (h->warp_stash) QCK_CUDA(h, cudaFree(h->warp_stash));
-            h->warp_stash = nullptr;
-            h->warp_stash_bytes = 0;
-            cudaError_t e = cudaMalloc(&h->warp_stash, need);
-            if (e != cudaSuccess) QCK_FAIL(h, QCK_ERR_NOMEM, "cudaMalloc(%zu bytes of branch stash): %s", need, cudaGetErrorString(e));
-            h->warp_stash_bytes = need;
+        v.split_bits = (v.mode == QCK_WARP_MODE_ACC && n_anc > warp_dfs_levels()) ? n_anc - warp_dfs_levels() : 0;
+        const int walk = n_anc - v.split_bits;
+        if (walk > max_walk) max_walk = walk;
+        v.item_begin = (int)items;
+        items += n_instances[idx[i]] << v.split_bits;
+        v.cnt_off = (int)cnts;
+        v.part_off = parts;
+        if (v.split_bits > 0) {
+            cnts += n_instances[idx[i]];
+            parts += (n_instances[idx[i]] << v.split_bits) << n_free;
         }
-        G.stash = reinterpret_cast<double2*>(reinterpret_cast<char*>(h->warp_stash) + per_slot * (size_t)slot);
+        if (items > 0x7fffffffll || cnts > 0x7fffffffll) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "too many instances in one group");
     }
-    const int smem = QCK_WARP_PER_CTA * (8 << (log_r + 5));
-    warp_kernel(log_r)<<<(unsigned)ctas, 32 * QCK_WARP_PER_CTA, smem, st>>>(G, d_out, (long long)out_row_stride);
-    QCK_CHECK_LAUNCH(h);
+    G.total = (int)items;
+    W->log_r = G.n_base > 5 ? G.n_base - 5 : 0;
+    W->ctas = (items + QCK_WARP_PER_CTA - 1) / QCK_WARP_PER_CTA;
+    const long long cap = (long long)h->sm_count * h->warp_occ[W->log_r];
+    if (W->ctas > cap) W->ctas = cap;
+    W->stash_bytes = max_walk > QCK_WARP_SMEM_LEVELS
+                         ? (size_t)W->ctas * QCK_WARP_PER_CTA * QCK_WARP_MAX_DEPTH * (32u << W->log_r) * sizeof(double2)
+                         : 0;
+    W->part_bytes = ((size_t)parts * sizeof(double) + 255) & ~(size_t)255;
+    W->cnt_bytes = ((size_t)cnts * sizeof(unsigned) + 255) & ~(size_t)255;
     return QCK_OK;
+}
+
+// scratch layout of the handle: [counters of every group (zero between launches) | stash + partial rows ...]
+static int warp_groups_run(qck_handle* h, WarpGroupHost* W, int n_groups, cudaStream_t* streams, double* d_out,
+                           int64_t out_row_stride) {
+    size_t cnt_total = 0, rest_total = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        cnt_total += W[g].cnt_bytes;
+        rest_total += W[g].stash_bytes + W[g].part_bytes;
+    }
+    const size_t need = cnt_total + rest_total;
+    if (need > h->warp_stash_bytes) {  // grows only; synchronous, first use of a larger shape only
+        if (h->warp_stash) QCK_CUDA(h, cudaFree(h->warp_stash));
+        h->warp_stash = nullptr;
+        h->warp_stash_bytes = 0;
+        const size_t want = need + (need >> 2);
+        cudaError_t e = cudaMalloc(&h->warp_stash, want);
+        if (e != cudaSuccess) QCK_FAIL(h, QCK_ERR_NOMEM, "cudaMalloc(%zu bytes of branch scratch): %s", want, cudaGetErrorString(e));
+        h->warp_stash_bytes = want;
+        h->warp_cnt_bytes = 0;
+    }
+    if (cnt_total > h->warp_cnt_bytes) {  // the counter region grew over bytes that held other data: zero it once
+        QCK_CUDA(h, cudaMemset(h->warp_stash, 0, cnt_total));
+        h->warp_cnt_bytes = cnt_total;
+    }
+    char* cnt_ptr = reinterpret_cast<char*>(h->warp_stash);
+    char* rest_ptr = cnt_ptr + (h->warp_cnt_bytes > cnt_total ? h->warp_cnt_bytes : cnt_total);
+    if (rest_ptr + rest_total > reinterpret_cast<char*>(h->warp_stash) + h->warp_stash_bytes)
+        rest_ptr = cnt_ptr + cnt_total;  // (cannot happen: warp_cnt_bytes <= an earlier need)
+    for (int g = 0; g < n_groups; ++g) {
+        WarpGroupDev& G = W[g].G;
+        G.cnt = reinterpret_cast<unsigned*>(cnt_ptr);
+        cnt_ptr += W[g].cnt_bytes;
+        G.stash = W[g].stash_bytes ? reinterpret_cast<double2*>(rest_ptr) : nullptr;
+        rest_ptr += W[g].stash_bytes;
+        G.part = reinterpret_cast<double*>(rest_ptr);
+        rest_ptr += W[g].part_bytes;
+        const int smem = QCK_WARP_PER_CTA * (48 << (W[g].log_r + 5));
+        warp_kernel(W[g].log_r)<<<(unsigned)W[g].ctas, 32 * QCK_WARP_PER_CTA, smem, streams[g]>>>(
+            G, d_out, (long long)out_row_stride);
+        QCK_CHECK_LAUNCH(h);
+    }
+    return QCK_OK;
+}
+
+static int warp_single_plan(qck_handle* h, const qck_sim_plan* plan, const int32_t* d_labels, int64_t n_instances,
+                            double* d_out, int64_t out_row_stride, cudaStream_t st) {
+    const int one = 0;
+    const int32_t* labs[1] = {d_labels};
+    const int64_t cnt[1] = {n_instances};
+    std::unique_ptr<WarpGroupHost> W(new WarpGroupHost);
+    int rc = warp_group_layout(h, plan, &one, 1, labs, cnt, out_row_stride, W.get());
+    if (rc) return rc;
+    return warp_groups_run(h, W.get(), 1, &st, d_out, out_row_stride);
 }
 
 static int ensure_side_streams(qck_handle* h) {
@@ -1623,29 +1692,35 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
         }
     }
     // register-resident plans: most branch points first (they run longest), one launch per QCK_GROUP_MAX plans
-    int warp_slot = 0;
-    for (int N = 10; N >= 1 && n_warp_groups > 0; --N) {
-        int order[1024], n_sel = 0;
-        for (int a = QCK_WARP_MAX_DEPTH; a >= 0; --a)
-            for (int i = 0; i < n_plans && n_sel < 1024; ++i)
-                if (n_instances[i] > 0 && is_warp_plan(&plans[i]) && warp_base(&plans[i]) == N &&
-                    plans[i].n_state_qubits - N == a)
-                    order[n_sel++] = i;
-        for (int b = 0; b < n_sel; b += QCK_GROUP_MAX) {
-            const int cnt = n_sel - b < QCK_GROUP_MAX ? n_sel - b : QCK_GROUP_MAX;
-            cudaStream_t st = main_st;
-            if (fan) {
-                const int slot = k++ % QCK_SIDE_STREAMS;
-                st = h->side[slot];
-                if (slot >= used) {
-                    QCK_CUDA(h, cudaStreamWaitEvent(st, h->fork, 0));
-                    used = slot + 1;
+    if (n_warp_groups > 0) {
+        std::unique_ptr<WarpGroupHost[]> W(new WarpGroupHost[n_warp_groups]);
+        std::unique_ptr<cudaStream_t[]> wst(new cudaStream_t[n_warp_groups]);
+        int g = 0;
+        for (int N = 10; N >= 1; --N) {
+            int order[1024], n_sel = 0;
+            for (int a = QCK_WARP_MAX_DEPTH; a >= 0; --a)
+                for (int i = 0; i < n_plans && n_sel < 1024; ++i)
+                    if (n_instances[i] > 0 && is_warp_plan(&plans[i]) && warp_base(&plans[i]) == N &&
+                        plans[i].n_state_qubits - N == a)
+                        order[n_sel++] = i;
+            for (int b = 0; b < n_sel; b += QCK_GROUP_MAX) {
+                const int cnt = n_sel - b < QCK_GROUP_MAX ? n_sel - b : QCK_GROUP_MAX;
+                cudaStream_t st = main_st;
+                if (fan) {
+                    const int slot = k++ % QCK_SIDE_STREAMS;
+                    st = h->side[slot];
+                    if (slot >= used) {
+                        QCK_CUDA(h, cudaStreamWaitEvent(st, h->fork, 0));
+                        used = slot + 1;
+                    }
                 }
+                int rc = warp_group_layout(h, plans, order + b, cnt, d_labels, n_instances, out_row_stride, &W[g]);
+                if (rc) return rc;
+                wst[g++] = st;
             }
-            int rc = launch_warp_group(h, plans, order + b, cnt, d_labels, n_instances, d_out, out_row_stride, st,
-                                       warp_slot++, n_warp_groups);
-            if (rc) return rc;
         }
+        int rc = warp_groups_run(h, W.get(), g, wst.get(), d_out, out_row_stride);
+        if (rc) return rc;
     }
     for (int s = 0; s < used; ++s) {  // join
         QCK_CUDA(h, cudaEventRecord(h->side_done[s], h->side[s]));

@@ -184,8 +184,23 @@ def run_program_deduped(program, fold=True):
     return out[src]
 
 
-def run_plan_warp(program, plan, label):
-    """The register-resident kernel (csrc/sim_warp_kernel.inc) step for step: the state holds only the
+def run_plan_warp(program, plan, label, dfs_levels=2):
+    """The register-resident kernel with its outcome tree split over warps: when no outcome bit is a column
+    bit and the plan has more than ``dfs_levels`` branch points, the first ones are FORCED per work item
+    (2^split items per instance), every item accumulates its leaves, and the partial rows are added in item
+    order (csrc/sim_warp_kernel.inc: the last warp to arrive does that)."""
+    nb = plan.warp_base
+    n_anc = plan.n_state - nb
+    acc_mode = all(p < nb for p in plan.out_pos)
+    split = n_anc - dfs_levels if (acc_mode and n_anc > dfs_levels) else 0
+    row = np.zeros(1 << len(plan.out_pos))
+    for forced in range(1 << split):
+        row = row + _run_plan_warp_item(program, plan, label, split, forced)
+    return row
+
+
+def _run_plan_warp_item(program, plan, label, split, forced):
+    """One work item of the register-resident kernel (csrc/sim_warp_kernel.inc) step for step: the state holds only the
     ``plan.warp_base`` fragment qubits, a CX onto a state bit >= warp_base is a branch point walked depth
     first (stash, project onto 0, run to the end, fold the leaf, restore, project onto 1), the leaf fold
     takes the outcome bits as the virtual state bits above warp_base.  Must equal ``run_plan`` (the same
@@ -212,9 +227,14 @@ def run_plan_warp(program, plan, label):
                 moff = mat + (digits[sel] * stride if sel >= 0 else 0)
                 psi = apply_op(psi, idx, kind, q0, 0, mats, moff)
             elif kind == _lib.OP_CX and q1 >= nb:  # branch point
-                stack.append((pc, psi.copy(), q0, q1 - nb))
-                outcomes &= ~(1 << (q1 - nb))
-                psi = np.where(_bits(idx, q0) == 1, 0.0, psi)
+                k = q1 - nb
+                keep = 0
+                if k < split:                      # forced by the work item: no walk
+                    keep = (forced >> k) & 1
+                else:
+                    stack.append((pc, psi.copy(), q0, k))
+                outcomes = (outcomes & ~(1 << k)) | (keep << k)
+                psi = np.where(_bits(idx, q0) == keep, psi, 0.0)
             elif kind in (_lib.OP_CX, _lib.OP_CZ):
                 assert q0 < nb and q1 < nb
                 psi = apply_op(psi, idx, kind, q0, q1, mats, 0)
