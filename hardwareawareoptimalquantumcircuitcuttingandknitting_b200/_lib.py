@@ -70,6 +70,8 @@ _PROTOTYPES = {
     "qck_sim_fragments_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(QckSimPlan), C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t,
                                           C.c_void_p]),
+    "qck_sim_region_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "qck_sim_region_end": (C.c_int, [C.c_void_p, C.c_void_p]),
     "qck_sim_statevector": (C.c_int, [C.c_void_p, C.POINTER(QckSimPlan), C.c_int32, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
     "qck_host_cluster_ops": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
@@ -183,15 +185,15 @@ class Handle:
 
     SCRATCH_CACHE_MAX = 256 << 20
 
-    def scratch(self, torch, nbytes: int, device, stream: int):
+    def scratch(self, torch, nbytes: int, device, stream: int, tag=0):
         """Device scratch of at least ``nbytes`` for work enqueued on ``stream``.  Buffers up to
         ``SCRATCH_CACHE_MAX`` are kept per (device, stream) and grow only - the handle is thread-local and
         work on one stream is ordered, so consecutive runs can share them; larger ones belong to the caller."""
         if nbytes > self.SCRATCH_CACHE_MAX:
             return torch.empty(nbytes, dtype=torch.uint8, device=device)
         cache = self.__dict__.setdefault("_scratch", {})
-        key = (str(device), int(stream))
-        buf = cache.get(key)
+        key = (str(device), int(stream), tag)      # tag: users whose work overlaps on the device (fragments of
+        buf = cache.get(key)                        # one region) must not share a buffer
         if buf is None or buf.numel() < nbytes:
             buf = cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
         return buf

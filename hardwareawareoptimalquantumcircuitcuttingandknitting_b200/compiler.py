@@ -854,8 +854,12 @@ class FragmentExecutor:
         st.d_mats = self.d_blob.data_ptr()
         return st
 
-    def run(self, handle: "_lib.Handle", out=None, label_range: tuple[int, int] | None = None):
-        """-> device tensor [num_labels, row_len] float64 (rows outside label_range untouched / 0)."""
+    def run(self, handle: "_lib.Handle", out=None, label_range: tuple[int, int] | None = None,
+            scratch_tag=0, defer_broadcast: bool = False):
+        """-> device tensor [num_labels, row_len] float64 (rows outside label_range untouched / 0).
+        ``scratch_tag``: executors whose runs overlap on the device (one ``qck_sim_region``) pass different tags
+        and get different work buffers; ``defer_broadcast``: inside a region the rows of identical instances
+        can only be copied after the region has been joined - the caller then calls ``finish(handle, out)``."""
         torch = self.torch
         if self.d_blob is None:
             self.upload()
@@ -877,7 +881,8 @@ class FragmentExecutor:
                     free, _ = torch.cuda.mem_get_info(self.device)
                     n = max(1, min(prog.num_labels, int(free * 0.5) // per, 64))
                 self._work_bytes = n * per
-        self._work = handle.scratch(torch, self._work_bytes, self.device, stream) if self._work_bytes else None
+        self._work = (handle.scratch(torch, self._work_bytes, self.device, stream, scratch_tag)
+                      if self._work_bytes else None)
         n = len(self._structs)
         plans = (_lib.QckSimPlan * n)()
         label_ptrs = (C.c_void_p * n)()
@@ -906,7 +911,16 @@ class FragmentExecutor:
         work_bytes = self._work.numel() if self._work is not None else 0
         handle.check(handle.lib.qck_sim_fragments_batch(handle.ptr, n, plans, label_ptrs, counts, out.data_ptr(),
                                                         self.row_len, work_ptr, work_bytes, stream))
-        if dedupe is not None:
-            handle.check(handle.lib.qck_rows_broadcast(handle.ptr, out.data_ptr(), self.row_len, self.row_len,
-                                                       self.d_blob.data_ptr() + dedupe[2], prog.num_labels, stream))
+        self._pending_broadcast = dedupe is not None
+        if not defer_broadcast:
+            self.finish(handle, out)
         return out
+
+    def finish(self, handle: "_lib.Handle", out) -> None:
+        """Rows of instances identical to their representative (qck_rows_broadcast), on the current stream."""
+        if getattr(self, "_pending_broadcast", False):
+            stream = self.torch.cuda.current_stream(self.device).cuda_stream
+            handle.check(handle.lib.qck_rows_broadcast(handle.ptr, out.data_ptr(), self.row_len, self.row_len,
+                                                       self.d_blob.data_ptr() + self._dedupe[2],
+                                                       self.program.num_labels, stream))
+            self._pending_broadcast = False

@@ -29,6 +29,9 @@ struct qck_handle {
     cudaEvent_t side_done[QCK_SIDE_STREAMS];
     cudaEvent_t fork;
     int side_ready;
+    int region;            // a qck_sim_region is open: batch calls fan out and do not join
+    unsigned region_used;  // side streams the open region has launched on
+    unsigned side_next;    // rotating pick of the next side stream
     // workspace of nearest_probability_distribution (npd.cu): state, bins, per-CTA partials
     void* npd_ws;
     // register-resident simulator (sim_warp_kernel.inc): branch stash (grows only) and CTAs per SM per variant

@@ -1248,7 +1248,7 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
             pdl.n_stage = L->n_stage;
             unsigned long long grid = L->n_work < (unsigned long long)h->sm_count ? L->n_work : (unsigned long long)h->sm_count;
             unsigned long long* counter = nullptr;
-            if (tma_dynamic && L->n_work > grid) {  // reserved tail of the reduction scratch (qck_common.cuh)
+            if (tma_dynamic && L->n_work > grid && !h->region) {  // reserved tail of the reduction scratch (qck_common.cuh)
                 counter = reinterpret_cast<unsigned long long*>(h->d_partials + h->partials_count - 4);
                 QCK_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
             }
@@ -1402,7 +1402,7 @@ static WarpKernelFn warp_kernel(int log_r) {
 
 static int qck_warp_init(qck_handle* h) {
     for (int r = 0; r <= 5; ++r) {
-        const int smem = QCK_WARP_PER_CTA * (48 << (r + 5));
+        const int smem = QCK_WARP_PER_CTA * ((48 << (r + 5)) + (int)sizeof(WarpStagedOp) * QCK_WARP_STAGE);
         QCK_CUDA(h, cudaFuncSetAttribute(warp_kernel(r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
         QCK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, warp_kernel(r), 32 * QCK_WARP_PER_CTA, smem));
@@ -1539,7 +1539,7 @@ static int warp_groups_run(qck_handle* h, WarpGroupHost* W, int n_groups, cudaSt
         rest_ptr += W[g].stash_bytes;
         G.part = reinterpret_cast<double*>(rest_ptr);
         rest_ptr += W[g].part_bytes;
-        const int smem = QCK_WARP_PER_CTA * (48 << (W[g].log_r + 5));
+        const int smem = QCK_WARP_PER_CTA * ((48 << (W[g].log_r + 5)) + (int)sizeof(WarpStagedOp) * QCK_WARP_STAGE);
         warp_kernel(W[g].log_r)<<<(unsigned)W[g].ctas, 32 * QCK_WARP_PER_CTA, smem, streams[g]>>>(
             G, d_out, (long long)out_row_stride);
         QCK_CHECK_LAUNCH(h);
@@ -1632,6 +1632,47 @@ static int launch_group(qck_handle* h, const qck_sim_plan* plans, const int* idx
     return QCK_OK;
 }
 
+// Region: several qck_sim_fragments_batch calls (the fragments of one cut circuit) whose launches should
+// OVERLAP on the device.  Between begin and end every call puts its launches on the handle's side streams
+// (rotating, so that consecutive calls land on different ones) and does not join; end joins them all into
+// `stream`.  One region per handle at a time; outputs and work buffers of the calls must not alias.
+extern "C" int qck_sim_region_begin(qck_handle* h, qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    if (h->region) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "qck_sim_region_begin: a region is already open on this handle");
+    DeviceGuard guard(h->device);
+    int rc = ensure_side_streams(h);
+    if (rc) return rc;
+    QCK_CUDA(h, cudaEventRecord(h->fork, (cudaStream_t)stream));
+    h->region = 1;
+    h->region_used = 0;
+    return QCK_OK;
+}
+
+extern "C" int qck_sim_region_end(qck_handle* h, qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    if (!h->region) return QCK_OK;
+    DeviceGuard guard(h->device);
+    h->region = 0;
+    for (int s = 0; s < QCK_SIDE_STREAMS; ++s) {
+        if (!((h->region_used >> s) & 1u)) continue;
+        QCK_CUDA(h, cudaEventRecord(h->side_done[s], h->side[s]));
+        QCK_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->side_done[s], 0));
+    }
+    h->region_used = 0;
+    return QCK_OK;
+}
+
+// next side stream of a fan-out; *used: the side streams already ordered after the fork point
+static int pick_side_stream(qck_handle* h, unsigned* used, cudaStream_t* st) {
+    const int slot = (int)(h->side_next++ % QCK_SIDE_STREAMS);
+    *st = h->side[slot];
+    if (!((*used >> slot) & 1u)) {
+        QCK_CUDA(h, cudaStreamWaitEvent(*st, h->fork, 0));
+        *used |= 1u << slot;
+    }
+    return QCK_OK;
+}
+
 extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim_plan* plans,
                                        const int32_t* const* d_labels, const int64_t* n_instances, double* d_out,
                                        int64_t out_row_stride, void* d_work, size_t work_bytes, qck_stream stream) {
@@ -1661,10 +1702,12 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
         n_warp_groups += (cnt + QCK_GROUP_MAX - 1) / QCK_GROUP_MAX;
     }
     n_groups += n_warp_groups;
-    const bool fan = n_groups >= 2;
-    int used = 0, k = 0;
+    const bool region = h->region != 0;
+    const bool fan = region || n_groups >= 2;
+    unsigned used_local = 0;
+    unsigned* used = region ? &h->region_used : &used_local;
     size_t work_used = 0;  // snapshots of shared prefixes: disjoint slices of d_work (groups run concurrently)
-    if (fan) {
+    if (fan && !region) {
         int rc = ensure_side_streams(h);
         if (rc) return rc;
         QCK_CUDA(h, cudaEventRecord(h->fork, main_st));
@@ -1677,12 +1720,8 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
             if (cnt == QCK_GROUP_MAX || (i == n_plans && cnt > 0)) {
                 cudaStream_t st = main_st;
                 if (fan) {
-                    const int slot = k++ % QCK_SIDE_STREAMS;
-                    st = h->side[slot];
-                    if (slot >= used) {  // first use in this call: order after the fork point
-                        QCK_CUDA(h, cudaStreamWaitEvent(st, h->fork, 0));
-                        used = slot + 1;
-                    }
+                    int rc = pick_side_stream(h, used, &st);
+                    if (rc) return rc;
                 }
                 int rc = launch_group(h, plans, idx, cnt, d_labels, n_instances, d_out, out_row_stride, st,
                                       (char*)d_work, work_bytes, &work_used);
@@ -1707,12 +1746,8 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
                 const int cnt = n_sel - b < QCK_GROUP_MAX ? n_sel - b : QCK_GROUP_MAX;
                 cudaStream_t st = main_st;
                 if (fan) {
-                    const int slot = k++ % QCK_SIDE_STREAMS;
-                    st = h->side[slot];
-                    if (slot >= used) {
-                        QCK_CUDA(h, cudaStreamWaitEvent(st, h->fork, 0));
-                        used = slot + 1;
-                    }
+                    int rc = pick_side_stream(h, used, &st);
+                    if (rc) return rc;
                 }
                 int rc = warp_group_layout(h, plans, order + b, cnt, d_labels, n_instances, out_row_stride, &W[g]);
                 if (rc) return rc;
@@ -1722,15 +1757,24 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
         int rc = warp_groups_run(h, W.get(), g, wst.get(), d_out, out_row_stride);
         if (rc) return rc;
     }
-    for (int s = 0; s < used; ++s) {  // join
+    for (int s = 0; s < QCK_SIDE_STREAMS && !region; ++s) {  // join (a region joins at its end)
+        if (!((used_local >> s) & 1u)) continue;
         QCK_CUDA(h, cudaEventRecord(h->side_done[s], h->side[s]));
         QCK_CUDA(h, cudaStreamWaitEvent(main_st, h->side_done[s], 0));
     }
-    // streaming plans: one after the other on the caller's stream, sharing d_work
+    // streaming plans: one after the other, sharing d_work - on the caller's stream, or inside a region on ONE
+    // side stream of their own (the streaming fragments of a cut circuit then overlap each other)
+    cudaStream_t stream_st = main_st;
+    bool picked = false;
     for (int i = 0; i < n_plans; ++i) {
         if (n_instances[i] <= 0 || is_onchip(&plans[i]) || is_warp_plan(&plans[i])) continue;
+        if (region && !picked) {
+            int rc = pick_side_stream(h, used, &stream_st);
+            if (rc) return rc;
+            picked = true;
+        }
         int rc = qck_sim_fragments(h, &plans[i], d_labels[i], n_instances[i], d_out, out_row_stride, d_work, work_bytes,
-                                   (qck_stream)main_st);
+                                   (qck_stream)stream_st);
         if (rc) return rc;
     }
     return QCK_OK;

@@ -270,13 +270,27 @@ class VirtualCircuit:
         keeps the config bits as extra column bits (input of the reference-faithful knit)."""
         device = default_device() if device is None else device
         handle = _lib.get_handle(getattr(device, "index", None) or 0)
-        tables = {}
-        for frag in self.active_fragments():
-            ex = self.executor(frag, device, fold)
-            rng = None
-            if label_range is not None and self._vgate_instrs:
-                rng = self.fragment_label_range(frag, *label_range)
-            tables[frag] = ex.run(handle, label_range=rng)
+        import torch
+        stream = torch.cuda.current_stream(device).cuda_stream
+        tables, runs = {}, []
+        frags = self.active_fragments()
+        # the fragments are independent jobs (run.py:36-43): inside a region their launches overlap on the GPU
+        overlap = len(frags) > 1
+        if overlap:
+            handle.check(handle.lib.qck_sim_region_begin(handle.ptr, stream))
+        try:
+            for i, frag in enumerate(frags):
+                ex = self.executor(frag, device, fold)
+                rng = None
+                if label_range is not None and self._vgate_instrs:
+                    rng = self.fragment_label_range(frag, *label_range)
+                tables[frag] = ex.run(handle, label_range=rng, scratch_tag=i, defer_broadcast=overlap)
+                runs.append((ex, tables[frag]))
+        finally:
+            if overlap:
+                handle.check(handle.lib.qck_sim_region_end(handle.ptr, stream))
+        for ex, table in runs:
+            ex.finish(handle, table)
         return tables
 
     def output_masks(self, fragments=None) -> tuple[dict, int]:

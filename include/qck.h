@@ -176,6 +176,13 @@ QCK_API int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim_pl
                                     double* d_out, int64_t out_row_stride, void* d_work, size_t work_bytes,
                                     qck_stream stream);
 
+/* Overlap the qck_sim_fragments_batch calls of several fragments (their instances are independent:
+ * run.py:36-43 submits one job per fragment).  Between begin and end every batch call launches on the handle's
+ * side streams and returns without joining; end makes `stream` wait for all of them.  d_out and d_work of the
+ * calls inside one region must not alias.  One region per handle at a time. */
+QCK_API int qck_sim_region_begin(qck_handle* h, qck_stream stream);
+QCK_API int qck_sim_region_end(qck_handle* h, qck_stream stream);
+
 /* Final statevector of ONE instance in the streaming regime left in d_work
  * (used for the uncut reference run, Utilities.py:39-69). */
 QCK_API int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t label,
