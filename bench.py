@@ -336,7 +336,8 @@ def sim_work(virt, frags, device, fold: bool = True) -> dict:
     amplitude for a one-qubit gate on complex128 (28 per amplitude pair), 30 for a general two-qubit gate,
     0 for cx / cz, on 2^n_f amplitudes.  ``flops_executed`` / ``smem_bytes_executed`` count what the compiled
     programs really do (fused gates, ancilla-enlarged states, live-amplitude limits, identical instances
-    simulated once): one shared-memory read + write of the live state per pass."""
+    simulated once; the tree walk: every shared prefix once): one shared-memory read + write of the live
+    state per pass (none for the register-resident kernels)."""
     from importlib import import_module
     import numpy as np
     lib = import_module(f"{PKG}._lib")
@@ -360,7 +361,33 @@ def sim_work(virt, frags, device, fold: bool = True) -> dict:
         alg += per_inst * prog.num_labels
         inst_total += prog.num_labels
         canon = prog.canonical_labels()
-        dedupe = virt.executor(f, device, fold)._dedupe is not None
+        ex = virt.executor(f, device, fold)
+        if getattr(ex, "tree", None) is not None:      # tree walk: every shared prefix once
+            tree = ex.tree
+            amps = float(1 << tree.n_base)
+
+            def seg_cost(seg):
+                fl, sm = 0.0, 0
+                for row in tree.ops[seg[0]:seg[1]].tolist():
+                    if row[0] == lib.OP_U1:
+                        m = prog._mat_by_off.get(row[3])
+                        diag = m is not None and m.shape == (2, 2) and m[0, 1] == 0 and m[1, 0] == 0
+                        fl += (6.0 if diag else 14.0) * amps
+                    sm += 1
+                return fl, sm
+            for lv, L in enumerate(tree.levels):
+                items = tree.node_counts[lv + 1]
+                fl, np_ = seg_cost(L.seg)
+                if lv == 0:
+                    f0, n0 = seg_cost(tree.seg0)
+                    fl, np_ = fl + f0, np_ + n0
+                fl += 14.0 * amps * ((L.pre_off >= 0) + (L.post_off >= 0))
+                execd += fl * items
+                passes += (np_ + 2) * items
+            execd += 4.0 * amps * tree.node_counts[-1]
+            runs += tree.node_counts[-1]
+            continue
+        dedupe = ex._dedupe is not None
         for plan in prog.plans(fold):
             n_inst = int((canon[plan.labels] == plan.labels).sum()) if dedupe else len(plan.labels)
             runs += n_inst

@@ -48,6 +48,26 @@ class QckSimPlan(C.Structure):
                 ("sum_mask", C.c_uint64), ("sign_mask", C.c_uint64)]
 
 
+TREE_MAX_LEVELS, TREE_MAX_CHOICES = 24, 16
+TREE_SLOT, TREE_TERMINAL, TREE_MMEAS = 0, 1, 2
+
+
+class QckTreeLevel(C.Structure):
+    _fields_ = [("seg_begin", C.c_int32), ("seg_end", C.c_int32), ("kind", C.c_int32), ("qubit", C.c_int32),
+                ("digit", C.c_int32), ("pre_off", C.c_int32), ("post_off", C.c_int32), ("n_choices", C.c_int32),
+                ("col_bit", C.c_int32), ("meas_mask", C.c_uint32), ("canon", C.c_uint32),
+                ("choice_variant", C.c_uint8 * TREE_MAX_CHOICES), ("choice_outcome", C.c_int8 * TREE_MAX_CHOICES),
+                ("first_choice", C.c_int8 * 8)]
+
+
+class QckSimTreePlan(C.Structure):
+    _fields_ = [("n_base", C.c_int32), ("n_levels", C.c_int32), ("n_digits", C.c_int32), ("n_out_bits", C.c_int32),
+                ("seg0_begin", C.c_int32), ("seg0_end", C.c_int32), ("n_free", C.c_int32),
+                ("free_bit", C.c_int8 * 16), ("free_pos", C.c_int8 * 16), ("base_sum", C.c_uint64),
+                ("d_ops", C.c_void_p), ("d_mats", C.c_void_p), ("radix", C.c_int32 * MAX_DIGITS),
+                ("level", QckTreeLevel * TREE_MAX_LEVELS)]
+
+
 class QckFaithfulGate(C.Structure):
     _fields_ = [("n_variants", C.c_int32), ("form", C.c_int32), ("degenerate", C.c_int32), ("reserved", C.c_int32),
                 ("sign", C.c_double * MAX_VARIANTS), ("cos_half", C.c_double), ("sin_half", C.c_double),
@@ -72,6 +92,9 @@ _PROTOTYPES = {
                                           C.c_void_p]),
     "qck_sim_region_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "qck_sim_region_end": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "qck_sim_tree_work_bytes": (C.c_size_t, [C.POINTER(QckSimTreePlan)]),
+    "qck_sim_tree": (C.c_int, [C.c_void_p, C.POINTER(QckSimTreePlan), C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "qck_sim_statevector": (C.c_int, [C.c_void_p, C.POINTER(QckSimPlan), C.c_int32, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
     "qck_host_cluster_ops": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),

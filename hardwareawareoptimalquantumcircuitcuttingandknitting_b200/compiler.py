@@ -51,6 +51,11 @@ import os as _os
 WARP_MAX_QUBITS = 10
 WARP_MAX_DEPTH = 8          # QCK_WARP_MAX_DEPTH: measurements whose qubit lives on, per program
 WARP = _os.environ.get("QCK_SIM_WARP", "1") != "0"
+# Tree-walk simulation (csrc/sim_tree_kernel.inc): register-regime fragments whose every virtual gate
+# has ONE endpoint in the fragment run all their instances level by level, every shared prefix once, from ONE
+# program (no per-pattern programs).  QCK_SIM_TREE=0 keeps them on the per-instance warp kernel.
+TREE = _os.environ.get("QCK_SIM_TREE", "1") != "0"
+TREE_MAX_WORK_BYTES = 2 << 30
 
 STREAM_TILE = int(_os.environ.get("QCK_STREAM_TILE", "12"))   # 64 KiB tiles; env override = tuning knob
 LOW_RUN = 5                 # tiles always hold qubits 0..4: 32 amplitudes = 512 contiguous bytes
@@ -92,6 +97,32 @@ class Slot:
     post: list                  # per variant: 2x2 complex matrix
     pre_off: int = -1           # matrix-pool offsets (doubles); -1: all identity
     post_off: int = -1
+
+
+@dataclass
+class TreeLevel:
+    kind: int                   # _lib.TREE_SLOT / TREE_TERMINAL / TREE_MMEAS
+    qubit: int
+    digit: int                  # label digit of the slot's gate (-1: mid-circuit measurement of the input)
+    pre_off: int
+    post_off: int
+    choices: list               # [(representative variant, outcome or -1)]
+    canon: list                 # per variant: its representative
+    meas: list                  # per variant: measures?
+    col_bit: int                # TREE_MMEAS: row bit of the outcome
+    seg: tuple = (0, 0)         # ops after this branching op
+
+
+@dataclass
+class TreeHost:
+    n_base: int
+    ops: np.ndarray             # [n_ops, 8] int32: label-independent ops on state bit positions
+    seg0: tuple
+    levels: list
+    free: list                  # [(row bit, state position)]
+    n_out_bits: int
+    base_sum: int
+    node_counts: list           # nodes before each level, then the leaves
 
 
 @dataclass
@@ -367,6 +398,84 @@ class FragmentProgram:
         for q in list(pending):
             flush_pending(q)
         return out
+
+    # ------------------------------------------------------------------ tree-walk program
+    def tree(self):
+        """The fragment as ONE tree program (TreeHost), or None when it is not eligible: register regime only, at
+        least one branching op, every virtual gate with exactly one endpoint here, folded rows."""
+        cached = getattr(self, "_tree", False)
+        if cached is not False:
+            return cached
+        self._tree = None
+        if not (self.warp and TREE):
+            return None
+        rows, levels, seen = [], [], set()
+        seg_begin, seg0 = 0, None
+        mmeas_clbits = [t[2] for t in self.tops if t[0] == "mmeas"]
+        bits = sorted([(c, p) for c, p in self.out_bits] + [(c, ("mmeas", c)) for c in mmeas_clbits],
+                      key=lambda t: t[0])
+        row_bit_of_clbit = {c: j for j, (c, _) in enumerate(bits)}
+        free = [(j, p) for j, (c, p) in enumerate(bits) if not isinstance(p, tuple)]
+
+        def close_segment():
+            nonlocal seg_begin, seg0
+            seg = (seg_begin, len(rows))
+            if levels:
+                levels[-1].seg = seg
+            else:
+                seg0 = seg
+            seg_begin = len(rows)
+
+        for top in self.tops:
+            if top[0] == "u1":
+                rows.append([_lib.OP_U1, top[1], 0, top[2], -1, 0, 0, 0])
+            elif top[0] == "cx":
+                rows.append([_lib.OP_CX, top[1], top[2], 0, -1, 0, 0, 0])
+            elif top[0] == "cz":
+                rows.append([_lib.OP_CZ, top[1], top[2], 0, -1, 0, 0, 0])
+            elif top[0] == "mmeas":
+                close_segment()
+                levels.append(TreeLevel(_lib.TREE_MMEAS, top[1], -1, -1, -1, [(0, 0), (0, 1)], [0], [True],
+                                        row_bit_of_clbit[top[2]]))
+            elif top[0] == "slot":
+                slot = self.slots[top[1]]
+                if slot.digit in seen:
+                    return None                      # both ends of a virtual gate in one fragment
+                seen.add(slot.digit)
+                close_segment()
+                r = self.radix[slot.digit]
+                first, canon = {}, []
+                for v in range(r):
+                    key = ((slot.pre[v] + 0.0).tobytes(), bool(slot.meas[v]), (slot.post[v] + 0.0).tobytes())
+                    canon.append(first.setdefault(key, v))
+                choices = []
+                for v in sorted(set(canon)):
+                    if slot.meas[v] and not slot.terminal:
+                        choices += [(v, 0), (v, 1)]
+                    else:
+                        choices.append((v, -1))
+                levels.append(TreeLevel(_lib.TREE_TERMINAL if slot.terminal else _lib.TREE_SLOT, slot.qubit, slot.digit,
+                                        slot.pre_off, slot.post_off if not slot.terminal else -1, choices, canon,
+                                        [bool(m) for m in slot.meas], -1))
+            else:
+                return None
+        close_segment()
+        if not levels or len(levels) > _lib.TREE_MAX_LEVELS or any(len(l.choices) > _lib.TREE_MAX_CHOICES for l in levels):
+            return None
+        if len(seen) != len(self.radix):
+            return None
+        counts = [1]
+        for l in levels:
+            counts.append(counts[-1] * len(l.choices))
+        state_bytes = 16 << max(self.n_qubits, 5)
+        inner = max(counts[1:-1], default=0)
+        if 2 * inner * state_bytes + counts[-1] * (8 << len(free)) > TREE_MAX_WORK_BYTES:
+            return None
+        used = {p for _, p in free}
+        base_sum = sum(1 << b for b in range(self.n_qubits) if b not in used)
+        ops = np.asarray(rows, dtype=np.int32).reshape(-1, 8) if rows else np.zeros((0, 8), np.int32)
+        self._tree = TreeHost(self.n_qubits, ops, seg0, levels, free, len(bits), base_sum, counts)
+        return self._tree
 
     # ------------------------------------------------------------------ identical instances
     def canonical_labels(self) -> np.ndarray:
@@ -756,6 +865,21 @@ class FragmentExecutor:
         self.program = program
         self.device = torch.device(device)
         self.fold = fold
+        self.tree = program.tree() if fold else None
+        if self.tree is not None:
+            host = program.__dict__.setdefault("_tree_image", None)
+            if host is None:
+                host = program._tree_image = self._build_tree_image(program, self.tree)
+            self._blob, self._off_ops, self._tree_struct = host
+            self.plans, self._structs, self._dedupe = [], [], None
+            self.h2d_bytes = int(self._blob.nbytes)
+            self.d_blob = None
+            self.row_len = program.row_len(fold)
+            self.max_state = program.n_qubits
+            self.streaming = False
+            self._work = None
+            self._work_bytes = None
+            return
         self.plans = program.plans(fold)
         # Host image of the program (blob + plan structs): a pure function of the program, built once and
         # shared by every executor of it (programs are cached process-wide; run() only ever copies the
@@ -773,6 +897,39 @@ class FragmentExecutor:
         self.streaming = self.max_state > program.onchip_max and not program.warp
         self._work = None
         self._work_bytes = None
+
+    @staticmethod
+    def _build_tree_image(program: FragmentProgram, tree: "TreeHost"):
+        """-> (blob [mats f64 | ops i32], offset of the ops, qck_sim_tree_plan with the host fields filled)."""
+        mats = np.ascontiguousarray(program.mats, dtype=np.float64)
+        ops = tree.ops if len(tree.ops) else np.zeros((1, 8), np.int32)
+        off_ops = (mats.nbytes + 255) & ~255
+        blob = np.zeros(off_ops + ops.nbytes, dtype=np.uint8)
+        blob[:mats.nbytes] = mats.view(np.uint8)
+        blob[off_ops:] = np.ascontiguousarray(ops).view(np.uint8).reshape(-1)
+        st = _lib.QckSimTreePlan()
+        st.n_base, st.n_levels, st.n_digits, st.n_out_bits = tree.n_base, len(tree.levels), len(program.radix), tree.n_out_bits
+        st.seg0_begin, st.seg0_end = tree.seg0
+        st.n_free = len(tree.free)
+        for r, (j, p) in enumerate(tree.free):
+            st.free_bit[r], st.free_pos[r] = j, p
+        st.base_sum = tree.base_sum
+        for k, r in enumerate(program.radix):
+            st.radix[k] = r
+        for i, lv in enumerate(tree.levels):
+            L = st.level[i]
+            L.seg_begin, L.seg_end = lv.seg
+            L.kind, L.qubit, L.digit, L.pre_off, L.post_off = lv.kind, lv.qubit, lv.digit, lv.pre_off, lv.post_off
+            L.n_choices, L.col_bit = len(lv.choices), lv.col_bit
+            L.meas_mask = sum(1 << v for v, m in enumerate(lv.meas) if m)
+            L.canon = sum(c << (4 * v) for v, c in enumerate(lv.canon))
+            for v in range(8):
+                L.first_choice[v] = -1
+            for c, (v, o) in enumerate(lv.choices):
+                L.choice_variant[c], L.choice_outcome[c] = v, o
+                if L.first_choice[v] < 0:
+                    L.first_choice[v] = c
+        return blob, off_ops, st
 
     @staticmethod
     def _build_host_image(program: FragmentProgram, plans: list):
@@ -868,6 +1025,18 @@ class FragmentExecutor:
             alloc = torch.zeros if label_range is not None else torch.empty
             out = alloc((prog.num_labels, self.row_len), dtype=torch.float64, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self.tree is not None:
+            st = _lib.QckSimTreePlan.from_buffer_copy(self._tree_struct)
+            st.d_ops = self.d_blob.data_ptr() + self._off_ops
+            st.d_mats = self.d_blob.data_ptr()
+            if self._work_bytes is None:
+                self._work_bytes = int(handle.lib.qck_sim_tree_work_bytes(C.byref(st)))
+            work = handle.scratch(torch, self._work_bytes, self.device, stream, scratch_tag)
+            l0, l1 = label_range if label_range is not None else (0, prog.num_labels)
+            handle.check(handle.lib.qck_sim_tree(handle.ptr, C.byref(st), l0, l1, out.data_ptr(), self.row_len,
+                                                 work.data_ptr(), work.numel(), stream))
+            self._pending_broadcast = False
+            return out
         # Scratch comes from the handle's cache, keyed by (device, stream): it is fetched on EVERY run for the
         # stream this run is enqueued on (work on one stream is ordered; another stream gets its own buffer).
         # Only the size is remembered: the shared-prefix snapshots, or as many streaming states as fit.

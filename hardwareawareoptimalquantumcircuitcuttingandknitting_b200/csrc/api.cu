@@ -68,7 +68,8 @@ extern "C" int qck_destroy(qck_handle* h) {
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->scratch) cudaFree(h->scratch);
     if (h->npd_ws) cudaFree(h->npd_ws);
-    if (h->warp_stash) cudaFree(h->warp_stash);
+    for (int i = 0; i < QCK_SIDE_STREAMS; ++i)
+        if (h->warp_stash[i]) cudaFree(h->warp_stash[i]);
     if (h->side_ready) {
         for (int i = 0; i < QCK_SIDE_STREAMS; ++i) {
             cudaStreamDestroy(h->side[i]);

@@ -35,10 +35,13 @@ struct qck_handle {
     // workspace of nearest_probability_distribution (npd.cu): state, bins, per-CTA partials
     void* npd_ws;
     // register-resident simulator (sim_warp_kernel.inc): branch stash (grows only) and CTAs per SM per variant
-    void* warp_stash;
-    size_t warp_stash_bytes;
-    size_t warp_cnt_bytes;  // leading bytes of warp_stash that hold arrival counters (kept zero between launches)
+    // (one buffer per call slot: the calls of one qck_sim_region overlap on the device and must not share it)
+    void* warp_stash[QCK_SIDE_STREAMS];
+    size_t warp_stash_bytes[QCK_SIDE_STREAMS];
+    size_t warp_cnt_bytes[QCK_SIDE_STREAMS];  // leading bytes that hold arrival counters (zero between launches)
+    unsigned region_calls;                     // batch calls made inside the open region
     int warp_occ[6];
+    int tree_occ[6];
 };
 
 #define QCK_FAIL(h, code, ...)                                    \

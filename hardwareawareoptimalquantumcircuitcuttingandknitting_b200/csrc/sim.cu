@@ -577,6 +577,7 @@ __global__ void __launch_bounds__(256) sim_onchip_group_kernel(const __grid_cons
 }
 
 #include "sim_warp_kernel.inc"
+#include "sim_tree_kernel.inc"
 
 // ------------------------------------------------------------------ streaming regime
 __global__ void __launch_bounds__(256) sim_sweep_kernel(PlanDev plan, SweepDev sw,
@@ -1290,6 +1291,8 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
 }
 
 static int qck_warp_init(qck_handle* h);
+static int qck_tree_init(qck_handle* h);
+static int pick_side_stream(qck_handle* h, unsigned* used, cudaStream_t* st);
 static int warp_single_plan(qck_handle* h, const qck_sim_plan* plan, const int32_t* d_labels, int64_t n_instances,
                             double* d_out, int64_t out_row_stride, cudaStream_t st);
 
@@ -1385,7 +1388,8 @@ int qck_sim_init(qck_handle* h) {
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_wide_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_sharded_kernel, h->max_smem_optin));
     QCK_CUDA(h, qck_allow_max_smem(sim_sweep_tma_sharded_wide_kernel, h->max_smem_optin));
-    return qck_warp_init(h);
+    int rc = qck_warp_init(h);
+    return rc ? rc : qck_tree_init(h);
 }
 
 typedef void (*WarpKernelFn)(const WarpGroupDev, double*, long long);
@@ -1402,7 +1406,7 @@ static WarpKernelFn warp_kernel(int log_r) {
 
 static int qck_warp_init(qck_handle* h) {
     for (int r = 0; r <= 5; ++r) {
-        const int smem = QCK_WARP_PER_CTA * ((48 << (r + 5)) + (int)sizeof(WarpStagedOp) * QCK_WARP_STAGE);
+        const int smem = QCK_WARP_PER_CTA * ((32 << (r + 5)) + (int)sizeof(WarpStagedOp) * QCK_WARP_STAGE);
         QCK_CUDA(h, cudaFuncSetAttribute(warp_kernel(r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
         QCK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, warp_kernel(r), 32 * QCK_WARP_PER_CTA, smem));
@@ -1507,30 +1511,40 @@ static int warp_group_layout(qck_handle* h, const qck_sim_plan* plans, const int
 // scratch layout of the handle: [counters of every group (zero between launches) | stash + partial rows ...]
 static int warp_groups_run(qck_handle* h, WarpGroupHost* W, int n_groups, cudaStream_t* streams, double* d_out,
                            int64_t out_row_stride) {
+    const int cs = h->region ? (int)(h->region_calls++ % QCK_SIDE_STREAMS) : 0;  // scratch slot of this call
     size_t cnt_total = 0, rest_total = 0;
     for (int g = 0; g < n_groups; ++g) {
         cnt_total += W[g].cnt_bytes;
         rest_total += W[g].stash_bytes + W[g].part_bytes;
     }
     const size_t need = cnt_total + rest_total;
-    if (need > h->warp_stash_bytes) {  // grows only; synchronous, first use of a larger shape only
-        if (h->warp_stash) QCK_CUDA(h, cudaFree(h->warp_stash));
-        h->warp_stash = nullptr;
-        h->warp_stash_bytes = 0;
+    if (need > h->warp_stash_bytes[cs]) {  // grows only; synchronous, first use of a larger shape only
+        if (h->warp_stash[cs]) QCK_CUDA(h, cudaFree(h->warp_stash[cs]));
+        h->warp_stash[cs] = nullptr;
+        h->warp_stash_bytes[cs] = 0;
         const size_t want = need + (need >> 2);
-        cudaError_t e = cudaMalloc(&h->warp_stash, want);
+        cudaError_t e = cudaMalloc(&h->warp_stash[cs], want);
         if (e != cudaSuccess) QCK_FAIL(h, QCK_ERR_NOMEM, "cudaMalloc(%zu bytes of branch scratch): %s", want, cudaGetErrorString(e));
-        h->warp_stash_bytes = want;
-        h->warp_cnt_bytes = 0;
+        h->warp_stash_bytes[cs] = want;
+        h->warp_cnt_bytes[cs] = 0;
     }
-    if (cnt_total > h->warp_cnt_bytes) {  // the counter region grew over bytes that held other data: zero it once
-        QCK_CUDA(h, cudaMemset(h->warp_stash, 0, cnt_total));
-        h->warp_cnt_bytes = cnt_total;
+    if (cnt_total > h->warp_cnt_bytes[cs]) {  // the counter region grew over bytes that held other data: zero it once
+        QCK_CUDA(h, cudaMemset(h->warp_stash[cs], 0, cnt_total));
+        h->warp_cnt_bytes[cs] = cnt_total;
     }
-    char* cnt_ptr = reinterpret_cast<char*>(h->warp_stash);
-    char* rest_ptr = cnt_ptr + (h->warp_cnt_bytes > cnt_total ? h->warp_cnt_bytes : cnt_total);
-    if (rest_ptr + rest_total > reinterpret_cast<char*>(h->warp_stash) + h->warp_stash_bytes)
-        rest_ptr = cnt_ptr + cnt_total;  // (cannot happen: warp_cnt_bytes <= an earlier need)
+    char* cnt_ptr = reinterpret_cast<char*>(h->warp_stash[cs]);
+    char* rest_ptr = cnt_ptr + h->warp_cnt_bytes[cs];
+    if (h->warp_cnt_bytes[cs] + rest_total > h->warp_stash_bytes[cs]) {  // counters once needed more than now: regrow
+        QCK_CUDA(h, cudaFree(h->warp_stash[cs]));
+        h->warp_stash[cs] = nullptr;
+        const size_t want = h->warp_cnt_bytes[cs] + rest_total + (rest_total >> 2);
+        cudaError_t e = cudaMalloc(&h->warp_stash[cs], want);
+        if (e != cudaSuccess) QCK_FAIL(h, QCK_ERR_NOMEM, "cudaMalloc(%zu bytes of branch scratch): %s", want, cudaGetErrorString(e));
+        h->warp_stash_bytes[cs] = want;
+        QCK_CUDA(h, cudaMemset(h->warp_stash[cs], 0, h->warp_cnt_bytes[cs]));
+        cnt_ptr = reinterpret_cast<char*>(h->warp_stash[cs]);
+        rest_ptr = cnt_ptr + h->warp_cnt_bytes[cs];
+    }
     for (int g = 0; g < n_groups; ++g) {
         WarpGroupDev& G = W[g].G;
         G.cnt = reinterpret_cast<unsigned*>(cnt_ptr);
@@ -1539,11 +1553,135 @@ static int warp_groups_run(qck_handle* h, WarpGroupHost* W, int n_groups, cudaSt
         rest_ptr += W[g].stash_bytes;
         G.part = reinterpret_cast<double*>(rest_ptr);
         rest_ptr += W[g].part_bytes;
-        const int smem = QCK_WARP_PER_CTA * ((48 << (W[g].log_r + 5)) + (int)sizeof(WarpStagedOp) * QCK_WARP_STAGE);
+        const int smem = QCK_WARP_PER_CTA * ((32 << (W[g].log_r + 5)) + (int)sizeof(WarpStagedOp) * QCK_WARP_STAGE);
         warp_kernel(W[g].log_r)<<<(unsigned)W[g].ctas, 32 * QCK_WARP_PER_CTA, smem, streams[g]>>>(
             G, d_out, (long long)out_row_stride);
         QCK_CHECK_LAUNCH(h);
     }
+    return QCK_OK;
+}
+
+// ---- tree-walk simulation ----------------------------------------------------------------------
+typedef void (*TreeKernelFn)(const TreeDev, int, long long, const double2*, double2*, double*);
+static TreeKernelFn tree_kernel(int log_r) {
+    switch (log_r) {
+        case 0: return sim_tree_level_kernel<0>;
+        case 1: return sim_tree_level_kernel<1>;
+        case 2: return sim_tree_level_kernel<2>;
+        case 3: return sim_tree_level_kernel<3>;
+        case 4: return sim_tree_level_kernel<4>;
+        default: return sim_tree_level_kernel<5>;
+    }
+}
+static int tree_smem(int log_r) { return QCK_WARP_PER_CTA * ((8 << (log_r + 5)) + (int)sizeof(WarpStagedOp) * QCK_WARP_STAGE); }
+
+static int qck_tree_init(qck_handle* h) {
+    for (int r = 0; r <= 5; ++r) {
+        QCK_CUDA(h, cudaFuncSetAttribute(tree_kernel(r), cudaFuncAttributeMaxDynamicSharedMemorySize, tree_smem(r)));
+        int occ = 0;
+        QCK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tree_kernel(r), 32 * QCK_WARP_PER_CTA, tree_smem(r)));
+        h->tree_occ[r] = occ < 1 ? 1 : occ;
+    }
+    return QCK_OK;
+}
+
+// nodes per level (n[l] = nodes BEFORE branching op l; n[n_levels] = leaves); false when out of range
+static bool tree_counts(const qck_sim_tree_plan* p, long long* n) {
+    if (!p || p->n_levels < 1 || p->n_levels > QCK_TREE_MAX_LEVELS || p->n_base < 1 || p->n_base > 10) return false;
+    n[0] = 1;
+    for (int l = 0; l < p->n_levels; ++l) {
+        const int b = p->level[l].n_choices;
+        if (b < 1 || b > QCK_TREE_MAX_CHOICES) return false;
+        n[l + 1] = n[l] * b;
+        if (n[l + 1] > (1ll << 40)) return false;
+    }
+    return true;
+}
+static void tree_layout(const qck_sim_tree_plan* p, const long long* n, size_t* state_bytes, size_t* part_bytes) {
+    long long max_inner = 0;
+    for (int l = 1; l < p->n_levels; ++l)
+        if (n[l] > max_inner) max_inner = n[l];
+    const int nq = p->n_base > 5 ? p->n_base : 5;
+    *state_bytes = (((size_t)max_inner * sizeof(double2)) << nq) + 256;
+    *part_bytes = (((size_t)n[p->n_levels] * sizeof(double)) << p->n_free) + 256;
+}
+
+extern "C" size_t qck_sim_tree_work_bytes(const qck_sim_tree_plan* plan) {
+    long long n[QCK_TREE_MAX_LEVELS + 1];
+    if (!tree_counts(plan, n)) return 0;
+    size_t sb, pb;
+    tree_layout(plan, n, &sb, &pb);
+    return 2 * sb + pb;
+}
+
+extern "C" int qck_sim_tree(qck_handle* h, const qck_sim_tree_plan* plan, int64_t label_begin, int64_t label_end,
+                            double* d_out, int64_t out_row_stride, void* d_work, size_t work_bytes,
+                            qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    long long n[QCK_TREE_MAX_LEVELS + 1];
+    if (!tree_counts(plan, n)) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "tree plan out of range");
+    if (!d_out || !plan->d_ops || !plan->d_mats || label_begin < 0 || label_end < label_begin)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad tree arguments");
+    if (plan->n_out_bits < 0 || plan->n_out_bits > 20 || plan->n_free < 0 || plan->n_free > plan->n_out_bits ||
+        plan->n_free > plan->n_base || out_row_stride < (1ll << plan->n_out_bits) || plan->n_digits > QCK_MAX_DIGITS)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad tree row layout");
+    if (label_end == label_begin) return QCK_OK;
+    size_t sb, pb;
+    tree_layout(plan, n, &sb, &pb);
+    if (!d_work || work_bytes < 2 * sb + pb)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "tree simulation needs %zu bytes of work space, got %zu", 2 * sb + pb, work_bytes);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->region) {  // the levels are dependent launches: the whole call goes on ONE side stream of the region
+        int rc = pick_side_stream(h, &h->region_used, &st);
+        if (rc) return rc;
+    }
+    std::unique_ptr<TreeDev> T(new TreeDev);
+    memset(T.get(), 0, sizeof(TreeDev));
+    T->n_base = plan->n_base;
+    T->n_levels = plan->n_levels;
+    T->n_digits = plan->n_digits;
+    T->n_out_bits = plan->n_out_bits;
+    T->seg0_begin = plan->seg0_begin;
+    T->seg0_end = plan->seg0_end;
+    T->n_free = plan->n_free;
+    memcpy(T->free_bit, plan->free_bit, sizeof(T->free_bit));
+    memcpy(T->free_pos, plan->free_pos, sizeof(T->free_pos));
+    T->base_sum = plan->base_sum;
+    T->ops = plan->d_ops;
+    T->mats = plan->d_mats;
+    long long div = 1, total = 1;
+    for (int k = QCK_MAX_DIGITS - 1; k >= 0; --k) {
+        T->radix[k] = k < plan->n_digits ? plan->radix[k] : 1;
+        T->div[k] = (int)div;
+        if (k < plan->n_digits) div *= plan->radix[k];
+        if (div > 0x7fffffffll) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "fragment label space exceeds 2^31");
+    }
+    total = div;
+    if (label_end > total) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "label range exceeds the %lld labels of the fragment", total);
+    for (int l = 0; l < plan->n_levels; ++l) {
+        T->level[l] = plan->level[l];
+        const qck_tree_level& L = plan->level[l];
+        if (L.qubit < 0 || L.qubit >= plan->n_base || (L.kind != QCK_TREE_MMEAS && (L.digit < 0 || L.digit >= plan->n_digits)))
+            QCK_FAIL(h, QCK_ERR_INVALID_ARG, "tree level %d: bad qubit / digit", l);
+    }
+    const int log_r = plan->n_base > 5 ? plan->n_base - 5 : 0;
+    double2* sbuf[2] = {reinterpret_cast<double2*>(d_work), reinterpret_cast<double2*>((char*)d_work + sb)};
+    double* part = reinterpret_cast<double*>((char*)d_work + 2 * sb);
+    const long long cap = (long long)h->sm_count * h->tree_occ[log_r];
+    for (int l = 0; l < plan->n_levels; ++l) {
+        const long long items = n[l + 1];
+        long long ctas = (items + QCK_WARP_PER_CTA - 1) / QCK_WARP_PER_CTA;
+        if (ctas > cap) ctas = cap;
+        tree_kernel(log_r)<<<(unsigned)ctas, 32 * QCK_WARP_PER_CTA, tree_smem(log_r), st>>>(
+            *T, l, items, sbuf[(l + 1) & 1], sbuf[l & 1], part);
+        QCK_CHECK_LAUNCH(h);
+    }
+    const unsigned long long cols = (unsigned long long)(label_end - label_begin) << plan->n_out_bits;
+    unsigned long long cg = (cols + 255) / 256;
+    if (cg > (unsigned long long)h->sm_count * 16) cg = (unsigned long long)h->sm_count * 16;
+    sim_tree_combine_kernel<<<(unsigned)cg, 256, 0, st>>>(*T, label_begin, label_end, part, d_out, (long long)out_row_stride);
+    QCK_CHECK_LAUNCH(h);
     return QCK_OK;
 }
 
@@ -1645,6 +1783,7 @@ extern "C" int qck_sim_region_begin(qck_handle* h, qck_stream stream) {
     QCK_CUDA(h, cudaEventRecord(h->fork, (cudaStream_t)stream));
     h->region = 1;
     h->region_used = 0;
+    h->region_calls = 0;
     return QCK_OK;
 }
 

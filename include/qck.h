@@ -183,6 +183,47 @@ QCK_API int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim_pl
 QCK_API int qck_sim_region_begin(qck_handle* h, qck_stream stream);
 QCK_API int qck_sim_region_end(qck_handle* h, qck_stream stream);
 
+/* ------------------------------------------------------------------ tree-walk simulation
+ * ALL instances of a fragment of <= 10 qubits (ops: QCK_OP_U1 / CX / CZ) in one call, every shared prefix
+ * simulated once.  The program is cut at its BRANCHING OPS - virtual-gate endpoints ("slots",
+ * virtual_gates.py:127-150) and mid-circuit measurements of the input circuit - into label-independent
+ * segments; level l of the tree = the l-th branching op, a choice = (representative variant of the slot's
+ * gate, outcome of its measurement if that variant measures and the qubit lives on).  One launch per level
+ * (one warp per parent node x choice, state in registers, states of a level in d_work), then one launch that
+ * writes the row of EVERY label in [label_begin, label_end): the sum, in a fixed order, of the partial rows of
+ * its outcome leaves (labels whose variants are identical to a representative's read the same leaves).
+ * Rows are the signed-folded rows of qck_sim_fragments (config bits folded with (-1)^bit). */
+#define QCK_TREE_MAX_LEVELS 24
+#define QCK_TREE_MAX_CHOICES 16
+enum { QCK_TREE_SLOT = 0,       /* slot whose qubit lives on: a measuring variant forks into two outcomes   */
+       QCK_TREE_TERMINAL = 1,   /* slot on a wire that ends there: a measuring variant signs the qubit's bit */
+       QCK_TREE_MMEAS = 2 };    /* mid-circuit measurement of the input circuit: the outcome is row bit col_bit */
+typedef struct {
+    int32_t seg_begin, seg_end;   /* ops AFTER this branching op, up to the next one (indices into d_ops)   */
+    int32_t kind, qubit, digit;   /* digit: label digit of the slot's gate (-1: QCK_TREE_MMEAS)              */
+    int32_t pre_off, post_off;    /* variant matrices in d_mats (doubles, 8 per variant), -1: all identity   */
+    int32_t n_choices, col_bit;
+    uint32_t meas_mask;           /* bit v: variant v measures                                               */
+    uint32_t canon;               /* 4 bits per variant: its representative (identical pre / meas / post)    */
+    uint8_t choice_variant[QCK_TREE_MAX_CHOICES];
+    int8_t choice_outcome[QCK_TREE_MAX_CHOICES];   /* -1: no projection; a fork lists outcome 0 then 1       */
+    int8_t first_choice[8];                        /* per representative variant: its first choice           */
+} qck_tree_level;
+typedef struct {
+    int32_t n_base, n_levels, n_digits, n_out_bits;
+    int32_t seg0_begin, seg0_end; /* ops before the first branching op                                       */
+    int32_t n_free;               /* row bits that are fragment qubits: row bit free_bit[r] <- state bit free_pos[r] */
+    int8_t free_bit[16], free_pos[16];
+    uint64_t base_sum;            /* fragment qubits summed out                                              */
+    const qck_op* d_ops;          /* device: ops on STATE bit positions, no label-selected matrices          */
+    const double* d_mats;         /* device                                                                  */
+    int32_t radix[QCK_MAX_DIGITS];
+    qck_tree_level level[QCK_TREE_MAX_LEVELS];
+} qck_sim_tree_plan;
+QCK_API size_t qck_sim_tree_work_bytes(const qck_sim_tree_plan* plan);
+QCK_API int qck_sim_tree(qck_handle* h, const qck_sim_tree_plan* plan, int64_t label_begin, int64_t label_end,
+                         double* d_out, int64_t out_row_stride, void* d_work, size_t work_bytes, qck_stream stream);
+
 /* Final statevector of ONE instance in the streaming regime left in d_work
  * (used for the uncut reference run, Utilities.py:39-69). */
 QCK_API int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t label,

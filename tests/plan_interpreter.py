@@ -279,3 +279,99 @@ def _run_plan_warp_item(program, plan, label, split, forced):
         if not resumed:
             break
     return row
+
+
+def run_tree(program, label_range=None):
+    """The tree-walk simulation (csrc/sim_tree_kernel.inc) step for step: level kernels over (parent node,
+    choice) items, partial rows of the leaves, then the per-(label, column) combine.  -> [num_labels, row_len]"""
+    tree = program.tree()
+    assert tree is not None
+    mats = program.mats
+    nb = tree.n_base
+    idx = np.arange(1 << nb)
+
+    def u1(psi, q, off):
+        return apply_op(psi, idx, _lib.OP_U1, q, 0, mats, off)
+
+    def segment(psi, seg):
+        for row in tree.ops[seg[0]:seg[1]]:
+            kind, q0, q1, mat = (int(x) for x in row[:4])
+            psi = apply_op(psi, idx, kind, q0, q1, mats, mat)
+        return psi
+
+    states = None
+    n_levels = len(tree.levels)
+    part = None
+    for lv, L in enumerate(tree.levels):
+        n_items = tree.node_counts[lv + 1]
+        B = len(L.choices)
+        new_states = np.zeros((n_items, 1 << nb), dtype=np.complex128)
+        for it in range(n_items):
+            parent, c = divmod(it, B)
+            if lv == 0:
+                psi = np.zeros(1 << nb, dtype=np.complex128)
+                psi[0] = 1.0
+                psi = segment(psi, tree.seg0)
+            else:
+                psi = states[parent]
+            v, oc = L.choices[c]
+            if L.pre_off >= 0:
+                psi = u1(psi, L.qubit, L.pre_off + 8 * v)
+            if oc >= 0:
+                psi = np.where(_bits(idx, L.qubit) == oc, psi, 0.0)
+            if L.post_off >= 0:
+                psi = u1(psi, L.qubit, L.post_off + 8 * v)
+            new_states[it] = segment(psi, L.seg)
+        states = new_states
+    # leaves -> partial rows
+    n_free = len(tree.free)
+    part = np.zeros((tree.node_counts[-1], 1 << n_free))
+    for it in range(tree.node_counts[-1]):
+        node, parity, base_sign = it, 0, 0
+        for L in reversed(tree.levels):
+            node, cl = divmod(node, len(L.choices))
+            v, oc = L.choices[cl]
+            if L.kind == _lib.TREE_SLOT and oc > 0:
+                parity ^= 1
+            elif L.kind == _lib.TREE_TERMINAL and L.meas[v]:
+                base_sign |= 1 << L.qubit
+        prob = states[it].real ** 2 + states[it].imag ** 2
+        sgn = np.array([(-1.0) ** (bin(int(i) & base_sign).count("1") + parity) for i in idx])
+        P = sgn * prob
+        for o in range(1 << n_free):
+            base = sum(1 << p for r, (_, p) in enumerate(tree.free) if (o >> r) & 1)
+            sub, acc = 0, 0.0
+            while True:
+                acc += P[base | sub]
+                sub = (sub - tree.base_sum) & tree.base_sum
+                if sub == 0:
+                    break
+            part[it, o] = acc
+    # combine: one (label, column) at a time
+    out = np.zeros((program.num_labels, 1 << tree.n_out_bits))
+    labels = range(program.num_labels) if label_range is None else range(*label_range)
+    for label in labels:
+        digits = list(np.unravel_index(label, program.radix)) if program.radix else []
+        for col in range(1 << tree.n_out_bits):
+            o = sum(1 << r for r, (j, _) in enumerate(tree.free) if (col >> j) & 1)
+            base, fork = [], []
+            for L in tree.levels:
+                if L.kind == _lib.TREE_MMEAS:
+                    base.append((col >> L.col_bit) & 1)
+                    fork.append(0)
+                else:
+                    rep = L.canon[int(digits[L.digit])]
+                    base.append([c for c, (v, _) in enumerate(L.choices) if v == rep][0])
+                    fork.append(1 if (L.kind == _lib.TREE_SLOT and L.meas[rep]) else 0)
+            acc = 0.0
+            for combo in range(1 << sum(fork)):
+                node, k = 0, 0
+                for L, b, f in zip(tree.levels, base, fork):
+                    c = b
+                    if f:
+                        c += (combo >> k) & 1
+                        k += 1
+                    node = node * len(L.choices) + c
+                acc += part[node, o]
+            out[label, col] = acc
+    return out

@@ -1009,3 +1009,84 @@ def test_mid_circuit_measurement_end_to_end(dev):
     ref, _ = oracle_knit(cut, 0.0)
     got = dense_res.to_dict()
     assert max(abs(got.get(k, 0.0) - ref.get(k, 0.0)) for k in set(got) | set(ref)) < TOL_P
+
+
+# ------------------------------------------------------------------ register-resident kernels
+@pytest.mark.parametrize("cfg", ["bv16", "syc16d5", "hwe16d5", "semcheck"])
+def test_tree_warp_and_shared_memory_kernels_agree(dev, cfg):
+    """Three simulators of the same fragment tables: the level-by-level tree walk (sim_tree_kernel), one
+    warp per instance with a depth-first walk over the measurement outcomes (sim_warp_kernel) and one CTA per
+    instance with the state in shared memory (sim_onchip_group_kernel) - all against each other, and a
+    sample of rows against the oracle."""
+    if cfg == "semcheck":
+        _, cut = make_semcheck_circuit("cx")
+    else:
+        _, cut = cutting.make_baseline(cfg, seed=2)
+    virt = vcm.VirtualCircuit(cut)
+    ov = oi.OracleVirtualCircuit(cut)
+    h = _lib.get_handle(0)
+    K = len(virt.vgates)
+    rng = np.random.default_rng(5)
+    for f in virt.active_fragments():
+        circ_f = virt.fragment_circuits[f]
+        p_tree = compiler.FragmentProgram(circ_f, f, virt.num_clbits)
+        assert p_tree.warp and p_tree.tree() is not None
+        old = compiler.TREE
+        compiler.TREE = False
+        try:
+            p_warp = compiler.FragmentProgram(circ_f, f, virt.num_clbits)
+            assert p_warp.warp and p_warp.tree() is None
+        finally:
+            compiler.TREE = old
+        p_smem = compiler.FragmentProgram(circ_f, f, virt.num_clbits, warp=False)
+        assert not p_smem.warp
+        e_tree = compiler.FragmentExecutor(p_tree, dev)
+        assert e_tree.tree is not None
+        t_tree = e_tree.run(h).cpu().numpy()
+        t_warp = compiler.FragmentExecutor(p_warp, dev).run(h).cpu().numpy()
+        t_smem = compiler.FragmentExecutor(p_smem, dev).run(h).cpu().numpy()
+        assert np.abs(t_tree - t_warp).max() < 1e-13
+        assert np.abs(t_tree - t_smem).max() < 1e-13
+        labels = ov.instance_labels(f)
+        for li in rng.choice(len(labels), size=min(6, len(labels)), replace=False):
+            want = od.signed_fold(sv.exact_distribution(ov.instance(f, labels[li])), ov.n_clbits, K, p_tree.out_mask)
+            assert np.abs(want - t_tree[li]).max() < TOL_P
+        # a label range writes exactly its rows
+        lo, hi = len(labels) // 3, len(labels)
+        part = torch.zeros_like(torch.from_numpy(t_tree)).to(dev)
+        e_tree.run(h, out=part, label_range=(lo, hi))
+        part = part.cpu().numpy()
+        assert np.array_equal(part[lo:hi], t_tree[lo:hi]) and not part[:lo].any()
+
+
+@pytest.mark.parametrize("cfg", ["syc16d5", "hwe16d5"])
+def test_back_to_back_runs_are_bit_identical(dev, cfg):
+    """Several steps enqueued without a synchronisation in between (what bench.py does): the fragments of one
+    step overlap on side streams (qck_sim_region), consecutive steps reuse the scratch - no step may see
+    another's data.  Every result identical to the first and equal to the oracle's."""
+    circ, cut = cutting.make_baseline(cfg, seed=0)
+    virt = vcm.VirtualCircuit(cut)
+    outs = []
+    for _ in range(6):
+        tabs = virt.simulate_fragments(dev)
+        outs.append(virt.knit_tables(tabs, dev).clone())
+    torch.cuda.synchronize()
+    want = cport.simulate_probabilities(circ)
+    assert np.abs(outs[0].cpu().numpy() - want).max() < TOL_P
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    old = compiler.TREE
+    compiler.TREE = False
+    try:
+        vcm.clear_program_cache()
+        v2 = vcm.VirtualCircuit(cut)
+        outs2 = []
+        for _ in range(6):
+            outs2.append(v2.knit_tables(v2.simulate_fragments(dev), dev).clone())
+        torch.cuda.synchronize()
+    finally:
+        compiler.TREE = old
+        vcm.clear_program_cache()
+    assert np.abs(outs2[0].cpu().numpy() - want).max() < TOL_P
+    for o in outs2[1:]:
+        assert torch.equal(o, outs2[0])

@@ -99,3 +99,61 @@ def test_random_cut_circuits(seed):
         prog = virt.program(f)
         if prog.warp:          # (fragments holding a general two-qubit gate keep the other kernels)
             _check_program(prog, True, n_labels=3, seed=seed)
+
+
+# ------------------------------------------------------------------ tree-walk simulation (sim_tree_kernel.inc)
+@pytest.mark.parametrize("gname,theta", [("cx", None), ("cz", None), ("cy", None), ("rzz", 0.83), ("cp", 0.83)])
+def test_tree_tables_equal_per_instance_tables(gname, theta):
+    """The level-by-level tree walk (every shared prefix once, one representative per class of identical
+    variants, partial rows per outcome leaf, per-label combine) gives the table the per-instance programs give."""
+    qc, cut = make_semcheck_circuit(gname, theta)
+    virt = vcm.VirtualCircuit(cut)
+    for f in virt.active_fragments():
+        prog = virt.program(f)
+        tree = prog.tree()
+        assert tree is not None
+        want = pi.run_program(prog, True)
+        got = pi.run_tree(prog)
+        assert np.abs(got - want).max() < 1e-14
+
+
+def test_tree_on_a_baseline_fragment_and_with_mid_circuit_measurement():
+    circ, cut = cutting.make_baseline("bv16", seed=0)
+    virt = vcm.VirtualCircuit(cut)
+    for f in virt.active_fragments():
+        prog = virt.program(f)
+        assert prog.tree() is not None
+        assert np.abs(pi.run_tree(prog) - pi.run_program(prog, True)).max() < 1e-14
+    # mid-circuit measurement of the input circuit next to a gate cut: a level whose outcome is a column bit
+    q4 = circuit.QuantumCircuit(circuit.QuantumRegister(4, "q"), circuit.ClassicalRegister(5, "c"))
+    for q in range(4):
+        q4.ry(0.3 + 0.2 * q, q)
+    q4.cx(0, 1); q4.measure(0, 4); q4.h(0); q4.cx(2, 3); q4.cx(1, 2); q4.rx(0.4, 1); q4.cx(0, 1); q4.ry(0.2, 2)
+    for q in range(4):
+        q4.measure(q, q)
+    gidx = [i for i, ins in enumerate(q4.data) if ins.operation.name == "cx"][2]
+    virt = vcm.VirtualCircuit(cutting.apply_cuts(q4, cutting.CutSpec(gate_cuts=[gidx])))
+    kinds = set()
+    for f in virt.active_fragments():
+        prog = virt.program(f)
+        tree = prog.tree()
+        assert tree is not None
+        kinds |= {l.kind for l in tree.levels}
+        assert np.abs(pi.run_tree(prog) - pi.run_program(prog, True)).max() < 1e-14
+    assert _lib.TREE_MMEAS in kinds and _lib.TREE_SLOT in kinds
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_tree_random_cut_circuits(seed):
+    rng = random.Random(1300 + seed)
+    n = rng.randint(4, 8)
+    qc = rc.random_circuit(rng, n, rng.randint(15, 30))
+    cut = cutting.apply_cuts(qc, rc.random_cut(rng, qc, max_gate_cuts=2, wire_cut=(seed % 2 == 0)))
+    virt = vcm.VirtualCircuit(cut)
+    for f in virt.active_fragments():
+        prog = virt.program(f)
+        if prog.tree() is not None and prog.num_labels <= 64:
+            assert np.abs(pi.run_tree(prog) - pi.run_program(prog, True)).max() < 1e-13
+            lo, hi = prog.num_labels // 3, prog.num_labels
+            part = pi.run_tree(prog, (lo, hi))
+            assert np.abs(part[lo:hi] - pi.run_program(prog, True)[lo:hi]).max() < 1e-13 and not part[:lo].any()
