@@ -61,6 +61,8 @@ def parse_args():
                     help="log2 of the output entries the CPU baseline knits per sampled step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the compact other_workloads section")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="enqueue every resident step launch by launch instead of replaying its CUDA graph")
     ap.add_argument("--uncut-statevector", action="store_true", default=None,
                     help="also simulate the UNCUT circuit as one statevector on this GPU (64 GiB at 32 qubits), "
                          "report the streaming simulator against the HBM roofline and the dense fidelity "
@@ -428,6 +430,7 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
     import torch
     import torch.distributed as dist
     qdist, cutting, vc, runm, fid, lib = (env[k] for k in ("qdist", "cutting", "vc", "runm", "fid", "lib"))
+    import torch.distributed as dist
     rank, world, device, handle = env["rank"], env["world"], env["device"], env["handle"]
     steps, warmup = (args.steps, max(args.warmup, 3)) if primary else (min(args.steps, 10), 3)
     stream = torch.cuda.current_stream(device).cuda_stream
@@ -442,52 +445,12 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
     L = virt.num_global_labels()
     faithful = accuracy > 0.0
 
-    # partition over the ranks
-    mode = "single"
-    if world > 1:
-        mode = "output index by top bits" if K == 0 else qdist.partition_mode(virt, world, faithful)
-    if K == 0:
-        y0, y1 = qdist.shard_pow2(n_out, rank, world) if world > 1 else (0, 1 << n_out)
-        label_range = None
-    else:
-        y0, y1 = 0, 1 << n_out
-        label_range = (qdist.shard_range(L, rank, world, align=virt.global_radices()[-1])
-                       if mode == "label range + all-reduce" else None)
-    out = torch.empty(y1 - y0, dtype=torch.float64, device=device)
-    stats = torch.zeros(4, dtype=torch.float64, device=device)
-    ws = handle.npd_workspace(torch, device)
-    for f in frags:                                  # programs resident in HBM before the timed region
-        virt.executor(f, device, not faithful).upload()
-    holder, ev_log = {}, []
-
-    def step_resident(record: bool) -> None:
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
-        if record:
-            ev[0].record()
-        tables = virt.simulate_fragments(device, label_range=label_range, fold=not faithful)
-        holder["t"] = tables
-        if record:
-            ev[1].record()
-        if faithful:
-            virt.knit_tables_faithful(tables, accuracy, device, out=out)
-        elif K == 0:
-            virt.knit_tables(tables, device, stats=stats, y_range=(y0, y1) if world > 1 else None, out=out)
-        else:
-            virt.knit_tables(tables, device, label_range=label_range, out=out)
-        if record:
-            ev[2].record()
-        if K == 0:
-            if world > 1:
-                qdist.allreduce_stats(stats)         # min >= 0 by construction: no npd pass over 2^32 entries
-        else:
-            if label_range is not None:
-                qdist.allreduce_sum_(out)
-            # statistics + nearest_probability_distribution (run.py:71), enqueued: no host round trip
-            handle.check(handle.lib.qck_npd_async(handle.ptr, out.data_ptr(), out.numel(), accuracy,
-                                                  ws.data_ptr(), stream))
-        if record:
-            ev[3].record()
-            ev_log.append(ev)
+    # the resident step: programs in HBM, buffers allocated once, the whole step one CUDA graph
+    resm = env["resident"]
+    rs = resm.ResidentStep(virt, device, nearest=True, rank=rank, world_size=world, accuracy=accuracy, graph=False)
+    mode, label_range, y0, y1, out, stats, ws = rs.mode, rs.label_range, rs.y0, rs.y1, rs.out, rs.stats, rs.ws
+    holder = {"t": rs.tables}
+    use_graph = not (args.no_graph or args.profile)
 
     def barrier() -> None:
         if world > 1:
@@ -500,33 +463,53 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(warmup):
-        step_resident(False)
+    l0 = handle.launch_count
+    rs.enqueue()                                      # (also the first warm-up step)
+    launches_per_step = handle.launch_count - l0
+    for _ in range(warmup - 1):
+        rs.enqueue()
+    barrier()
+    step = rs.enqueue
+    if use_graph:
+        graph = rs.capture()
+        step = graph.replay
+        for _ in range(2):
+            step()
     barrier()
     sampler = ClockSampler(env["local_rank"]) if (rank == 0 and primary) else None
     time.sleep(0.15 if sampler else 0.0)
     barrier()
-    launches0 = handle.launch_count
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
-        step_resident(True)
+        step()
     e1.record()
+    host_ms = (time.perf_counter() - h0) * 1e3 / steps     # what the host spends enqueueing a step
     barrier()
     t_wall1 = time.time()
-    launches = handle.launch_count - launches0
+    launches = launches_per_step * steps
     ms_per_step = reduce_max(e0.elapsed_time(e1)) / steps
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    # the three phases of the step, each on its own (graph replays, or eager launches under --no-graph)
+    phases = rs.capture(phases=True) if use_graph else None
+    fns = [g.replay for g in phases] if phases else [rs.enqueue_simulation, rs.enqueue_knit, rs.enqueue_post]
+    ev_log = []
+    n_phase = min(steps, 10)
+    for _ in range(n_phase):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        for i, fn in enumerate(fns):
+            fn()
+            ev[i + 1].record()
+        ev_log.append(ev)
+    barrier()
     sim_ms = reduce_max(sum(e[0].elapsed_time(e[1]) for e in ev_log) / len(ev_log))
     knit_ms = reduce_max(sum(e[1].elapsed_time(e[2]) for e in ev_log) / len(ev_log))
     post_ms = reduce_max(sum(e[2].elapsed_time(e[3]) for e in ev_log) / len(ev_log))
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    if K == 0:
-        host_stats = stats.cpu().numpy().copy()
-        r_sum, r_min = float(host_stats[0]), float(host_stats[1])
-    else:
-        st = runm._check_npd_state(ws)
-        r_sum, r_min = float(st[0]), float(st[1])
+    res = rs.result()
+    r_sum, r_min = res.total, res.minimum
     result_after = out.clone() if out.numel() <= (1 << 26) else out       # e2e reuses `out`
 
     # ---- e2e: public API, fresh VirtualCircuit per step (host compile + H2D + kernels + D2H)
@@ -651,6 +634,9 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": launches,
+        "resident_step": {"cuda_graph": use_graph, "launches_per_step": launches_per_step,
+                          "host_enqueue_ms_per_step": host_ms,
+                          "phase_ms": {"simulation": sim_ms, "knit": knit_ms, "npd+collective": post_ms}},
         "roofline": roofline,
         "cpu_baseline": cpu_rep,
         "result_sum": r_sum, "result_min": r_min,
@@ -693,7 +679,8 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
     env = {k: import_module(f"{PKG}.{m}") for k, m in (("qdist", "dist"), ("cutting", "cutting"),
                                                         ("vc", "virtual_circuit"), ("runm", "run"),
-                                                        ("fid", "fidelity"), ("lib", "_lib"))}
+                                                        ("fid", "fidelity"), ("lib", "_lib"),
+                                                        ("resident", "resident"))}
     import ctypes as C
     import torch.distributed as dist
     rank, local_rank, world = env["qdist"].init_from_env("nccl")

@@ -17,7 +17,7 @@ __all__ = [
     "VIRTUAL_GATE_TYPES", "VirtualBinaryGate", "VirtualCPhase", "VirtualCX", "VirtualCY", "VirtualCZ",
     "VirtualGateEndpoint", "VirtualMove", "VirtualRZZ", "WireCut",
     "VirtualCircuit", "QuasiDistr", "run_virtual_circuit", "run_virtual_circuit_dense", "RunTimeInfo",
-    "B200Backend", "hellinger_fidelity",
+    "B200Backend", "hellinger_fidelity", "ResidentStep",
 ]
 
 _LAZY = {
@@ -28,6 +28,7 @@ _LAZY = {
     "RunTimeInfo": ("run", "RunTimeInfo"),
     "B200Backend": ("backend", "B200Backend"),
     "hellinger_fidelity": ("fidelity", "hellinger_fidelity"),
+    "ResidentStep": ("resident", "ResidentStep"),
 }
 
 

@@ -627,6 +627,98 @@ __global__ void __launch_bounds__(256) contract_dmma_kernel(const __grid_constan
         }
 }
 
+// The same contraction with the gather PIPELINED (ncu, round 1: the kernel above keeps the DMMA pipe 32 % busy -
+// gather -> barrier -> multiply -> barrier per 16 labels, and the weight multiplication sits in the gather).
+// Here the table rows of the next two label chunks are in flight (cp.async.cg, 16 bytes per request, zero-fill
+// for padding) while the tensor cores work on the current one; the label weights are applied to the A fragments
+// as they leave shared memory, so both operands are plain copies.  Three stages of [16 labels][64 + 8] doubles
+// per operand = 54 KiB of dynamic shared memory.
+#define GS 3
+struct ContractStage {
+    double A[GK][GP];
+    double B[GK][GP];
+    double W[GK];
+};
+__device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256) contract_dmma_pipe_kernel(const __grid_constant__ ContractParams P, int n_split,
+                                                                 double* __restrict__ partial, int M, int N, int Mr,
+                                                                 int Nr) {
+    extern __shared__ __align__(16) unsigned char cps_raw[];
+    ContractStage* stage = reinterpret_cast<ContractStage*>(cps_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wi = (warp >> 2) * 32, wj = (warp & 3) * 16;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int i0 = blockIdx.x * GT, j0 = blockIdx.y * GT;
+    const long long per = (P.count + n_split - 1) / n_split;
+    const long long lb = per * blockIdx.z, le = (lb + per < P.count) ? lb + per : P.count;
+    const int* rowA = P.rows;
+    const int* rowB = P.rows + P.count;
+    const long long n_chunks = le > lb ? (le - lb + GK - 1) / GK : 0;
+    // this thread's share of a stage: 4 requests of 16 bytes (2 doubles) - rows rr, columns cc..cc+1
+    auto issue = [&](long long chunk) {
+        ContractStage& S = stage[chunk % GS];
+        const long long l0 = lb + chunk * GK;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int e = tid + 256 * k;           // 512 requests per operand
+            const int rr = e >> 5, cc = (e & 31) * 2;
+            const long long l = l0 + rr;
+            const bool in = l < le;
+            const long long ra = in ? (long long)__ldg(rowA + l) : 0, rb = in ? (long long)__ldg(rowB + l) : 0;
+            cp_async16_zfill(&S.A[rr][cc], P.table[0] + ra * P.row_stride[0] + i0 + cc, in && (i0 + cc < Mr));
+            cp_async16_zfill(&S.B[rr][cc], P.table[1] + rb * P.row_stride[1] + j0 + cc, in && (j0 + cc < Nr));
+        }
+        if (tid < GK) {
+            const long long l = l0 + tid;
+            S.W[tid] = l < le ? __ldg(P.w + l) : 0.0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double acc[4][2][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int c = 0; c < GS - 1; ++c) {
+        if (c < n_chunks) issue(c);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (long long c = 0; c < n_chunks; ++c) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(GS - 2) : "memory");
+        __syncthreads();  // chunk c has landed for everyone; everyone is done with chunk c - 1's buffer
+        if (c + GS - 1 < n_chunks) issue(c + GS - 1);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const ContractStage& S = stage[c % GS];
+#pragma unroll
+        for (int k4 = 0; k4 < GK; k4 += 4) {
+            const double w = S.W[k4 + tig];
+            double af[4], bf[2];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = w * S.A[k4 + tig][wi + 8 * a + gid];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) bf[b] = S.B[k4 + tig][wj + 8 * b + gid];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+    }
+    double* dst = partial + (long long)blockIdx.z * M * N;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const long long r = i0 + wi + 8 * a + gid, cidx = j0 + wj + 8 * b + 2 * tig;
+            dst[r * N + cidx] = acc[a][b][0];
+            dst[r * N + cidx + 1] = acc[a][b][1];
+        }
+}
+
 __global__ void __launch_bounds__(256) contract_scatter_kernel(const double* __restrict__ partial, int n_split, int M,
                                                                int N, unsigned long long maskA,
                                                                unsigned long long maskB, int n_out_bits,
@@ -683,7 +775,10 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
     size_t partial_bytes = 0;
     if (gemm) {
         long long tiles = (1ll << (mAp - 6)) * (1ll << (mBp - 6));
-        long long want = (4ll * h->sm_count + tiles - 1) / tiles;
+        // ~2 CTAs per SM: the pipelined kernel hides its own latency, more splits only add partial-sum traffic
+        const char* split_env = getenv("QCK_CONTRACT_CTAS_PER_SM");
+        const long long per_sm = split_env ? atoi(split_env) : 2;
+        long long want = ((per_sm > 0 ? per_sm : 2) * h->sm_count + tiles - 1) / tiles;
         long long maxs = (count + 4 * GK - 1) / (4 * GK);
         n_split = (int)(want < maxs ? want : maxs);
         if (n_split < 1) n_split = 1;
@@ -738,8 +833,21 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
         dim3 grid(M / GT, N / GT, n_split);
         // FP64 tensor cores (DMMA) by default; QCK_CONTRACT_FMA=1 selects the FMA-pipe tile kernel
         const char* fma_env = getenv("QCK_CONTRACT_FMA");
+        // pipelined gather (cp.async, 16-byte requests): rows must start on 16-byte boundaries and be even
+        const char* pipe_env = getenv("QCK_CONTRACT_PIPE");
+        const bool aligned = ((reinterpret_cast<uintptr_t>(d_tables[0]) | reinterpret_cast<uintptr_t>(d_tables[1])) & 15) == 0 &&
+                             ((row_strides[0] | row_strides[1]) & 1) == 0 && Mr >= 2 && Nr >= 2;
         if (fma_env && atoi(fma_env) == 1)
             contract_gemm_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N, Mr, Nr);
+        else if (aligned && !(pipe_env && atoi(pipe_env) == 0)) {
+            static bool attr_set = false;  // process-wide function attribute, same value from every thread
+            if (!attr_set) {
+                QCK_CUDA(h, cudaFuncSetAttribute(contract_dmma_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(GS * sizeof(ContractStage))));
+                attr_set = true;
+            }
+            contract_dmma_pipe_kernel<<<grid, 256, GS * sizeof(ContractStage), st>>>(cp, n_split, d_partial, M, N, Mr, Nr);
+        }
         else
             contract_dmma_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N, Mr, Nr);
         QCK_CHECK_LAUNCH(h);

@@ -1677,10 +1677,13 @@ extern "C" int qck_sim_tree(qck_handle* h, const qck_sim_tree_plan* plan, int64_
             *T, l, items, sbuf[(l + 1) & 1], sbuf[l & 1], part);
         QCK_CHECK_LAUNCH(h);
     }
-    const unsigned long long cols = (unsigned long long)(label_end - label_begin) << plan->n_out_bits;
-    unsigned long long cg = (cols + 255) / 256;
-    if (cg > (unsigned long long)h->sm_count * 16) cg = (unsigned long long)h->sm_count * 16;
-    sim_tree_combine_kernel<<<(unsigned)cg, 256, 0, st>>>(*T, label_begin, label_end, part, d_out, (long long)out_row_stride);
+    int n_fork_max = 0;
+    for (int l = 0; l < plan->n_levels; ++l) n_fork_max += plan->level[l].kind == QCK_TREE_SLOT;
+    if (n_fork_max > 8) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "more than 8 measuring slots whose qubit lives on");
+    unsigned long long cg = ((unsigned long long)(label_end - label_begin) + QCK_TREE_COMBINE_WARPS - 1) / QCK_TREE_COMBINE_WARPS;
+    if (cg > (unsigned long long)h->sm_count * 8) cg = (unsigned long long)h->sm_count * 8;
+    sim_tree_combine_kernel<<<(unsigned)cg, 32 * QCK_TREE_COMBINE_WARPS, 0, st>>>(*T, label_begin, label_end, part, d_out,
+                                                                                 (long long)out_row_stride);
     QCK_CHECK_LAUNCH(h);
     return QCK_OK;
 }

@@ -264,10 +264,11 @@ class VirtualCircuit:
         return strides
 
     def simulate_fragments(self, device=None, label_range: tuple[int, int] | None = None,
-                           fold: bool = True) -> dict:
+                           fold: bool = True, out: dict | None = None) -> dict:
         """All instances of all active fragments -> {fragment: device tensor [L_f, 2^m_f]}.
         ``label_range`` (global labels) restricts the work to what one rank needs.  ``fold=False``
-        keeps the config bits as extra column bits (input of the reference-faithful knit)."""
+        keeps the config bits as extra column bits (input of the reference-faithful knit).  ``out``: tables to
+        write into (a resident step reuses its buffers)."""
         device = default_device() if device is None else device
         handle = _lib.get_handle(getattr(device, "index", None) or 0)
         import torch
@@ -284,7 +285,8 @@ class VirtualCircuit:
                 rng = None
                 if label_range is not None and self._vgate_instrs:
                     rng = self.fragment_label_range(frag, *label_range)
-                tables[frag] = ex.run(handle, label_range=rng, scratch_tag=i, defer_broadcast=overlap)
+                tables[frag] = ex.run(handle, out=None if out is None else out[frag], label_range=rng,
+                                      scratch_tag=i, defer_broadcast=overlap)
                 runs.append((ex, tables[frag]))
         finally:
             if overlap:

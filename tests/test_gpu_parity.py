@@ -1090,3 +1090,37 @@ def test_back_to_back_runs_are_bit_identical(dev, cfg):
     assert np.abs(outs2[0].cpu().numpy() - want).max() < TOL_P
     for o in outs2[1:]:
         assert torch.equal(o, outs2[0])
+
+
+@pytest.mark.parametrize("cfg", ["bv16", "syc16d5", "hwe16d5", "syc20"])
+def test_resident_step_graph_replay(dev, cfg):
+    """ResidentStep: the whole step (fragment simulations fanned out over side streams, knit, statistics,
+    nearest_probability_distribution) captured ONCE as a CUDA graph - replays give the bits of the eager
+    launches, equal the oracle, and survive being replayed back to back."""
+    resm = import_module(f"{PKG}.resident")
+    if cfg == "syc20":
+        c = gen.gen_circ("syc", 20, 1, seed=0).decompose_two_qubit()
+        cut = cutting.apply_cuts(c, cutting.CutSpec(partitions=[list(range(10)), list(range(10, 20))]))
+        circ = c
+    else:
+        circ, cut = cutting.make_baseline(cfg, seed=0)
+    want = cport.simulate_probabilities(circ)
+    eager = resm.ResidentStep(vcm.VirtualCircuit(cut), dev, graph=False)
+    eager.run()
+    ref = eager.result()
+    ref_vals = ref.values.clone()
+    assert np.abs(ref_vals.cpu().numpy() - want).max() < TOL_P
+    rs = resm.ResidentStep(vcm.VirtualCircuit(cut), dev, graph=True)
+    h = _lib.get_handle(0)
+    for i in range(5):
+        rs.run()
+    l0 = h.launch_count
+    rs.run()
+    assert h.launch_count == l0                     # a replay: nothing is launched kernel by kernel any more
+    got = rs.result()
+    assert torch.equal(got.values, ref_vals)
+    assert got.total == ref.total and got.minimum == ref.minimum and abs(got.total - 1.0) < 1e-9
+    g_sim, g_knit, g_post = rs.capture(phases=True)
+    rs.out.zero_()
+    g_sim.replay(); g_knit.replay(); g_post.replay()
+    assert torch.equal(rs.result().values, ref_vals)
