@@ -469,7 +469,7 @@ class FragmentProgram:
             counts.append(counts[-1] * len(l.choices))
         state_bytes = 16 << max(self.n_qubits, 5)
         inner = max(counts[1:-1], default=0)
-        if 2 * inner * state_bytes + counts[-1] * (8 << len(free)) > TREE_MAX_WORK_BYTES:
+        if 2 * inner * state_bytes + counts[-1] * (8 << len(free)) > TREE_MAX_WORK_BYTES or counts[-1] >= 2 ** 31:
             return None
         used = {p for _, p in free}
         base_sum = sum(1 << b for b in range(self.n_qubits) if b not in used)

@@ -188,6 +188,7 @@ __device__ void npd_select_tail(NpdWs w) {
     }
     if (status != NPD_SEARCH) return;
     constexpr int PER = NPD_BINS / NPD_THREADS;  // consecutive bins per thread
+    static_assert(PER == 32, "the second search level is one warp wide");
     const int b0 = threadIdx.x * PER;
     unsigned long long c = 0ull;
     long long q = 0ll;
@@ -211,19 +212,41 @@ __device__ void npd_select_tail(NpdWs w) {
     const int qexp = (int)s->qexp;
     const double rest = s->alive - s->under_cnt, under = s->under_sum;
     const unsigned long long width = (unsigned long long)hi - (unsigned long long)lo;
-    int mine = NPD_BINS;
-    for (int i = 0; i < PER; ++i) {
-        const int j = b0 + i;
-        c_ex += w.bin_cnt[j];
-        q_ex += w.bin_q[j];
+    // G at the upper boundary of bin j, given the entries (count c, integer sum q) of bins 0..j
+    auto g_at = [&](int j, unsigned long long c, long long q, bool* is_last) -> double {
         unsigned long long off = ((unsigned long long)(j + 1)) << shift;  // keys up to lo + off belong to bins <= j
         if (off > width || (shift > 0 && (off >> shift) != (unsigned long long)(j + 1))) off = width;
+        *is_last = off == width;
         const double ub = npd_val(lo + (long long)off);
-        const double g = under + ((double)c_ex * lo_val + scalbn((double)q_ex, -qexp)) + ub * (rest - (double)c_ex);
-        if (g >= 0.0 || off == width) {  // G(hi) >= 0 in exact arithmetic: the last bin closes the search
-            mine = j;
-            break;
+        return under + ((double)c * lo_val + scalbn((double)q, -qexp)) + ub * (rest - (double)c);
+    };
+    // two-level search (G is non-decreasing): first the 32-bin block whose END has G >= 0 - one evaluation
+    // per thread -, then the bin inside that block - one evaluation per lane of warp 0
+    __shared__ int found_block;
+    if (threadIdx.x == 0) found_block = NPD_THREADS;
+    __syncthreads();
+    {
+        bool is_last;
+        const double g = g_at(b0 + PER - 1, c_ex + c, q_ex + q, &is_last);
+        if (g >= 0.0 || is_last) atomicMin(&found_block, (int)threadIdx.x);
+    }
+    __syncthreads();
+    const int blk = found_block;
+    int mine = NPD_BINS;
+    if (threadIdx.x < PER) {  // (PER == 32: warp 0)
+        unsigned long long cb = 0ull;
+        long long qb = 0ll;
+        for (int t = 0; t < blk; ++t) {
+            cb += sc[t];
+            qb += sq[t];
         }
+        for (int i = 0; i <= (int)threadIdx.x; ++i) {
+            cb += w.bin_cnt[blk * PER + i];
+            qb += w.bin_q[blk * PER + i];
+        }
+        bool is_last;
+        const double g = g_at(blk * PER + (int)threadIdx.x, cb, qb, &is_last);
+        if (g >= 0.0 || is_last) mine = blk * PER + (int)threadIdx.x;
     }
     atomicMin(&found, mine);
     __syncthreads();
@@ -388,6 +411,8 @@ __global__ void __launch_bounds__(NPD_THREADS) npd_apply_kernel(double* __restri
 }
 
 // ------------------------------------------------------------------ host side
+// (4 elements per thread.  Fewer, fatter CTAs - 32 per thread, 8 CTAs at n = 2^16 - measured slower: every
+// pass is latency bound, 0.087 -> 0.121 ms for the eight launches of hwe-16 d5's npd.)
 static int npd_grid(qck_handle* h, unsigned long long n) {
     unsigned long long want = (n + NPD_THREADS * 4 - 1) / (NPD_THREADS * 4);
     unsigned long long cap = (unsigned long long)h->sm_count * 8;

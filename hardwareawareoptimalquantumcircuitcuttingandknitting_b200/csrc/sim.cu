@@ -1573,7 +1573,9 @@ static TreeKernelFn tree_kernel(int log_r) {
         default: return sim_tree_level_kernel<5>;
     }
 }
-static int tree_smem(int log_r) { return QCK_WARP_PER_CTA * ((8 << (log_r + 5)) + (int)sizeof(WarpStagedOp) * QCK_WARP_STAGE); }
+static int tree_smem(int log_r) {
+    return QCK_WARP_PER_CTA * ((8 << (log_r + 5)) + (int)sizeof(WarpStagedOp) * QCK_WARP_STAGE + 16 * 64);
+}
 
 static int qck_tree_init(qck_handle* h) {
     for (int r = 0; r <= 5; ++r) {
@@ -1593,7 +1595,7 @@ static bool tree_counts(const qck_sim_tree_plan* p, long long* n) {
         const int b = p->level[l].n_choices;
         if (b < 1 || b > QCK_TREE_MAX_CHOICES) return false;
         n[l + 1] = n[l] * b;
-        if (n[l + 1] > (1ll << 40)) return false;
+        if (n[l + 1] > 0x7fffffffll) return false;  // node indices are 32-bit on the device
     }
     return true;
 }
@@ -1669,7 +1671,11 @@ extern "C" int qck_sim_tree(qck_handle* h, const qck_sim_tree_plan* plan, int64_
     double2* sbuf[2] = {reinterpret_cast<double2*>(d_work), reinterpret_cast<double2*>((char*)d_work + sb)};
     double* part = reinterpret_cast<double*>((char*)d_work + 2 * sb);
     const long long cap = (long long)h->sm_count * h->tree_occ[log_r];
+    int dbg_skip = 0;
+    if (const char* e = getenv("QCK_TREE_DEBUG_SKIP")) dbg_skip = atoi(e);  // timing experiments only
     for (int l = 0; l < plan->n_levels; ++l) {
+        if ((dbg_skip & 2) && l == plan->n_levels - 1) continue;
+        if ((dbg_skip & 4) && l < plan->n_levels - 1) continue;
         const long long items = n[l + 1];
         long long ctas = (items + QCK_WARP_PER_CTA - 1) / QCK_WARP_PER_CTA;
         if (ctas > cap) ctas = cap;
@@ -1678,13 +1684,31 @@ extern "C" int qck_sim_tree(qck_handle* h, const qck_sim_tree_plan* plan, int64_
         QCK_CHECK_LAUNCH(h);
     }
     int n_fork_max = 0;
-    for (int l = 0; l < plan->n_levels; ++l) n_fork_max += plan->level[l].kind == QCK_TREE_SLOT;
+    long long n_rep_labels = 1, n_eq_max = 1;
+    for (int l = 0; l < plan->n_levels; ++l) {
+        const qck_tree_level& L = plan->level[l];
+        if (L.kind == QCK_TREE_MMEAS) continue;
+        n_fork_max += L.kind == QCK_TREE_SLOT;
+        int reps = 0, biggest = 1;
+        for (int v = 0; v < 8; ++v) {
+            if (L.first_choice[v] < 0) continue;
+            ++reps;
+            int cls = 0;
+            for (int d = 0; d < plan->radix[L.digit]; ++d) cls += (int)((L.canon >> (4 * d)) & 15u) == v;
+            if (cls > biggest) biggest = cls;
+        }
+        n_rep_labels *= reps;
+        n_eq_max *= biggest;
+    }
     if (n_fork_max > 8) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "more than 8 measuring slots whose qubit lives on");
-    unsigned long long cg = ((unsigned long long)(label_end - label_begin) + QCK_TREE_COMBINE_WARPS - 1) / QCK_TREE_COMBINE_WARPS;
-    if (cg > (unsigned long long)h->sm_count * 8) cg = (unsigned long long)h->sm_count * 8;
-    sim_tree_combine_kernel<<<(unsigned)cg, 32 * QCK_TREE_COMBINE_WARPS, 0, st>>>(*T, label_begin, label_end, part, d_out,
-                                                                                 (long long)out_row_stride);
-    QCK_CHECK_LAUNCH(h);
+    if (n_eq_max > 256) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "more than 256 labels share one representative");
+    if (!(dbg_skip & 1)) {
+        unsigned long long cg = ((unsigned long long)n_rep_labels + QCK_TREE_COMBINE_WARPS - 1) / QCK_TREE_COMBINE_WARPS;
+        if (cg > (unsigned long long)h->sm_count * 8) cg = (unsigned long long)h->sm_count * 8;
+        sim_tree_combine_kernel<<<(unsigned)cg, 32 * QCK_TREE_COMBINE_WARPS, 0, st>>>(
+            *T, n_rep_labels, label_begin, label_end, part, d_out, (long long)out_row_stride);
+        QCK_CHECK_LAUNCH(h);
+    }
     return QCK_OK;
 }
 
