@@ -1050,8 +1050,16 @@ class FragmentExecutor:
                     free, _ = torch.cuda.mem_get_info(self.device)
                     n = max(1, min(prog.num_labels, int(free * 0.5) // per, 64))
                 self._work_bytes = n * per
-        self._work = (handle.scratch(torch, self._work_bytes, self.device, stream, scratch_tag)
-                      if self._work_bytes else None)
+        if not self._work_bytes:
+            self._work = None
+        elif self._work_bytes > handle.SCRATCH_CACHE_MAX:
+            # too large for the handle's cache (a 64 GiB state): this executor owns it, per stream
+            if self._work is None or self._work_key != (stream, scratch_tag):
+                self._work = None                      # (free the old one first)
+                self._work = handle.scratch(torch, self._work_bytes, self.device, stream, scratch_tag)
+                self._work_key = (stream, scratch_tag)
+        else:
+            self._work = handle.scratch(torch, self._work_bytes, self.device, stream, scratch_tag)
         n = len(self._structs)
         plans = (_lib.QckSimPlan * n)()
         label_ptrs = (C.c_void_p * n)()
