@@ -546,9 +546,15 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
     extra = {}
     if not args.profile:
         rep = oracle_parity(virt, circ, cut, holder["t"], result_after, y0, y1, K, n_out, faithful)
-        oracle = {k: reduce_max(v) for k, v in sorted(rep.items()) if isinstance(v, float)}
+        # the SAME collectives on every rank whatever happened locally: a fixed key list, -1 where a rank has none
+        keys = (["fidelity_oracle", "max_abs_err_fragment_tables_vs_oracle", "max_abs_err_knit_windows_vs_oracle"]
+                if K == 0 else ["fidelity_oracle", "max_abs_err_vs_uncut_oracle" + ("_pruned_1e-5_mode" if faithful else "")])
+        oracle = {k: reduce_max(float(rep[k]) if isinstance(rep.get(k), float) else -1.0) for k in keys}
+        oracle["ranks_with_errors"] = int(reduce_max(1.0 if "oracle_parity_error" in rep else 0.0))
         oracle["ranks_checked"] = world
         oracle.update({k: v for k, v in rep.items() if not isinstance(v, float)})
+        if K == 0:                                   # fidelity: the smallest over the ranks is the honest one
+            oracle["fidelity_oracle"] = -reduce_max(-float(rep.get("fidelity_oracle", 2.0)))
         extra["oracle"] = oracle
         if rank == 0:
             extra.update(gpu_fidelity_report(virt, circ, holder["t"], result_after, device, fid, vc, handle, K, n_out,
@@ -644,7 +650,8 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
     if K == 0:
         line["hbm_gbs"] = roofline["achieved"]
     line.update(extra)
-    del out
+    barrier()                                         # nothing of this workload is in flight when its graphs,
+    del rs, out                                       # buffers and executors go away
     return line
 
 

@@ -65,6 +65,7 @@ class ResidentStep:
             self.tables[f] = alloc((ex.program.num_labels, ex.row_len), dtype=torch.float64, device=dev)
             self.execs.append(ex)
         self._graph = None
+        self._graph_body = None
         self._phase_graphs = None
         self.want_graph = graph
 
@@ -118,20 +119,38 @@ class ResidentStep:
                 self.enqueue()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        # A phase with an NCCL collective is NOT captured: NCCL registers the buffers of graph-captured
+        # collectives with the communicator, and tearing the graph down later (its private memory pool goes with
+        # it) left a 2-rank run with an illegal memory access in the next eager collective.  The collective and
+        # what follows it are a handful of launches; they stay eager.
+        post_has_collective = self.world > 1 and (self.K == 0 or self.label_range is not None)
+
+        class _Eager:                                  # same interface as a CUDAGraph
+            def __init__(self, fn):
+                self.replay = fn
+
+        def graph_of(fn):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            return g
+
         if phases:
-            graphs = []
-            for fn in (self.enqueue_simulation, self.enqueue_knit, self.enqueue_post):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    fn()
-                graphs.append(g)
+            graphs = [graph_of(self.enqueue_simulation), graph_of(self.enqueue_knit),
+                      _Eager(self.enqueue_post) if post_has_collective else graph_of(self.enqueue_post)]
             self._phase_graphs = graphs
             return graphs
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.enqueue()
-        self._graph = g
-        return g
+        if post_has_collective:
+            body = graph_of(lambda: (self.enqueue_simulation(), self.enqueue_knit()))
+
+            def replay():
+                body.replay()
+                self.enqueue_post()
+            self._graph = _Eager(replay)
+            self._graph_body = body
+        else:
+            self._graph = graph_of(self.enqueue)
+        return self._graph
 
     def run(self) -> None:
         """One step on the current stream: a graph replay once captured, else eager launches."""
