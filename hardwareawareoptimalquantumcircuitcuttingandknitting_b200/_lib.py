@@ -125,6 +125,9 @@ _PROTOTYPES = {
     "qck_hellinger": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "qck_npd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.POINTER(C.c_double),
                           C.POINTER(C.c_double), C.c_void_p]),
+    "qck_stats_exchange_mailbox_bytes": (C.c_size_t, [C.c_int]),
+    "qck_stats_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
+    "qck_mem_zero": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "qck_npd_workspace_bytes": (C.c_size_t, []),
     "qck_npd_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_void_p]),
     "qck_npd_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_int,

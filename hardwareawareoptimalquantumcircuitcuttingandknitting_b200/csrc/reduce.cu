@@ -155,3 +155,105 @@ extern "C" int qck_hellinger(qck_handle* h, const double* d_p, const double* d_q
     QCK_CHECK_LAUNCH(h);
     return QCK_OK;
 }
+
+// ---- cross-rank reduction of a qck_stats over peer-mapped mailboxes
+// A sharded result needs one exchange per step: (sum, min, ...) of every rank's slice.  Through NCCL that is a
+// collective launch plus the small kernels that combine the gathered values (measured: 46 us of a 2.4 ms step
+// on two GPUs, of a 0.64 ms step on eight).  Here every rank writes its four doubles straight into a slot of
+// every peer's mailbox (NVLink stores into cudaIpc-mapped memory), publishes a sequence number, waits until its
+// own mailbox holds the current sequence number from every rank and adds the slots in rank order (the same
+// bits on every rank).  One launch of one warp; the sequence counter lives on the device, so the launch can be
+// captured in a CUDA graph and replayed.  Slots are double buffered by the parity of the sequence number: a
+// rank can only be two exchanges ahead of another one after that one has finished reading.
+struct StatsSlot {
+    double sum, min, sum_sqrt, nnz;
+    unsigned long long seq;
+    unsigned long long pad[3];
+};
+struct ExchangeParams {
+    StatsSlot* box[QCK_MAX_RANKS];  // mailbox of every rank: [2][world] slots
+    int rank, world;
+};
+
+__global__ void __launch_bounds__(32) stats_exchange_kernel(const __grid_constant__ ExchangeParams P, qck_stats* stats,
+                                                            unsigned long long* seq_counter) {
+    const int lane = threadIdx.x;
+    unsigned long long seq = 0;
+    if (lane == 0) seq = *seq_counter + 1ull;
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    const int buf = (int)(seq & 1ull);
+    if (lane < P.world) {  // my values into slot [rank] of rank `lane`'s mailbox, the sequence number last
+        volatile StatsSlot* dst = P.box[lane] + buf * P.world + P.rank;
+        dst->sum = stats->sum;
+        dst->min = stats->min;
+        dst->sum_sqrt = stats->sum_sqrt;
+        dst->nnz = stats->nnz;
+        __threadfence_system();
+        dst->seq = seq;
+    }
+    double s = 0.0, m = INFINITY, q = 0.0, z = 0.0;
+    bool tracked = true;
+    if (lane < P.world) {  // wait for rank `lane`'s values in my own mailbox
+        volatile StatsSlot* src = P.box[P.rank] + buf * P.world + lane;
+        const long long t0 = clock64();
+        while (src->seq != seq) {
+            if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer never came
+                printf("qck: stats_exchange_kernel: rank %d waited in vain for rank %d (sequence %llu)\n", P.rank, lane, seq);
+                __trap();
+            }
+        }
+        __threadfence_system();
+        s = src->sum;
+        m = src->min;
+        q = src->sum_sqrt;
+        z = src->nnz;
+        tracked = !(z < 0.0);
+    }
+    // rank order, one lane after the other: identical bits on every rank
+    double ss = 0.0, mm = INFINITY, qq = 0.0, zz = 0.0;
+    bool all_tracked = true;
+    for (int r = 0; r < P.world; ++r) {
+        ss += __shfl_sync(0xffffffffu, s, r);
+        mm = fmin(mm, __shfl_sync(0xffffffffu, m, r));
+        qq += __shfl_sync(0xffffffffu, q, r);
+        zz += __shfl_sync(0xffffffffu, z, r);
+        all_tracked = all_tracked && __shfl_sync(0xffffffffu, (int)tracked, r);
+    }
+    if (lane == 0) {
+        stats->sum = ss;
+        stats->min = mm;
+        stats->sum_sqrt = qq;
+        stats->nnz = all_tracked ? zz : -1.0;
+        *seq_counter = seq;
+    }
+}
+
+extern "C" size_t qck_stats_exchange_mailbox_bytes(int world) { return sizeof(StatsSlot) * 2 * (size_t)world + 64; }
+
+extern "C" int qck_stats_exchange(qck_handle* h, qck_stats* d_stats, int rank, int world, void* const* d_mailboxes,
+                                  qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    if (!d_stats || !d_mailboxes || world < 1 || world > QCK_MAX_RANKS || rank < 0 || rank >= world)
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad stats exchange arguments");
+    DeviceGuard guard(h->device);
+    ExchangeParams P;
+    memset(&P, 0, sizeof(P));
+    for (int r = 0; r < world; ++r) {
+        if (!d_mailboxes[r]) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "mailbox of rank %d is NULL", r);
+        P.box[r] = reinterpret_cast<StatsSlot*>(reinterpret_cast<char*>(d_mailboxes[r]) + 64);
+    }
+    P.rank = rank;
+    P.world = world;
+    // the sequence counter is the first 8 bytes of this rank's own mailbox allocation
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(d_mailboxes[rank]);
+    stats_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(P, d_stats, counter);
+    QCK_CHECK_LAUNCH(h);
+    return QCK_OK;
+}
+
+extern "C" int qck_mem_zero(qck_handle* h, void* d_ptr, size_t bytes, qck_stream stream) {
+    if (!h || !d_ptr) return QCK_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    QCK_CUDA(h, cudaMemsetAsync(d_ptr, 0, bytes, (cudaStream_t)stream));
+    return QCK_OK;
+}

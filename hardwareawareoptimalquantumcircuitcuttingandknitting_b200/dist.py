@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import os
 
-__all__ = ["shard_range", "shard_pow2", "init_from_env", "allreduce_stats", "allreduce_sum_", "npd_sharded", "partition_mode", "simulation_work", "world"]
+__all__ = ["shard_range", "shard_pow2", "init_from_env", "allreduce_stats", "allreduce_sum_", "npd_sharded", "StatsExchange", "stats_exchange", "partition_mode", "simulation_work", "world"]
 
 
 def shard_range(total: int, rank: int, world_size: int, align: int = 1) -> tuple[int, int]:
@@ -96,12 +96,90 @@ def init_from_env(backend: str | None = None):
     return rank, local_rank, world_size
 
 
-def allreduce_stats(stats, group=None):
+class StatsExchange:
+    """Peer mailboxes for ``qck_stats_exchange``: one small cudaMalloc block per rank, exported through CUDA
+    IPC and mapped by every other rank of the box.  Built collectively (every rank of ``group`` at the same
+    point); ``available`` is False when the ranks cannot map each other's memory (not one box, no peer access,
+    a CPU backend) - the caller then keeps the NCCL path."""
+
+    def __init__(self, handle, device, group=None) -> None:
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        self.handle, self.device = handle, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.available = False
+        self._own = C.c_void_p()
+        self._peers = []
+        ok, ipc = 1, b""
+        try:
+            if not torch.cuda.is_available() or self.world > 16:
+                raise RuntimeError("no CUDA / too many ranks")
+            lib = handle.lib
+            nbytes = int(lib.qck_stats_exchange_mailbox_bytes(self.world))
+            handle.check(lib.qck_mem_alloc(handle.ptr, nbytes, C.byref(self._own)))
+            handle.check(lib.qck_mem_zero(handle.ptr, self._own, nbytes, None))
+            torch.cuda.synchronize(device)
+            buf = C.create_string_buffer(64)
+            handle.check(lib.qck_ipc_export(handle.ptr, self._own, buf))
+            ipc = bytes(buf.raw)
+        except Exception:
+            ok = 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (ok, ipc), group=group)
+        ptrs = (C.c_void_p * self.world)()
+        if all(o for o, _ in handles):
+            try:
+                for r, (_, hb) in enumerate(handles):
+                    if r == self.rank:
+                        ptrs[r] = self._own.value
+                    else:
+                        p = C.c_void_p()
+                        handle.check(handle.lib.qck_ipc_open(handle.ptr, hb, C.byref(p)))
+                        self._peers.append(p)
+                        ptrs[r] = p.value
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=group)      # also: every rank has mapped before anyone writes
+        self.available = all(flags)
+        self._ptrs = ptrs
+
+    def reduce(self, stats, stream: int) -> None:
+        h = self.handle
+        h.check(h.lib.qck_stats_exchange(h.ptr, stats.data_ptr(), self.rank, self.world, self._ptrs, stream))
+
+
+_exchanges: dict = {}
+
+
+def stats_exchange(handle, device, group=None):
+    """The (cached) StatsExchange of this handle and group, or None when peer mailboxes are not available.
+    QCK_STATS_NCCL=1 keeps the NCCL path."""
+    if os.environ.get("QCK_STATS_NCCL", "0") == "1":
+        return None
+    key = (id(handle), str(device), id(group))
+    ex = _exchanges.get(key)
+    if ex is None:
+        ex = _exchanges[key] = StatsExchange(handle, device, group)
+    return ex if ex.available else None
+
+
+def allreduce_stats(stats, group=None, handle=None):
     """``stats`` = tensor [sum, min, sum_sqrt, nnz] (a qck_stats); reduced in place across ranks:
-    sums are added, the minimum is min-reduced."""
+    sums are added, the minimum is min-reduced.  With a ``handle`` on a CUDA box the values travel through peer
+    mailboxes (one launch, no collective); else through NCCL / gloo."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return stats
+    if handle is not None and stats.is_cuda:
+        import torch
+        ex = stats_exchange(handle, stats.device, group)
+        if ex is not None:
+            ex.reduce(stats, torch.cuda.current_stream(stats.device).cuda_stream)
+            return stats
     # ONE collective: every rank gathers all ranks' four scalars and combines them itself, in rank order
     # (deterministic) - a SUM and a MIN all-reduce would be two launch-latency-bound collectives
     world_size = dist.get_world_size(group)

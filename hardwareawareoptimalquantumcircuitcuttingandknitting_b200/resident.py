@@ -91,7 +91,7 @@ class ResidentStep:
         h = self.handle
         if self.K == 0:
             if self.world > 1:
-                self.qdist.allreduce_stats(self.stats, self.group)   # min >= 0 by construction: no npd pass
+                self.qdist.allreduce_stats(self.stats, self.group, self.handle)   # min >= 0: no npd pass
             return
         if self.label_range is not None:
             self.qdist.allreduce_sum_(self.out, self.group)
@@ -123,7 +123,8 @@ class ResidentStep:
         # collectives with the communicator, and tearing the graph down later (its private memory pool goes with
         # it) left a 2-rank run with an illegal memory access in the next eager collective.  The collective and
         # what follows it are a handful of launches; they stay eager.
-        post_has_collective = self.world > 1 and (self.K == 0 or self.label_range is not None)
+        mailboxes = self.world > 1 and self.K == 0 and self.qdist.stats_exchange(self.handle, self.device, self.group)
+        post_has_collective = self.world > 1 and ((self.K == 0 and not mailboxes) or self.label_range is not None)
 
         class _Eager:                                  # same interface as a CUDAGraph
             def __init__(self, fn):

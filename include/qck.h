@@ -359,6 +359,20 @@ QCK_API int qck_hellinger(qck_handle* h, const double* d_p, const double* d_q, u
 QCK_API int qck_npd(qck_handle* h, double* d_p, uint64_t n, double acc, double* host_beta, double* host_num,
             qck_stream stream);
 
+/* Cross-rank reduction of a qck_stats (sums added, min min-reduced, in rank order: the same bits on every
+ * rank) for results sharded over the GPUs of one box ("scalar allreduce for min / sum"), WITHOUT a
+ * collective launch: every rank writes its values into every peer's mailbox with NVLink stores and waits for
+ * the peers' values in its own.  Setup (once): every rank allocates qck_stats_exchange_mailbox_bytes(world)
+ * bytes with qck_mem_alloc, zeroes them (qck_mem_zero), exports them (qck_ipc_export) and opens the peers'
+ * (qck_ipc_open); d_mailboxes = HOST array of `world` device pointers in rank order (own + mapped).  Every
+ * rank must call it the same number of times; a rank whose peers never arrive traps after ~4 s instead of
+ * hanging.  One launch, capturable in a CUDA graph. */
+#define QCK_MAX_RANKS 16
+QCK_API size_t qck_stats_exchange_mailbox_bytes(int world);
+QCK_API int qck_stats_exchange(qck_handle* h, qck_stats* d_stats, int rank, int world, void* const* d_mailboxes,
+                       qck_stream stream);
+QCK_API int qck_mem_zero(qck_handle* h, void* d_ptr, size_t bytes, qck_stream stream);
+
 /* The same without any host round trip: 8 launches enqueued on `stream` (statistics, <= 5 radix
  * refinement levels of 13 bits each on the ordered integer image of the doubles + one summation pass,
  * apply), each looking at the state the previous one left in the workspace; launches with nothing

@@ -84,6 +84,56 @@ def main() -> None:
         assert err < 1e-13, (make, rank, err)
         worst = max(worst, err)
 
+    # (4) the peer-mailbox exchange of (sum, min, ...) against its definition, many times back to back (the
+    #     slots are double buffered by sequence parity) and from inside a CUDA graph
+    h = lib.get_handle(local_rank)
+    ex = qdist.stats_exchange(h, dev, None)
+    assert ex is not None, "peer mailboxes unavailable on this box"
+    want_sum = sum(r + 0.5 for r in range(world))
+    for it in range(64):
+        st = torch.tensor([rank + 0.5 + it, -float(rank) - it, 0.25 * rank, 3.0], dtype=torch.float64, device=dev)
+        qdist.allreduce_stats(st, None, h)
+        got = st.cpu().numpy()
+        assert got[0] == want_sum + world * it and got[1] == -(world - 1) - it and got[3] == 3.0 * world, (rank, it, got)
+    st = torch.zeros(4, dtype=torch.float64, device=dev)
+    src = torch.tensor([1.0 + rank, float(rank), 0.0, 1.0], dtype=torch.float64, device=dev)
+    stream = torch.cuda.Stream(dev)
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            st.copy_(src)
+            qdist.allreduce_stats(st, None, h)
+    torch.cuda.current_stream(dev).wait_stream(stream)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        st.copy_(src)
+        qdist.allreduce_stats(st, None, h)
+    for _ in range(20):
+        g.replay()
+    torch.cuda.synchronize(dev)
+    got = st.cpu().numpy()
+    assert got[0] == sum(1.0 + r for r in range(world)) and got[1] == 0.0 and got[3] == world, (rank, got)
+    del g
+
+    # (5) ResidentStep over the ranks: graph replays == eager == oracle (output sharded, statistics exchanged)
+    resm = import_module(f"{PKG}.resident")
+    eager = resm.ResidentStep(vcm.VirtualCircuit(cut20), dev, rank=rank, world_size=world, graph=False)
+    eager.run()
+    ref = eager.result()
+    rs = resm.ResidentStep(vcm.VirtualCircuit(cut20), dev, rank=rank, world_size=world, graph=True)
+    for _ in range(4):
+        rs.run()
+    got = rs.result()
+    assert torch.equal(got.values, ref.values) and got.total == ref.total and abs(got.total - 1.0) < 1e-9
+    want, _, _ = cport.knit_outer(o_tabs, o_masks, got.y_begin, got.y_begin + span)
+    err = float(np.abs(got.values.cpu().numpy() - want).max())
+    assert err < 1e-10, (rank, err)
+    worst = max(worst, err)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    del rs, eager
+
     t = torch.tensor([worst], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
