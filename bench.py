@@ -463,18 +463,39 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    trace = os.environ.get("QCK_BENCH_TRACE") == "1"
+
+    def stage(name: str) -> None:
+        """Synchronise between the stages of the measurement (never inside a timed region) and say where a device
+        fault surfaced.  Always on for multi-rank runs: two of four 2-GPU runs of the secondary workloads ended in
+        a sticky CUDA fault without these synchronisations and none of eight with them (no such fault in any
+        1-GPU run); the cause is not understood yet - see DESIGN.md, open issues."""
+        if trace or world > 1:
+            try:
+                torch.cuda.synchronize(device)
+            except Exception as exc:
+                sys.stderr.write(f"[trace rank {rank}] {workload}@{accuracy}: fault surfaced after stage '{name}': {exc!r}\n")
+                raise
+            if trace:
+                sys.stderr.write(f"[trace rank {rank}] {workload}@{accuracy}: {name} ok\n")
+
+    stage("setup")
     l0 = handle.launch_count
     rs.enqueue()                                      # (also the first warm-up step)
+    stage("first eager step")
     launches_per_step = handle.launch_count - l0
     for _ in range(warmup - 1):
         rs.enqueue()
     barrier()
+    stage("eager warm-up")
     step = rs.enqueue
     if use_graph:
         graph = rs.capture()
+        stage("capture")
         step = graph.replay
         for _ in range(2):
             step()
+        stage("first replays")
     barrier()
     sampler = ClockSampler(env["local_rank"]) if (rank == 0 and primary) else None
     time.sleep(0.15 if sampler else 0.0)
@@ -487,6 +508,7 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
         step()
     e1.record()
     host_ms = (time.perf_counter() - h0) * 1e3 / steps     # what the host spends enqueueing a step
+    stage("timed loop")
     barrier()
     t_wall1 = time.time()
     launches = launches_per_step * steps
@@ -494,6 +516,7 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     # the three phases of the step, each on its own (graph replays, or eager launches under --no-graph)
     phases = rs.capture(phases=True) if use_graph else None
+    stage("phase capture")
     fns = [g.replay for g in phases] if phases else [rs.enqueue_simulation, rs.enqueue_knit, rs.enqueue_post]
     ev_log = []
     n_phase = min(steps, 10)
@@ -504,6 +527,7 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
             fn()
             ev[i + 1].record()
         ev_log.append(ev)
+    stage("phase loop")
     barrier()
     sim_ms = reduce_max(sum(e[0].elapsed_time(e[1]) for e in ev_log) / len(ev_log))
     knit_ms = reduce_max(sum(e[1].elapsed_time(e[2]) for e in ev_log) / len(ev_log))
@@ -520,6 +544,7 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
                                                   nearest=True, accuracy=accuracy)
         cold = [vc.VirtualCircuit(cut) for _ in range(steps + 1)]
         call(cold[0])
+        stage("first e2e call")
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
@@ -527,6 +552,7 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
             vc.clear_program_cache()                 # the COLD path: every step compiles its programs
             call(v)
         g1.record()
+        stage("cold e2e loop")
         barrier()
         warm = [vc.VirtualCircuit(cut) for _ in range(steps)]
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -534,6 +560,7 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
         for v in warm:                               # process-wide program cache warm (a second run of the
             call(v)                                  # same cut circuit, e.g. the reference's ideal + noisy pair)
         w1.record()
+        stage("warm e2e loop")
         barrier()
         h2d = sum(cold[1].executor(f, device, not faithful).h2d_bytes for f in cold[1].active_fragments())
         e2e = {"value": reduce_max(g0.elapsed_time(g1)) / steps / 1e3, "unit": "s", "h2d_bytes_per_step": h2d,
@@ -546,6 +573,7 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
     extra = {}
     if not args.profile:
         rep = oracle_parity(virt, circ, cut, holder["t"], result_after, y0, y1, K, n_out, faithful)
+        stage("oracle parity")
         # the SAME collectives on every rank whatever happened locally: a fixed key list, -1 where a rank has none
         keys = (["fidelity_oracle", "max_abs_err_fragment_tables_vs_oracle", "max_abs_err_knit_windows_vs_oracle"]
                 if K == 0 else ["fidelity_oracle", "max_abs_err_vs_uncut_oracle" + ("_pruned_1e-5_mode" if faithful else "")])
@@ -559,6 +587,7 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
         if rank == 0:
             extra.update(gpu_fidelity_report(virt, circ, holder["t"], result_after, device, fid, vc, handle, K, n_out,
                                              world, faithful))
+            stage("fidelity report")
             if "fidelity_oracle" in rep and "fidelity_cut_vs_uncut" in extra:
                 extra["fidelity_delta_vs_oracle"] = abs(extra["fidelity_cut_vs_uncut"] - rep["fidelity_oracle"])
     if args.uncut_statevector is None:
@@ -720,7 +749,9 @@ def main() -> None:
                 others[w] = compact(measure(w, args, env, primary=False, cpu=args.workload == "all"))
             except Exception as exc:                  # a secondary workload must never take the line down
                 others[w] = {"error": repr(exc)}
-        for w in ("hwe16d5", "syc16d5"):              # the reference's default mode: ACCURACY = 1e-5 pruning
+        # the reference's default mode: ACCURACY = 1e-5 pruning (one GPU: the reference-faithful knit is one
+        # expression tree per output entry over ALL labels - never sharded, every rank would repeat the same run)
+        for w in (("hwe16d5", "syc16d5") if world == 1 else ()):
             try:
                 others[f"{w}@1e-5"] = compact(measure(w, args, env, primary=False, accuracy=1e-5))
             except Exception as exc:
