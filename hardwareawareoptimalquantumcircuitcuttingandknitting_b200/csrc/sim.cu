@@ -953,7 +953,7 @@ static size_t tma_smem_bytes(int n_tile, int n_records) {
 // Can this sweep run on the TMA kernel?  (pure host logic, no CUDA calls: unit-testable)
 // Fills everything but the tensor maps.  live_before: state bits some earlier sweep had in its tile.
 static bool tma_describe(const qck_sim_plan* plan, int i, unsigned long long live_before, bool last, int batch,
-                         int max_smem_optin, TmaLaunch& L, const TmaShard* shard = nullptr) {
+                         int max_smem_optin, TmaLaunch& L, const TmaShard* shard = nullptr, bool skip_dead = false) {
     const qck_sweep& sw = plan->sweeps[i];
     const int T = sw.n_tile, N = plan->n_state_qubits;
     const int n_loc = shard ? shard->n_local : N;  // bits a single buffer indexes
@@ -1064,7 +1064,9 @@ static bool tma_describe(const qck_sim_plan* plan, int i, unsigned long long liv
     for (int j = 0; j < T; ++j) tile_mask |= 1ull << sw.pos[j];
     const unsigned long long all = N >= 64 ? ~0ull : ((1ull << N) - 1ull);
     d.n_local = n_loc;
-    d.enum_mask = (last ? all : live_before) & ~tile_mask;
+    // (skip_dead: the caller has zero-filled the dead region itself - zero_dead_kernel - so the last sweep visits
+    // the live tiles only, like every other sweep)
+    d.enum_mask = ((last && !skip_dead) ? all : live_before) & ~tile_mask;
     if (shard) {
         // Which rank works on which tile: the rank bits OUTSIDE the tile are the rank's own (its shard); for
         // every rank bit INSIDE the tile (the tile spans the buffers of two ranks) one of the highest non-tile
@@ -1208,6 +1210,42 @@ static int tma_mode() {  // QCK_SIM_TMA: 0 = never, 1 = when eligible (default)
 
 // fold_row != NULL: the caller wants the probabilities of the single instance in fold_row instead of the
 // final state (only honoured - *folded = true - when the plan runs on the TMA kernels).
+// Zero-fill of the DEAD region of a state / probability row: the indices with a bit set that no sweep ever had
+// in a tile (that qubit is still |0>).  The last sweep used to write those tiles itself - zero-filling a
+// shared-memory stage and TMA-storing it, tile by tile, through the full producer / consumer hand-shake: for a
+// shallow circuit that is almost the whole buffer (uncut syc-32 d1: 2^23 of 2^32 amplitudes are ever non-zero)
+// and ran at 0.46 of the HBM peak.  A plain streaming store kernel does it at memset speed, before the sweeps.
+// One warp per run of 2^c contiguous elements (c = contiguous low live bits).
+__global__ void __launch_bounds__(256) zero_dead_kernel(unsigned char* __restrict__ base, unsigned long long inst_stride_bytes,
+                                                        int n_bits, unsigned long long live_after, int c, int log_es) {
+    const unsigned long long n_runs = 1ull << (n_bits - c);
+    const unsigned long long run_bytes = (1ull << c) << log_es;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    unsigned char* inst = base + (unsigned long long)blockIdx.y * inst_stride_bytes;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (unsigned long long r = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_runs; r += n_warps) {
+        if (((r << c) & ~live_after) == 0ull) continue;  // a live run: the sweeps write it
+        uint4* dst = reinterpret_cast<uint4*>(inst + r * run_bytes);
+        for (unsigned long long o = lane; o < run_bytes / 16ull; o += 32) __stcs(dst + o, z);
+    }
+}
+
+static int zero_dead_region(qck_handle* h, void* base, unsigned long long inst_stride_bytes, int batch, int n_bits,
+                            unsigned long long live_after, int log_es, cudaStream_t st) {
+    int c = 0;
+    while (c < n_bits && ((live_after >> c) & 1ull)) ++c;
+    if (c >= n_bits) return QCK_OK;  // nothing dead
+    if (((1ull << c) << log_es) < 512ull) c = 0;  // (tiles always hold qubits 0-4: runs are >= 256 bytes; be safe)
+    unsigned long long runs = 1ull << (n_bits - c);
+    unsigned long long grid = (runs + 7) / 8;
+    if (grid > (unsigned long long)h->sm_count * 16) grid = (unsigned long long)h->sm_count * 16;
+    zero_dead_kernel<<<dim3((unsigned)grid, (unsigned)batch), 256, 0, st>>>(reinterpret_cast<unsigned char*>(base), inst_stride_bytes,
+                                                                           n_bits, live_after, c, log_es);
+    QCK_CHECK_LAUNCH(h);
+    return QCK_OK;
+}
+
 static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd, const int32_t* d_labels,
                       int inst_base, int batch, double2* work, unsigned long long state_stride,
                       cudaStream_t st, double* fold_row = nullptr, bool* folded = nullptr) {
@@ -1225,13 +1263,30 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
     }
     if (use_tma) {
         unsigned long long live = 0;
+        // The dead region is zero-filled by a streaming kernel up front (QCK_TMA_PREZERO=0: by the last sweep
+        // itself, tile by tile, as in round 1); the last sweep then visits the live tiles only.
+        bool prezero = true;
+        if (const char* env = getenv("QCK_TMA_PREZERO")) prezero = atoi(env) != 0;
+        {
+            unsigned long long live_after = 0;
+            for (int i = 0; i < plan->n_sweeps; ++i)
+                for (int j = 0; j < plan->sweeps[i].n_tile; ++j) live_after |= 1ull << plan->sweeps[i].pos[j];
+            const unsigned long long all = plan->n_state_qubits >= 64 ? ~0ull : ((1ull << plan->n_state_qubits) - 1ull);
+            if ((live_after & all) == all) prezero = false;  // nothing is dead
+            if (prezero) {
+                const bool to_row = fold_row && batch == 1;
+                int rc = zero_dead_region(h, to_row ? (void*)fold_row : (void*)work, state_stride * 16ull, to_row ? 1 : batch,
+                                          plan->n_state_qubits, live_after, to_row ? 3 : 4, st);
+                if (rc) return rc;
+            }
+        }
         // Tile scheduling: static round robin by default.  Pulling tiles from a counter (QCK_TMA_DYNAMIC=1)
         // measured 1-2 % faster on compute-heavy sweeps but 13 % slower on the write-only expansion sweep
         // of syc-32 d1 (15.1 vs 13.4 ms): neighbouring CTAs on neighbouring tiles suit the TMA stores.
         int tma_dynamic = 0;
         if (const char* env = getenv("QCK_TMA_DYNAMIC")) tma_dynamic = atoi(env);
         for (int i = 0; i < plan->n_sweeps; ++i) {
-            tma_describe(plan, i, live, i == plan->n_sweeps - 1, batch, h->max_smem_optin, *L);
+            tma_describe(plan, i, live, i == plan->n_sweeps - 1, batch, h->max_smem_optin, *L, nullptr, prezero);
             for (int j = 0; j < plan->sweeps[i].n_tile; ++j) live |= 1ull << plan->sweeps[i].pos[j];
             int rc = tma_encode(h, L->sd, batch, work, true, &L->maps.sh0.st);
             if (rc) return rc;
