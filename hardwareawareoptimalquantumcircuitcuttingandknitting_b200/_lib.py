@@ -98,6 +98,13 @@ _PROTOTYPES = {
     "qck_sim_statevector": (C.c_int, [C.c_void_p, C.POINTER(QckSimPlan), C.c_int32, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
     "qck_host_cluster_ops": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "qck_host_lower": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "qck_host_program_free": (None, [C.c_void_p]),
+    "qck_host_program_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_uint64]),
+    "qck_host_program_build": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "qck_host_program_get": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "qck_debug_tma_describe": (C.c_int, [C.POINTER(QckSimPlan), C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
                                          C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),

@@ -85,6 +85,150 @@ def _is_identity(m: np.ndarray) -> bool:
     return m.shape == (2, 2) and m[0, 0] == 1 and m[1, 1] == 1 and m[0, 1] == 0 and m[1, 0] == 0
 
 
+# Host compiler in C++ (csrc/host_program.cu): the fragment circuit is flattened into integer records + a matrix
+# pool (which double as the structure key of the process-wide program cache) and lowered / fused natively.
+# QCK_HOST_COMPILE=py keeps the Python originals below (the reference the native compiler is tested against).
+NATIVE = _os.environ.get("QCK_HOST_COMPILE", "native") != "py"
+
+IN_G1, IN_G2, IN_CX, IN_CZ, IN_MEASURE, IN_ENDPOINT = 1, 2, 3, 4, 5, 6
+T_U1, T_CX, T_CZ, T_U2, T_SLOT, T_MMEAS = 0, 1, 2, 3, 4, 5
+_TOP_NAMES = ("u1", "cx", "cz", "u2", "slot", "mmeas")
+
+_gate_matrix_cache: dict = {}
+_endpoint_table_cache: dict = {}
+
+
+def _endpoint_table(vg: VirtualBinaryGate, side: int):
+    """-> (pre [n, 2, 2], meas flags, post [n, 2, 2]) of one end of a virtual gate: the one-qubit share of every
+    instantiation (``virtual_gates.py:134-150``) as matrix before / measure? / matrix after."""
+    key = (type(vg), tuple(vg.params), side)
+    hit = _endpoint_table_cache.get(key)
+    if hit is not None:
+        return hit
+    pre, meas, post = [], [], []
+    for inst in vg._table():
+        a, b, seen = _I2, _I2, False
+        for name, params, q in inst:
+            if q != side:
+                continue
+            if name == "measure":
+                if seen:
+                    raise ValueError("instantiation measures a qubit twice")
+                seen = True
+                continue
+            m = Gate(name, 1, params).to_matrix()
+            if seen:
+                b = m @ b
+            else:
+                a = m @ a
+        pre.append(a)
+        meas.append(seen)
+        post.append(b)
+    if len(pre) > _lib.MAX_VARIANTS:
+        raise NotImplementedError("a virtual gate has more instantiations than QCK_MAX_VARIANTS")
+    hit = (np.stack(pre).astype(np.complex128), tuple(meas), np.stack(post).astype(np.complex128))
+    if len(_endpoint_table_cache) < 4096:
+        _endpoint_table_cache[key] = hit
+    return hit
+
+
+class FlatCircuit:
+    """A fragment circuit as the C ABI takes it (``qck_host_lower``): instruction records, endpoint records, matrix
+    pool.  ``key`` identifies everything a program depends on."""
+    __slots__ = ("n_qubits", "n_clbits", "instr", "endpoints", "pool", "tables", "key")
+
+
+def flatten(circ: QuantumCircuit, fragment: QuantumRegister) -> FlatCircuit:
+    n_q = len(fragment)
+    creg_off, off = {}, 0
+    for r in circ.cregs:
+        creg_off[id(r)] = off
+        off += len(r)
+    rows, eps, tables = [], [], []
+    pool, pool_len, mat_off = [], 0, {}
+    add = rows.append
+    try:
+        for ins in circ.data:
+            op = ins.operation
+            kind = type(op)
+            if kind is Gate or isinstance(op, Gate):
+                qs = ins.qubits
+                for q in qs:
+                    if q.register is not fragment:
+                        raise KeyError(q)
+                nq = op.num_qubits
+                m = op._matrix
+                if nq == 2 and m is None and (op.name == "cx" or op.name == "cz"):
+                    add((IN_CX if op.name == "cx" else IN_CZ, qs[0].index, qs[1].index, -1, -1, -1))
+                    continue
+                if nq > 2:
+                    raise NotImplementedError(f"{op.name}: gates on more than two qubits are not supported")
+                mkey = (op.name, tuple(op.params)) if m is None else m.tobytes()
+                o = mat_off.get(mkey)
+                if o is None:
+                    if m is None:
+                        m = _gate_matrix_cache.get(mkey)
+                        if m is None:
+                            m = np.ascontiguousarray(op.to_matrix(), dtype=np.complex128)
+                            if len(_gate_matrix_cache) < 65536:
+                                _gate_matrix_cache[mkey] = m
+                    if m.size != (4 if nq == 1 else 16):
+                        raise ValueError(f"{op.name}: matrix of the wrong size")
+                    o = mat_off[mkey] = pool_len
+                    pool.append(np.ascontiguousarray(m, dtype=np.complex128).reshape(-1).view(np.float64))
+                    pool_len += 2 * m.size
+                if nq == 1:
+                    add((IN_G1, qs[0].index, 0, -1, o, -1))
+                else:
+                    add((IN_G2, qs[0].index, qs[1].index, -1, o, -1))
+            elif isinstance(op, VirtualGateEndpoint):
+                q = ins.qubits[0]
+                if q.register is not fragment:
+                    raise KeyError(q)
+                vg = op.virtual_gate
+                tkey = (type(vg), tuple(vg.params), op.qubit_idx)
+                o = mat_off.get(tkey)
+                pre, meas, post = _endpoint_table(vg, op.qubit_idx)
+                if o is None:
+                    o = mat_off[tkey] = pool_len
+                    pool.append(pre.reshape(-1).view(np.float64))
+                    pool.append(post.reshape(-1).view(np.float64))
+                    pool_len += 16 * len(pre)
+                add((IN_ENDPOINT, q.index, 0, -1, -1, len(eps)))
+                eps.append((op.vgate_idx, op.qubit_idx, len(pre), sum(1 << v for v, f in enumerate(meas) if f),
+                            o, o + 8 * len(pre)))
+                tables.append((pre, meas, post))
+            elif isinstance(op, Barrier):
+                continue
+            elif isinstance(op, Measure):
+                q, c = ins.qubits[0], ins.clbits[0]
+                if q.register is not fragment:
+                    raise KeyError(q)
+                add((IN_MEASURE, q.index, 0, creg_off[id(c.register)] + c.index, -1, -1))
+            else:
+                raise TypeError(f"cannot lower operation {op!r}")
+    except KeyError:
+        raise ValueError("Circuit contains gates that act on multiple fragments.") from None
+    flat = FlatCircuit()
+    flat.n_qubits, flat.n_clbits = n_q, off
+    flat.instr = np.asarray(rows, dtype=np.int32).reshape(-1, 6)
+    flat.endpoints = np.asarray(eps, dtype=np.int32).reshape(-1, 6)
+    flat.pool = np.concatenate(pool) if pool else np.zeros(0, np.float64)
+    flat.tables = tables
+    flat.key = (n_q, off, flat.instr.tobytes(), flat.endpoints.tobytes(), flat.pool.tobytes())
+    return flat
+
+
+def _host_get(lib, ptr, what: int, dtype) -> np.ndarray:
+    n = lib.qck_host_program_get(ptr, what, None, 0)
+    if n < 0:
+        raise RuntimeError("qck_host_program_get failed")
+    out = np.empty(n // np.dtype(dtype).itemsize, dtype=dtype)
+    if n:
+        lib.qck_host_program_get(ptr, what, out.ctypes.data, n)
+    return out
+
+
 @dataclass
 class Slot:
     digit: int                  # position of the owning virtual gate in the fragment label
@@ -147,7 +291,7 @@ class FragmentProgram:
     def __init__(self, frag_circuit: QuantumCircuit, fragment: QuantumRegister, num_clbits: int,
                  onchip_max: int = ONCHIP_MAX_QUBITS, stream_tile: int = STREAM_TILE,
                  cluster: bool = True, fuse: bool = True, early_bits: int = 0, share_prefix=None,
-                 warp=None) -> None:
+                 warp=None, flat: "FlatCircuit | None" = None, native=None) -> None:
         self.share_prefix = SHARE_PREFIX if share_prefix is None else share_prefix      # True / False / "auto"
         # register-resident regime wanted?  (only default-shaped programs: the knobs below select other kernels)
         self.warp_wanted = (WARP if warp is None else bool(warp)) and onchip_max == ONCHIP_MAX_QUBITS \
@@ -165,7 +309,11 @@ class FragmentProgram:
         self._pool: list[np.ndarray] = []
         self._pool_len = 0
         self._mat_by_off: dict[int, np.ndarray] = {}
-        self._lower(frag_circuit)
+        self.native = NATIVE if native is None else bool(native)
+        if self.native:
+            self._lower_native(flat if flat is not None else flatten(frag_circuit, fragment))
+        else:
+            self._lower(frag_circuit)
         self._plans: dict[bool, list[PlanHost]] = {}
 
     # ------------------------------------------------------------------ template
@@ -176,6 +324,92 @@ class FragmentProgram:
         self._pool_len += flat.size
         self._mat_by_off[off] = np.asarray(m, dtype=np.complex128)
         return off
+
+    def _lower_native(self, flat: "FlatCircuit") -> None:
+        """``_lower`` + ``_fuse_pairs`` in C++ (``qck_host_lower``): same tops, slots and matrix pool."""
+        lib = _lib.load()
+        ptr = C.c_void_p()
+        flags = (1 if self.warp_wanted else 0) | (2 if self.fuse else 0)
+        rc = lib.qck_host_lower(flat.instr.ctypes.data, len(flat.instr), flat.endpoints.ctypes.data,
+                                len(flat.endpoints), flat.pool.ctypes.data, len(flat.pool), flat.n_qubits,
+                                flat.n_clbits, flags, WARP_MAX_QUBITS, WARP_MAX_DEPTH, C.byref(ptr))
+        if rc == -1:
+            raise ValueError("two terminal measurements write the same clbit")
+        if rc != 0:
+            raise _lib._EXC.get(rc, RuntimeError)(f"qck_host_lower failed ({rc})")
+        self._hp, self._hp_lib = ptr, lib
+        self._flat_tables = flat.tables
+        meta = _host_get(lib, ptr, 11, np.int32).tolist()
+        n_dig, n_touched, n_outc = meta[6], meta[8], meta[9]
+        self.vgate_indices = meta[10:10 + n_touched]
+        self.radix = meta[10 + n_touched:10 + n_touched + n_dig]
+        self.out_clbits = meta[10 + n_touched + n_dig:10 + n_touched + n_dig + n_outc]
+        self._pool_len = -1                    # the pool is fetched when somebody asks for it
+        del self._mat_by_off                   # (materialised on demand, with tops / slots / qubit_order / out_bits)
+        self.warp = bool(meta[1])
+        self.has_mid_measure = meta[2] > 0
+        self.out_mask = 0
+        for c in self.out_clbits:
+            self.out_mask |= 1 << c
+        self.measures_anything = bool(meta[3])
+        self.num_labels = 1
+        for r in self.radix:
+            self.num_labels *= r
+
+    _LAZY = ("tops", "slots", "qubit_order", "out_bits", "_mat_by_off")
+
+    def __getattr__(self, name):
+        # native programs keep their op list in the C++ object; the Python views of it (tests, bench statistics,
+        # the reference-faithful knit's slot table) are built on first use
+        if name in FragmentProgram._LAZY and self.__dict__.get("_hp") is not None:
+            self._materialise()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _native_pool(self) -> np.ndarray:
+        n = self._hp_lib.qck_host_program_get(self._hp, 9, None, 0) // 8
+        if n != self._pool_len:
+            pool = _host_get(self._hp_lib, self._hp, 9, np.float64)
+            self._pool, self._pool_len, self._mats_cache = ([pool] if len(pool) else []), len(pool), None
+        return self._pool[0] if self._pool else np.zeros(0)
+
+    def _materialise(self) -> None:
+        lib, ptr = self._hp_lib, self._hp
+        tops = _host_get(lib, ptr, 1, np.int32).reshape(-1, 4).tolist()
+        slot_rows = _host_get(lib, ptr, 2, np.int32).reshape(-1, 9).tolist()
+        slot_pre = _host_get(lib, ptr, 3, np.float64).view(np.complex128).reshape(-1, _lib.MAX_VARIANTS, 2, 2)
+        order = _host_get(lib, ptr, 4, np.int32).tolist()
+        out_bits = _host_get(lib, ptr, 5, np.int32).reshape(-1, 2).tolist()
+        frag_qubits = list(self.fragment)
+        d = self.__dict__
+        d["qubit_order"] = [frag_qubits[i] for i in order]
+        cview = self._native_pool().view(np.complex128)
+        mats = d["_mat_by_off"] = {}
+        slots = []
+        for i, (digit, vgate_idx, side, qubit, terminal, n_var, _mask, pre_off, post_off) in enumerate(slot_rows):
+            _pre, meas, post = self._flat_tables[i]
+            slots.append(Slot(digit=digit, vgate_idx=vgate_idx, side=side, qubit=qubit, terminal=bool(terminal),
+                              pre=list(slot_pre[i, :n_var]), meas=list(meas), post=list(post),
+                              pre_off=pre_off, post_off=post_off))
+            if pre_off >= 0:
+                mats[pre_off] = cview[pre_off // 2:pre_off // 2 + 4 * n_var].reshape(n_var, 2, 2)
+            if post_off >= 0:
+                mats[post_off] = cview[post_off // 2:post_off // 2 + 4 * n_var].reshape(n_var, 2, 2)
+        d["slots"] = slots
+        out = []
+        for kind, a, b, c in tops:
+            if kind == T_U1:
+                mats[b] = cview[b // 2:b // 2 + 4].reshape(2, 2)
+                out.append(("u1", a, b))
+            elif kind == T_U2:
+                mats[c] = cview[c // 2:c // 2 + 16].reshape(4, 4)
+                out.append(("u2", a, b, c))
+            elif kind == T_SLOT:
+                out.append(("slot", a))
+            else:
+                out.append((_TOP_NAMES[kind], a, b))
+        d["tops"] = out
+        d["out_bits"] = [(c, p) for c, p in out_bits]
 
     def _lower(self, circ: QuantumCircuit) -> None:
         frag_qubits = list(self.fragment)
@@ -303,10 +537,77 @@ class FragmentProgram:
         self.measures_anything = bool(out_bits) or mid_measures > 0 or any(any(s.meas) for s in slots)
         self.num_labels = int(np.prod(self.radix, dtype=np.int64)) if self.radix else 1
 
+    def __del__(self):  # pragma: no cover - best effort
+        hp = getattr(self, "_hp", None)
+        if hp is not None and hp.value:
+            self._hp = None
+            try:
+                self._hp_lib.qck_host_program_free(hp)
+            except Exception:
+                pass
+
+    def _native_build(self, stage: int, fold: bool = True) -> int:
+        """Run one stage of the C++ planner (0 tree, 1 plans, 2 host image, 3 canonical labels) with the CURRENT
+        module knobs, then pick up what it appended to the matrix pool."""
+        lib = self._hp_lib
+        mode = {True: 1, False: 0}.get(self.share_prefix, 2)
+        rc = lib.qck_host_program_configure(self._hp, self.onchip_max, min(self.stream_tile, _lib.MAX_TILE_QUBITS),
+                                            int(self.cluster), mode, int(TREE), {True: 1, False: 0}.get(DEDUPE, 2),
+                                            C.c_uint64(self.early_bits))
+        if rc == 0:
+            rc = lib.qck_host_program_build(self._hp, stage, int(bool(fold)))
+        if rc == -2:
+            raise ValueError("a clbit is written by more than one measurement")
+        if rc != 0 and not (stage == 0 and rc == 1):
+            raise _lib._EXC.get(rc, RuntimeError)(f"host planner failed ({rc}): program out of range "
+                                                  "(state > 40 qubits, an op that does not fit a tile, both ends of "
+                                                  "a virtual gate measuring in one fragment, or too many instances)")
+        return rc
+
+    def _native_plans(self, fold: bool) -> list:
+        self._native_build(1, fold)
+        lib, hp, base = self._hp_lib, self._hp, 100 + (20 if fold else 0)
+        meta = _host_get(lib, hp, base, np.int64).reshape(-1, 12).tolist()
+        labels = _host_get(lib, hp, base + 1, np.int32)
+        ops = _host_get(lib, hp, base + 2, np.int32).reshape(-1, 8)
+        sweeps = _host_get(lib, hp, base + 3, np.int32).reshape(-1, 43).tolist()
+        out_pos = _host_get(lib, hp, base + 4, np.int32).tolist()
+        plans, l0, o0, s0, p0 = [], 0, 0, 0, 0
+        for (pattern, n_labels, n_state, n_ops, n_sweeps, n_out, shared, warp_base, op_base, sum_mask, sign_mask,
+             _z) in meta:
+            sw = [(rec[3:3 + rec[0]], rec[1], rec[2]) for rec in sweeps[s0:s0 + n_sweeps]]
+            plans.append(PlanHost(pattern, labels[l0:l0 + n_labels], n_state, ops[o0:o0 + n_ops], sw,
+                                  out_pos[p0:p0 + n_out], sum_mask & (2 ** 64 - 1), sign_mask & (2 ** 64 - 1),
+                                  op_base=op_base, shared_prefix=bool(shared), warp_base=warp_base))
+            l0, o0, s0, p0 = l0 + n_labels, o0 + n_ops, s0 + n_sweeps, p0 + n_out
+        return plans
+
+    def _native_tree(self):
+        if self._native_build(0) != 1:
+            return None
+        lib, hp = self._hp_lib, self._hp
+        n_base, n_out_bits, seg0_b, seg0_e, base_sum, _n_levels, _n_ops, off_ops = _host_get(lib, hp, 50, np.int64).tolist()
+        ops = _host_get(lib, hp, 51, np.int32).reshape(-1, 8)
+        levels = []
+        for rec in _host_get(lib, hp, 52, np.int32).reshape(-1, 58).tolist():
+            kind, qubit, digit, pre_off, post_off, col_bit, seg_b, seg_e, n_ch, n_var = rec[:10]
+            levels.append(TreeLevel(kind, qubit, digit, pre_off, post_off,
+                                    [(rec[10 + 2 * c], rec[11 + 2 * c]) for c in range(n_ch)],
+                                    rec[42:42 + n_var], [bool(m) for m in rec[50:50 + n_var]], col_bit, (seg_b, seg_e)))
+        free = [tuple(x) for x in _host_get(lib, hp, 53, np.int32).reshape(-1, 2).tolist()]
+        counts = _host_get(lib, hp, 54, np.int64).tolist()
+        tree = TreeHost(n_base, ops, (seg0_b, seg0_e), levels, free, n_out_bits, base_sum & (2 ** 64 - 1), counts)
+        st = _lib.QckSimTreePlan.from_buffer_copy(_host_get(lib, hp, 55, np.uint8).tobytes())
+        self._tree_image = (_host_get(lib, hp, 56, np.uint8), off_ops, st)
+        return tree
+
     @property
     def mats(self) -> np.ndarray:
         """The matrix pool (float64, interleaved re/im).  Planning appends the tile-resolved variants
         of ops whose diag qubits stay outside a tile, so read it AFTER ``plans()``."""
+        if self.native:
+            pool = self._native_pool()
+            return pool if len(pool) else np.zeros(8)
         cached = getattr(self, "_mats_cache", None)
         if cached is None or cached[0] != len(self._pool):
             arr = np.concatenate(self._pool) if self._pool else np.zeros(8)
@@ -409,6 +710,9 @@ class FragmentProgram:
         self._tree = None
         if not (self.warp and TREE):
             return None
+        if self.native:
+            self._tree = self._native_tree()
+            return self._tree
         rows, levels, seen = [], [], set()
         seg_begin, seg0 = 0, None
         mmeas_clbits = [t[2] for t in self.tops if t[0] == "mmeas"]
@@ -485,6 +789,10 @@ class FragmentProgram:
         cached = getattr(self, "_canon", None)
         if cached is not None:
             return cached
+        if self.native:
+            self._native_build(3)
+            self._canon = _host_get(self._hp_lib, self._hp, 60, np.int32)
+            return self._canon
         n_dig = len(self.radix)
         maps = []
         for d in range(n_dig):
@@ -511,6 +819,9 @@ class FragmentProgram:
 
     def plans(self, fold: bool = True) -> list[PlanHost]:
         if fold in self._plans:
+            return self._plans[fold]
+        if self.native:
+            self._plans[fold] = self._native_plans(fold)
             return self._plans[fold]
         labels = np.arange(self.num_labels, dtype=np.int64)
         digits = self.label_digits(labels)
@@ -641,7 +952,7 @@ class FragmentProgram:
     @property
     def row_bits(self) -> int:
         """log2 of the folded output row length."""
-        return len(self.out_bits) + sum(1 for t in self.tops if t[0] == "mmeas")
+        return len(self.out_clbits)       # terminal measurements + mid-circuit measurements of the input circuit
 
     def row_len(self, fold: bool = True) -> int:
         bits = self.row_bits + (0 if fold else len(self.radix))
@@ -867,7 +1178,7 @@ class FragmentExecutor:
         self.fold = fold
         self.tree = program.tree() if fold else None
         if self.tree is not None:
-            host = program.__dict__.setdefault("_tree_image", None)
+            host = program.__dict__.setdefault("_tree_image", None)     # (the native planner leaves it there)
             if host is None:
                 host = program._tree_image = self._build_tree_image(program, self.tree)
             self._blob, self._off_ops, self._tree_struct = host
@@ -880,23 +1191,31 @@ class FragmentExecutor:
             self._work = None
             self._work_bytes = None
             return
-        self.plans = program.plans(fold)
+        if not program.native:
+            self.plans = program.plans(fold)
         # Host image of the program (blob + plan structs): a pure function of the program, built once and
         # shared by every executor of it (programs are cached process-wide; run() only ever copies the
         # struct templates, so sharing across threads is safe).
         host = program.__dict__.setdefault("_host_images", {}).get(fold)
         if host is None:
-            host = self._build_host_image(program, self.plans)
+            host = (self._native_host_image(program, fold) if program.native
+                    else self._build_host_image(program, self.plans))
             program._host_images[fold] = host
         (self._blob, self._off_ops, self._off_labels, self._labels_host, self._sweep_arrays, self._structs,
          self._dedupe) = host
         self.h2d_bytes = int(self._blob.nbytes)
         self.d_blob = None
         self.row_len = program.row_len(fold)
-        self.max_state = max(p.n_state for p in self.plans)
+        self.max_state = max(st.n_state_qubits for st, _o, _c in self._structs)
         self.streaming = self.max_state > program.onchip_max and not program.warp
         self._work = None
         self._work_bytes = None
+
+    def __getattr__(self, name):
+        if name == "plans" and "program" in self.__dict__:      # native programs: unpacked on first use only
+            self.plans = self.program.plans(self.fold)
+            return self.plans
+        raise AttributeError(name)
 
     @staticmethod
     def _build_tree_image(program: FragmentProgram, tree: "TreeHost"):
@@ -930,6 +1249,25 @@ class FragmentExecutor:
                 if L.first_choice[v] < 0:
                     L.first_choice[v] = c
         return blob, off_ops, st
+
+    @staticmethod
+    def _native_host_image(program: FragmentProgram, fold: bool):
+        """``_build_host_image`` in C++: the blob and the ``qck_sim_plan`` structs come filled (their ``sweeps``
+        pointers address memory owned by the program's native object, which the program keeps alive)."""
+        program._native_build(2, fold)
+        lib, hp, base = program._hp_lib, program._hp, 100 + (20 if fold else 0)
+        off_ops, off_labels, off_extra, off_src, dedupe, n_plans, _nb = _host_get(lib, hp, base + 5, np.int64).tolist()
+        blob = _host_get(lib, hp, base + 6, np.uint8)
+        raw = _host_get(lib, hp, base + 7, np.uint8).tobytes()
+        size = C.sizeof(_lib.QckSimPlan)
+        lab = _host_get(lib, hp, base + 9, np.int64).reshape(-1, 2).tolist()
+        structs = [(_lib.QckSimPlan.from_buffer_copy(raw, i * size), lab[i][0], lab[i][1]) for i in range(n_plans)]
+        labels = blob[off_labels:off_labels + 4 * (lab[-1][0] + lab[-1][1] if lab else 0)].view(np.int32)
+        dedupe_info = None
+        if dedupe:
+            reps = _host_get(lib, hp, base + 8, np.int64).reshape(-1, 2).tolist()
+            dedupe_info = (off_extra, [tuple(r) for r in reps], off_src)
+        return blob, off_ops, off_labels, labels, None, structs, dedupe_info
 
     @staticmethod
     def _build_host_image(program: FragmentProgram, plans: list):
@@ -1042,7 +1380,8 @@ class FragmentExecutor:
         # Only the size is remembered: the shared-prefix snapshots, or as many streaming states as fit.
         if self._work_bytes is None:
             if not self.streaming:
-                self._work_bytes = sum(16 << p.n_state for p in self.plans if p.shared_prefix)
+                self._work_bytes = sum(16 << st.n_state_qubits for st, _o, _c in self._structs
+                                       if st.sweeps[0].flags & _lib.SWEEP_SHARED)
             else:
                 per = 16 << self.max_state
                 n = 1

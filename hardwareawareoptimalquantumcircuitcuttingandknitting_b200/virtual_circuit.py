@@ -35,6 +35,7 @@ import numpy as np
 
 from . import _lib
 from .circuit import Barrier, ClassicalRegister, Gate, QuantumCircuit, QuantumRegister as Fragment
+from . import compiler as _compiler
 from .compiler import FragmentExecutor, FragmentProgram
 from .quasi_distr import QuasiDistr, default_device
 from .virtual_gates import VirtualBinaryGate, VirtualGateEndpoint, VirtualMove
@@ -168,10 +169,16 @@ class VirtualCircuit:
         (the reference runs every cut circuit at least twice, ``Utilities.py:85-86``)."""
         if fragment not in self._programs:
             circ = self._frag_circs[fragment]
-            key = _structure_key(circ, fragment) if PROGRAM_CACHE_SIZE > 0 else None
+            flat = None
+            if _compiler.NATIVE:
+                # the flattened circuit (input of the C++ compiler) is also the structure key
+                flat = _compiler.flatten(circ, fragment)
+                key = flat.key if PROGRAM_CACHE_SIZE > 0 else None
+            else:
+                key = _structure_key(circ, fragment) if PROGRAM_CACHE_SIZE > 0 else None
             prog = _program_cache.get(key) if key is not None else None
             if prog is None:
-                prog = FragmentProgram(circ, fragment, self.num_clbits)
+                prog = FragmentProgram(circ, fragment, self.num_clbits, flat=flat)
                 if key is not None:
                     with _program_cache_lock:
                         _program_cache[key] = prog

@@ -237,6 +237,36 @@ QCK_API int qck_sim_statevector(qck_handle* h, const qck_sim_plan* plan, int32_t
 QCK_API int qck_host_cluster_ops(const int32_t* ops, int n_ops, int n_tile, int max_cluster_ops,
                                  int32_t* out, int* n_out);
 
+/* Host half of the program compiler, first stage (no CUDA call, re-entrant): a flattened fragment circuit ->
+ * the op list the device programs are made of.  Replaces what the reference does per INSTANCE with Qiskit
+ * objects (virtual_circuit.py:183-213: copy, splice `instantiate(label[k])`, `.decompose()`): the fragment is
+ * lowered once, virtual-gate endpoints become slots whose variant matrices a label digit selects.
+ *   instr     [n_instr][6] int32: kind (1 one-qubit gate, 2 two-qubit gate with a matrix, 3 cx, 4 cz, 5 measure,
+ *             6 virtual-gate endpoint), qubit 0, qubit 1, clbit, matrix offset (doubles into `pool`), endpoint row;
+ *             qubits are indices into the fragment's register, barriers are already dropped
+ *   endpoints [n_endpoints][6] int32: virtual-gate index, side, variants, bit mask of the variants that measure,
+ *             offsets of the variants' pre- and post-measurement 2x2 matrices (8 doubles each, variant-major)
+ *   flags     bit 0: register-resident (warp) programs wanted, bit 1: pair fusion
+ * Products of consecutive one-qubit gates, pair fusion (cost model of compiler.py) and the qubit order (finally
+ * measured qubits first, by clbit) are done here.  Returns -1 when two terminal measurements write one clbit.
+ * The result is read back with qck_host_program_get (sizes first, with buf == NULL; see host_program.cu for the
+ * list of items) and released with qck_host_program_free. */
+typedef struct qck_host_program qck_host_program;
+QCK_API int qck_host_lower(const int32_t* instr, int n_instr, const int32_t* endpoints, int n_endpoints,
+                           const double* pool, int64_t pool_len, int n_qubits, int n_clbits, int flags,
+                           int warp_max_qubits, int warp_max_depth, qck_host_program** out);
+/* Second stage, on the lowered program: planning knobs (compiler.py's constructor arguments and module constants:
+ * share_prefix / dedupe 0 off, 1 on, 2 auto), then one of: stage 0 the tree program (returns 1 when the fragment
+ * is eligible - register regime, every virtual gate with one endpoint here - else 0), 1 the per-pattern plans
+ * (sweep scheduling for streaming states, register clusters for on-chip ones), 2 their host image (the blob the
+ * executor uploads + filled qck_sim_plan structs), 3 the canonical label of every label (identical instances).
+ * Errors: QCK_ERR_UNSUPPORTED (state > 40 bits, an op that fits no tile, ...), -2 (a clbit written twice). */
+QCK_API int qck_host_program_configure(qck_host_program* p, int onchip_max, int stream_tile, int cluster,
+                                       int share_prefix, int tree, int dedupe, uint64_t early_bits);
+QCK_API int qck_host_program_build(qck_host_program* p, int stage, int fold);
+QCK_API void qck_host_program_free(qck_host_program* p);
+QCK_API int64_t qck_host_program_get(const qck_host_program* p, int what, void* buf, int64_t cap_bytes);
+
 /* Host-logic probe (no CUDA call, usable without a GPU; not re-entrant): how the TMA sweep kernel
  * would run sweep `sweep` of `plan` when the state bits in `live_before` are live (some earlier
  * sweep had them in its tile; all other qubits are still |0>).  Returns 1 and fills the arrays when
