@@ -153,17 +153,26 @@ def flatten(circ: QuantumCircuit, fragment: QuantumRegister) -> FlatCircuit:
             kind = type(op)
             if kind is Gate or isinstance(op, Gate):
                 qs = ins.qubits
-                for q in qs:
-                    if q.register is not fragment:
-                        raise KeyError(q)
-                nq = op.num_qubits
+                nq = len(qs)
+                q0 = qs[0]
+                if q0.register is not fragment or (nq == 2 and qs[1].register is not fragment):
+                    raise KeyError(q0)
                 m = op._matrix
-                if nq == 2 and m is None and (op.name == "cx" or op.name == "cz"):
-                    add((IN_CX if op.name == "cx" else IN_CZ, qs[0].index, qs[1].index, -1, -1, -1))
-                    continue
-                if nq > 2:
+                name = op.name
+                if m is None:
+                    if nq == 2:
+                        if name == "cx":
+                            add((IN_CX, q0.index, qs[1].index, -1, -1, -1))
+                            continue
+                        if name == "cz":
+                            add((IN_CZ, q0.index, qs[1].index, -1, -1, -1))
+                            continue
+                    params = op.params
+                    mkey = (name, params[0]) if len(params) == 1 else (name, *params)
+                else:
+                    mkey = m.tobytes()
+                if nq > 2 or nq != op.num_qubits:
                     raise NotImplementedError(f"{op.name}: gates on more than two qubits are not supported")
-                mkey = (op.name, tuple(op.params)) if m is None else m.tobytes()
                 o = mat_off.get(mkey)
                 if o is None:
                     if m is None:

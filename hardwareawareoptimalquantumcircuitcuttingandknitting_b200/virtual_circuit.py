@@ -51,12 +51,14 @@ class VirtualCircuit:
         if not isinstance(circuit, QuantumCircuit):      # a qiskit circuit (duck typed): convert
             from .adapters import circuit_from_qiskit
             circuit = circuit_from_qiskit(circuit)
+        # (plain gates are the common case: `type(op) is Gate` spares them the abstract-base-class checks;
+        # VirtualMove is a VirtualBinaryGate here, the reference tests for both)
         self._vgate_instrs = [
-            instr for instr in circuit
-            if isinstance(instr.operation, VirtualBinaryGate) or isinstance(instr.operation, VirtualMove)
+            instr for instr in circuit.data
+            if type(instr.operation) is not Gate and isinstance(instr.operation, VirtualBinaryGate)
         ]
-        self._circuit = self._replace_vgates_with_endpoints(circuit)
-        self._frag_circs = {qreg: self._circuit_on_fragment(self._circuit, qreg) for qreg in circuit.qregs}
+        self._circuit = self._replace_vgates_with_endpoints(circuit) if self._vgate_instrs else circuit
+        self._frag_circs = self._circuits_on_fragments(self._circuit)
         self._frag_to_backend = {qreg: B200Backend() for qreg in self._frag_circs.keys()}
         self._programs: dict[Fragment, FragmentProgram] = {}
         self._executors: dict = {}
@@ -112,7 +114,7 @@ class VirtualCircuit:
         data = new_circuit.data
         for instr in circuit.data:
             op = instr.operation
-            if isinstance(op, VirtualBinaryGate):
+            if type(op) is not Gate and isinstance(op, VirtualBinaryGate):
                 for i in range(2):
                     new_circuit.append(VirtualGateEndpoint(op, vgate_idx=vgate_index, qubit_idx=i),
                                        [instr.qubits[i]], [])
@@ -120,6 +122,37 @@ class VirtualCircuit:
                 continue
             data.append(instr)          # instructions are never modified in place: shared, not copied
         return new_circuit
+
+    @staticmethod
+    def _circuits_on_fragments(circuit: QuantumCircuit) -> dict:
+        """``{qreg: _circuit_on_fragment(circuit, qreg)}`` for every register, in ONE pass over the instructions."""
+        circs = {qreg: QuantumCircuit(qreg, *circuit.cregs) for qreg in circuit.qregs}
+        lists = {id(qreg): c.data for qreg, c in circs.items()}
+        if len(circs) == 1:
+            only = next(iter(lists.values()))
+        else:
+            only = None
+        for instr in circuit.data:
+            qs = instr.qubits
+            if len(qs) == 1:
+                lists[id(qs[0].register)].append(instr)
+            elif only is not None:
+                only.append(instr)
+            elif len(qs) == 2 and qs[0].register is qs[1].register:
+                lists[id(qs[0].register)].append(instr)
+            else:
+                regs = {id(q.register) for q in qs}
+                if len(regs) == 1:
+                    lists[regs.pop()].append(instr)
+                elif not regs:
+                    for data in lists.values():
+                        data.append(instr)
+                else:
+                    op = instr.operation
+                    if isinstance(op, Barrier) and not isinstance(op, VirtualGateEndpoint):
+                        continue
+                    raise ValueError(f"Circuit contains gates that act on multiple fragments. {op}")
+        return circs
 
     @staticmethod
     def _circuit_on_fragment(circuit: QuantumCircuit, fragment: Fragment) -> QuantumCircuit:

@@ -223,15 +223,18 @@ class VirtualCZ(VirtualBinaryGate):
         return [(0.5 * s, -0.5 * s) for s in signs]
 
 
+_CX_TABLE = _wrap(_CZ_TABLE, (("h", (), 1),), (("h", (), 1),))
+_CY_TABLE = _wrap(_CX_TABLE, (("rz", (-pi / 2,), 1),), (("rz", (pi / 2,), 1),))
+
+
 class VirtualCX(VirtualCZ):
     def _table(self):
-        h1 = (("h", (), 1),)
-        return _wrap(super()._table(), h1, h1)
+        return _CX_TABLE
 
 
 class VirtualCY(VirtualCX):
     def _table(self):
-        return _wrap(super()._table(), (("rz", (-pi / 2,), 1),), (("rz", (pi / 2,), 1),))
+        return _CY_TABLE
 
 
 class VirtualRZZ(VirtualBinaryGate):
