@@ -733,6 +733,57 @@ __global__ void __launch_bounds__(256) contract_scatter_kernel(const double* __r
     }
 }
 
+// Three and more fragments (virtual_circuit.py:139-163 handles any number; Cutter.py:40 maxNPartitions): the
+// fragments are split into two GROUPS and the rows of a group with several members are multiplied out once per
+// group label - merged[lg][c] = prod_{f in g} Q_f[row_f(lg)][pext(c, mask_f inside the group)] - so that the
+// label contraction itself is the two-operand tensor-core tile kernel above (the per-output generic kernel walks
+// all labels serially: 19.5 ms against 0.3 ms on 32 768 labels in round 1).
+struct MergeParams {
+    int n_frag, n_digits, m_bits;
+    const double* table[KO_MAXF];
+    long long row_stride[KO_MAXF];
+    unsigned long long cmask[KO_MAXF];     // the fragment's output bits among the group's
+    int stride[KO_MAXF][QCK_MAX_DIGITS];   // fragment label strides of the digits
+    int radix[QCK_MAX_DIGITS];
+    int touched[QCK_MAX_DIGITS];           // digit is part of the group label
+    long long n_labels;
+    double* out;                           // [n_labels][2^m_bits]
+};
+
+__global__ void __launch_bounds__(256) contract_merge_kernel(const __grid_constant__ MergeParams P) {
+    __shared__ long long row[KO_MAXF];
+    const long long cols = 1ll << P.m_bits;
+    for (long long lg = blockIdx.x; lg < P.n_labels; lg += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < P.n_frag) {
+            long long rem = lg, r = 0;
+            for (int k = P.n_digits - 1; k >= 0; --k) {
+                if (!P.touched[k]) continue;
+                r += (rem % P.radix[k]) * P.stride[threadIdx.x][k];
+                rem /= P.radix[k];
+            }
+            row[threadIdx.x] = r * P.row_stride[threadIdx.x];
+        }
+        __syncthreads();
+        for (long long c = threadIdx.x; c < cols; c += blockDim.x) {
+            double v = 1.0;
+            for (int f = 0; f < P.n_frag; ++f) v *= __ldg(P.table[f] + row[f] + soft_pext((unsigned long long)c, P.cmask[f]));
+            P.out[lg * cols + c] = v;
+        }
+    }
+}
+
+static unsigned long long compress_mask(unsigned long long mask, unsigned long long within) {
+    unsigned long long out = 0;
+    int j = 0;
+    for (int b = 0; b < 64; ++b)
+        if ((within >> b) & 1ull) {
+            if ((mask >> b) & 1ull) out |= 1ull << j;
+            ++j;
+        }
+    return out;
+}
+
 int qck_ensure_scratch(qck_handle* h, size_t bytes, void** out);  // api.cu
 
 extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
@@ -763,13 +814,86 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
         if (!accumulate) QCK_CUDA(h, cudaMemsetAsync(d_out, 0, sizeof(double) << n_out_bits, st));
         return QCK_OK;
     }
-    // scratch: w[count] + rows[n_frag][count] (+ split partials for the GEMM path)
-    const int mA = __builtin_popcountll(masks[0]);
-    const int mB = n_frag >= 2 ? __builtin_popcountll(masks[1]) : 0;
+    // ---- three and more fragments: two groups (see contract_merge_kernel)
+    const bool full_cover = seen == (n_out_bits >= 64 ? ~0ull : (1ull << n_out_bits) - 1ull);
+    const char* group_env = getenv("QCK_CONTRACT_GROUPS");
+    const double* eff_tables[2];
+    uint64_t eff_masks[2];
+    int64_t eff_row_strides[2];
+    int32_t eff_stride[2 * QCK_MAX_DIGITS];
+    size_t merged_bytes[2] = {0, 0};
+    long long group_labels[2] = {0, 0};
+    int group_of_frag = 0;  // bit f set: fragment f belongs to group 1
+    bool grouped = false;
+    if (n_frag >= 3 && full_cover && !(group_env && atoi(group_env) == 0)) {
+        double best = -1.0;
+        for (int pick = 1; pick < (1 << (n_frag - 1)); ++pick) {  // fragment n_frag-1 always in group 0
+            double cost = 0.0;
+            int bits[2] = {0, 0};
+            bool ok = true;
+            for (int g = 0; g < 2; ++g) {
+                int members = 0;
+                long long lg = 1;
+                for (int f = 0; f < n_frag; ++f)
+                    if (((pick >> f) & 1) == g) {
+                        ++members;
+                        bits[g] += __builtin_popcountll(masks[f]);
+                    }
+                for (int k = 0; k < n_digits; ++k) {
+                    bool touched = false;
+                    for (int f = 0; f < n_frag; ++f)
+                        if (((pick >> f) & 1) == g && frag_stride[f * QCK_MAX_DIGITS + k] != 0) touched = true;
+                    if (touched) lg *= radix[k];
+                    if (lg >= (1ll << 31)) ok = false;
+                }
+                if (members > 1) cost += 2.0 * (double)lg * (double)(1ull << bits[g]);
+            }
+            const int pa = bits[0] < 6 ? 6 : bits[0], pb = bits[1] < 6 ? 6 : bits[1];
+            cost += (double)count * (double)(1ull << (pa + pb)) / 6.0;
+            if (ok && (best < 0 || cost < best)) best = cost, group_of_frag = pick;
+        }
+        grouped = best >= 0;
+        if (grouped) {
+            for (int g = 0; g < 2 && grouped; ++g) {
+                int members = 0, bits = 0, last = -1;
+                uint64_t gmask = 0;
+                long long acc = 1;
+                for (int f = 0; f < n_frag; ++f)
+                    if (((group_of_frag >> f) & 1) == g) ++members, bits += __builtin_popcountll(masks[f]), gmask |= masks[f], last = f;
+                for (int k = n_digits - 1; k >= 0; --k) {
+                    bool touched = false;
+                    for (int f = 0; f < n_frag; ++f)
+                        if (((group_of_frag >> f) & 1) == g && frag_stride[f * QCK_MAX_DIGITS + k] != 0) touched = true;
+                    eff_stride[g * QCK_MAX_DIGITS + k] = touched ? (int32_t)acc : 0;
+                    if (touched) acc *= radix[k];
+                }
+                eff_masks[g] = gmask;
+                group_labels[g] = acc;
+                if (members == 1) {
+                    eff_tables[g] = d_tables[last];
+                    eff_row_strides[g] = row_strides[last];
+                    for (int k = 0; k < n_digits; ++k) eff_stride[g * QCK_MAX_DIGITS + k] = frag_stride[last * QCK_MAX_DIGITS + k];
+                } else {
+                    eff_tables[g] = nullptr;  // filled once the scratch is known
+                    eff_row_strides[g] = 1ll << bits;
+                    merged_bytes[g] = (((size_t)acc << bits) * sizeof(double) + 255) & ~(size_t)255;
+                }
+            }
+            if (merged_bytes[0] + merged_bytes[1] > ((size_t)16 << 30)) grouped = false;  // fall back: generic kernel
+        }
+    }
+    const int n_eff = grouped ? 2 : n_frag;
+    const double* const* tabs = grouped ? eff_tables : d_tables;
+    const uint64_t* msk = grouped ? eff_masks : masks;
+    const int64_t* rstr = grouped ? eff_row_strides : row_strides;
+    const int32_t* fstr = grouped ? eff_stride : frag_stride;
+    // scratch: w[count] + rows[n_frag][count] (+ split partials for the GEMM path, + merged group tables)
+    const int mA = __builtin_popcountll(msk[0]);
+    const int mB = n_eff >= 2 ? __builtin_popcountll(msk[1]) : 0;
     // two fragments always take the tile kernels: rows shorter than a tile (a fragment with fewer than 6 output
     // bits, e.g. the 5-bit side of aqft-16 with five wire cuts) are padded with zeros inside the tile - the
     // per-output generic kernel walks all labels serially (19.5 ms against 0.3 ms for those 32 768 labels)
-    const bool gemm = (n_frag == 2);
+    const bool gemm = (n_eff == 2);
     const int mAp = mA < 6 ? 6 : mA, mBp = mB < 6 ? 6 : mB;
     int n_split = 1;
     size_t partial_bytes = 0;
@@ -786,22 +910,52 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
         partial_bytes = (size_t)n_split * sizeof(double) << (mAp + mBp);
     }
     size_t w_bytes = ((size_t)count * sizeof(double) + 255) & ~(size_t)255;
-    size_t r_bytes = ((size_t)count * n_frag * sizeof(int) + 255) & ~(size_t)255;
+    size_t r_bytes = ((size_t)count * n_eff * sizeof(int) + 255) & ~(size_t)255;
+    partial_bytes = (partial_bytes + 255) & ~(size_t)255;
     void* scratch = nullptr;
-    int rc = qck_ensure_scratch(h, w_bytes + r_bytes + partial_bytes, &scratch);
+    int rc = qck_ensure_scratch(h, w_bytes + r_bytes + partial_bytes + merged_bytes[0] + merged_bytes[1], &scratch);
     if (rc) return rc;
     double* d_w = (double*)scratch;
     int* d_rows = (int*)((char*)scratch + w_bytes);
     double* d_partial = (double*)((char*)scratch + w_bytes + r_bytes);
+    if (grouped) {
+        char* at = (char*)scratch + w_bytes + r_bytes + partial_bytes;
+        for (int g = 0; g < 2; ++g) {
+            if (!merged_bytes[g]) continue;
+            MergeParams mp;
+            memset(&mp, 0, sizeof(mp));
+            mp.n_digits = n_digits;
+            mp.m_bits = __builtin_popcountll(eff_masks[g]);
+            for (int f = 0; f < n_frag; ++f)
+                if (((group_of_frag >> f) & 1) == g) {
+                    const int j = mp.n_frag++;
+                    mp.table[j] = d_tables[f];
+                    mp.row_stride[j] = row_strides[f];
+                    mp.cmask[j] = compress_mask(masks[f], eff_masks[g]);
+                    for (int k = 0; k < n_digits; ++k) mp.stride[j][k] = frag_stride[f * QCK_MAX_DIGITS + k];
+                }
+            for (int k = 0; k < n_digits; ++k) {
+                mp.radix[k] = radix[k];
+                mp.touched[k] = eff_stride[g * QCK_MAX_DIGITS + k] != 0;
+            }
+            mp.n_labels = group_labels[g];
+            mp.out = (double*)at;
+            eff_tables[g] = (const double*)at;
+            at += merged_bytes[g];
+            const long long want = group_labels[g] < (long long)h->sm_count * 16 ? group_labels[g] : (long long)h->sm_count * 16;
+            contract_merge_kernel<<<(int)want, 256, 0, st>>>(mp);
+            QCK_CHECK_LAUNCH(h);
+        }
+    }
 
     PrepParams pp;
     memset(&pp, 0, sizeof(pp));
     pp.n_digits = n_digits;
-    pp.n_frag = n_frag;
+    pp.n_frag = n_eff;
     for (int k = 0; k < n_digits; ++k) {
         pp.radix[k] = radix[k];
         for (int v = 0; v < QCK_MAX_VARIANTS; ++v) pp.coef[k][v] = coef[k * QCK_MAX_VARIANTS + v];
-        for (int f = 0; f < n_frag; ++f) pp.stride[f][k] = frag_stride[f * QCK_MAX_DIGITS + k];
+        for (int f = 0; f < n_eff; ++f) pp.stride[f][k] = fstr[f * QCK_MAX_DIGITS + k];
     }
     pp.l_begin = l_begin;
     pp.count = count;
@@ -813,11 +967,11 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
 
     ContractParams cp;
     memset(&cp, 0, sizeof(cp));
-    cp.n_frag = n_frag;
-    for (int f = 0; f < n_frag; ++f) {
-        cp.table[f] = d_tables[f];
-        cp.mask[f] = masks[f];
-        cp.row_stride[f] = row_strides[f];
+    cp.n_frag = n_eff;
+    for (int f = 0; f < n_eff; ++f) {
+        cp.table[f] = tabs[f];
+        cp.mask[f] = msk[f];
+        cp.row_stride[f] = rstr[f];
     }
     cp.n_out_bits = n_out_bits;
     cp.count = count;
@@ -828,15 +982,15 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
     const unsigned long long n = 1ull << n_out_bits;
     int ggrid = (int)((n + 255) / 256 < (unsigned long long)h->sm_count * 8 ? (n + 255) / 256
                                                                            : (unsigned long long)h->sm_count * 8);
-    if (gemm && (seen == (n_out_bits >= 64 ? ~0ull : (1ull << n_out_bits) - 1ull))) {
+    if (gemm && full_cover) {
         const int M = 1 << mAp, N = 1 << mBp, Mr = 1 << mA, Nr = 1 << mB;
         dim3 grid(M / GT, N / GT, n_split);
         // FP64 tensor cores (DMMA) by default; QCK_CONTRACT_FMA=1 selects the FMA-pipe tile kernel
         const char* fma_env = getenv("QCK_CONTRACT_FMA");
         // pipelined gather (cp.async, 16-byte requests): rows must start on 16-byte boundaries and be even
         const char* pipe_env = getenv("QCK_CONTRACT_PIPE");
-        const bool aligned = ((reinterpret_cast<uintptr_t>(d_tables[0]) | reinterpret_cast<uintptr_t>(d_tables[1])) & 15) == 0 &&
-                             ((row_strides[0] | row_strides[1]) & 1) == 0 && Mr >= 2 && Nr >= 2;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(tabs[0]) | reinterpret_cast<uintptr_t>(tabs[1])) & 15) == 0 &&
+                             ((rstr[0] | rstr[1]) & 1) == 0 && Mr >= 2 && Nr >= 2;
         if (fma_env && atoi(fma_env) == 1)
             contract_gemm_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N, Mr, Nr);
         else if (aligned && !(pipe_env && atoi(pipe_env) == 0)) {
@@ -851,7 +1005,7 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
         else
             contract_dmma_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N, Mr, Nr);
         QCK_CHECK_LAUNCH(h);
-        contract_scatter_kernel<<<ggrid, 256, 0, st>>>(d_partial, n_split, M, N, masks[0], masks[1], n_out_bits,
+        contract_scatter_kernel<<<ggrid, 256, 0, st>>>(d_partial, n_split, M, N, msk[0], msk[1], n_out_bits,
                                                         d_out, accumulate);
         QCK_CHECK_LAUNCH(h);
     } else {

@@ -786,6 +786,79 @@ def test_knit_contract_generic_vs_oracle(dev):
     assert np.abs(out.cpu().numpy() - want).max() < 1e-12
 
 
+def _contract_call(dev, tables, touches, coeffs, masks, radices, n_out, l0=None, l1=None, accumulate=0, out=None):
+    F, K = len(tables), len(radices)
+    h = _lib.get_handle(0)
+    d_t = [torch.from_numpy(np.ascontiguousarray(t)).to(dev) for t in tables]
+    ptrs = (C.c_void_p * F)(*[t.data_ptr() for t in d_t])
+    cm = (C.c_uint64 * F)(*masks)
+    rs = (C.c_int64 * F)(*[t.shape[1] for t in tables])
+    rad = (C.c_int32 * K)(*radices)
+    coef = (C.c_double * (K * _lib.MAX_VARIANTS))()
+    for k in range(K):
+        for i, v in enumerate(coeffs[k]):
+            coef[k * _lib.MAX_VARIANTS + i] = v
+    st = (C.c_int32 * (F * _lib.MAX_DIGITS))()
+    for f in range(F):
+        acc = 1
+        for k in reversed(range(K)):
+            if touches[f][k]:
+                st[f * _lib.MAX_DIGITS + k] = acc
+                acc *= radices[k]
+    if out is None:
+        out = torch.empty(1 << n_out, dtype=torch.float64, device=dev)
+    total = int(np.prod(radices))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    h.check(h.lib.qck_knit_contract(h.ptr, F, ptrs, cm, rs, n_out, K, rad, coef, st, 0 if l0 is None else l0,
+                                    total if l1 is None else l1, out.data_ptr(), accumulate, stream))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("case", ["chain3", "star4", "narrow3"])
+def test_knit_contract_three_and_more_fragments_grouped(dev, case, monkeypatch):
+    """-p 3 / -p 4 cuts (virtual_circuit.py:139-163 with -1 labels): the fragments are merged into two groups and
+    contracted by the tensor-core tile kernel; against the dense oracle, against the per-output generic kernel
+    (QCK_CONTRACT_GROUPS=0) and with the label range split in two (accumulate)."""
+    rng = np.random.default_rng(11)
+    if case == "chain3":        # A -g0,g1- B -g2,g3- C, 14 output bits
+        radices = [6, 6, 8, 6]
+        masks = [0b00000000011111, 0b00000111100000, 0b11111000000000]
+        touches = [[True, True, False, False], [True, True, True, True], [False, False, True, True]]
+    elif case == "star4":       # B in the middle of A, C, D; 13 output bits, interleaved masks
+        radices = [6, 8, 6]
+        masks = [0b0000000010101, 0b0000011101010, 0b0011100000000, 0b1100000000000]
+        touches = [[True, False, False], [True, True, True], [False, True, False], [False, False, True]]
+    else:                       # rows narrower than a tile on both sides
+        radices = [6, 6]
+        masks = [0b0011, 0b0100, 0b1000]
+        touches = [[True, False], [True, True], [False, True]]
+    n_out = sum(bin(m).count("1") for m in masks)
+    tables = []
+    for m, t in zip(masks, touches):
+        lf = int(np.prod([r for r, tt in zip(radices, t) if tt]))
+        tables.append(rng.normal(size=(lf, 1 << bin(m).count("1"))))
+    coeffs = [list(rng.normal(size=r)) for r in radices]
+    want = od.contract(tables, touches, coeffs, masks, n_out)
+    scale = np.abs(want).max()
+    h = _lib.get_handle(0)
+    before = h.launch_count
+    got = _contract_call(dev, tables, touches, coeffs, masks, radices, n_out)
+    launches = h.launch_count - before
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-12 * max(1.0, scale)
+    assert launches >= 4          # merge + prep + tile kernel + scatter: not the single generic launch
+    total = int(np.prod(radices))
+    cut = (total // 3) // radices[-1] * radices[-1]
+    part = _contract_call(dev, tables, touches, coeffs, masks, radices, n_out, 0, cut)
+    part = _contract_call(dev, tables, touches, coeffs, masks, radices, n_out, cut, total, accumulate=1, out=part)
+    assert np.abs(part.cpu().numpy() - want).max() < 1e-12 * max(1.0, scale)
+    monkeypatch.setenv("QCK_CONTRACT_GROUPS", "0")
+    before = h.launch_count
+    generic = _contract_call(dev, tables, touches, coeffs, masks, radices, n_out)
+    assert h.launch_count - before == 2       # prep + generic
+    assert (generic - got).abs().max().item() < 1e-12 * max(1.0, scale)
+
+
 def test_label_sharded_run_equals_full(dev):
     """What two ranks would compute, emulated on one GPU: partial contractions add up."""
     circ, cut = cutting.make_baseline("syc16d5", seed=2)
