@@ -508,7 +508,7 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
         fault surfaced.  Always on for multi-rank runs: two of four 2-GPU runs of the secondary workloads ended in
         a sticky CUDA fault without these synchronisations and none of eight with them (no such fault in any
         1-GPU run); the cause is not understood yet - see DESIGN.md, open issues."""
-        if trace or world > 1:
+        if trace or (world > 1 and os.environ.get("QCK_BENCH_STAGE_SYNC", "1") != "0"):
             try:
                 torch.cuda.synchronize(device)
             except Exception as exc:

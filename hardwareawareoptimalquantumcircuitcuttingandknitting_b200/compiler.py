@@ -1348,6 +1348,11 @@ class FragmentExecutor:
         self.d_blob = torch.empty(self._blob.nbytes, dtype=torch.uint8, device=self.device)
         self.d_blob.copy_(stage[:self._blob.nbytes], non_blocking=True)
 
+    def alloc_out(self, label_range=None):
+        """The table a run fills: [num_labels, row_len] float64 (zero-filled when only a label range is written)."""
+        alloc = self.torch.zeros if label_range is not None else self.torch.empty
+        return alloc((self.program.num_labels, self.row_len), dtype=self.torch.float64, device=self.device)
+
     def plan_struct(self, i: int = 0) -> "_lib.QckSimPlan":
         """A private copy of plan i's ``qck_sim_plan`` with the device pointers of THIS executor filled in
         (for direct C-ABI calls such as ``qck_sim_statevector``); uploads the program if necessary."""
@@ -1369,8 +1374,7 @@ class FragmentExecutor:
             self.upload()
         prog = self.program
         if out is None:
-            alloc = torch.zeros if label_range is not None else torch.empty
-            out = alloc((prog.num_labels, self.row_len), dtype=torch.float64, device=self.device)
+            out = self.alloc_out(label_range)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         if self.tree is not None:
             st = _lib.QckSimTreePlan.from_buffer_copy(self._tree_struct)

@@ -31,6 +31,7 @@ struct qck_handle {
     int side_ready;
     int region;            // a qck_sim_region is open: batch calls fan out and do not join
     unsigned region_used;  // side streams the open region has launched on
+    unsigned region_forked;  // side streams that already wait for the CURRENT call's fork point
     unsigned side_next;    // rotating pick of the next side stream
     // workspace of nearest_probability_distribution (npd.cu): state, bins, per-CTA partials
     void* npd_ws;

@@ -1348,6 +1348,7 @@ static int run_sweeps(qck_handle* h, const qck_sim_plan* plan, const PlanDev& pd
 static int qck_warp_init(qck_handle* h);
 static int qck_tree_init(qck_handle* h);
 static int pick_side_stream(qck_handle* h, unsigned* used, cudaStream_t* st);
+static int region_fork_call(qck_handle* h, cudaStream_t main_st);
 static int warp_single_plan(qck_handle* h, const qck_sim_plan* plan, const int32_t* d_labels, int64_t n_instances,
                             double* d_out, int64_t out_row_stride, cudaStream_t st);
 
@@ -1690,7 +1691,9 @@ extern "C" int qck_sim_tree(qck_handle* h, const qck_sim_tree_plan* plan, int64_
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (h->region) {  // the levels are dependent launches: the whole call goes on ONE side stream of the region
-        int rc = pick_side_stream(h, &h->region_used, &st);
+        int rc = region_fork_call(h, st);
+        if (rc) return rc;
+        rc = pick_side_stream(h, &h->region_used, &st);
         if (rc) return rc;
     }
     std::unique_ptr<TreeDev> T(new TreeDev);
@@ -1865,6 +1868,7 @@ extern "C" int qck_sim_region_begin(qck_handle* h, qck_stream stream) {
     QCK_CUDA(h, cudaEventRecord(h->fork, (cudaStream_t)stream));
     h->region = 1;
     h->region_used = 0;
+    h->region_forked = 0;
     h->region_calls = 0;
     return QCK_OK;
 }
@@ -1887,10 +1891,23 @@ extern "C" int qck_sim_region_end(qck_handle* h, qck_stream stream) {
 static int pick_side_stream(qck_handle* h, unsigned* used, cudaStream_t* st) {
     const int slot = (int)(h->side_next++ % QCK_SIDE_STREAMS);
     *st = h->side[slot];
-    if (!((*used >> slot) & 1u)) {
+    // inside a region every CALL has its own fork point (region_fork_call): what the caller enqueued on its stream
+    // between region_begin and the call - the H2D copy of the program, a memset of the output - is ordered
+    // before the call's launches, too
+    unsigned* forked = h->region ? &h->region_forked : used;
+    if (!((*forked >> slot) & 1u)) {
         QCK_CUDA(h, cudaStreamWaitEvent(*st, h->fork, 0));
-        *used |= 1u << slot;
+        *forked |= 1u << slot;
     }
+    *used |= 1u << slot;
+    return QCK_OK;
+}
+
+// first thing a simulation call does inside a region: a fresh fork point on the caller's stream
+static int region_fork_call(qck_handle* h, cudaStream_t main_st) {
+    if (!h->region) return QCK_OK;
+    QCK_CUDA(h, cudaEventRecord(h->fork, main_st));
+    h->region_forked = 0;
     return QCK_OK;
 }
 
@@ -1932,6 +1949,10 @@ extern "C" int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim
         int rc = ensure_side_streams(h);
         if (rc) return rc;
         QCK_CUDA(h, cudaEventRecord(h->fork, main_st));
+    }
+    if (region) {
+        int rc = region_fork_call(h, main_st);
+        if (rc) return rc;
     }
     for (int N = QCK_MAX_TILE_QUBITS; N >= 1; --N) {  // largest states first: they run longest
         int idx[QCK_GROUP_MAX], cnt = 0;

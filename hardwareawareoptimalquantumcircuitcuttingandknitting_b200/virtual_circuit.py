@@ -317,16 +317,26 @@ class VirtualCircuit:
         frags = self.active_fragments()
         # the fragments are independent jobs (run.py:36-43): inside a region their launches overlap on the GPU
         overlap = len(frags) > 1
+        # Everything that enqueues work on the caller's stream - the H2D copy of a program, the zero-fill of a
+        # partially written table - happens BEFORE the region opens: the launches of a region are ordered after
+        # what precedes them on the stream.  (Round 2: uploads used to happen inside the region, after its fork
+        # point; a side-stream kernel could then read a program that had not arrived yet - the intermittent
+        # illegal-address fault of the cold end-to-end path.  The C side now also re-forks at every call.)
+        prepared = []
+        for frag in frags:
+            ex = self.executor(frag, device, fold)
+            if ex.d_blob is None:
+                ex.upload()
+            rng = None
+            if label_range is not None and self._vgate_instrs:
+                rng = self.fragment_label_range(frag, *label_range)
+            table = out[frag] if out is not None else ex.alloc_out(rng)
+            prepared.append((frag, ex, rng, table))
         if overlap:
             handle.check(handle.lib.qck_sim_region_begin(handle.ptr, stream))
         try:
-            for i, frag in enumerate(frags):
-                ex = self.executor(frag, device, fold)
-                rng = None
-                if label_range is not None and self._vgate_instrs:
-                    rng = self.fragment_label_range(frag, *label_range)
-                tables[frag] = ex.run(handle, out=None if out is None else out[frag], label_range=rng,
-                                      scratch_tag=i, defer_broadcast=overlap)
+            for i, (frag, ex, rng, table) in enumerate(prepared):
+                tables[frag] = ex.run(handle, out=table, label_range=rng, scratch_tag=i, defer_broadcast=overlap)
                 runs.append((ex, tables[frag]))
         finally:
             if overlap:

@@ -178,8 +178,10 @@ QCK_API int qck_sim_fragments_batch(qck_handle* h, int n_plans, const qck_sim_pl
 
 /* Overlap the qck_sim_fragments_batch calls of several fragments (their instances are independent:
  * run.py:36-43 submits one job per fragment).  Between begin and end every batch call launches on the handle's
- * side streams and returns without joining; end makes `stream` wait for all of them.  d_out and d_work of the
- * calls inside one region must not alias.  One region per handle at a time. */
+ * side streams and returns without joining; end makes `stream` wait for all of them.  The launches of a call
+ * are ordered after everything enqueued on `stream` before THAT call (each call forks anew: a program uploaded
+ * or an output zero-filled between begin and the call is seen).  d_out and d_work of the calls inside one
+ * region must not alias.  One region per handle at a time. */
 QCK_API int qck_sim_region_begin(qck_handle* h, qck_stream stream);
 QCK_API int qck_sim_region_end(qck_handle* h, qck_stream stream);
 
