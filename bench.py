@@ -796,7 +796,7 @@ def main() -> None:
                 others[w] = {"error": repr(exc)}
         # the reference's default mode: ACCURACY = 1e-5 pruning (one GPU: the reference-faithful knit is one
         # expression tree per output entry over ALL labels - never sharded, every rank would repeat the same run)
-        for w in (("hwe16d5", "syc16d5") if world == 1 else ()):
+        for w in (("hwe16d5", "syc16d5") if (world == 1 or os.environ.get("QCK_BENCH_FAITHFUL_MULTI") == "1") else ()):
             try:
                 others[f"{w}@1e-5"] = compact(measure(w, args, env, primary=False, accuracy=1e-5))
             except Exception as exc:
