@@ -33,6 +33,7 @@ struct FaithParams {
     double c1[FA_MAXK], s1[FA_MAXK];    // rzz: cos(m/2), sin(m/2)
     double c2[FA_MAXK], s2[FA_MAXK];    // rzz: cos^2, sin^2 (as Python's ** 2)
     int frag_stride[FA_MAXF][FA_MAXK];  // fragment label = sum_k digit_k * stride
+    long long row_step[FA_MAXF][FA_MAXK];  // frag_stride * row_stride: table offset per unit of digit k
     int cfg_bit[FA_MAXF][FA_MAXK];      // position of gate k's config bit among f's extra row bits, -1: untouched
     unsigned char measures[FA_MAXF][FA_MAXK][FA_MAXV];  // does f's instance measure gate k under variant v
     unsigned char any_measure[FA_MAXK][FA_MAXV];
@@ -44,30 +45,43 @@ __device__ __forceinline__ double prn(double v, double acc) { return fabs(v) > a
 struct EvalCtx {
     const FaithParams* P;
     unsigned long long xf[FA_MAXF];  // x restricted to each fragment's output bits (compact)
+    long long off[FA_MAXF];          // table offset of the fragment's row under the current digits
+    unsigned long long cf[FA_MAXF];  // config bits of the fragment's row index under the current path
     int d[FA_MAXK];
 };
 
-// merged_l(x, c): left fold over the fragments of prune(p_f) with a prune after each product
-__device__ double leaf(EvalCtx& C, unsigned c) {
+// the path below gate k takes variant i with config bit `bit`: row offsets and config bits follow incrementally
+// (recomputing them at every leaf - K multiply-adds per fragment - was most of the leaf's cost)
+__device__ __forceinline__ void enter(EvalCtx& C, int k, int i, int bit) {
     const FaithParams& P = *C.P;
-    // every set config bit needs a fragment that measures it in this label
-    for (int k = 0; k < P.K; ++k)
-        if (((c >> k) & 1u) && !P.any_measure[k][C.d[k]]) return 0.0;
+    const int delta = i - C.d[k];
+    C.d[k] = i;
+    for (int f = 0; f < P.n_frag; ++f) {
+        C.off[f] += (long long)delta * P.row_step[f][k];
+        if (bit && P.cfg_bit[f][k] >= 0 && P.measures[f][k][i]) C.cf[f] |= 1ull << P.cfg_bit[f][k];
+    }
+}
+__device__ __forceinline__ void leave(EvalCtx& C, int k, int bit) {
+    const FaithParams& P = *C.P;
+    if (bit)
+        for (int f = 0; f < P.n_frag; ++f)
+            if (P.cfg_bit[f][k] >= 0) C.cf[f] &= ~(1ull << P.cfg_bit[f][k]);
+}
+
+// merged_l(x, c): left fold over the fragments of prune(p_f) with a prune after each product.  (A config bit is
+// only ever set under a variant that measures it somewhere - knit_formula skips the other children - so no leaf
+// needs the "does anybody measure this bit" test.)
+__device__ __forceinline__ double leaf(EvalCtx& C) {
+    const FaithParams& P = *C.P;
     double v = 0.0;
     for (int f = 0; f < P.n_frag; ++f) {
-        long long row = 0;
-        unsigned long long cf = 0;
-        for (int k = 0; k < P.K; ++k) {
-            row += (long long)C.d[k] * P.frag_stride[f][k];
-            if (((c >> k) & 1u) && P.cfg_bit[f][k] >= 0 && P.measures[f][k][C.d[k]]) cf |= 1ull << P.cfg_bit[f][k];
-        }
-        const double pf = prn(__ldg(P.table[f] + row * P.row_stride[f] + (C.xf[f] | (cf << P.m_bits[f]))), P.acc);
+        const double pf = prn(__ldg(P.table[f] + C.off[f] + (C.xf[f] | (C.cf[f] << P.m_bits[f]))), P.acc);
         v = f == 0 ? pf : prn(v * pf, P.acc);
     }
     return v;
 }
 
-__device__ double eval(EvalCtx& C, int k, unsigned c);
+__device__ double eval(EvalCtx& C, int k);
 
 // apply gate k's knit formula given a functor child(i, bit) -> level-(k+1) value
 template <typename Child>
@@ -95,18 +109,20 @@ __device__ __forceinline__ double knit_formula(const FaithParams& P, int k, Chil
     return prn(head + prn(prn(mixed * P.c1[k], acc) * P.s1[k], acc), acc);
 }
 
-__device__ double eval(EvalCtx& C, int k, unsigned c) {
+__device__ double eval(EvalCtx& C, int k) {
     const FaithParams& P = *C.P;
-    if (k == P.K) return leaf(C, c);
+    if (k == P.K) return leaf(C);
     return knit_formula(P, k, [&](int i, int bit) {
-        C.d[k] = i;
-        return eval(C, k + 1, bit ? (c | (1u << k)) : c);
+        enter(C, k, i, bit);
+        const double v = eval(C, k + 1);
+        leave(C, k, bit);
+        return v;
     });
 }
 
 __device__ __forceinline__ void init_ctx(EvalCtx& C, const FaithParams& P, unsigned long long x) {
     C.P = &P;
-    for (int f = 0; f < P.n_frag; ++f) C.xf[f] = soft_pext(x, P.mask[f]);
+    for (int f = 0; f < P.n_frag; ++f) C.xf[f] = soft_pext(x, P.mask[f]), C.off[f] = 0, C.cf[f] = 0;
     for (int k = 0; k < FA_MAXK; ++k) C.d[k] = 0;
 }
 
@@ -123,8 +139,8 @@ __global__ void __launch_bounds__(128) faith_subtree_kernel(const __grid_constan
         if (!bit || P.any_measure[0][i]) {
             EvalCtx C;
             init_ctx(C, P, x);
-            C.d[0] = i;
-            v = eval(C, 1, bit ? 1u : 0u);
+            enter(C, 0, i, bit);
+            v = eval(C, 1);
         }
         scratch[t] = v;
     }
@@ -146,7 +162,143 @@ __global__ void __launch_bounds__(256) faith_leaf_kernel(const __grid_constant__
          x += (unsigned long long)gridDim.x * blockDim.x) {
         EvalCtx C;
         init_ctx(C, P, x);
-        out[x] = leaf(C, 0u);
+        out[x] = leaf(C);
+    }
+}
+
+// ---- sparsity: the reference's dictionaries simply do not hold pruned entries (quasi_distr.py:7-10), which is
+// where its speed on concentrated distributions (hwe) comes from.  Dense counterpart: a leaf is a pruned product
+// with one factor per fragment taken from COLUMN pext(x, mask_f) of that fragment's table, so when a column holds
+// no entry above the threshold in any row (any label, any config bits) every leaf under x is 0 and so is every
+// level above it (each formula maps zeros to +0).  The alive columns of every fragment are listed once; the
+// expression trees are evaluated only for the product set of the lists, the other outputs are +0 from a memset.
+struct AliveParams {
+    int n_frag;
+    const double* table[FA_MAXF];
+    long long n_rows[FA_MAXF], row_stride[FA_MAXF];
+    int m_bits[FA_MAXF];
+    unsigned* flags[FA_MAXF];  // [2^m_bits], zeroed
+    double acc;
+};
+
+__global__ void __launch_bounds__(256) faith_alive_kernel(const __grid_constant__ AliveParams A) {
+    const int f = blockIdx.y;
+    if (f >= A.n_frag) return;
+    const long long total = A.n_rows[f] * A.row_stride[f];
+    const long long cmask = (1ll << A.m_bits[f]) - 1;
+    const double* __restrict__ t = A.table[f];
+    unsigned* __restrict__ fl = A.flags[f];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        if (fabs(__ldg(t + e)) > A.acc) {
+            const long long col = (e % A.row_stride[f]) & cmask;
+            if (!fl[col]) fl[col] = 1u;  // every writer stores the same value
+        }
+}
+
+// ascending list of the set flags + their number (one CTA per fragment: the order is fixed)
+__global__ void __launch_bounds__(1024) faith_compact_kernel(const __grid_constant__ AliveParams A, int* __restrict__ lists,
+                                                             long long list_stride, int* __restrict__ counts) {
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    const int f = blockIdx.x;
+    const long long n_cols = 1ll << A.m_bits[f];
+    const unsigned* fl = A.flags[f];
+    int* list = lists + f * list_stride;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (long long c0 = 0; c0 < n_cols; c0 += blockDim.x) {
+        const long long c = c0 + threadIdx.x;
+        const int on = (c < n_cols && fl[c]) ? 1 : 0;
+        const unsigned ballot = __ballot_sync(0xffffffffu, on);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) warp_tot[warp] = __popc(ballot);
+        __syncthreads();
+        int before = base;
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        if (on) list[before + __popc(ballot & ((1u << lane) - 1u))] = (int)c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[f] = base;
+}
+
+struct SparseCtx {
+    const int* lists;
+    long long list_stride;
+    const int* counts;
+};
+
+// j-th element of the product set -> x and the per-fragment columns
+__device__ __forceinline__ unsigned long long alive_point(const FaithParams& P, const SparseCtx& S, unsigned long long j,
+                                                          EvalCtx& C) {
+    unsigned long long x = 0;
+    C.P = &P;
+    for (int f = 0; f < P.n_frag; ++f) {
+        const unsigned long long cnt = (unsigned long long)S.counts[f];
+        const unsigned long long col = (unsigned long long)S.lists[f * S.list_stride + (long long)(j % cnt)];
+        j /= cnt;
+        C.xf[f] = col;
+        C.off[f] = 0;
+        C.cf[f] = 0;
+        unsigned long long m = P.mask[f], src = col;  // deposit the column's bits at the mask's positions
+        while (m) {
+            const unsigned long long low = m & (~m + 1ull);
+            if (src & 1ull) x |= low;
+            src >>= 1;
+            m ^= low;
+        }
+    }
+    for (int k = 0; k < FA_MAXK; ++k) C.d[k] = 0;
+    return x;
+}
+__device__ __forceinline__ unsigned long long alive_total(const FaithParams& P, const SparseCtx& S) {
+    unsigned long long t = 1;
+    for (int f = 0; f < P.n_frag; ++f) t *= (unsigned long long)S.counts[f];
+    return t;
+}
+
+__global__ void __launch_bounds__(128) faith_subtree_sparse_kernel(const __grid_constant__ FaithParams P, const SparseCtx S,
+                                                                   double* __restrict__ scratch) {
+    const unsigned long long alive = alive_total(P, S);
+    const unsigned long long total = alive * (unsigned long long)(2 * P.radix[0]);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t / alive), i = j >> 1, bit = j & 1;
+        EvalCtx C;
+        const unsigned long long x = alive_point(P, S, t % alive, C);
+        double v = 0.0;
+        if (!bit || P.any_measure[0][i]) {
+            enter(C, 0, i, bit);
+            v = eval(C, 1);
+        }
+        scratch[((unsigned long long)j << P.n_out_bits) | x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) faith_top_sparse_kernel(const __grid_constant__ FaithParams P, const SparseCtx S,
+                                                               const double* __restrict__ scratch, double* __restrict__ out) {
+    const unsigned long long alive = alive_total(P, S);
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < alive;
+         j += (unsigned long long)gridDim.x * blockDim.x) {
+        EvalCtx C;
+        const unsigned long long x = alive_point(P, S, j, C);
+        out[x] = knit_formula(P, 0, [&](int i, int bit) { return scratch[((unsigned long long)(2 * i + bit) << P.n_out_bits) | x]; });
+    }
+}
+
+__global__ void __launch_bounds__(256) faith_leaf_sparse_kernel(const __grid_constant__ FaithParams P, const SparseCtx S,
+                                                                double* __restrict__ out) {
+    const unsigned long long alive = alive_total(P, S);
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < alive;
+         j += (unsigned long long)gridDim.x * blockDim.x) {
+        EvalCtx C;
+        const unsigned long long x = alive_point(P, S, j, C);
+        out[x] = leaf(C);
     }
 }
 
@@ -195,6 +347,7 @@ extern "C" int qck_knit_faithful(qck_handle* h, int n_frag, const double* const*
         P.s2[k] = g.sin_half_sq;
         for (int f = 0; f < n_frag; ++f) {
             P.frag_stride[f][k] = frag_stride[f * FA_MAXK + k];
+            P.row_step[f][k] = (long long)frag_stride[f * FA_MAXK + k] * row_strides[f];
             P.cfg_bit[f][k] = cfg_bit[f * FA_MAXK + k];
             for (int v = 0; v < FA_MAXV; ++v) {
                 P.measures[f][k][v] = measures[(f * FA_MAXK + k) * FA_MAXV + v];
@@ -206,21 +359,78 @@ extern "C" int qck_knit_faithful(qck_handle* h, int n_frag, const double* const*
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned long long n = 1ull << n_out_bits;
     int grid = (int)((n + 255) / 256 < (unsigned long long)h->sm_count * 8 ? (n + 255) / 256 : (unsigned long long)h->sm_count * 8);
+    // ---- alive columns (accuracy > 0 and the masks cover the output: else every x is evaluated as before)
+    const char* sparse_env = getenv("QCK_FAITHFUL_SPARSE");
+    const bool sparse = accuracy > 0.0 && seen == (n_out_bits >= 64 ? ~0ull : (1ull << n_out_bits) - 1ull) &&
+                        !(sparse_env && atoi(sparse_env) == 0);
+    const unsigned long long total = n_gates ? n * (unsigned long long)(2 * P.radix[0]) : 0;
+    size_t tree_bytes = (total * sizeof(double) + 255) & ~(size_t)255, flag_bytes = 0, list_bytes = 0;
+    long long list_stride = 0;
+    AliveParams A;
+    memset(&A, 0, sizeof(A));
+    if (sparse) {
+        A.n_frag = n_frag;
+        A.acc = accuracy;
+        for (int f = 0; f < n_frag; ++f) {
+            long long rows = 1;
+            for (int k = 0; k < n_gates; ++k)
+                if (P.frag_stride[f][k] != 0) rows *= P.radix[k];
+            A.table[f] = P.table[f];
+            A.n_rows[f] = rows;
+            A.row_stride[f] = P.row_stride[f];
+            A.m_bits[f] = P.m_bits[f];
+            flag_bytes += (sizeof(unsigned) << P.m_bits[f]);
+            if ((1ll << P.m_bits[f]) > list_stride) list_stride = 1ll << P.m_bits[f];
+        }
+        flag_bytes = (flag_bytes + 255) & ~(size_t)255;
+        list_bytes = ((size_t)list_stride * n_frag * sizeof(int) + 255) & ~(size_t)255;
+    }
+    void* scratch = nullptr;
+    int rc = qck_ensure_scratch(h, tree_bytes + flag_bytes + list_bytes + 256, &scratch);
+    if (rc) return rc;
+    SparseCtx S;
+    memset(&S, 0, sizeof(S));
+    if (sparse) {
+        char* at = (char*)scratch + tree_bytes;
+        QCK_CUDA(h, cudaMemsetAsync(at, 0, flag_bytes, st));
+        for (int f = 0; f < n_frag; ++f) {
+            A.flags[f] = (unsigned*)at;
+            at += sizeof(unsigned) << P.m_bits[f];
+        }
+        int* lists = (int*)((char*)scratch + tree_bytes + flag_bytes);
+        int* counts = (int*)((char*)scratch + tree_bytes + flag_bytes + list_bytes);
+        long long most = 0;
+        for (int f = 0; f < n_frag; ++f) most = A.n_rows[f] * A.row_stride[f] > most ? A.n_rows[f] * A.row_stride[f] : most;
+        long long want_a = (most + 256 * 8 - 1) / (256 * 8);
+        dim3 agrid((unsigned)(want_a < (long long)h->sm_count * 8 ? (want_a < 1 ? 1 : want_a) : (long long)h->sm_count * 8), n_frag);
+        faith_alive_kernel<<<agrid, 256, 0, st>>>(A);
+        QCK_CHECK_LAUNCH(h);
+        faith_compact_kernel<<<n_frag, 1024, 0, st>>>(A, lists, list_stride, counts);
+        QCK_CHECK_LAUNCH(h);
+        QCK_CUDA(h, cudaMemsetAsync(d_out, 0, n * sizeof(double), st));
+        S.lists = lists;
+        S.list_stride = list_stride;
+        S.counts = counts;
+    }
     if (n_gates == 0) {
-        faith_leaf_kernel<<<grid, 256, 0, st>>>(P, d_out);
+        if (sparse) faith_leaf_sparse_kernel<<<grid, 256, 0, st>>>(P, S, d_out);
+        else faith_leaf_kernel<<<grid, 256, 0, st>>>(P, d_out);
         QCK_CHECK_LAUNCH(h);
         return QCK_OK;
     }
-    void* scratch = nullptr;
-    const unsigned long long total = n * (unsigned long long)(2 * P.radix[0]);
-    int rc = qck_ensure_scratch(h, total * sizeof(double), &scratch);
-    if (rc) return rc;
     // recursion depth <= K: make sure the per-thread stack can hold it
     size_t stack = 0;
     cudaDeviceGetLimit(&stack, cudaLimitStackSize);
     if (stack < 4096) QCK_CUDA(h, cudaDeviceSetLimit(cudaLimitStackSize, 4096));
     unsigned long long want = (total + 127) / 128;
     int sgrid = (int)(want < (unsigned long long)h->sm_count * 32 ? want : (unsigned long long)h->sm_count * 32);
+    if (sparse) {
+        faith_subtree_sparse_kernel<<<sgrid, 128, 0, st>>>(P, S, (double*)scratch);
+        QCK_CHECK_LAUNCH(h);
+        faith_top_sparse_kernel<<<grid, 256, 0, st>>>(P, S, (const double*)scratch, d_out);
+        QCK_CHECK_LAUNCH(h);
+        return QCK_OK;
+    }
     faith_subtree_kernel<<<sgrid, 128, 0, st>>>(P, (double*)scratch);
     QCK_CHECK_LAUNCH(h);
     faith_top_kernel<<<grid, 256, 0, st>>>(P, (const double*)scratch, d_out);

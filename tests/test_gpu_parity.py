@@ -993,6 +993,18 @@ def test_faithful_fused_baseline_configs(dev):
     assert np.abs(f - e).max() > 0.0                  # and the pruning is really applied
 
 
+@pytest.mark.parametrize("name", ["hwe16d5", "syc16d5", "bv16"])
+def test_faithful_alive_columns_equal_the_dense_evaluation(dev, name, monkeypatch):
+    """The alive-column evaluation of the reference-faithful knit (columns without any entry above ACCURACY are
+    skipped, as the reference's dictionaries never hold them) gives the same BITS as evaluating every output."""
+    circ, cut = cutting.make_baseline(name)
+    sparse, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=False, accuracy=1e-5)
+    monkeypatch.setenv("QCK_FAITHFUL_SPARSE", "0")
+    dense, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=False, accuracy=1e-5)
+    assert torch.equal(sparse.values, dense.values)
+    assert sparse.values.abs().sum().item() > 0.5
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_random_cut_circuits_on_device(dev, seed):
     """Randomised cut circuits (every virtual-gate kind, wire cuts, 2-4 fragments) end to end on the
