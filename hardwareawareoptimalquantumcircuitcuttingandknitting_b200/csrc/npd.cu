@@ -24,6 +24,7 @@
 // read-back round trips of a host-driven bisection.
 #include "qck_common.cuh"
 
+#include <cooperative_groups.h>
 #include <math.h>
 
 #define NPD_BINS 8192
@@ -196,16 +197,36 @@ __device__ void npd_select_tail(NpdWs w) {
         c += w.bin_cnt[b0 + i];
         q += w.bin_q[b0 + i];
     }
-    sc[threadIdx.x] = c;
-    sq[threadIdx.x] = q;
+    // exclusive prefix over the threads (integers: any order is exact) - warp scans + one pass over the warp
+    // totals.  (The serial form, thread t adding t shared-memory entries, was ~4 us per level: half of the time
+    // of a level at 2^16 entries.)
+    __shared__ unsigned long long wc[NPD_THREADS / 32];
+    __shared__ long long wq[NPD_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long c_in = c;
+    long long q_in = q;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long cu = __shfl_up_sync(0xffffffffu, c_in, o);
+        const long long qu = __shfl_up_sync(0xffffffffu, q_in, o);
+        if (lane >= o) {
+            c_in += cu;
+            q_in += qu;
+        }
+    }
+    if (lane == 31) {
+        wc[warp] = c_in;
+        wq[warp] = q_in;
+    }
     if (threadIdx.x == 0) found = NPD_BINS;
     __syncthreads();
-    unsigned long long c_ex = 0ull;
-    long long q_ex = 0ll;
-    for (int t = 0; t < (int)threadIdx.x; ++t) {  // 256 x 256 shared-memory reads: negligible, and exact
-        c_ex += sc[t];
-        q_ex += sq[t];
+    unsigned long long c_ex = c_in - c;
+    long long q_ex = q_in - q;
+    for (int t = 0; t < warp; ++t) {
+        c_ex += wc[t];
+        q_ex += wq[t];
     }
+    sc[threadIdx.x] = c_ex;  // exclusive prefixes: what precedes thread t's block of bins
+    sq[threadIdx.x] = q_ex;
     const long long lo = s->lo, hi = s->hi;
     const int shift = (int)s->shift;
     const double lo_val = npd_val(lo + 1);
@@ -233,17 +254,19 @@ __device__ void npd_select_tail(NpdWs w) {
     __syncthreads();
     const int blk = found_block;
     int mine = NPD_BINS;
-    if (threadIdx.x < PER) {  // (PER == 32: warp 0)
-        unsigned long long cb = 0ull;
-        long long qb = 0ll;
-        for (int t = 0; t < blk; ++t) {
-            cb += sc[t];
-            qb += sq[t];
+    if (threadIdx.x < PER) {  // (PER == 32: warp 0) - inclusive scan of the block's 32 bins on top of its prefix
+        unsigned long long cb = w.bin_cnt[blk * PER + (int)threadIdx.x];
+        long long qb = w.bin_q[blk * PER + (int)threadIdx.x];
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long cu = __shfl_up_sync(0xffffffffu, cb, o);
+            const long long qu = __shfl_up_sync(0xffffffffu, qb, o);
+            if (lane >= o) {
+                cb += cu;
+                qb += qu;
+            }
         }
-        for (int i = 0; i <= (int)threadIdx.x; ++i) {
-            cb += w.bin_cnt[blk * PER + i];
-            qb += w.bin_q[blk * PER + i];
-        }
+        cb += sc[blk];
+        qb += sq[blk];
         bool is_last;
         const double g = g_at(blk * PER + (int)threadIdx.x, cb, qb, &is_last);
         if (g >= 0.0 || is_last) mine = blk * PER + (int)threadIdx.x;
@@ -410,6 +433,140 @@ __global__ void __launch_bounds__(NPD_THREADS) npd_apply_kernel(double* __restri
     }
 }
 
+// ---- small vectors: the whole search as ONE cooperative launch.  At 2^16 entries (every 16-qubit configuration)
+// each of the eight launches above lasts 5-14 us and does microseconds of work; here the passes are separated by
+// grid-wide barriers instead of launches, CTA 0 runs the tails, and the level loop stops as soon as the partition
+// is located instead of enqueueing every level unconditionally.  Same arithmetic in the same order: same bits.
+__global__ void __launch_bounds__(NPD_THREADS) npd_fused_kernel(double* __restrict__ p, unsigned long long n, double acc,
+                                                                void* ws_raw) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    NpdWs w = npd_ws(ws_raw);
+    __shared__ double red[8];
+    unsigned int* h_cnt = reinterpret_cast<unsigned int*>(npd_smem);
+    unsigned long long* h_q = reinterpret_cast<unsigned long long*>(npd_smem + 4 * NPD_BINS);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // pass 1: statistics
+    {
+        double s = 0.0, m = INFINITY, ns = 0.0, z = 0.0, nz = 0.0;
+        for (unsigned long long i = first; i < n; i += stride) {
+            const double v = p[i];
+            if (fabs(v) > acc) {
+                s += v;
+                m = fmin(m, v);
+                z += 1.0;
+                if (v < 0.0) {
+                    ns += v;
+                    nz += 1.0;
+                }
+            }
+        }
+        s = block_sum(s, red);
+        m = block_min(m, red);
+        ns = block_sum(ns, red);
+        z = block_sum(z, red);
+        nz = block_sum(nz, red);
+        if (threadIdx.x == 0) {
+            double* o = w.partials + 8 * blockIdx.x;
+            o[0] = s; o[1] = m; o[2] = ns; o[3] = z; o[4] = nz;
+        }
+    }
+    grid.sync();
+    if (blockIdx.x == 0) {
+        double s = 0.0, m = INFINITY, ns = 0.0, z = 0.0, nz = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+            const double* o = w.partials + 8 * i;
+            s += __ldcg(o + 0); m = fmin(m, __ldcg(o + 1)); ns += __ldcg(o + 2); z += __ldcg(o + 3); nz += __ldcg(o + 4);
+        }
+        s = block_sum(s, red);
+        m = block_min(m, red);
+        ns = block_sum(ns, red);
+        z = block_sum(z, red);
+        nz = block_sum(nz, red);
+        if (threadIdx.x == 0) {
+            w.st->sum = s; w.st->vmin = m; w.st->neg_sum = ns; w.st->alive = z; w.st->neg_cnt = nz;
+        }
+        __syncthreads();
+        npd_plan_tail(w);
+    }
+    grid.sync();
+    // levels (+ the final pass that takes (sum, count) of the dropped entries)
+    for (int level = 0; level <= NPD_LEVELS + 1; ++level) {
+        const int status = (int)__ldcg(&w.st->status);  // written by CTA 0 before the barrier: read past L1
+        if (status != NPD_SEARCH && status != NPD_LOCATED) break;
+        const bool bins = status == NPD_SEARCH;
+        if (bins)
+            for (int i = threadIdx.x; i < NPD_BINS; i += blockDim.x) {
+                h_cnt[i] = 0u;
+                h_q[i] = 0ull;
+            }
+        const long long lo = __ldcg(&w.st->lo), hi = __ldcg(&w.st->hi);
+        const int shift = (int)__ldcg(&w.st->shift);
+        const double lo_val = npd_val(lo + 1);
+        const int qexp = (int)__ldcg(&w.st->qexp);
+        __syncthreads();
+        double us = 0.0, uc = 0.0;
+        for (unsigned long long i = first; i < n; i += stride) {
+            const double v = p[i];
+            if (!(fabs(v) > acc)) continue;
+            const long long k = npd_key(v);
+            if (k <= lo) {
+                us += v;
+                uc += 1.0;
+            } else if (bins && k <= hi) {
+                const unsigned int b = (unsigned int)(((unsigned long long)k - (unsigned long long)lo - 1ull) >> shift);
+                atomicAdd(&h_cnt[b], 1u);
+                atomicAdd(&h_q[b], (unsigned long long)__double2ll_rn(scalbn(v - lo_val, qexp)));
+            }
+        }
+        us = block_sum(us, red);
+        uc = block_sum(uc, red);
+        if (threadIdx.x == 0) {
+            w.partials[8 * blockIdx.x + 0] = us;
+            w.partials[8 * blockIdx.x + 1] = uc;
+        }
+        if (bins) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < NPD_BINS; i += blockDim.x) {
+                const unsigned int c = h_cnt[i];
+                if (c) {
+                    atomicAdd(&w.bin_cnt[i], (unsigned long long)c);
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&w.bin_q[i]), h_q[i]);
+                }
+            }
+        }
+        grid.sync();
+        if (blockIdx.x == 0) {
+            us = 0.0;
+            uc = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+                us += __ldcg(w.partials + 8 * i + 0);
+                uc += __ldcg(w.partials + 8 * i + 1);
+            }
+            us = block_sum(us, red);
+            uc = block_sum(uc, red);
+            if (threadIdx.x == 0) {
+                w.st->under_sum = us;
+                w.st->under_cnt = uc;
+            }
+            __syncthreads();
+            npd_select_tail(w);
+        }
+        grid.sync();
+    }
+    // apply
+    const int status = (int)__ldcg(&w.st->status);
+    if (status == NPD_IDENTITY && !(acc > 0.0)) return;
+    if (status != NPD_IDENTITY && status != NPD_SOLVED) return;
+    const long long lo = status == NPD_SOLVED ? __ldcg(&w.st->lo) : (long long)0x8000000000000000ull;
+    const double shift_val = status == NPD_SOLVED ? __ldcg(&w.st->shift_val) : 0.0;
+    for (unsigned long long i = first; i < n; i += stride) {
+        const double v = p[i];
+        p[i] = (fabs(v) > acc && npd_key(v) > lo) ? v + shift_val : 0.0;
+    }
+}
+
 // ------------------------------------------------------------------ host side
 // (4 elements per thread.  Fewer, fatter CTAs - 32 per thread, 8 CTAs at n = 2^16 - measured slower: every
 // pass is latency bound, 0.087 -> 0.121 ms for the eight launches of hwe-16 d5's npd.)
@@ -422,6 +579,7 @@ static int npd_grid(qck_handle* h, unsigned long long n) {
 
 int qck_npd_init(qck_handle* h) {
     QCK_CUDA(h, cudaFuncSetAttribute(npd_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NPD_BINS));
+    QCK_CUDA(h, cudaFuncSetAttribute(npd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NPD_BINS));
     QCK_CUDA(h, cudaMalloc(&h->npd_ws, NPD_WS_BYTES));
     QCK_CUDA(h, cudaMemset(h->npd_ws, 0, NPD_WS_BYTES));
     return QCK_OK;
@@ -451,6 +609,23 @@ extern "C" int qck_npd_stage(qck_handle* h, int stage, double* d_p, uint64_t n, 
 }
 
 extern "C" int qck_npd_async(qck_handle* h, double* d_p, uint64_t n, double acc, void* d_ws, qck_stream stream) {
+    if (!h) return QCK_ERR_INVALID_ARG;
+    if (!d_p && n > 0) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "NULL argument");
+    // QCK_NPD_FUSED=1: one cooperative launch while all CTAs of the grid are co-resident with room to spare.
+    // Opt-in: measured on hwe-16 d5 / bv-16 (2^16 entries, inside the step's CUDA graph) it saves 2-4 us of the
+    // 75 / 53 us the eight launches take - the passes themselves, not the launches, are the cost - which does not
+    // pay for depending on cooperative launches inside captured graphs.
+    const char* fused_env = getenv("QCK_NPD_FUSED");
+    if (n > 0 && npd_grid(h, n) <= h->sm_count && fused_env && atoi(fused_env) == 1) {
+        DeviceGuard guard(h->device);
+        void* ws = d_ws ? d_ws : h->npd_ws;
+        unsigned long long nn = n;
+        void* args[] = {&d_p, &nn, &acc, &ws};
+        QCK_CUDA(h, cudaLaunchCooperativeKernel((const void*)npd_fused_kernel, dim3(npd_grid(h, n)), dim3(NPD_THREADS), args,
+                                                12 * NPD_BINS, (cudaStream_t)stream));
+        h->launches++;
+        return QCK_OK;
+    }
     int rc = qck_npd_stage(h, QCK_NPD_STATS, d_p, n, acc, d_ws, 1, stream);
     for (int l = 0; l <= NPD_LEVELS && !rc; ++l) rc = qck_npd_stage(h, QCK_NPD_LEVEL, d_p, n, acc, d_ws, 1, stream);
     if (!rc) rc = qck_npd_stage(h, QCK_NPD_APPLY, d_p, n, acc, d_ws, 1, stream);

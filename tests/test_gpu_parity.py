@@ -581,11 +581,24 @@ def _npd_async(dev, v, acc=0.0, shards=1):
     full = torch.from_numpy(np.asarray(v, dtype=np.float64)).to(dev)
     n_ws = h.lib.qck_npd_workspace_bytes() // 8
     if shards == 1:
-        ws = torch.zeros(n_ws, dtype=torch.int64, device=dev)
-        l0 = h.launch_count
-        h.check(h.lib.qck_npd_async(h.ptr, full.data_ptr(), full.numel(), acc, ws.data_ptr(), stream))
-        assert h.launch_count - l0 == 8                 # statistics + 6 level passes + apply, no round trip
-        return full.cpu().numpy(), ws[:32].cpu()
+        # small vectors: ONE cooperative launch (npd_fused_kernel); else statistics + 6 level passes + apply.
+        # Either way no host round trip, and the two forms give the same bits.
+        import os
+        results = []
+        for fused in ("1", "0"):
+            os.environ["QCK_NPD_FUSED"] = fused
+            try:
+                data = full.clone()
+                ws = torch.zeros(n_ws, dtype=torch.int64, device=dev)
+                l0 = h.launch_count
+                h.check(h.lib.qck_npd_async(h.ptr, data.data_ptr(), data.numel(), acc, ws.data_ptr(), stream))
+                small = (data.numel() + 1023) // 1024 <= torch.cuda.get_device_properties(dev).multi_processor_count
+                assert h.launch_count - l0 == (1 if (fused == "1" and small) else 8)
+                results.append((data.cpu().numpy(), ws[:32].cpu()))
+            finally:
+                os.environ.pop("QCK_NPD_FUSED", None)
+        assert np.array_equal(results[0][0], results[1][0]) and int(results[0][1][5]) == int(results[1][1][5])
+        return results[0]
     parts = list(torch.tensor_split(full, shards))
     wss = [torch.zeros(n_ws, dtype=torch.int64, device=dev) for _ in parts]
     S, B = _lib.NPD_STATE_SLOTS, _lib.NPD_BINS
