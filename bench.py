@@ -794,9 +794,10 @@ def main() -> None:
                 others[w] = compact(measure(w, args, env, primary=False, cpu=True))
             except Exception as exc:                  # a secondary workload must never take the line down
                 others[w] = {"error": repr(exc)}
-        # the reference's default mode: ACCURACY = 1e-5 pruning (one GPU: the reference-faithful knit is one
-        # expression tree per output entry over ALL labels - never sharded, every rank would repeat the same run)
-        for w in (("hwe16d5", "syc16d5") if (world == 1 or os.environ.get("QCK_BENCH_FAITHFUL_MULTI") == "1") else ()):
+        # the reference's default mode: ACCURACY = 1e-5 pruning (the reference-faithful knit is one expression tree
+        # per output entry over ALL labels: at world > 1 every rank evaluates its share of the entries and one
+        # all-reduce adds the shares - qck_knit_faithful_part)
+        for w in (("hwe16d5", "syc16d5") if os.environ.get("QCK_BENCH_FAITHFUL", "1") != "0" else ()):
             try:
                 others[f"{w}@1e-5"] = compact(measure(w, args, env, primary=False, accuracy=1e-5))
             except Exception as exc:

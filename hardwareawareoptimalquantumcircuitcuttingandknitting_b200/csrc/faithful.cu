@@ -38,6 +38,7 @@ struct FaithParams {
     unsigned char measures[FA_MAXF][FA_MAXK][FA_MAXV];  // does f's instance measure gate k under variant v
     unsigned char any_measure[FA_MAXK][FA_MAXV];
     double acc;
+    int part, n_parts;  // this call evaluates part `part` of `n_parts` of the outputs (the others stay +0)
 };
 
 __device__ __forceinline__ double prn(double v, double acc) { return fabs(v) > acc ? v : 0.0; }
@@ -130,10 +131,12 @@ __device__ __forceinline__ void init_ctx(EvalCtx& C, const FaithParams& P, unsig
 __global__ void __launch_bounds__(128) faith_subtree_kernel(const __grid_constant__ FaithParams P,
                                                             double* __restrict__ scratch) {
     const unsigned long long n = 1ull << P.n_out_bits;
+    const unsigned long long x0 = n / P.n_parts * P.part, x1 = P.part + 1 == P.n_parts ? n : n / P.n_parts * (P.part + 1);
     const unsigned long long total = n * (unsigned long long)(2 * P.radix[0]);
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long x = t & (n - 1);
+        if (x < x0 || x >= x1) continue;
         const int j = (int)(t >> P.n_out_bits), i = j >> 1, bit = j & 1;
         double v = 0.0;
         if (!bit || P.any_measure[0][i]) {
@@ -150,7 +153,8 @@ __global__ void __launch_bounds__(128) faith_subtree_kernel(const __grid_constan
 __global__ void __launch_bounds__(256) faith_top_kernel(const __grid_constant__ FaithParams P,
                                                         const double* __restrict__ scratch, double* __restrict__ out) {
     const unsigned long long n = 1ull << P.n_out_bits;
-    for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < n;
+    const unsigned long long x0 = n / P.n_parts * P.part, x1 = P.part + 1 == P.n_parts ? n : n / P.n_parts * (P.part + 1);
+    for (unsigned long long x = x0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < x1;
          x += (unsigned long long)gridDim.x * blockDim.x)
         out[x] = knit_formula(P, 0, [&](int i, int bit) { return scratch[((unsigned long long)(2 * i + bit) << P.n_out_bits) | x]; });
 }
@@ -158,7 +162,8 @@ __global__ void __launch_bounds__(256) faith_top_kernel(const __grid_constant__ 
 // no virtual gates: the pruned merge only
 __global__ void __launch_bounds__(256) faith_leaf_kernel(const __grid_constant__ FaithParams P, double* __restrict__ out) {
     const unsigned long long n = 1ull << P.n_out_bits;
-    for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < n;
+    const unsigned long long x0 = n / P.n_parts * P.part, x1 = P.part + 1 == P.n_parts ? n : n / P.n_parts * (P.part + 1);
+    for (unsigned long long x = x0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < x1;
          x += (unsigned long long)gridDim.x * blockDim.x) {
         EvalCtx C;
         init_ctx(C, P, x);
@@ -264,13 +269,15 @@ __device__ __forceinline__ unsigned long long alive_total(const FaithParams& P, 
 
 __global__ void __launch_bounds__(128) faith_subtree_sparse_kernel(const __grid_constant__ FaithParams P, const SparseCtx S,
                                                                    double* __restrict__ scratch) {
-    const unsigned long long alive = alive_total(P, S);
+    const unsigned long long all = alive_total(P, S);
+    const unsigned long long j0 = all / P.n_parts * P.part, j1 = P.part + 1 == P.n_parts ? all : all / P.n_parts * (P.part + 1);
+    const unsigned long long alive = j1 - j0;
     const unsigned long long total = alive * (unsigned long long)(2 * P.radix[0]);
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (unsigned long long)gridDim.x * blockDim.x) {
         const int j = (int)(t / alive), i = j >> 1, bit = j & 1;
         EvalCtx C;
-        const unsigned long long x = alive_point(P, S, t % alive, C);
+        const unsigned long long x = alive_point(P, S, j0 + t % alive, C);
         double v = 0.0;
         if (!bit || P.any_measure[0][i]) {
             enter(C, 0, i, bit);
@@ -282,8 +289,9 @@ __global__ void __launch_bounds__(128) faith_subtree_sparse_kernel(const __grid_
 
 __global__ void __launch_bounds__(256) faith_top_sparse_kernel(const __grid_constant__ FaithParams P, const SparseCtx S,
                                                                const double* __restrict__ scratch, double* __restrict__ out) {
-    const unsigned long long alive = alive_total(P, S);
-    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < alive;
+    const unsigned long long all = alive_total(P, S);
+    const unsigned long long j0 = all / P.n_parts * P.part, j1 = P.part + 1 == P.n_parts ? all : all / P.n_parts * (P.part + 1);
+    for (unsigned long long j = j0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < j1;
          j += (unsigned long long)gridDim.x * blockDim.x) {
         EvalCtx C;
         const unsigned long long x = alive_point(P, S, j, C);
@@ -293,8 +301,9 @@ __global__ void __launch_bounds__(256) faith_top_sparse_kernel(const __grid_cons
 
 __global__ void __launch_bounds__(256) faith_leaf_sparse_kernel(const __grid_constant__ FaithParams P, const SparseCtx S,
                                                                 double* __restrict__ out) {
-    const unsigned long long alive = alive_total(P, S);
-    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < alive;
+    const unsigned long long all = alive_total(P, S);
+    const unsigned long long j0 = all / P.n_parts * P.part, j1 = P.part + 1 == P.n_parts ? all : all / P.n_parts * (P.part + 1);
+    for (unsigned long long j = j0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < j1;
          j += (unsigned long long)gridDim.x * blockDim.x) {
         EvalCtx C;
         const unsigned long long x = alive_point(P, S, j, C);
@@ -308,7 +317,17 @@ extern "C" int qck_knit_faithful(qck_handle* h, int n_frag, const double* const*
                                  const int64_t* row_strides, int n_out_bits, int n_gates, const qck_faithful_gate* gates,
                                  const int32_t* frag_stride, const int32_t* cfg_bit, const uint8_t* measures,
                                  double accuracy, double* d_out, qck_stream stream) {
+    return qck_knit_faithful_part(h, n_frag, d_tables, masks, row_strides, n_out_bits, n_gates, gates, frag_stride, cfg_bit,
+                                  measures, accuracy, d_out, 0, 1, stream);
+}
+
+extern "C" int qck_knit_faithful_part(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
+                                      const int64_t* row_strides, int n_out_bits, int n_gates,
+                                      const qck_faithful_gate* gates, const int32_t* frag_stride, const int32_t* cfg_bit,
+                                      const uint8_t* measures, double accuracy, double* d_out, int part, int n_parts,
+                                      qck_stream stream) {
     if (!h) return QCK_ERR_INVALID_ARG;
+    if (n_parts < 1 || n_parts > 64 || part < 0 || part >= n_parts) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "part %d of %d", part, n_parts);
     if (n_frag < 1 || n_frag > FA_MAXF) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_frag=%d out of range", n_frag);
     if (n_gates < 0 || n_gates > FA_MAXK) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_gates=%d out of range", n_gates);
     if (!d_tables || !masks || !row_strides || !d_out || (n_gates > 0 && (!gates || !frag_stride || !cfg_bit || !measures)))
@@ -321,6 +340,8 @@ extern "C" int qck_knit_faithful(qck_handle* h, int n_frag, const double* const*
     P.K = n_gates;
     P.n_out_bits = n_out_bits;
     P.acc = accuracy;
+    P.part = part;
+    P.n_parts = n_parts;
     uint64_t seen = 0;
     for (int f = 0; f < n_frag; ++f) {
         if (!d_tables[f]) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "table %d is NULL", f);
@@ -407,11 +428,11 @@ extern "C" int qck_knit_faithful(qck_handle* h, int n_frag, const double* const*
         QCK_CHECK_LAUNCH(h);
         faith_compact_kernel<<<n_frag, 1024, 0, st>>>(A, lists, list_stride, counts);
         QCK_CHECK_LAUNCH(h);
-        QCK_CUDA(h, cudaMemsetAsync(d_out, 0, n * sizeof(double), st));
         S.lists = lists;
         S.list_stride = list_stride;
         S.counts = counts;
     }
+    if (sparse || n_parts > 1) QCK_CUDA(h, cudaMemsetAsync(d_out, 0, n * sizeof(double), st));
     if (n_gates == 0) {
         if (sparse) faith_leaf_sparse_kernel<<<grid, 256, 0, st>>>(P, S, d_out);
         else faith_leaf_kernel<<<grid, 256, 0, st>>>(P, d_out);

@@ -65,11 +65,14 @@ def simulation_work(virt) -> float:
 
 def partition_mode(virt, world_size: int, faithful: bool = False) -> str:
     """How a cut WITH virtual gates is spread over ``world_size`` ranks: "label range + all-reduce" or
-    "replicated (below the sharding threshold)".  The reference-faithful knit (one expression tree per output
-    entry over ALL labels) is never label-sharded."""
+    "replicated (below the sharding threshold)".  The reference-faithful knit is one expression tree per output
+    entry over ALL labels: it is never label-sharded - every rank simulates the fragments and evaluates its
+    share of the OUTPUT ENTRIES ("output entries + all-reduce")."""
     if world_size <= 1:
         return "single"
-    if faithful or simulation_work(virt) < SHARD_MIN_WORK:
+    if faithful:
+        return "output entries + all-reduce"
+    if simulation_work(virt) < SHARD_MIN_WORK:
         return "replicated (below the sharding threshold)"
     return "label range + all-reduce"
 

@@ -46,6 +46,7 @@ class ResidentStep:
             self.mode = ("output index by top bits" if self.K == 0
                          else qdist.partition_mode(virt, world_size, self.faithful))
         self.label_range = None
+        self.entry_sharded = self.mode == "output entries + all-reduce" and self.K > 0
         if self.K == 0:
             self.y0, self.y1 = (qdist.shard_pow2(self.n_out, rank, world_size) if world_size > 1
                                 else (0, 1 << self.n_out))
@@ -77,7 +78,8 @@ class ResidentStep:
     def enqueue_knit(self) -> None:
         virt, dev = self.virt, self.device
         if self.faithful:
-            virt.knit_tables_faithful(self.tables, self.accuracy, dev, out=self.out)
+            virt.knit_tables_faithful(self.tables, self.accuracy, dev, out=self.out,
+                                      part=(self.rank, self.world) if self.entry_sharded else (0, 1))
         elif self.K == 0:
             virt.knit_tables(self.tables, dev, stats=self.stats,
                              y_range=(self.y0, self.y1) if self.world > 1 else None, out=self.out)
@@ -93,7 +95,7 @@ class ResidentStep:
             if self.world > 1:
                 self.qdist.allreduce_stats(self.stats, self.group, self.handle)   # min >= 0: no npd pass
             return
-        if self.label_range is not None:
+        if self.label_range is not None or self.entry_sharded:
             self.qdist.allreduce_sum_(self.out, self.group)
         if self.nearest:
             h.check(h.lib.qck_npd_async(h.ptr, self.out.data_ptr(), self.out.numel(), self.accuracy,
@@ -124,7 +126,8 @@ class ResidentStep:
         # it) left a 2-rank run with an illegal memory access in the next eager collective.  The collective and
         # what follows it are a handful of launches; they stay eager.
         mailboxes = self.world > 1 and self.K == 0 and self.qdist.stats_exchange(self.handle, self.device, self.group)
-        post_has_collective = self.world > 1 and ((self.K == 0 and not mailboxes) or self.label_range is not None)
+        post_has_collective = self.world > 1 and ((self.K == 0 and not mailboxes) or self.label_range is not None
+                                                  or self.entry_sharded)
 
         class _Eager:                                  # same interface as a CUDAGraph
             def __init__(self, fn):

@@ -104,7 +104,7 @@ def run_virtual_circuit_dense(virt: VirtualCircuit, shots: int = 20000, device=N
     from . import quasi_distr as _qd
     accuracy = _qd.ACCURACY if accuracy is None else float(accuracy)
     if accuracy > 0.0:
-        return _run_faithful(virt, device, handle, nearest, accuracy, world_size, out)
+        return _run_faithful(virt, device, handle, nearest, accuracy, rank, world_size, group, out)
     label_range = None
     if K > 0 and world_size > 1 and qdist.partition_mode(virt, world_size) == "label range + all-reduce":
         label_range = qdist.shard_range(virt.num_global_labels(), rank, world_size,
@@ -179,18 +179,23 @@ def _check_npd_state(ws, solved: bool = True):
     return state
 
 
-def _run_faithful(virt, device, handle, nearest, accuracy, world_size, out):
+def _run_faithful(virt, device, handle, nearest, accuracy, rank, world_size, group, out):
     """ACCURACY > 0: exact instance distributions, then the reference's pruned algebra in the
     reference's order, fused per output entry (``qck_knit_faithful``).  Every output entry is an
-    independent expression tree, so a multi-rank run evaluates the whole (small) result on every rank."""
+    independent expression tree: with ``world_size > 1`` every rank simulates the (small) fragments itself,
+    evaluates its share of the output entries and the shares are added up with one all-reduce."""
     import torch
+    from . import dist as qdist
     stream = torch.cuda.current_stream(device).cuda_stream
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
     tables = virt.simulate_fragments(device, fold=False)
     ev[1].record()
     logger.info("Knitting...")
-    values = virt.knit_tables_faithful(tables, accuracy, device, out=out)
+    sharded = world_size > 1 and len(virt._vgate_instrs) > 0
+    values = virt.knit_tables_faithful(tables, accuracy, device, out=out, part=(rank, world_size) if sharded else (0, 1))
+    if sharded:
+        qdist.allreduce_sum_(values, group)
     ws = handle.npd_workspace(torch, device)
     if nearest:
         handle.check(handle.lib.qck_npd_async(handle.ptr, values.data_ptr(), values.numel(), accuracy,

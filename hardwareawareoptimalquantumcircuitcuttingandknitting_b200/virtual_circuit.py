@@ -415,7 +415,8 @@ class VirtualCircuit:
         if any(self.program(f).num_labels >= 2 ** 31 for f in self.active_fragments()):
             raise NotImplementedError("a fragment has 2^31 or more instances: label strides are int32")
 
-    def knit_tables_faithful(self, tables: dict, accuracy: float, device=None, out=None, stats=None):
+    def knit_tables_faithful(self, tables: dict, accuracy: float, device=None, out=None, stats=None,
+                             part: tuple[int, int] = (0, 1)):
         """Reference-faithful knit (``ACCURACY = accuracy`` pruning after every operation, reference
         order) of UNFOLDED fragment tables (``simulate_fragments(fold=False)``), fused per output
         entry on the device (``qck_knit_faithful``)."""
@@ -449,9 +450,11 @@ class VirtualCircuit:
                         measures[(i * _lib.MAX_DIGITS + slot.vgate_idx) * _lib.MAX_VARIANTS + v] = 1
         if out is None:
             out = torch.empty(1 << n_out, dtype=torch.float64, device=device)
-        handle.check(handle.lib.qck_knit_faithful(handle.ptr, len(frags), ptrs, cm, row_strides, n_out, K, gates,
-                                                  strides, cfg_bit, measures, float(accuracy), out.data_ptr(),
-                                                  stream))
+        # part = (rank, world): this call evaluates its share of the output entries, the others stay +0 (the
+        # ranks' results then ADD up to the full vector)
+        handle.check(handle.lib.qck_knit_faithful_part(handle.ptr, len(frags), ptrs, cm, row_strides, n_out, K, gates,
+                                                       strides, cfg_bit, measures, float(accuracy), out.data_ptr(),
+                                                       int(part[0]), int(part[1]), stream))
         if stats is not None:
             handle.check(handle.lib.qck_stats_dense(handle.ptr, out.data_ptr(), out.numel(), float(accuracy),
                                                     stats.data_ptr(), stream))

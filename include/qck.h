@@ -376,6 +376,15 @@ QCK_API int qck_knit_faithful(qck_handle* h, int n_frag, const double* const* d_
                               const int64_t* row_strides, int n_out_bits, int n_gates,
                               const qck_faithful_gate* gates, const int32_t* frag_stride, const int32_t* cfg_bit,
                               const uint8_t* measures, double accuracy, double* d_out, qck_stream stream);
+/* The same evaluation restricted to part `part` of `n_parts` of the output entries (every entry is an independent
+ * expression tree): the entries of the other parts are written as +0, so the parts of the ranks ADD up to the full
+ * vector (one all-reduce).  With accuracy > 0 the parts split the list of alive entries (entries none of whose
+ * fragment columns is pruned away entirely), else the index range. */
+QCK_API int qck_knit_faithful_part(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
+                                   const int64_t* row_strides, int n_out_bits, int n_gates,
+                                   const qck_faithful_gate* gates, const int32_t* frag_stride, const int32_t* cfg_bit,
+                                   const uint8_t* measures, double accuracy, double* d_out, int part, int n_parts,
+                                   qck_stream stream);
 
 /* ------------------------------------------------------------------ reductions
  * qck_stats_dense: sum / min / nnz of a dense vector (entries |v| <= acc count as absent).

@@ -134,6 +134,26 @@ def main() -> None:
     torch.cuda.synchronize(dev)
     del rs, eager
 
+    # (6) reference-default mode (ACCURACY = 1e-5): every rank evaluates its share of the output entries, one
+    #     all-reduce adds the shares - the same BITS as the one-GPU evaluation, eagerly and as a resident step
+    for cfg in ("syc16d5", "hwe16d5"):
+        circ, cut = cutting.make_baseline(cfg, seed=1)
+        assert qdist.partition_mode(vcm.VirtualCircuit(cut), world, faithful=True) == "output entries + all-reduce"
+        one, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=False, accuracy=1e-5)
+        many, _ = runm.run_virtual_circuit_dense(vcm.VirtualCircuit(cut), device=dev, nearest=False, accuracy=1e-5,
+                                                 rank=rank, world_size=world)
+        assert torch.equal(one.values, many.values), (cfg, rank)
+        rs = resm.ResidentStep(vcm.VirtualCircuit(cut), dev, nearest=False, rank=rank, world_size=world,
+                               accuracy=1e-5, graph=True)
+        for _ in range(2):
+            rs.run()
+        assert torch.equal(rs.result().values, one.values), (cfg, rank)
+        uncut = cport.simulate_probabilities(circ)
+        assert float(np.abs(many.values.cpu().numpy() - uncut).max()) < 7776 * 1e-5      # within the pruning error
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        del rs
+
     t = torch.tensor([worst], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

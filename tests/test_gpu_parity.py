@@ -1018,6 +1018,24 @@ def test_faithful_alive_columns_equal_the_dense_evaluation(dev, name, monkeypatc
     assert sparse.values.abs().sum().item() > 0.5
 
 
+@pytest.mark.parametrize("sparse", ["1", "0"])
+def test_faithful_parts_add_up_to_the_whole(dev, sparse, monkeypatch):
+    """qck_knit_faithful_part: the parts of the output entries (what the ranks of a multi-GPU run evaluate) are
+    disjoint and add up to the one-call result bit for bit - alive-entry lists and plain index ranges alike."""
+    monkeypatch.setenv("QCK_FAITHFUL_SPARSE", sparse)
+    circ, cut = cutting.make_baseline("syc16d5", seed=1)
+    virt = vcm.VirtualCircuit(cut)
+    tables = virt.simulate_fragments(dev, fold=False)
+    whole = virt.knit_tables_faithful(tables, 1e-5, dev)
+    acc = torch.zeros_like(whole)
+    support = torch.zeros_like(whole)
+    for part in range(3):
+        piece = virt.knit_tables_faithful(tables, 1e-5, dev, part=(part, 3))
+        acc += piece
+        support += (piece != 0).double()
+    assert torch.equal(acc, whole) and support.max().item() <= 1.0
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_random_cut_circuits_on_device(dev, seed):
     """Randomised cut circuits (every virtual-gate kind, wire cuts, 2-4 fragments) end to end on the
