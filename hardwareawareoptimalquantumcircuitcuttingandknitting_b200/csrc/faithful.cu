@@ -287,6 +287,54 @@ __global__ void __launch_bounds__(128) faith_subtree_sparse_kernel(const __grid_
     }
 }
 
+// Two levels split off (K >= 2): one thread per (alive entry, variant and config bit of gate 0, of gate 1).  A
+// concentrated distribution leaves few alive entries (hwe-16 d5: a few hundred) and 2 * n_0 subtrees per entry are
+// too few threads for 148 SMs - the evaluation then lasts as long as ONE thread's walk over the other K - 1 levels.
+__global__ void __launch_bounds__(128) faith_subtree2_sparse_kernel(const __grid_constant__ FaithParams P, const SparseCtx S,
+                                                                    double* __restrict__ scratch2) {
+    const unsigned long long all = alive_total(P, S);
+    const unsigned long long j0 = all / P.n_parts * P.part, j1 = P.part + 1 == P.n_parts ? all : all / P.n_parts * (P.part + 1);
+    const unsigned long long alive = j1 - j0;
+    const int w0 = 2 * P.radix[0], w1 = 2 * P.radix[1];
+    const unsigned long long total = alive * (unsigned long long)(w0 * w1);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const int c = (int)(t / alive), c0 = c / w1, c1 = c % w1;
+        const int i0 = c0 >> 1, b0 = c0 & 1, i1 = c1 >> 1, b1 = c1 & 1;
+        EvalCtx C;
+        const unsigned long long x = alive_point(P, S, j0 + t % alive, C);
+        double v = 0.0;
+        if ((!b0 || P.any_measure[0][i0]) && (!b1 || P.any_measure[1][i1])) {
+            enter(C, 0, i0, b0);
+            enter(C, 1, i1, b1);
+            v = eval(C, 2);
+        }
+        scratch2[((unsigned long long)c << P.n_out_bits) | x] = v;
+    }
+}
+
+// gate 1's formula over the stored subtrees -> the level-1 values the top kernel reads
+__global__ void __launch_bounds__(256) faith_mid_sparse_kernel(const __grid_constant__ FaithParams P, const SparseCtx S,
+                                                               const double* __restrict__ scratch2, double* __restrict__ scratch) {
+    const unsigned long long all = alive_total(P, S);
+    const unsigned long long j0 = all / P.n_parts * P.part, j1 = P.part + 1 == P.n_parts ? all : all / P.n_parts * (P.part + 1);
+    const unsigned long long alive = j1 - j0;
+    const int w0 = 2 * P.radix[0], w1 = 2 * P.radix[1];
+    const unsigned long long total = alive * (unsigned long long)w0;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(t / alive), i0 = c0 >> 1, b0 = c0 & 1;
+        EvalCtx C;
+        const unsigned long long x = alive_point(P, S, j0 + t % alive, C);
+        double v = 0.0;
+        if (!b0 || P.any_measure[0][i0])
+            v = knit_formula(P, 1, [&](int i, int bit) {
+                return scratch2[((unsigned long long)(c0 * w1 + 2 * i + bit) << P.n_out_bits) | x];
+            });
+        scratch[((unsigned long long)c0 << P.n_out_bits) | x] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) faith_top_sparse_kernel(const __grid_constant__ FaithParams P, const SparseCtx S,
                                                                const double* __restrict__ scratch, double* __restrict__ out) {
     const unsigned long long all = alive_total(P, S);
@@ -386,6 +434,13 @@ extern "C" int qck_knit_faithful_part(qck_handle* h, int n_frag, const double* c
                         !(sparse_env && atoi(sparse_env) == 0);
     const unsigned long long total = n_gates ? n * (unsigned long long)(2 * P.radix[0]) : 0;
     size_t tree_bytes = (total * sizeof(double) + 255) & ~(size_t)255, flag_bytes = 0, list_bytes = 0;
+    // second split level (sparse path): scratch for the (gate 0, gate 1) subtrees, bounded at 1 GiB
+    const char* split_env = getenv("QCK_FAITHFUL_SPLIT2");
+    const unsigned long long total2 = n_gates >= 2 ? total * (unsigned long long)(2 * P.radix[1]) : 0;
+    const bool split2 = sparse && n_gates >= 2 && total2 * sizeof(double) <= ((size_t)1 << 30) &&
+                        !(split_env && atoi(split_env) == 0);
+    const size_t tree1_bytes = tree_bytes;
+    if (split2) tree_bytes += (total2 * sizeof(double) + 255) & ~(size_t)255;
     long long list_stride = 0;
     AliveParams A;
     memset(&A, 0, sizeof(A));
@@ -445,6 +500,18 @@ extern "C" int qck_knit_faithful_part(qck_handle* h, int n_frag, const double* c
     if (stack < 4096) QCK_CUDA(h, cudaDeviceSetLimit(cudaLimitStackSize, 4096));
     unsigned long long want = (total + 127) / 128;
     int sgrid = (int)(want < (unsigned long long)h->sm_count * 32 ? want : (unsigned long long)h->sm_count * 32);
+    if (sparse && split2) {
+        double* scratch2 = (double*)((char*)scratch + tree1_bytes);
+        const unsigned long long want2 = (total2 + 127) / 128;
+        const int sgrid2 = (int)(want2 < (unsigned long long)h->sm_count * 32 ? want2 : (unsigned long long)h->sm_count * 32);
+        faith_subtree2_sparse_kernel<<<sgrid2, 128, 0, st>>>(P, S, scratch2);
+        QCK_CHECK_LAUNCH(h);
+        faith_mid_sparse_kernel<<<sgrid, 128 * 2, 0, st>>>(P, S, scratch2, (double*)scratch);
+        QCK_CHECK_LAUNCH(h);
+        faith_top_sparse_kernel<<<grid, 256, 0, st>>>(P, S, (const double*)scratch, d_out);
+        QCK_CHECK_LAUNCH(h);
+        return QCK_OK;
+    }
     if (sparse) {
         faith_subtree_sparse_kernel<<<sgrid, 128, 0, st>>>(P, S, (double*)scratch);
         QCK_CHECK_LAUNCH(h);
