@@ -795,13 +795,23 @@ static int build_plans(qck_host_program& P, bool fold) {
     if (num_labels >= ((int64_t)1 << 31) || P.slots.size() > 62) return QCK_ERR_UNSUPPORTED;
     // measurement pattern of every label
     std::vector<int64_t> pat(num_labels, 0);
-    std::vector<int64_t> stride(n_dig, 1);
-    for (int d = n_dig - 2; d >= 0; --d) stride[d] = stride[d + 1] * P.radix[d + 1];
-    for (size_t s = 0; s < P.slots.size(); ++s) {
-        const Slot& sl = P.slots[s];
-        if (!sl.meas_mask) continue;
-        for (int64_t l = 0; l < num_labels; ++l)
-            if ((sl.meas_mask >> ((l / stride[sl.digit]) % P.radix[sl.digit])) & 1) pat[l] |= (int64_t)1 << s;
+    {   // contribution of (digit, variant) to the pattern, then an odometer over the labels (no divisions)
+        std::vector<int64_t> contrib((size_t)n_dig * QCK_MAX_VARIANTS, 0);
+        for (size_t s = 0; s < P.slots.size(); ++s) {
+            const Slot& sl = P.slots[s];
+            for (int v = 0; v < sl.n_var; ++v)
+                if ((sl.meas_mask >> v) & 1) contrib[(size_t)sl.digit * QCK_MAX_VARIANTS + v] |= (int64_t)1 << s;
+        }
+        std::vector<int> dig(n_dig, 0);
+        for (int64_t l = 0; l < num_labels; ++l) {
+            int64_t p = 0;
+            for (int d = 0; d < n_dig; ++d) p |= contrib[(size_t)d * QCK_MAX_VARIANTS + dig[d]];
+            pat[l] = p;
+            for (int d = n_dig - 1; d >= 0; --d) {
+                if (++dig[d] < P.radix[d]) break;
+                dig[d] = 0;
+            }
+        }
     }
     std::vector<int64_t> uniq(pat);
     std::sort(uniq.begin(), uniq.end());
