@@ -375,6 +375,10 @@ class FragmentProgram:
             return self.__dict__[name]
         raise AttributeError(name)
 
+    def work_estimate(self) -> float:
+        """Sum over the labels of 2^(state bits) x op records of the label's program (``dist.simulation_work``)."""
+        return float(_host_get(self._hp_lib, self._hp, 12, np.float64)[0])
+
     def _native_pool(self) -> np.ndarray:
         n = self._hp_lib.qck_host_program_get(self._hp, 9, None, 0) // 8
         if n != self._pool_len:

@@ -101,6 +101,7 @@ struct ImageH {
 struct qck_host_program {
     int n_qubits = 0, n_clbits = 0;
     int warp = 0, mid_measures = 0, measures_anything = 0;
+    double work = 0.0;  // sum over the labels of 2^(state bits) x op records: dist.py's sharding threshold
     std::vector<double> pool;
     std::vector<Top> tops;
     std::vector<Slot> slots;
@@ -418,6 +419,28 @@ extern "C" int qck_host_lower(const int32_t* instr, int n_instr, const int32_t* 
         if (t.kind == T_MMEAS) P->out_clbits.push_back(t.b);
     std::sort(P->out_clbits.begin(), P->out_clbits.end());
     P->measures_anything = !terminal.empty() || P->mid_measures > 0 || any_slot_meas;
+    {   // work = sum_l 2^(n + a(l)) (base + a(l)), a(l) = ancillas of label l's pattern: a product over the digits
+        double base = 0.0;
+        for (const Top& t : P->tops) {
+            if (t.kind == T_SLOT) base += (P->slots[t.a].pre_off >= 0) + (P->slots[t.a].post_off >= 0);
+            else base += 1.0;
+        }
+        const int n_dig = (int)P->radix.size();
+        std::vector<double> S(n_dig, 0.0), T(n_dig, 0.0);
+        for (int d = 0; d < n_dig; ++d)
+            for (int v = 0; v < P->radix[d]; ++v) {
+                int a = 0;
+                for (const Slot& sl : P->slots)
+                    if (sl.digit == d && !sl.terminal && ((sl.meas_mask >> v) & 1)) ++a;
+                S[d] += ldexp(1.0, a);
+                T[d] += a * ldexp(1.0, a);
+            }
+        double prod = 1.0, extra = 0.0;
+        for (int d = 0; d < n_dig; ++d) prod *= S[d];
+        for (int d = 0; d < n_dig; ++d)
+            if (S[d] > 0) extra += T[d] * prod / S[d];
+        P->work = ldexp(1.0, n_qubits + P->mid_measures) * ((base > 1.0 ? base : 1.0) * prod + extra);
+    }
     *out_prog = P;
     return QCK_OK;
 }
@@ -1083,7 +1106,7 @@ extern "C" int qck_host_program_build(qck_host_program* p, int stage, int fold) 
 //   1 tops   int32 [n_tops][4]          2 slots int32 [n_slots][9]     3 slot pre  f64 [n_slots][8][8]
 //   4 order  int32 [n_qubits]           5 out_bits int32 [n][2]        6 touched int32   7 radix int32
 //   8 out_clbits int32                  9 pool f64 (grows while plans are built)        10 slot post f64
-//  11 summary int32: item 0 + {n_touched, n_out_clbits}, then touched, radix, out_clbits
+//  11 summary int32: item 0 + {n_touched, n_out_clbits}, then touched, radix, out_clbits      12 work estimate f64
 //  50 tree meta int64 {n_base, n_out_bits, seg0_begin, seg0_end, base_sum, n_levels, n_ops, blob offset of the ops}
 //  51 tree ops int32 [n][8]            52 tree levels int32 [n][58]   53 free bits int32 [n][2]
 //  54 node counts int64                55 qck_sim_tree_plan bytes     56 tree blob bytes
@@ -1209,6 +1232,7 @@ extern "C" int64_t qck_host_program_get(const qck_host_program* p, int what, voi
                 iv.insert(iv.end(), p->radix.begin(), p->radix.end());
                 iv.insert(iv.end(), p->out_clbits.begin(), p->out_clbits.end());
                 break;
+            case 12: type = 1, dv = {p->work}; break;
             case 60: type = 3, raw = p->canon.data(), bytes = (int64_t)p->canon.size() * 4; break;
             default: return -1;
         }

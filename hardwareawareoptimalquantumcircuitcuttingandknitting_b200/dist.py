@@ -58,7 +58,13 @@ def simulation_work(virt) -> float:
     """Cost estimate of the fragment simulation: sum over programs of instances x 2^n_state x op records."""
     work = 0.0
     for f in virt.active_fragments():
-        for plan in virt.program(f).plans(True):
+        prog = virt.program(f)
+        if getattr(prog, "native", False):
+            # the C++ compiler's closed form of the same sum (no per-pattern plans are built for it: on a
+            # multi-rank run this estimate used to cost the cold end-to-end call more than the compile itself)
+            work += prog.work_estimate()
+            continue
+        for plan in prog.plans(True):
             work += float(len(plan.labels)) * float(1 << plan.n_state) * max(len(plan.ops), 1)
     return work
 
