@@ -120,6 +120,9 @@ _PROTOTYPES = {
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "qck_knit_outer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int,
                                  C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qck_knit_outer_exchange": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int,
+                                          C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                          C.POINTER(C.c_void_p), C.c_void_p]),
     "qck_knit_contract": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int32),
                                     C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int64, C.c_int64,

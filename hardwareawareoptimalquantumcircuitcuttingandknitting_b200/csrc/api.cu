@@ -45,8 +45,12 @@ extern "C" int qck_create(int device, qck_handle** out) {
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     h->partials_count = 1 << 16;
     if (cudaMalloc(&h->d_partials, h->partials_count * sizeof(double)) != cudaSuccess ||
-        cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) != cudaSuccess) {
+        cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->knit_ctr, (1024 + 8) * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(h->knit_ctr, 0, (1024 + 8) * sizeof(unsigned long long)) != cudaSuccess) {
         if (h->d_partials) cudaFree(h->d_partials);
+        if (h->h_pinned) cudaFreeHost(h->h_pinned);
+        if (h->knit_ctr) cudaFree(h->knit_ctr);
         delete full;
         return QCK_ERR_NOMEM;
     }
@@ -68,6 +72,7 @@ extern "C" int qck_destroy(qck_handle* h) {
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->scratch) cudaFree(h->scratch);
     if (h->npd_ws) cudaFree(h->npd_ws);
+    if (h->knit_ctr) cudaFree(h->knit_ctr);
     for (int i = 0; i < QCK_SIDE_STREAMS; ++i)
         if (h->warp_stash[i]) cudaFree(h->warp_stash[i]);
     if (h->side_ready) {

@@ -37,7 +37,12 @@ struct OuterParams {
     unsigned long long y_begin;
     double* out;
     double* partials;
-    unsigned long long* work_counter;  // [n_rows] counters, zeroed before the launch
+    unsigned long long* work_counter;  // [n_rows] counters: zero when the launch starts, reset by its last CTA
+    unsigned long long* ticket;        // arrival counter of the CTAs (same protocol)
+    qck_stats* stats;                  // the last CTA reduces the partials into it (fixed order) ...
+    int exchange;                      // ... and, on a sharded result, exchanges it with the peers (xp, seq_counter)
+    ExchangeParams xp;
+    unsigned long long* seq_counter;
     int n_fast;                         // low bits of the chunk number that do not change any row
     int n_rows;                         // 2^(n_free - n_fast)
     unsigned long long batches_per_row;
@@ -68,6 +73,47 @@ __device__ __forceinline__ void make_desc(const OuterParams& P, unsigned long lo
     }
     d->y_hi = y_hi;
     d->scal = prod;
+}
+
+// The LAST CTA of a knit_outer launch finishes the call (round 2: this was a separate one-warp launch, a memset node
+// in front of the kernel and, on a sharded result, the exchange launch - three dependent graph nodes of a 0.68 ms
+// step at 8 GPUs).  It resets the work counters and the ticket for the next launch, reduces the per-CTA partials
+// in the fixed order of finalize_stats_kernel (same bits) and runs the peer exchange.  Not inlined: its registers
+// (spin loop, printf) must not weigh on the streaming loop.
+__device__ __noinline__ void knit_outer_tail(const OuterParams& P) {
+    const int tid = threadIdx.x;
+    __shared__ int is_last;
+    if (tid == 0) {
+        __threadfence();
+        const unsigned long long t = atomicAdd(P.ticket, 1ull);
+        is_last = t == (unsigned long long)gridDim.x - 1ull;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = tid; i < P.n_rows; i += KO_THREADS) P.work_counter[i] = 0ull;
+    if (tid == 0) *P.ticket = 0ull;
+    if (tid < 32 && P.stats && P.partials) {
+        double s = 0.0, m = INFINITY, z = 0.0, zmin = 0.0;
+        for (int i = tid; i < (int)gridDim.x; i += 32) {
+            s += __ldcg(P.partials + 3 * i + 0);
+            m = fmin(m, __ldcg(P.partials + 3 * i + 1));
+            z += __ldcg(P.partials + 3 * i + 2);
+            zmin = fmin(zmin, __ldcg(P.partials + 3 * i + 2));
+        }
+        s = warp_sum(s);
+        m = warp_min(m);
+        z = warp_sum(z);
+        zmin = warp_min(zmin);
+        if (tid == 0) {
+            P.stats->sum = s;
+            P.stats->min = m;
+            P.stats->sum_sqrt = 0.0;
+            P.stats->nnz = zmin < 0.0 ? -1.0 : z;
+        }
+        __syncwarp();
+        if (P.exchange) stats_exchange_warp(P.xp, P.stats, P.seq_counter);
+    }
 }
 
 // Streaming outer product.  Per chunk and thread the inner loop is 16 multiplies and four
@@ -204,6 +250,7 @@ __global__ void __launch_bounds__(KO_THREADS) knit_outer_kernel(const __grid_con
         P.partials[3 * blockIdx.x + 1] = m;
         P.partials[3 * blockIdx.x + 2] = -1.0;  // nnz is not tracked on the streaming path
     }
+    knit_outer_tail(P);
 }
 
 // generic fallback: one thread per element (small or unaligned ranges, many vector fragments)
@@ -312,7 +359,18 @@ static cudaError_t launch_outer(int n_vec, int grid, size_t smem, cudaStream_t s
 extern "C" int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
                               int n_out_bits, uint64_t y_begin, uint64_t y_end, double* d_out, qck_stats* d_stats,
                               qck_stream stream) {
+    return qck_knit_outer_exchange(h, n_frag, d_tables, masks, n_out_bits, y_begin, y_end, d_out, d_stats, 0, 1, nullptr,
+                                   stream);
+}
+
+extern "C" int qck_knit_outer_exchange(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
+                                       int n_out_bits, uint64_t y_begin, uint64_t y_end, double* d_out,
+                                       qck_stats* d_stats, int rank, int world, void* const* d_mailboxes,
+                                       qck_stream stream) {
     if (!h) return QCK_ERR_INVALID_ARG;
+    const bool exchange = world > 1;
+    if (exchange && (!d_stats || !d_mailboxes || world > QCK_MAX_RANKS || rank < 0 || rank >= world))
+        QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad stats exchange arguments");
     if (n_frag < 1 || n_frag > KO_MAXF) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_frag=%d out of range [1,%d]", n_frag, KO_MAXF);
     if (!d_tables || !masks) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "tables / masks NULL");
     if (n_out_bits < 0 || n_out_bits > QCK_MAX_OUT_BITS) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "n_out_bits=%d", n_out_bits);
@@ -322,8 +380,8 @@ extern "C" int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_
         if (masks[f] & ~full) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "mask %d has bits >= n_out_bits", f);
     }
     if (y_end < y_begin || y_end > (1ull << n_out_bits)) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "bad output range");
-    if (y_end == y_begin) return QCK_OK;
-    if (!d_out && !d_stats) return QCK_OK;
+    if ((y_end == y_begin || (!d_out && !d_stats)) && !exchange) return QCK_OK;
+    if (y_end == y_begin) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "an exchange needs a non-empty slice on every rank");
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
 
@@ -397,13 +455,26 @@ extern "C" int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_
         P.n_fast = n_fast;
         P.n_rows = 1 << (n_free - n_fast);
         P.batches_per_row = ((1ull << n_fast) + KO_BATCH - 1) / KO_BATCH;
-        int rc = qck_ensure_partials(h, (size_t)grid * 3 + P.n_rows);
+        int rc = qck_ensure_partials(h, (size_t)grid * 3);
         if (rc) return rc;
+        if (P.n_rows > 1024) QCK_FAIL(h, QCK_ERR_UNSUPPORTED, "knit_outer: %d work rows", P.n_rows);
         P.partials = d_stats ? h->d_partials : nullptr;
-        P.work_counter = reinterpret_cast<unsigned long long*>(h->d_partials + (size_t)grid * 3);
-        QCK_CUDA(h, cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned long long) * P.n_rows, st));
+        P.work_counter = h->knit_ctr;          // zero between launches (the last CTA of a launch resets them)
+        P.ticket = h->knit_ctr + 1024;
+        P.stats = d_stats;
+        P.exchange = exchange ? 1 : 0;
+        if (exchange) {
+            for (int r2 = 0; r2 < world; ++r2) {
+                if (!d_mailboxes[r2]) QCK_FAIL(h, QCK_ERR_INVALID_ARG, "mailbox of rank %d is NULL", r2);
+                P.xp.box[r2] = reinterpret_cast<StatsSlot*>(reinterpret_cast<char*>(d_mailboxes[r2]) + 64);
+            }
+            P.xp.rank = rank;
+            P.xp.world = world;
+            P.seq_counter = reinterpret_cast<unsigned long long*>(d_mailboxes[rank]);
+        }
         QCK_CUDA(h, d_out ? launch_outer<true>(n_vec, grid, smem, st, P) : launch_outer<false>(n_vec, grid, smem, st, P));
         QCK_CHECK_LAUNCH(h);
+        return QCK_OK;
     } else {
         OuterSimpleParams P;
         memset(&P, 0, sizeof(P));
@@ -427,6 +498,7 @@ extern "C" int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_
         finalize_stats_kernel<<<1, 32, 0, st>>>(h->d_partials, grid, d_stats);
         QCK_CHECK_LAUNCH(h);
     }
+    if (exchange) return qck_stats_exchange(h, d_stats, rank, world, d_mailboxes, stream);
     return QCK_OK;
 }
 

@@ -1,6 +1,7 @@
 // Shared plumbing for libqck.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -43,6 +44,8 @@ struct qck_handle {
     unsigned region_calls;                     // batch calls made inside the open region
     int warp_occ[6];
     int tree_occ[6];
+    // knit_outer: work counters [1024] + arrival ticket (zeroed once; the last CTA of a launch resets them)
+    unsigned long long* knit_ctr;
 };
 
 #define QCK_FAIL(h, code, ...)                                    \
@@ -136,4 +139,71 @@ __device__ __forceinline__ double warp_min(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// ---- cross-rank exchange of a qck_stats through peer mailboxes (reduce.cu: stats_exchange_kernel; knit.cu: the
+// tail of knit_outer).  Every rank writes its four doubles straight into a slot of every peer's mailbox (NVLink
+// stores into cudaIpc-mapped memory), publishes a sequence number, waits until its own mailbox holds the current
+// sequence number from every rank and adds the slots in rank order (the same bits on every rank).  Slots are
+// double buffered by the parity of the sequence number.
+struct StatsSlot {
+    double sum, min, sum_sqrt, nnz;
+    unsigned long long seq;
+    unsigned long long pad[3];
+};
+struct ExchangeParams {
+    StatsSlot* box[QCK_MAX_RANKS];  // mailbox of every rank: [2][world] slots
+    int rank, world;
+};
+// one full warp; `stats` holds this rank's values on entry and the combined ones on return (lane 0 writes)
+__device__ __forceinline__ void stats_exchange_warp(const ExchangeParams& P, qck_stats* stats, unsigned long long* seq_counter) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long seq = 0;
+    if (lane == 0) seq = *seq_counter + 1ull;
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    const int buf = (int)(seq & 1ull);
+    if (lane < P.world) {  // my values into slot [rank] of rank `lane`'s mailbox, the sequence number last
+        volatile StatsSlot* dst = P.box[lane] + buf * P.world + P.rank;
+        dst->sum = stats->sum;
+        dst->min = stats->min;
+        dst->sum_sqrt = stats->sum_sqrt;
+        dst->nnz = stats->nnz;
+        __threadfence_system();
+        dst->seq = seq;
+    }
+    double s = 0.0, m = INFINITY, q = 0.0, z = 0.0;
+    bool tracked = true;
+    if (lane < P.world) {  // wait for rank `lane`'s values in my own mailbox
+        volatile StatsSlot* src = P.box[P.rank] + buf * P.world + lane;
+        const long long t0 = clock64();
+        while (src->seq != seq) {
+            if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer never came
+                printf("qck: stats exchange: rank %d waited in vain for rank %d (sequence %llu)\n", P.rank, lane, seq);
+                __trap();
+            }
+        }
+        __threadfence_system();
+        s = src->sum;
+        m = src->min;
+        q = src->sum_sqrt;
+        z = src->nnz;
+        tracked = !(z < 0.0);
+    }
+    // rank order, one lane after the other: identical bits on every rank
+    double ss = 0.0, mm = INFINITY, qq = 0.0, zz = 0.0;
+    bool all_tracked = true;
+    for (int r = 0; r < P.world; ++r) {
+        ss += __shfl_sync(0xffffffffu, s, r);
+        mm = fmin(mm, __shfl_sync(0xffffffffu, m, r));
+        qq += __shfl_sync(0xffffffffu, q, r);
+        zz += __shfl_sync(0xffffffffu, z, r);
+        all_tracked = all_tracked && __shfl_sync(0xffffffffu, (int)tracked, r);
+    }
+    if (lane == 0) {
+        stats->sum = ss;
+        stats->min = mm;
+        stats->sum_sqrt = qq;
+        stats->nnz = all_tracked ? zz : -1.0;
+        *seq_counter = seq;
+    }
 }

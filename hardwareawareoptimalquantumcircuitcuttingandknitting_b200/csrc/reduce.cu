@@ -165,67 +165,11 @@ extern "C" int qck_hellinger(qck_handle* h, const double* d_p, const double* d_q
 // bits on every rank).  One launch of one warp; the sequence counter lives on the device, so the launch can be
 // captured in a CUDA graph and replayed.  Slots are double buffered by the parity of the sequence number: a
 // rank can only be two exchanges ahead of another one after that one has finished reading.
-struct StatsSlot {
-    double sum, min, sum_sqrt, nnz;
-    unsigned long long seq;
-    unsigned long long pad[3];
-};
-struct ExchangeParams {
-    StatsSlot* box[QCK_MAX_RANKS];  // mailbox of every rank: [2][world] slots
-    int rank, world;
-};
-
+// (StatsSlot, ExchangeParams and the warp-level protocol live in qck_common.cuh: knit_outer runs the same exchange
+// in its tail)
 __global__ void __launch_bounds__(32) stats_exchange_kernel(const __grid_constant__ ExchangeParams P, qck_stats* stats,
                                                             unsigned long long* seq_counter) {
-    const int lane = threadIdx.x;
-    unsigned long long seq = 0;
-    if (lane == 0) seq = *seq_counter + 1ull;
-    seq = __shfl_sync(0xffffffffu, seq, 0);
-    const int buf = (int)(seq & 1ull);
-    if (lane < P.world) {  // my values into slot [rank] of rank `lane`'s mailbox, the sequence number last
-        volatile StatsSlot* dst = P.box[lane] + buf * P.world + P.rank;
-        dst->sum = stats->sum;
-        dst->min = stats->min;
-        dst->sum_sqrt = stats->sum_sqrt;
-        dst->nnz = stats->nnz;
-        __threadfence_system();
-        dst->seq = seq;
-    }
-    double s = 0.0, m = INFINITY, q = 0.0, z = 0.0;
-    bool tracked = true;
-    if (lane < P.world) {  // wait for rank `lane`'s values in my own mailbox
-        volatile StatsSlot* src = P.box[P.rank] + buf * P.world + lane;
-        const long long t0 = clock64();
-        while (src->seq != seq) {
-            if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer never came
-                printf("qck: stats_exchange_kernel: rank %d waited in vain for rank %d (sequence %llu)\n", P.rank, lane, seq);
-                __trap();
-            }
-        }
-        __threadfence_system();
-        s = src->sum;
-        m = src->min;
-        q = src->sum_sqrt;
-        z = src->nnz;
-        tracked = !(z < 0.0);
-    }
-    // rank order, one lane after the other: identical bits on every rank
-    double ss = 0.0, mm = INFINITY, qq = 0.0, zz = 0.0;
-    bool all_tracked = true;
-    for (int r = 0; r < P.world; ++r) {
-        ss += __shfl_sync(0xffffffffu, s, r);
-        mm = fmin(mm, __shfl_sync(0xffffffffu, m, r));
-        qq += __shfl_sync(0xffffffffu, q, r);
-        zz += __shfl_sync(0xffffffffu, z, r);
-        all_tracked = all_tracked && __shfl_sync(0xffffffffu, (int)tracked, r);
-    }
-    if (lane == 0) {
-        stats->sum = ss;
-        stats->min = mm;
-        stats->sum_sqrt = qq;
-        stats->nnz = all_tracked ? zz : -1.0;
-        *seq_counter = seq;
-    }
+    stats_exchange_warp(P, stats, seq_counter);
 }
 
 extern "C" size_t qck_stats_exchange_mailbox_bytes(int world) { return sizeof(StatsSlot) * 2 * (size_t)world + 64; }

@@ -82,7 +82,8 @@ class ResidentStep:
                                       part=(self.rank, self.world) if self.entry_sharded else (0, 1))
         elif self.K == 0:
             virt.knit_tables(self.tables, dev, stats=self.stats,
-                             y_range=(self.y0, self.y1) if self.world > 1 else None, out=self.out)
+                             y_range=(self.y0, self.y1) if self.world > 1 else None, out=self.out,
+                             exchange=self._exchange())
         else:
             virt.knit_tables(self.tables, dev, label_range=self.label_range, out=self.out)
 
@@ -92,7 +93,7 @@ class ResidentStep:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         h = self.handle
         if self.K == 0:
-            if self.world > 1:
+            if self.world > 1 and self._exchange() is None:     # (else exchanged in the knit kernel's tail)
                 self.qdist.allreduce_stats(self.stats, self.group, self.handle)   # min >= 0: no npd pass
             return
         if self.label_range is not None or self.entry_sharded:
@@ -103,6 +104,14 @@ class ResidentStep:
         else:
             h.check(h.lib.qck_npd_stage(h.ptr, _lib.NPD_STATS, self.out.data_ptr(), self.out.numel(), self.accuracy,
                                         self.ws.data_ptr(), 1, stream))
+
+    def _exchange(self):
+        """Peer mailboxes of a result sharded by output index (K = 0, world > 1), or None (NCCL path)."""
+        if self.world <= 1 or self.K != 0 or self.faithful:
+            return None
+        if not hasattr(self, "_ex"):
+            self._ex = self.qdist.stats_exchange(self.handle, self.device, self.group)
+        return self._ex
 
     def enqueue(self) -> None:
         self.enqueue_simulation()

@@ -127,8 +127,10 @@ def run_virtual_circuit_dense(virt: VirtualCircuit, shots: int = 20000, device=N
         n_out = bin(union).count("1")
         y_range = qdist.shard_pow2(n_out, rank, world_size) if world_size > 1 else None
         y_begin = y_range[0] if y_range else 0
-        values = virt.knit_tables(tables, device, stats=stats, y_range=y_range, out=out)
-        qdist.allreduce_stats(stats, group, handle)
+        ex = qdist.stats_exchange(handle, device, group) if world_size > 1 else None
+        values = virt.knit_tables(tables, device, stats=stats, y_range=y_range, out=out, exchange=ex)
+        if ex is None:                            # (else the knit kernel's tail has exchanged them already)
+            qdist.allreduce_stats(stats, group, handle)
         host_stats = stats.cpu().numpy()          # the step's device -> host read (synchronises)
         total, minimum = float(host_stats[0]), float(host_stats[1])
         if nearest and minimum < 0.0:

@@ -358,7 +358,7 @@ class VirtualCircuit:
         return masks, union
 
     def knit_tables(self, tables: dict, device=None, label_range: tuple[int, int] | None = None,
-                    out=None, y_range: tuple[int, int] | None = None, stats=None):
+                    out=None, y_range: tuple[int, int] | None = None, stats=None, exchange=None):
         """Dense exact knit.  Returns a device tensor over the written clbits (index bit j = j-th
         written clbit in ascending order; for ``measure_all`` circuits index == key)."""
         import torch
@@ -376,6 +376,13 @@ class VirtualCircuit:
             y0, y1 = y_range if y_range is not None else (0, 1 << n_out)
             if out is None:
                 out = torch.empty(y1 - y0, dtype=torch.float64, device=device)
+            if exchange is not None and stats is not None:
+                # sharded result: the slices' statistics are combined across the ranks in the kernel's own tail
+                # (``exchange`` = dist.StatsExchange: peer mailboxes)
+                handle.check(handle.lib.qck_knit_outer_exchange(handle.ptr, len(frags), ptrs, cm, n_out, y0, y1,
+                                                                out.data_ptr(), stats.data_ptr(), exchange.rank,
+                                                                exchange.world, exchange._ptrs, stream))
+                return out
             handle.check(handle.lib.qck_knit_outer(handle.ptr, len(frags), ptrs, cm, n_out, y0, y1, out.data_ptr(),
                                                    stats.data_ptr() if stats is not None else None, stream))
             return out

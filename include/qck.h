@@ -343,6 +343,14 @@ typedef struct {
 QCK_API int qck_knit_outer(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
                    int n_out_bits, uint64_t y_begin, uint64_t y_end, double* d_out,
                    qck_stats* d_stats, qck_stream stream);
+/* The same call on a result SHARDED over `world` ranks by output index: the statistics of the slices are combined
+ * across the ranks in the kernel's own tail (the last CTA to finish writes them into the peers' mailboxes, see
+ * qck_stats_exchange) - no further launch, no collective.  d_mailboxes as for qck_stats_exchange; every rank
+ * calls it with a non-empty slice.  world == 1: plain qck_knit_outer. */
+QCK_API int qck_knit_outer_exchange(qck_handle* h, int n_frag, const double* const* d_tables, const uint64_t* masks,
+                                    int n_out_bits, uint64_t y_begin, uint64_t y_end, double* d_out,
+                                    qck_stats* d_stats, int rank, int world, void* const* d_mailboxes,
+                                    qck_stream stream);
 
 /* K >= 1: out[y] (+)= sum_{l in [l_begin, l_end)} w(l) prod_f Q_f[lf(l)][pext(y, masks[f])]
  * with l the global label (last virtual gate fastest), w(l) = prod_k coef[k][l_k],
