@@ -127,11 +127,11 @@ __device__ __forceinline__ bool last_cta(unsigned long long* ticket) {
 }
 
 // bins and quantisation of the current range (one thread)
-__device__ void npd_set_level(NpdState* s) {
+__device__ void npd_set_level(NpdState* s, int bin_bits = NPD_BIN_BITS) {
     const unsigned long long width = (unsigned long long)s->hi - (unsigned long long)s->lo;  // >= 1
     int bits = 64 - __clzll((long long)(width - 1ull));                                      // ceil(log2(width))
     if (width <= 1ull) bits = 0;
-    s->shift = bits > NPD_BIN_BITS ? bits - NPD_BIN_BITS : 0;
+    s->shift = bits > bin_bits ? bits - bin_bits : 0;
     const double w = npd_val(s->hi) - npd_val(s->lo + 1);
     long long cnt = s->sel_cnt < 1 ? 1 : s->sel_cnt;
     const int cbits = 64 - __clzll(cnt);  // cnt < 2^cbits
@@ -567,6 +567,319 @@ __global__ void __launch_bounds__(NPD_THREADS) npd_fused_kernel(double* __restri
     }
 }
 
+// ---- vectors of at most 2^16 entries (every 16-qubit configuration): the whole search as ONE launch of ONE
+// thread-block cluster.  Eight CTAs hold the vector in registers (16 entries per thread); the passes are separated
+// by cluster barriers instead of launches; the bins (2048 per level: 11 key bits) live in shared memory.  After a
+// pass CTA r adds up bins [256 r, 256 r + 256) of all eight CTAs through distributed shared memory, the slice totals
+// tell every CTA which slice holds t0, the CTA owning that slice picks the bin and writes the new search state into
+// the shared memory of all eight.  Nothing but the vector itself and the final state touches global memory.
+// (Every CTA reading all eight histograms was tried first: 196 KB through a 17-21 B/clk DSMEM port per level.)
+// Same definitions as the staged kernels above (key ranges, integer quantisation, G at the bin boundaries, the
+// under-range sums in a fixed order): the partition is the same set, beta may differ in the last bit (another
+// summation order).
+#define NPC_CTAS 8
+#define NPC_THREADS 512
+#define NPC_WARPS (NPC_THREADS / 32)
+#define NPC_VPT 16
+#define NPC_BINS 2048
+#define NPC_BIN_BITS 11
+#define NPC_SLICE (NPC_BINS / NPC_CTAS)
+#define NPC_LEVELS 6
+#define NPC_CAPACITY (NPC_CTAS * NPC_THREADS * NPC_VPT)
+static_assert(NPC_SLICE == 256 && NPC_BINS % NPC_THREADS == 0 && NPC_LEVELS * NPC_BIN_BITS >= 64, "npd cluster kernel geometry");
+
+struct NpcShared {
+    unsigned int cnt[NPC_BINS];           // bins of this CTA's entries
+    unsigned int q_lo[NPC_BINS], q_hi[NPC_BINS];  // integer sums (64 bits in two words)
+    double part[8];                       // this CTA's statistics / (sum, count) of its entries at or below lo
+    long long slice_tot[2];               // (count, integer sum) of this CTA's slice of the bins, all CTAs added
+    double gathered[NPC_CTAS * 5];
+    long long gathered_slices[NPC_CTAS * 2];
+    double red[NPC_WARPS][5];
+    long long wtot[NPC_SLICE / 32][2];
+    int found;
+    NpdState st;                          // every CTA keeps a copy of the search state
+};
+
+// sums (index 1: minimum) of N per-thread values over the CTA in a fixed order -> out[0..N) (valid after the next barrier)
+template <int N>
+__device__ __forceinline__ void npc_block_reduce(double (&x)[N], NpcShared& S, double* out, bool second_is_min) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = (second_is_min && i == 1) ? warp_min(x[i]) : warp_sum(x[i]);
+    if ((tid & 31) == 0)
+#pragma unroll
+        for (int i = 0; i < N; ++i) S.red[tid >> 5][i] = x[i];
+    __syncthreads();
+    if (tid < N) {
+        double a = (second_is_min && tid == 1) ? INFINITY : 0.0;
+        for (int w = 0; w < NPC_WARPS; ++w) a = (second_is_min && tid == 1) ? fmin(a, S.red[w][tid]) : a + S.red[w][tid];
+        out[tid] = a;
+    }
+}
+
+__global__ void __cluster_dims__(NPC_CTAS, 1, 1) __launch_bounds__(NPC_THREADS)
+    npd_cluster_kernel(double* __restrict__ p, unsigned long long n, double acc, void* ws_raw, int mode) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    NpcShared& S = *reinterpret_cast<NpcShared*>(npd_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int rank = cluster.block_rank();
+    NpdState* s = &S.st;
+    long long tmark[12];
+    int nmark = 0;
+#define NPC_MARK() do { if (nmark < 12) tmark[nmark++] = clock64(); } while (0)
+    NPC_MARK();
+
+    // the vector, 16 entries per thread (entry i of the vector: CTA i / 8192, then coalesced)
+    double v[NPC_VPT];
+    unsigned int alive = 0u;
+    const unsigned long long base = (unsigned long long)rank * (NPC_THREADS * NPC_VPT) + tid;
+#pragma unroll
+    for (int j = 0; j < NPC_VPT; ++j) {
+        const unsigned long long i = base + (unsigned long long)j * NPC_THREADS;
+        v[j] = i < n ? p[i] : 0.0;
+        if (i < n && fabs(v[j]) > acc) alive |= 1u << j;
+    }
+    // statistics: sum, minimum, sum of the negative entries, number of alive / negative entries
+    {
+        double x[5] = {0.0, INFINITY, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < NPC_VPT; ++j)
+            if (alive >> j & 1u) {
+                x[0] += v[j];
+                x[1] = fmin(x[1], v[j]);
+                x[3] += 1.0;
+                if (v[j] < 0.0) {
+                    x[2] += v[j];
+                    x[4] += 1.0;
+                }
+            }
+        npc_block_reduce<5>(x, S, S.part, true);
+    }
+    cluster.sync();
+    if (tid < NPC_CTAS * 5) S.gathered[tid] = cluster.map_shared_rank(S.part, tid / 5)[tid % 5];
+    __syncthreads();
+    if (tid == 0) {  // rank order: the same bits in every CTA
+        double sm = 0.0, m = INFINITY, ns = 0.0, z = 0.0, nz = 0.0;
+        for (int r = 0; r < NPC_CTAS; ++r) {
+            sm += S.gathered[5 * r + 0];
+            m = fmin(m, S.gathered[5 * r + 1]);
+            ns += S.gathered[5 * r + 2];
+            z += S.gathered[5 * r + 3];
+            nz += S.gathered[5 * r + 4];
+        }
+        memset(s, 0, sizeof(NpdState));
+        s->sum = sm; s->vmin = m; s->neg_sum = ns; s->alive = z; s->neg_cnt = nz;
+        s->num = z;
+        s->t0 = -INFINITY;
+        if (!(z > 0.0) || !(m < 0.0)) {
+            s->status = NPD_IDENTITY;
+        } else if (sm < 0.0) {
+            s->status = NPD_NEGATIVE_TOTAL;
+        } else {
+            s->status = NPD_SEARCH;
+            // G(0) = neg_sum < 0: t0 > 0, every entry <= 0 is dropped - the search starts above zero
+            s->lo = (mode & 32) ? npd_key(m) - 1 : 0ll;
+            s->hi = npd_key(-ns * (1.0 + 1e-9));
+            s->sel_cnt = (long long)z;
+            npd_set_level(s, NPC_BIN_BITS);
+        }
+    }
+    cluster.sync();  // (also: S.part has been read by every CTA before the first pass overwrites it)
+    NPC_MARK();
+
+    for (int level = 0; level <= NPC_LEVELS + 1; ++level) {
+        const int status = (int)s->status;
+        if (status != NPD_SEARCH && status != NPD_LOCATED) break;  // the same decision in every CTA
+        const bool bins = status == NPD_SEARCH;
+        if (bins) {
+#pragma unroll
+            for (int i = 0; i < NPC_BINS / NPC_THREADS; ++i) {
+                S.cnt[tid + i * NPC_THREADS] = 0u;
+                S.q_lo[tid + i * NPC_THREADS] = 0u;
+                S.q_hi[tid + i * NPC_THREADS] = 0u;
+            }
+        }
+        const long long lo = s->lo, hi = s->hi;
+        const int shift = (int)s->shift;
+        const double lo_val = npd_val(lo + 1);
+        const int qexp = (int)s->qexp;
+        const double alive_total = s->alive;
+        __syncthreads();
+        double x[2] = {0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < NPC_VPT; ++j) {
+            const long long k = npd_key(v[j]);
+            const bool a = alive >> j & 1u;
+            if (a && k <= lo) {
+                x[0] += v[j];
+                x[1] += 1.0;
+            }
+            if (bins && a && k > lo && k <= hi) {
+                const unsigned int b = (unsigned int)(((unsigned long long)k - (unsigned long long)lo - 1ull) >> shift);
+                const unsigned long long qv = (unsigned long long)__double2ll_rn(scalbn(v[j] - lo_val, qexp));  // < 2^61
+                // 64-bit integer sum as two native 32-bit shared-memory atomics, the carry added by the thread whose
+                // addition wrapped (a 64-bit atomicAdd on shared memory compiles to a compare-and-swap spin loop).
+                // (Adding up lanes with the same bin inside the warp first - __match_any_sync, or the bin of the first
+                // pending lane - was slower on every knitted result tried: rounding noise spreads over many binades.)
+                atomicAdd(&S.cnt[b], 1u);
+                const unsigned int ql = (unsigned int)qv, qh = (unsigned int)(qv >> 32);
+                const unsigned int old = atomicAdd(&S.q_lo[b], ql);
+                const unsigned int carry = old + ql < old ? 1u : 0u;
+                if (qh + carry) atomicAdd(&S.q_hi[b], qh + carry);
+            }
+        }
+        npc_block_reduce<2>(x, S, S.part, false);
+        NPC_MARK();
+        cluster.sync();  // bins and partial sums of every CTA are complete
+        if (tid < NPC_CTAS * 2) S.gathered[tid] = cluster.map_shared_rank(S.part, tid / 2)[tid % 2];
+        unsigned int c_bin = 0u;
+        long long q_bin = 0ll, c_in = 0ll, q_in = 0ll;
+        if (bins && tid < NPC_SLICE) {  // my slice of the bins, all CTAs added (integers)
+            const int bin = (int)rank * NPC_SLICE + tid;
+#pragma unroll
+            for (int r = 0; r < NPC_CTAS; ++r) {
+                c_bin += cluster.map_shared_rank(S.cnt, r)[bin];
+                q_bin += (long long)(((unsigned long long)cluster.map_shared_rank(S.q_hi, r)[bin] << 32) +
+                                     (unsigned long long)cluster.map_shared_rank(S.q_lo, r)[bin]);
+            }
+            // inclusive prefix inside the slice: warp scans, then the warp totals
+            c_in = (long long)c_bin;
+            q_in = q_bin;
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long cu = __shfl_up_sync(0xffffffffu, c_in, o);
+                const long long qu = __shfl_up_sync(0xffffffffu, q_in, o);
+                if (lane >= o) {
+                    c_in += cu;
+                    q_in += qu;
+                }
+            }
+            if (lane == 31) {
+                S.wtot[warp][0] = c_in;
+                S.wtot[warp][1] = q_in;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0, b = 0.0;
+            for (int r = 0; r < NPC_CTAS; ++r) {
+                a += S.gathered[2 * r + 0];
+                b += S.gathered[2 * r + 1];
+            }
+            s->under_sum = a;
+            s->under_cnt = b;
+            if (!bins) {  // this pass only took (sum, count) of the dropped entries
+                s->beta = a;
+                s->num = s->alive - b;
+                s->shift_val = s->num > 0.0 ? s->beta / s->num : 0.0;
+                s->t0 = npd_val(s->lo + 1);
+                s->status = NPD_SOLVED;
+            } else {
+                long long ct = 0ll, qt = 0ll;
+                for (int w = 0; w < NPC_SLICE / 32; ++w) {
+                    ct += S.wtot[w][0];
+                    qt += S.wtot[w][1];
+                }
+                S.slice_tot[0] = ct;
+                S.slice_tot[1] = qt;
+            }
+            S.found = NPC_BINS;
+        }
+        if (!bins) {
+            __syncthreads();
+            NPC_MARK();
+            continue;  // every CTA has computed the same state
+        }
+        NPC_MARK();
+        cluster.sync();  // slice totals
+        if (tid < NPC_CTAS * 2) S.gathered_slices[tid] = cluster.map_shared_rank(S.slice_tot, tid / 2)[tid % 2];
+        __syncthreads();
+        const double rest = alive_total - s->under_cnt, under = s->under_sum;
+        const unsigned long long width = (unsigned long long)hi - (unsigned long long)lo;
+        // G at the upper boundary of bin j, given the entries (count cc, integer sum qq) of bins 0..j
+        auto g_at = [&](int j, long long cc, long long qq, bool* is_last) -> double {
+            unsigned long long off = ((unsigned long long)(j + 1)) << shift;
+            if (off > width || (shift > 0 && (off >> shift) != (unsigned long long)(j + 1))) off = width;
+            *is_last = off == width;
+            const double ub = npd_val(lo + (long long)off);
+            return under + ((double)cc * lo_val + scalbn((double)qq, -qexp)) + ub * (rest - (double)cc);
+        };
+        // the slice that holds t0: the first one whose END has G >= 0 (G is non-decreasing) - the same in every CTA
+        int owner = NPC_CTAS - 1;
+        long long c_before = 0ll, q_before = 0ll;
+        {
+            long long cc = 0ll, qq = 0ll;
+            for (int r = 0; r < NPC_CTAS; ++r) {
+                const long long c0 = cc, q0 = qq;
+                cc += S.gathered_slices[2 * r + 0];
+                qq += S.gathered_slices[2 * r + 1];
+                bool is_last;
+                const double g = g_at(r * NPC_SLICE + NPC_SLICE - 1, cc, qq, &is_last);
+                if (g >= 0.0 || is_last || r == NPC_CTAS - 1) {
+                    owner = r;
+                    c_before = c0;
+                    q_before = q0;
+                    break;
+                }
+            }
+        }
+        if ((int)rank == owner) {
+            if (tid < NPC_SLICE) {
+                for (int w = 0; w < warp; ++w) {
+                    c_in += S.wtot[w][0];
+                    q_in += S.wtot[w][1];
+                }
+                bool is_last;
+                const double g = g_at(owner * NPC_SLICE + tid, c_before + c_in, q_before + q_in, &is_last);
+                if (g >= 0.0 || is_last) atomicMin(&S.found, owner * NPC_SLICE + tid);
+            }
+            __syncthreads();
+            const int j = S.found;  // (always set: the last bin of the slice qualifies by the choice of the owner)
+            if (tid == j - owner * NPC_SLICE) {
+                unsigned long long off_lo = ((unsigned long long)j) << shift;
+                unsigned long long off_hi = ((unsigned long long)(j + 1)) << shift;
+                if (off_hi > width || (shift > 0 && (off_hi >> shift) != (unsigned long long)(j + 1))) off_hi = width;
+                s->lo = lo + (long long)off_lo;
+                s->hi = lo + (long long)off_hi;
+                s->sel_cnt = (long long)c_bin;
+                s->level += 1;
+                if (c_bin == 0u || off_hi - off_lo <= 1ull) {
+                    s->status = NPD_LOCATED;  // dropped = {key <= lo}; the next pass sums them
+                } else {
+                    npd_set_level(s, NPC_BIN_BITS);
+                }
+            }
+            __syncthreads();
+            // the new state into every CTA's copy (8-byte slots)
+            constexpr int SLOTS = (int)(sizeof(NpdState) / 8);
+            if (tid < NPC_CTAS * SLOTS && tid / SLOTS != owner)
+                reinterpret_cast<long long*>(cluster.map_shared_rank(s, tid / SLOTS))[tid % SLOTS] =
+                    reinterpret_cast<const long long*>(s)[tid % SLOTS];
+        }
+        cluster.sync();  // new state everywhere
+        NPC_MARK();
+    }
+    // apply
+    const int status = (int)s->status;
+    if (status == NPD_SOLVED || (status == NPD_IDENTITY && acc > 0.0)) {
+        const long long lo = status == NPD_SOLVED ? s->lo : (long long)0x8000000000000000ull;
+        const double shift_val = status == NPD_SOLVED ? s->shift_val : 0.0;
+#pragma unroll
+        for (int j = 0; j < NPC_VPT; ++j) {
+            const unsigned long long i = base + (unsigned long long)j * NPC_THREADS;
+            if (i < n) p[i] = ((alive >> j & 1u) && npd_key(v[j]) > lo) ? v[j] + shift_val : 0.0;
+        }
+    }
+    if (rank == 0 && tid < (int)(sizeof(NpdState) / 8) && tid != 17)  // (slot 17 = the ticket of the staged kernels)
+        reinterpret_cast<long long*>(ws_raw)[tid] = reinterpret_cast<const long long*>(s)[tid];
+    NPC_MARK();
+    if (rank == 0 && tid == 0 && (mode & 64))
+        for (int i = 0; i < 12; ++i) reinterpret_cast<long long*>(ws_raw)[19 + i] = i < nmark ? tmark[i] - tmark[0] : -1;
+    cluster.sync();  // no CTA leaves while its shared memory may still be read
+#undef NPC_MARK
+}
+
 // ------------------------------------------------------------------ host side
 // (4 elements per thread.  Fewer, fatter CTAs - 32 per thread, 8 CTAs at n = 2^16 - measured slower: every
 // pass is latency bound, 0.087 -> 0.121 ms for the eight launches of hwe-16 d5's npd.)
@@ -580,6 +893,7 @@ static int npd_grid(qck_handle* h, unsigned long long n) {
 int qck_npd_init(qck_handle* h) {
     QCK_CUDA(h, cudaFuncSetAttribute(npd_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NPD_BINS));
     QCK_CUDA(h, cudaFuncSetAttribute(npd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NPD_BINS));
+    QCK_CUDA(h, cudaFuncSetAttribute(npd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NpcShared)));
     QCK_CUDA(h, cudaMalloc(&h->npd_ws, NPD_WS_BYTES));
     QCK_CUDA(h, cudaMemset(h->npd_ws, 0, NPD_WS_BYTES));
     return QCK_OK;
@@ -615,6 +929,17 @@ extern "C" int qck_npd_async(qck_handle* h, double* d_p, uint64_t n, double acc,
     // Opt-in: measured on hwe-16 d5 / bv-16 (2^16 entries, inside the step's CUDA graph) it saves 2-4 us of the
     // 75 / 53 us the eight launches take - the passes themselves, not the launches, are the cost - which does not
     // pay for depending on cooperative launches inside captured graphs.
+    // n <= 2^16: one launch of one 8-CTA cluster, the vector in registers, bins in (distributed) shared memory
+    // (QCK_NPD_CLUSTER=0: the staged launches below)
+    const char* cluster_env = getenv("QCK_NPD_CLUSTER");
+    if (n <= NPC_CAPACITY && !(cluster_env && atoi(cluster_env) == 0)) {
+        DeviceGuard guard(h->device);
+        void* ws = d_ws ? d_ws : h->npd_ws;
+        const char* mode_env = getenv("QCK_NPC_MODE");
+        npd_cluster_kernel<<<NPC_CTAS, NPC_THREADS, sizeof(NpcShared), (cudaStream_t)stream>>>(d_p, n, acc, ws, mode_env ? atoi(mode_env) : 0);  // (debug bits: 32 = the staged kernels' first range, 64 = cycle marks into slots 19-30)
+        QCK_CHECK_LAUNCH(h);
+        return QCK_OK;
+    }
     const char* fused_env = getenv("QCK_NPD_FUSED");
     if (n > 0 && npd_grid(h, n) <= h->sm_count && fused_env && atoi(fused_env) == 1) {
         DeviceGuard guard(h->device);

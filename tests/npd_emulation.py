@@ -2,7 +2,9 @@
 the same statistics, key ranges, bins, integer quantisation and tails, step for step, so that the LOGIC of
 the kernels is pinned on CPU against the oracle (``oracle.dense.nearest_probability_distribution`` =
 quasi_distr.py:28-43) before any GPU time is spent.  ``shards > 1`` emulates the multi-rank form
-(qck_npd_stage with the statistics / bins summed across ranks between stage and tail)."""
+(qck_npd_stage with the statistics / bins summed across ranks between stage and tail).  ``bin_bits = 11`` is the
+geometry of the one-cluster kernel for vectors of at most 2^16 entries (npd_cluster_kernel: 2048 bins per level,
+six levels; otherwise the same definitions)."""
 import math
 
 import numpy as np
@@ -37,7 +39,7 @@ class State:
     pass
 
 
-def _set_level(s):
+def _set_level(s, BIN_BITS=BIN_BITS):
     width = (s.hi - s.lo)
     bits = 0 if width <= 1 else (width - 1).bit_length()
     s.shift = bits - BIN_BITS if bits > BIN_BITS else 0
@@ -50,7 +52,7 @@ def _set_level(s):
     s.qexp = e
 
 
-def _plan(s):
+def _plan(s, BIN_BITS=BIN_BITS, lo_zero=False):
     s.level, s.under_sum, s.under_cnt, s.beta, s.num, s.shift_val, s.t0 = 0, 0.0, 0.0, 0.0, s.alive, 0.0, -math.inf
     if not (s.alive > 0.0) or not (s.vmin < 0.0):
         s.status = IDENTITY
@@ -59,13 +61,15 @@ def _plan(s):
     else:
         s.status = SEARCH
         t_ub = -s.neg_sum * (1.0 + 1e-9)
-        s.lo = int(key_of_fast(np.array([s.vmin]))[0]) - 1
+        # (the cluster kernel starts above zero: G(0) = neg_sum < 0, so t0 > 0 and every entry <= 0 is dropped)
+        s.lo = 0 if lo_zero else int(key_of_fast(np.array([s.vmin]))[0]) - 1
         s.hi = int(key_of_fast(np.array([t_ub]))[0])
         s.sel_cnt = int(s.alive)
-        _set_level(s)
+        _set_level(s, BIN_BITS)
 
 
-def _select(s, bin_cnt, bin_q):
+def _select(s, bin_cnt, bin_q, BIN_BITS=BIN_BITS):
+    BINS = 1 << BIN_BITS
     if s.status == LOCATED:
         s.beta = s.under_sum
         s.num = s.alive - s.under_cnt
@@ -97,10 +101,10 @@ def _select(s, bin_cnt, bin_q):
     if cnt_j == 0 or off_hi - off_lo <= 1:
         s.status = LOCATED
     else:
-        _set_level(s)
+        _set_level(s, BIN_BITS)
 
 
-def nearest_probability_distribution(p, acc=0.0, shards=1):
+def nearest_probability_distribution(p, acc=0.0, shards=1, bin_bits=BIN_BITS):
     """-> (result, state).  Mirrors qck_npd_async (shards == 1) / the staged multi-rank flow."""
     p = np.asarray(p, dtype=np.float64).copy()
     parts = np.array_split(np.arange(len(p)), shards)
@@ -113,9 +117,11 @@ def nearest_probability_distribution(p, acc=0.0, shards=1):
     s.neg_sum = sum(float(p[i][alive[i] & (p[i] < 0)].sum()) for i in parts)
     s.alive = float(alive.sum())
     s.neg_cnt = float((alive & (p < 0)).sum())
-    _plan(s)
+    BINS, levels = 1 << bin_bits, -(-64 // bin_bits)
+    s.levels = levels
+    _plan(s, bin_bits, lo_zero=bin_bits == 11)
     passes = 0
-    for _ in range(LEVELS + 1):
+    for _ in range(levels + 1):
         if s.status not in (SEARCH, LOCATED):
             break
         passes += 1
@@ -139,7 +145,7 @@ def nearest_probability_distribution(p, acc=0.0, shards=1):
                     bin_q[bb] += qq
         assert all(int(x) < (1 << 62) for x in bin_q)
         s.under_sum, s.under_cnt = us, uc
-        _select(s, bin_cnt, bin_q)
+        _select(s, bin_cnt, bin_q, bin_bits)
     s.passes = passes
     if s.status == SOLVED:
         keep = alive & (keys > s.lo)

@@ -10,9 +10,12 @@ from oracle import dense as od
 
 
 def _check(v, acc=0.0, shards=1, tol=1e-15):
-    got, st = ne.nearest_probability_distribution(v, acc, shards)
     want = od.nearest_probability_distribution(np.asarray(v, float), acc)
+    got11, st11 = ne.nearest_probability_distribution(v, acc, 1, bin_bits=11)     # npd_cluster_kernel's geometry
+    assert np.abs(got11 - want).max() < tol and st11.passes <= st11.levels + 1
+    got, st = ne.nearest_probability_distribution(v, acc, shards)
     assert np.abs(got - want).max() < tol
+    assert st.status == st11.status and (st.status != ne.SOLVED or st.num == st11.num)   # the same partition
     return st
 
 
@@ -24,8 +27,8 @@ def test_golden_cases():
         want = np.zeros_like(dense)
         for k, v in c["out"]:
             want[int(k)] = v
-        for shards in (1, 3):
-            got, st = ne.nearest_probability_distribution(dense, c["acc"], shards)
+        for shards, bits in ((1, 13), (3, 13), (1, 11)):
+            got, st = ne.nearest_probability_distribution(dense, c["acc"], shards, bin_bits=bits)
             assert np.abs(got - want).max() < 1e-13
             assert st.status in (ne.IDENTITY, ne.SOLVED)
 
