@@ -705,10 +705,16 @@ __global__ void __launch_bounds__(256) contract_dmma_kernel(const __grid_constan
 // for padding) while the tensor cores work on the current one; the label weights are applied to the A fragments
 // as they leave shared memory, so both operands are plain copies.  Three stages of [16 labels][64 + 8] doubles
 // per operand = 54 KiB of dynamic shared memory.
+// Tile size (round 2, second half): at 64x64 every 16-label chunk brings 16 KiB from L2 for 131 kflop - 8 flop per
+// gathered byte, which makes the kernel an L2-gather kernel (ncu: DMMA 41 % of its peak on hwe-16 d5's 256x256
+// output, 304 CTAs each re-reading a quarter of both tables).  TT = 128 halves the bytes per flop and quarters the
+// barriers per flop: 16 warps of 32x32 (4x4 DMMA tiles, 8 LDS.64 for 16 DMMAs per k-step; or 8 warps of 64x32),
+// one CTA per SM.  Used when both padded dimensions are multiples of 128 and there are at least 4096 labels.
 #define GS 3
+template <int TT>
 struct ContractStage {
-    double A[GK][GP];
-    double B[GK][GP];
+    double A[GK][TT + 8];
+    double B[GK][TT + 8];
     double W[GK];
 };
 __device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, bool valid) {
@@ -717,28 +723,32 @@ __device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, boo
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(256) contract_dmma_pipe_kernel(const __grid_constant__ ContractParams P, int n_split,
-                                                                 double* __restrict__ partial, int M, int N, int Mr,
-                                                                 int Nr) {
+template <int TT, int NW>
+__global__ void __launch_bounds__(32 * NW)
+    contract_dmma_pipe_kernel(const __grid_constant__ ContractParams P, int n_split, double* __restrict__ partial, int M,
+                              int N, int Mr, int Nr) {
+    constexpr int WR = NW / 4;                              // warps: WR rows x 4 columns
+    constexpr int NA = TT / WR / 8, NB = TT / 4 / 8;        // DMMA tiles per warp: rows (x 8), columns (x 8)
+    constexpr int NT = 32 * NW;
     extern __shared__ __align__(16) unsigned char cps_raw[];
-    ContractStage* stage = reinterpret_cast<ContractStage*>(cps_raw);
+    ContractStage<TT>* stage = reinterpret_cast<ContractStage<TT>*>(cps_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wi = (warp >> 2) * 32, wj = (warp & 3) * 16;
+    const int wi = (warp >> 2) * (TT / WR), wj = (warp & 3) * (TT / 4);
     const int gid = lane >> 2, tig = lane & 3;
-    const int i0 = blockIdx.x * GT, j0 = blockIdx.y * GT;
+    const int i0 = blockIdx.x * TT, j0 = blockIdx.y * TT;
     const long long per = (P.count + n_split - 1) / n_split;
     const long long lb = per * blockIdx.z, le = (lb + per < P.count) ? lb + per : P.count;
     const int* rowA = P.rows;
     const int* rowB = P.rows + P.count;
     const long long n_chunks = le > lb ? (le - lb + GK - 1) / GK : 0;
-    // this thread's share of a stage: 4 requests of 16 bytes (2 doubles) - rows rr, columns cc..cc+1
+    // this thread's share of a stage: requests of 16 bytes (2 doubles) - rows rr, columns cc..cc+1
     auto issue = [&](long long chunk) {
-        ContractStage& S = stage[chunk % GS];
+        ContractStage<TT>& S = stage[chunk % GS];
         const long long l0 = lb + chunk * GK;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int e = tid + 256 * k;           // 512 requests per operand
-            const int rr = e >> 5, cc = (e & 31) * 2;
+        for (int k = 0; k < GK * (TT / 2) / NT; ++k) {
+            const int e = tid + NT * k;            // GK * TT / 2 requests per operand
+            const int rr = e / (TT / 2), cc = (e % (TT / 2)) * 2;
             const long long l = l0 + rr;
             const bool in = l < le;
             const long long ra = in ? (long long)__ldg(rowA + l) : 0, rb = in ? (long long)__ldg(rowB + l) : 0;
@@ -751,11 +761,11 @@ __global__ void __launch_bounds__(256) contract_dmma_pipe_kernel(const __grid_co
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    double acc[4][2][2];
+    double acc[NA][NB][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NA; ++a)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int b = 0; b < NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
     for (int c = 0; c < GS - 1; ++c) {
         if (c < n_chunks) issue(c);
         else asm volatile("cp.async.commit_group;" ::: "memory");
@@ -765,26 +775,26 @@ __global__ void __launch_bounds__(256) contract_dmma_pipe_kernel(const __grid_co
         __syncthreads();  // chunk c has landed for everyone; everyone is done with chunk c - 1's buffer
         if (c + GS - 1 < n_chunks) issue(c + GS - 1);
         else asm volatile("cp.async.commit_group;" ::: "memory");
-        const ContractStage& S = stage[c % GS];
+        const ContractStage<TT>& S = stage[c % GS];
 #pragma unroll
         for (int k4 = 0; k4 < GK; k4 += 4) {
             const double w = S.W[k4 + tig];
-            double af[4], bf[2];
+            double af[NA], bf[NB];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) af[a] = w * S.A[k4 + tig][wi + 8 * a + gid];
+            for (int a = 0; a < NA; ++a) af[a] = w * S.A[k4 + tig][wi + 8 * a + gid];
 #pragma unroll
-            for (int b = 0; b < 2; ++b) bf[b] = S.B[k4 + tig][wj + 8 * b + gid];
+            for (int b = 0; b < NB; ++b) bf[b] = S.B[k4 + tig][wj + 8 * b + gid];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < NA; ++a)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                for (int b = 0; b < NB; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
     }
     double* dst = partial + (long long)blockIdx.z * M * N;
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NA; ++a)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NB; ++b) {
             const long long r = i0 + wi + 8 * a + gid, cidx = j0 + wj + 8 * b + 2 * tig;
             dst[r * N + cidx] = acc[a][b][0];
             dst[r * N + cidx + 1] = acc[a][b][1];
@@ -968,13 +978,21 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
     const bool gemm = (n_eff == 2);
     const int mAp = mA < 6 ? 6 : mA, mBp = mB < 6 ? 6 : mB;
     int n_split = 1;
+    bool big_tile = false;
     size_t partial_bytes = 0;
     if (gemm) {
-        long long tiles = (1ll << (mAp - 6)) * (1ll << (mBp - 6));
-        // ~2 CTAs per SM: the pipelined kernel hides its own latency, more splits only add partial-sum traffic
+        // 128x128 tiles (one CTA per SM) when both padded dimensions allow it and there are labels enough to keep
+        // the three-stage ring busy; else 64x64 tiles, ~2 CTAs per SM (QCK_CONTRACT_TILE=64 / 128 forces one)
+        const char* tile_env = getenv("QCK_CONTRACT_TILE");
+        big_tile = mAp >= 7 && mBp >= 7 && count >= 4096;
+        if (tile_env) big_tile = atoi(tile_env) == 128 && mAp >= 7 && mBp >= 7;
+        const int tb = big_tile ? 7 : 6;
+        long long tiles = (1ll << (mAp - tb)) * (1ll << (mBp - tb));
+        // the pipelined kernel hides its own latency, more splits only add partial-sum traffic
         const char* split_env = getenv("QCK_CONTRACT_CTAS_PER_SM");
-        const long long per_sm = split_env ? atoi(split_env) : 2;
+        const long long per_sm = split_env ? atoi(split_env) : (big_tile ? 1 : 2);
         long long want = ((per_sm > 0 ? per_sm : 2) * h->sm_count + tiles - 1) / tiles;
+        if (big_tile && !split_env) want = h->sm_count / tiles > 0 ? h->sm_count / tiles : 1;  // one wave, never two
         long long maxs = (count + 4 * GK - 1) / (4 * GK);
         n_split = (int)(want < maxs ? want : maxs);
         if (n_split < 1) n_split = 1;
@@ -1066,13 +1084,27 @@ extern "C" int qck_knit_contract(qck_handle* h, int n_frag, const double* const*
         if (fma_env && atoi(fma_env) == 1)
             contract_gemm_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N, Mr, Nr);
         else if (aligned && !(pipe_env && atoi(pipe_env) == 0)) {
-            static bool attr_set = false;  // process-wide function attribute, same value from every thread
+            static bool attr_set = false;  // process-wide function attributes, same values from every thread
             if (!attr_set) {
-                QCK_CUDA(h, cudaFuncSetAttribute(contract_dmma_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(GS * sizeof(ContractStage))));
+                QCK_CUDA(h, cudaFuncSetAttribute(contract_dmma_pipe_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(GS * sizeof(ContractStage<64>))));
+                QCK_CUDA(h, cudaFuncSetAttribute(contract_dmma_pipe_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(GS * sizeof(ContractStage<128>))));
+                QCK_CUDA(h, cudaFuncSetAttribute(contract_dmma_pipe_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(GS * sizeof(ContractStage<128>))));
                 attr_set = true;
             }
-            contract_dmma_pipe_kernel<<<grid, 256, GS * sizeof(ContractStage), st>>>(cp, n_split, d_partial, M, N, Mr, Nr);
+            const char* warps_env = getenv("QCK_CONTRACT_WARPS");
+            // 16 warps of 32x32 by default (DMMA pipe 61 % busy on hwe-16 d5, 59 % with 8 warps of 64x32: QCK_CONTRACT_WARPS=8)
+            if (big_tile && !(warps_env && atoi(warps_env) == 8))
+                contract_dmma_pipe_kernel<128, 16><<<dim3(M / 128, N / 128, n_split), 512, GS * sizeof(ContractStage<128>), st>>>(
+                    cp, n_split, d_partial, M, N, Mr, Nr);
+            else if (big_tile)
+                contract_dmma_pipe_kernel<128, 8><<<dim3(M / 128, N / 128, n_split), 256, GS * sizeof(ContractStage<128>), st>>>(
+                    cp, n_split, d_partial, M, N, Mr, Nr);
+            else
+                contract_dmma_pipe_kernel<64, 8><<<grid, 256, GS * sizeof(ContractStage<64>), st>>>(cp, n_split, d_partial, M, N,
+                                                                                                   Mr, Nr);
         }
         else
             contract_dmma_kernel<<<grid, 256, 0, st>>>(cp, n_split, d_partial, M, N, Mr, Nr);
