@@ -649,14 +649,14 @@ def measure(workload: str, args, env: dict, primary: bool, accuracy: float = 0.0
         else:
             Ls = (label_range[1] - label_range[0]) if label_range is not None else L
             alg = 2.0 * Ls * float(np.prod([t.shape[1] for t in holder["t"].values()]))
-            kernel = "qck_knit_faithful" if faithful else "contract_dmma_kernel+contract_scatter_kernel"
+            kernel = "qck_knit_faithful" if faithful else "contract_dmma_pipe_kernel+contract_scatter_kernel"
             bound, unit, peak, src = "tensor", "TFLOP/s", peaks.get("dmma_tflops"), "qck_measure_peaks (FP64 DMMA m8n8k4, this run)"
             achieved = alg / (knit_ms * 1e-3) / 1e12
             key = "algorithmic_flops_per_step"
         kernel_ms = knit_ms
     else:
         alg = work["flops_algorithmic"] * ((label_range[1] - label_range[0]) / L if label_range is not None else 1.0)
-        kernel, bound, unit = "sim_onchip_*_kernel (all programs of all fragments)", "fp64", "TFLOP/s"
+        kernel, bound, unit = "sim_tree_level_kernel+sim_tree_combine_kernel (all instances of all fragments; sim_warp / sim_onchip kernels where the tree walk does not apply)", "fp64", "TFLOP/s"
         peak, src = peaks.get("fp64_fma_tflops"), "qck_measure_peaks (FP64 FMA issue rate, this run)"
         achieved = alg / (sim_ms * 1e-3) / 1e12
         kernel_ms, key = sim_ms, "algorithmic_flops_per_step"
