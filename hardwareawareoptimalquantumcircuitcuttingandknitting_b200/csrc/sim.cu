@@ -1618,7 +1618,7 @@ static int warp_groups_run(qck_handle* h, WarpGroupHost* W, int n_groups, cudaSt
 }
 
 // ---- tree-walk simulation ----------------------------------------------------------------------
-typedef void (*TreeKernelFn)(const TreeDev, int, long long, const double2*, double2*, double*);
+typedef void (*TreeKernelFn)(const TreeDev, int, int, long long, const double2*, double2*, double*);
 static TreeKernelFn tree_kernel(int log_r) {
     switch (log_r) {
         case 0: return sim_tree_level_kernel<0>;
@@ -1731,14 +1731,26 @@ extern "C" int qck_sim_tree(qck_handle* h, const qck_sim_tree_plan* plan, int64_
     const long long cap = (long long)h->sm_count * h->tree_occ[log_r];
     int dbg_skip = 0;
     if (const char* e = getenv("QCK_TREE_DEBUG_SKIP")) dbg_skip = atoi(e);  // timing experiments only
-    for (int l = 0; l < plan->n_levels; ++l) {
+    // the first levels in ONE launch (every warp replays its item's path from the root) while the last fused
+    // level has at most 300 items; QCK_TREE_FUSE_ITEMS overrides the limit (0: one launch per level).  Measured:
+    // hwe-16 d5 0.1735 -> 0.1689 ms, syc-16 d5 0.119 -> 0.113 ms per step with levels 0-2 (216 items) fused; fusing
+    // on to 1 296 items (one wave of warps) gives the gain back - a level is bound by its chain of gates, not by
+    // its launch, and the replay makes the chain longer.
+    long long fuse_cap = 300;
+    if (fuse_cap > cap * QCK_WARP_PER_CTA) fuse_cap = cap * QCK_WARP_PER_CTA;
+    if (const char* e = getenv("QCK_TREE_FUSE_ITEMS")) fuse_cap = atoll(e);
+    int fused_to = 0;
+    while (fused_to + 1 < plan->n_levels && n[fused_to + 2] <= fuse_cap) ++fused_to;
+    if (dbg_skip) fused_to = 0;
+    for (int l = fused_to; l < plan->n_levels; ++l) {
         if ((dbg_skip & 2) && l == plan->n_levels - 1) continue;
         if ((dbg_skip & 4) && l < plan->n_levels - 1) continue;
         const long long items = n[l + 1];
         long long ctas = (items + QCK_WARP_PER_CTA - 1) / QCK_WARP_PER_CTA;
         if (ctas > cap) ctas = cap;
+        const int first = l == fused_to ? 0 : l;
         tree_kernel(log_r)<<<(unsigned)ctas, 32 * QCK_WARP_PER_CTA, tree_smem(log_r), st>>>(
-            *T, l, items, sbuf[(l + 1) & 1], sbuf[l & 1], part);
+            *T, first, l, items, sbuf[(l + 1) & 1], sbuf[l & 1], part);
         QCK_CHECK_LAUNCH(h);
     }
     int n_fork_max = 0;
