@@ -674,6 +674,59 @@ def test_npd_async_no_host_round_trip(dev, shards):
     assert int(st[5]) == _lib.NPD_ST_NEGATIVE_TOTAL
 
 
+def test_npd_cluster_kernel_random_sizes_and_graph_replay(dev):
+    """npd_cluster_kernel (one 8-CTA cluster, at most 2^16 entries) on vectors of arbitrary length - ragged tails of
+    the 16-entries-per-thread layout, lengths below one CTA's share, a single entry - against the oracle
+    (quasi_distr.py:28-43 restated), and replayed from a CUDA graph on fresh data (the resident step's use)."""
+    h = _lib.get_handle(0)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    n_ws = h.lib.qck_npd_workspace_bytes() // 8
+    rng = np.random.default_rng(2024)
+    sizes = [1, 2, 31, 33, 511, 513, 4097, 8191, 8192, 8193, 40000, 65535, 65536] + [int(x) for x in rng.integers(2, 65537, 12)]
+    for n in sizes:
+        kind = int(rng.integers(0, 4))
+        if kind == 0:                                   # one peak + rounding noise of mixed sign
+            v = rng.normal(0, 1e-17, n); v[rng.integers(n)] += 1.0
+        elif kind == 1:                                 # a proper distribution with a few entries pushed negative
+            v = rng.random(n); v /= v.sum(); v[rng.choice(n, max(1, n // 50), replace=False)] -= 2.0 / n
+            v[0] += max(0.0, -v.sum()) + 0.5
+        elif kind == 2:                                 # many exact zeros, noise over many binades
+            v = np.where(rng.random(n) < 0.8, 0.0, rng.normal(0, 1, n) * 10.0 ** rng.integers(-30, -15, n)); v[-1] = 1.0
+        else:                                           # exact ties
+            v = rng.choice([-3e-17, -1e-17, 2e-17, 0.0, 1e-3], n); v[0] = 1.0
+        want = od.nearest_probability_distribution(v)
+        data = torch.from_numpy(v.copy()).to(dev)
+        ws = torch.zeros(n_ws, dtype=torch.int64, device=dev)
+        l0 = h.launch_count
+        h.check(h.lib.qck_npd_async(h.ptr, data.data_ptr(), n, 0.0, ws.data_ptr(), stream))
+        assert h.launch_count - l0 == 1
+        got = data.cpu().numpy()
+        assert int(ws[5]) in (_lib.NPD_ST_SOLVED, _lib.NPD_ST_IDENTITY), (n, kind, int(ws[5]))
+        assert np.abs(got - want).max() < 1e-13 * max(1.0, np.abs(v).max()), (n, kind)
+        assert got.min() >= 0.0
+    # from a CUDA graph: the same captured launch on new data
+    n = 1 << 16
+    data = torch.zeros(n, dtype=torch.float64, device=dev)
+    ws = torch.zeros(n_ws, dtype=torch.int64, device=dev)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        h.check(h.lib.qck_npd_async(h.ptr, data.data_ptr(), n, 0.0, ws.data_ptr(), side.cuda_stream))
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        h.check(h.lib.qck_npd_async(h.ptr, data.data_ptr(), n, 0.0, ws.data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream))
+    for trial in range(3):
+        v = rng.normal(0, 1e-17, n); v[trial] = 1.0
+        data.copy_(torch.from_numpy(v))
+        g.replay()
+        torch.cuda.synchronize(dev)
+        assert np.abs(data.cpu().numpy() - od.nearest_probability_distribution(v)).max() < 1e-13
+    del g
+
+
 def test_hellinger_identities_and_random(dev):
     p = {0: 0.25, 3: 0.75}
     assert abs(fidm.hellinger_fidelity(p, p) - 1.0) < 1e-15
