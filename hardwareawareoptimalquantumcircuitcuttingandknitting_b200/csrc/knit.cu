@@ -195,14 +195,33 @@ __global__ void __launch_bounds__(KO_THREADS) knit_outer_kernel(const __grid_con
                         }
                     }
                     __syncthreads();
+                    // y_lo = (e << 10) | (tid << 2) | j, and pext splits over disjoint bit ranges: the tid part (the only
+                    // one that needs a loop) once per fragment, the two-bit parts of j and e in closed form.  (A
+                    // soft_pext per entry made a row change cost ~1 300 instructions per thread - several us each
+                    // time a CTA moves to another row, which is what the CTAs do at the end of a launch.)
+                    static_assert(KO_THREADS == 256 && KO_ITEMS == 4 && KO_CHUNK_BITS == 12, "y_lo = (e << 10) | (tid << 2) | j");
+                    unsigned int tpart[FV > 0 ? FV : 1], mj[FV > 0 ? FV : 1], me[FV > 0 ? FV : 1], se[FV > 0 ? FV : 1];
+#pragma unroll
+                    for (int f = 0; f < FV; ++f) {
+                        const unsigned int m = P.lo_mask[f];
+                        mj[f] = m & 3u;
+                        me[f] = (m >> 10) & 3u;
+                        const unsigned int mt = (m >> 2) & 0xffu;
+                        const int sj = __popc(mj[f]);
+                        tpart[f] = (unsigned int)soft_pext((unsigned int)tid, mt) << sj;
+                        se[f] = (unsigned int)(sj + __popc(mt));
+                    }
+                    auto pext2 = [](unsigned int x, unsigned int m) -> unsigned int {  // x, m < 4
+                        return m == 3u ? x : (m == 1u ? (x & 1u) : (m == 2u ? (x >> 1) : 0u));
+                    };
 #pragma unroll
                     for (int e = 0; e < KO_ITEMS; ++e)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const unsigned int y_lo = 4u * (e * KO_THREADS + tid) + j;
-                            double v = rows[P.row_off[0] + soft_pext(y_lo, P.lo_mask[0])];
+                            double v = rows[P.row_off[0] + (pext2(j, mj[0]) | tpart[0] | (pext2(e, me[0]) << se[0]))];
 #pragma unroll
-                            for (int f = 1; f < FV; ++f) v *= rows[P.row_off[f] + soft_pext(y_lo, P.lo_mask[f])];
+                            for (int f = 1; f < FV; ++f)
+                                v *= rows[P.row_off[f] + (pext2(j, mj[f]) | tpart[f] | (pext2(e, me[f]) << se[f]))];
                             pv[e][j] = v;
                         }
                     pv_sum = 0.0;

@@ -13,7 +13,7 @@ virt = vcm.VirtualCircuit(cut)
 tables = virt.simulate_fragments(dev)
 out = torch.empty(1 << 32, dtype=torch.float64, device=dev)
 stats = torch.zeros(4, dtype=torch.float64, device=dev)
-for frac in (8, 4, 1):
+for frac in (32, 8, 4, 1):
     n = (1 << 32) // frac
     for which in (0, frac - 1):
         y0 = which * n
