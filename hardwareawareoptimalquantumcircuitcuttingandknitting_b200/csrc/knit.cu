@@ -143,24 +143,44 @@ __global__ void __launch_bounds__(KO_THREADS) knit_outer_kernel(const __grid_con
     // The chunk number is (row, column): the row bits select the rows of the vector fragments, the
     // column bits only scalar factors.  Each row has its own counter; a CTA stays on its row (no
     // reload) until it is exhausted, then steals from the following rows.
+    // When its row is exhausted warp 0 LOOKS at the counters of the other rows, 32 at a time, and jumps to the first
+    // one with work left: trying the rows one by one with the atomic itself is a chain of up to n_rows dependent
+    // atomics on contended counters before a CTA can conclude that nothing is left (a 4 GiB slice back to back:
+    // 0.619 -> 0.609 ms per launch).  Pulling sub-batches near the end of a row ("guided" pulls) was measured too: no
+    // gain on any slice size.
     __shared__ unsigned long long s_batch[2];
+    __shared__ int s_my_row;
     const unsigned long long DONE = ~0ull;
-    int my_row = (int)(blockIdx.x % (unsigned)P.n_rows), rows_tried = 0;
-    auto next_batch = [&]() -> unsigned long long {  // lane 0 of warp 0 only
-        while (rows_tried < P.n_rows) {
-            const unsigned long long b = atomicAdd(P.work_counter + my_row, 1ull);
-            if (b < P.batches_per_row)
-                return ((unsigned long long)my_row << P.n_fast) + b * KO_BATCH;
-            my_row = my_row + 1 == P.n_rows ? 0 : my_row + 1;
-            ++rows_tried;
+    if (tid == 0) s_my_row = (int)(blockIdx.x % (unsigned)P.n_rows);
+    __syncwarp();
+    auto next_batch = [&]() -> unsigned long long {  // all lanes of warp 0; the same result in every lane
+        for (;;) {
+            const int my_row = s_my_row;
+            unsigned long long b = 0ull;
+            if (tid == 0) b = atomicAdd(P.work_counter + my_row, 1ull);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b < P.batches_per_row) return ((unsigned long long)my_row << P.n_fast) + b * KO_BATCH;
+            int found = -1;
+            for (int base = 1; base < P.n_rows && found < 0; base += 32) {
+                const int off = base + tid;
+                int r = my_row + off;
+                r = r >= P.n_rows ? r - P.n_rows : r;
+                const bool has = off < P.n_rows && *(volatile unsigned long long*)(P.work_counter + r) < P.batches_per_row;
+                const unsigned int m = __ballot_sync(0xffffffffu, has);
+                if (m) {
+                    found = my_row + base + (__ffs(m) - 1);
+                    found = found >= P.n_rows ? found - P.n_rows : found;
+                }
+            }
+            if (found < 0) return DONE;
+            __syncwarp();
+            if (tid == 0) s_my_row = found;
+            __syncwarp();
         }
-        return DONE;
     };
     double sum = 0.0, mn = INFINITY;
     if (tid < 32) {
-        unsigned long long gb = 0;
-        if (tid == 0) gb = next_batch();
-        gb = __shfl_sync(0xffffffffu, gb, 0);
+        const unsigned long long gb = next_batch();
         if (tid < KO_BATCH && gb != DONE && gb + tid < P.n_chunks) make_desc(P, gb + tid, &desc[0][tid]);
         if (tid == 0) s_batch[0] = gb;
     }
@@ -169,9 +189,7 @@ __global__ void __launch_bounds__(KO_THREADS) knit_outer_kernel(const __grid_con
         const unsigned long long gb = s_batch[buf];
         if (gb == DONE) break;
         if (tid < 32) {  // fetch and describe the next batch while this one streams
-            unsigned long long gn = 0;
-            if (tid == 0) gn = next_batch();
-            gn = __shfl_sync(0xffffffffu, gn, 0);
+            const unsigned long long gn = next_batch();
             if (tid < KO_BATCH && gn != DONE && gn + tid < P.n_chunks) make_desc(P, gn + tid, &desc[buf ^ 1][tid]);
             if (tid == 0) s_batch[buf ^ 1] = gn;
         }
